@@ -1,0 +1,153 @@
+/*
+ * sdso_b200.h — C ABI of the B200-native photometric hot path for Stereo-DSO-g2o.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, caller-owned host
+ * buffers, int status returns, no exceptions and no Eigen/Sophus/torch types in any signature.
+ * The reference has no FFI layer of its own — its operators are C++ classes linked into libdso.a
+ * (CMakeLists.txt:159-163) — so every entry point below names the reference member function it
+ * replaces (file:line into the reference's src/). The C++ adapter classes that carry the
+ * reference's own names/signatures on top of this ABI live in
+ * stereo-dso-g2o_b200/host/dso_adapters.hpp; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - SE3 crosses the boundary as double[12], row-major 3x4 [R|t].
+ *   - AffLight crosses as double[2] = {a, b}  (util/NumType.h:152-175).
+ *   - Images are float32, row-major, w*h, values as produced by the reference's undistorter
+ *     (raw 0..255 in mode=1).
+ *   - Every function returns SDSO_OK (0) or a negative SDSO_E_* code; sdso_last_error() gives text.
+ *   - All work is enqueued on the context's CUDA stream (sdso_set_stream); calls that return data
+ *     to host buffers synchronise that stream before returning.
+ *   - There is NO CPU fallback: if no CUDA device is usable, sdso_ctx_create fails.
+ */
+#ifndef SDSO_B200_H_
+#define SDSO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDSO_OK 0
+#define SDSO_E_INVALID -1   /* bad argument */
+#define SDSO_E_CUDA -2      /* CUDA runtime error (see sdso_last_error) */
+#define SDSO_E_NODEVICE -3  /* no usable CUDA device */
+#define SDSO_E_STATE -4     /* call order violated (e.g. track before set_ref) */
+#define SDSO_E_NOMEM -5
+
+#define SDSO_PYR_LEVELS 6       /* util/settings.h:46 */
+#define SDSO_PATTERN_NUM 8      /* util/settings.h:177 */
+#define SDSO_MAX_RES_PER_POINT 8
+
+/* which of the reference's two algorithmic variants an operator follows */
+#define SDSO_VARIANT_SSE 0 /* original DSO arithmetic (calcRes/calcGSSSE, LM with multiplicative lambda) */
+#define SDSO_VARIANT_G2O 1 /* live fork code: g2o edges + restated g2o Levenberg */
+
+typedef struct sdso_ctx sdso_ctx;
+
+/* Tunables the hot path reads. Defaults = util/settings.cpp with main_dso_pangolin.cpp preset=0 mode=1. */
+typedef struct sdso_settings {
+  float huberTH;                    /* settings.cpp:95  */
+  float coarseCutoffTH;             /* :102 */
+  float outlierTH;                  /* :72  */
+  float outlierTHSumComponent;      /* :73  */
+  float overallEnergyTHWeight;      /* :101 */
+  float maxPixSearch;               /* :111 */
+  int32_t minTraceTestRadius;       /* :113 */
+  float trace_stepsize;             /* :115 */
+  int32_t trace_GNIterations;       /* :116 */
+  float trace_GNThreshold;          /* :117 */
+  float trace_extraSlackOnTH;       /* :118 */
+  float trace_slackInterval;        /* :119 */
+  float trace_minImprovementFactor; /* :120 */
+  float affineOptModeA;             /* main_dso_pangolin.cpp:326 */
+  float affineOptModeB;             /* :327 */
+  int32_t gammaWeightsPixelSelect;  /* settings.cpp:93 */
+  int32_t g2o_stop_flag_persists;   /* SURVEY.md Appendix C open point (1); default 1 */
+  int32_t cluster_size;             /* thread-block cluster size of the persistent kernels (0 = default 8) */
+  int32_t block_threads;            /* threads per CTA of the persistent kernels (0 = default 256) */
+} sdso_settings;
+
+void sdso_default_settings(sdso_settings* s);
+
+/* ---- context ---------------------------------------------------------------------------------
+ * Replaces the globals set by setGlobalCalib(w,h,K) (util/globalCalib.cpp:48-108): wG,hG,fxG..,KG,
+ * KiG,wM3G,hM3G,baseline,pyrLevelsUsed. K = {fx,fy,cx,cy} of the (already cropped) working image. */
+int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline,
+                    const sdso_settings* settings /* nullable */);
+void sdso_ctx_destroy(sdso_ctx* ctx);
+const char* sdso_last_error(const sdso_ctx* ctx);
+int sdso_set_stream(sdso_ctx* ctx, void* cuda_stream /* cudaStream_t, NULL = default */);
+int sdso_synchronize(sdso_ctx* ctx);
+int sdso_pyr_levels(const sdso_ctx* ctx);
+int sdso_level_size(const sdso_ctx* ctx, int lvl, int* w, int* h);
+/* per-level initial intrinsics KG[lvl], KiG[lvl] (row-major 3x3 float) */
+int sdso_level_K(const sdso_ctx* ctx, int lvl, float K[9], float Ki[9]);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t sdso_launch_count(const sdso_ctx* ctx);
+
+/* ---- A1: FrameHessian::makeImages (FullSystem/HessianBlocks.cpp:141-203) ------------------------
+ * A frame is a device-resident pyramid: per level float4{I,dx,dy,absSquaredGrad} (the reference's
+ * Vector3f dIp[lvl] + float absSquaredGrad[lvl], HessianBlocks.h:107-109, fused into one 16-byte
+ * texel). Border rows 0 and h-1 of dx/dy/absSquaredGrad, which the reference leaves uninitialised,
+ * are written as 0. */
+int sdso_frame_create(sdso_ctx* ctx, int* frame_id);
+int sdso_frame_release(sdso_ctx* ctx, int frame_id);
+/* host image -> H2D copy -> pyramid kernels. use_hcalib != 0 mirrors passing a non-null CalibHessian*
+ * (gamma-gradient factor on absSquaredGrad; B is the identity in mode=1). */
+int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float ab_exposure, int use_hcalib);
+/* same, image already on the device (device pointer, w*h floats) */
+int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_image, float ab_exposure, int use_hcalib);
+/* read back level lvl: dI3 = w_l*h_l*3 floats AoS {I,dx,dy} (the reference's layout), absgrad = w_l*h_l */
+int sdso_frame_download(sdso_ctx* ctx, int frame_id, int lvl, float* dI3 /* nullable */, float* absgrad /* nullable */);
+/* getInterpolatedElement33 / 33BiLin (util/globalFuncs.h:73-86, 160-184) at n points of level lvl */
+int sdso_interp33(sdso_ctx* ctx, int frame_id, int lvl, const float* xy, int n, float* out3, int bilin_variant);
+
+/* ---- A3/A4: CoarseTracker::makeK, setCoarseTrackingRef / makeCoarseDepthL0 ----------------------
+ * (FullSystem/CoarseTracker.cpp:108-136, 275-534, 809-825). */
+int sdso_tracker_make_k(sdso_ctx* ctx, const float K[4] /* optimised HCalib fxl,fyl,cxl,cyl */);
+/* STEP1 splat .. STEP5 compaction of makeCoarseDepthL0 from n splats {u,v,idepth,weight}
+ * (CoarseTracker.cpp:350-533); ref_aff = lastRef->aff_g2l(). */
+int sdso_tracker_set_ref(sdso_ctx* ctx, int ref_frame, const float* uvidw /* n*4 */, int n, const double ref_aff[2]);
+/* direct upload of pc_u/pc_v/pc_idepth/pc_color[lvl] (CoarseTracker.h:117-121) */
+int sdso_tracker_set_pc(sdso_ctx* ctx, int ref_frame, int lvl, int n, const float* u, const float* v,
+                        const float* idepth, const float* color, const double ref_aff[2]);
+int sdso_tracker_get_pc(sdso_ctx* ctx, int lvl, int* n, float* u, float* v, float* idepth, float* color /* nullable, capacity w_l*h_l */);
+
+/* ---- A5/A6: CoarseTracker::calcRes + calcGSSSE (CoarseTracker.cpp:600-792, 537-596) -------------
+ * One fused pass at (refToNew, aff): rs[6] as calcRes returns it, H/b as calcGSSSE returns them
+ * (8x8 row-major, scaled by SCALE_* as written at :584-595), warped_n = buf_warped_n (padded to x4).
+ * warped (nullable, capacity 8*(N_l+4)) receives the eight buf_warped_* arrays, each warped_n long, in
+ * the order idepth,u,v,dx,dy,residual,weight,refColor. */
+int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNew[12], const double aff[2],
+                     float cutoffTH, double rs[6], double H[64], double b[8], int* warped_n, float* warped);
+
+/* ---- E1: EdgeSE3PosePhotoDSO::computeError / linearizeOplus (dso_g2o_edge.cpp:395-500) ----------
+ * For every pc point of level lvl that passes calcRes's border test at T_select (CoarseTracker.cpp:696)
+ * evaluate the edge at (T_pose, photo): err[n_out], J[n_out*8] = {J_pose(6), J_photo(2)}. */
+int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[12], const double T_pose[12],
+                   const double photo[2], int* n_out, double* err, double* J8);
+
+/* ---- A7: CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:827-1069) --------------------------
+ * Whole coarse-to-fine optimisation in ONE persistent cluster kernel (no host round trips).
+ * T_io / aff_io: in = initial guess (lastToNew_out, aff_g2l_out), out = result.
+ * Returns (through *ok) what the reference returns. iterations[5] (nullable) = LM iterations per level. */
+int sdso_track(sdso_ctx* ctx, int new_frame, double T_io[12], double aff_io[2], int coarsest_lvl,
+               const double minResForAbort[5], int variant, double lastResiduals[5], double flowIndicators[3],
+               int iterations[5], int* ok);
+/* Batched form: nb independent (initial pose, aff) hypotheses against the same reference and the same
+ * or different new frames, one cluster each, one launch (FullSystem.cpp:351-376,441-501 tries them
+ * sequentially). Arrays are nb-strided versions of sdso_track's. */
+int sdso_track_batch(sdso_ctx* ctx, int nb, const int* new_frames, double* T_io, double* aff_io, int coarsest_lvl,
+                     const double* minResForAbort, int variant, double* lastResiduals, double* flowIndicators,
+                     int* iterations, int* ok);
+/* async pair used by bench.py so that CUDA events bracket the kernels without host syncs */
+int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const double* T_in, const double* aff_in,
+                       int coarsest_lvl, const double* minResForAbort, int variant);
+int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, double* lastResiduals,
+                       double* flowIndicators, int* iterations, int* ok, uint64_t* evals /* nullable, total */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDSO_B200_H_ */

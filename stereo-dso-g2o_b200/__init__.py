@@ -1,0 +1,241 @@
+"""sdso_b200 — thin ctypes view of libsdso_b200.so (the C ABI in include/sdso_b200.h).
+
+This module is test/bench plumbing: it owns no algorithm. Every method forwards to one C entry
+point, which in turn launches the hand-written sm_100a kernels under csrc/. There is no CPU
+fallback: importing succeeds without a GPU (so the symbol table can be checked), but creating a
+context without a usable CUDA device raises, and a missing shared library raises at import.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdso_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sdso_b200.h")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C {_HERE}` (or __graft_entry__.build()). "
+        "The B200 hot path has no CPU fallback.")
+lib = C.CDLL(LIB_PATH)
+
+VARIANT_SSE, VARIANT_G2O = 0, 1
+OK = 0
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("huberTH", C.c_float), ("coarseCutoffTH", C.c_float), ("outlierTH", C.c_float),
+        ("outlierTHSumComponent", C.c_float), ("overallEnergyTHWeight", C.c_float), ("maxPixSearch", C.c_float),
+        ("minTraceTestRadius", C.c_int32), ("trace_stepsize", C.c_float), ("trace_GNIterations", C.c_int32),
+        ("trace_GNThreshold", C.c_float), ("trace_extraSlackOnTH", C.c_float), ("trace_slackInterval", C.c_float),
+        ("trace_minImprovementFactor", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
+        ("gammaWeightsPixelSelect", C.c_int32), ("g2o_stop_flag_persists", C.c_int32), ("cluster_size", C.c_int32),
+        ("block_threads", C.c_int32),
+    ]
+
+
+def default_settings():
+    s = Settings()
+    lib.sdso_default_settings(C.byref(s))
+    return s
+
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+lib.sdso_last_error.restype = C.c_char_p
+lib.sdso_launch_count.restype = C.c_uint64
+lib.sdso_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.POINTER(Settings)]
+lib.sdso_ctx_destroy.argtypes = [C.c_void_p]
+lib.sdso_last_error.argtypes = [C.c_void_p]
+lib.sdso_launch_count.argtypes = [C.c_void_p]
+lib.sdso_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+lib.sdso_synchronize.argtypes = [C.c_void_p]
+lib.sdso_pyr_levels.argtypes = [C.c_void_p]
+lib.sdso_level_size.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+lib.sdso_level_K.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
+lib.sdso_frame_create.argtypes = [C.c_void_p, _ip]
+lib.sdso_frame_release.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_make_images.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int]
+lib.sdso_make_images_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int]
+lib.sdso_frame_download.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp]
+lib.sdso_interp33.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_int]
+lib.sdso_tracker_make_k.argtypes = [C.c_void_p, _fp]
+lib.sdso_tracker_set_ref.argtypes = [C.c_void_p, C.c_int, _fp, C.c_int, _dp]
+lib.sdso_tracker_set_pc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _dp]
+lib.sdso_tracker_get_pc.argtypes = [C.c_void_p, C.c_int, _ip, _fp, _fp, _fp, _fp]
+lib.sdso_calc_res_gs.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_float, _dp, _dp, _dp, _ip, _fp]
+lib.sdso_track.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _ip, _ip]
+lib.sdso_track_enqueue.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_int, _dp, C.c_int]
+lib.sdso_track_collect.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip, C.POINTER(C.c_uint64)]
+
+
+class SdsoError(RuntimeError):
+    pass
+
+
+class Context:
+    """One sdso_ctx (one GPU, one working resolution)."""
+
+    def __init__(self, w, h, K, baseline=0.0, device=0, settings=None):
+        self._h = C.c_void_p()
+        Kc = (C.c_float * 4)(*[float(x) for x in K])
+        sp = C.byref(settings) if settings is not None else None
+        rc = lib.sdso_ctx_create(C.byref(self._h), device, w, h, Kc, float(baseline), sp)
+        if rc != OK:
+            self._h = C.c_void_p()
+            raise SdsoError(f"sdso_ctx_create failed with code {rc} (no CUDA device? there is no CPU fallback)")
+        self.w, self.h = w, h
+        self.levels = lib.sdso_pyr_levels(self._h)
+
+    def close(self):
+        if self._h:
+            lib.sdso_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise SdsoError(f"sdso error {rc}: {lib.sdso_last_error(self._h).decode()}")
+
+    # -- plumbing
+    def set_stream(self, stream_ptr):
+        self._ck(lib.sdso_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def synchronize(self):
+        self._ck(lib.sdso_synchronize(self._h))
+
+    def launch_count(self):
+        return int(lib.sdso_launch_count(self._h))
+
+    def level_size(self, lvl):
+        w, h = C.c_int(), C.c_int()
+        self._ck(lib.sdso_level_size(self._h, lvl, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level_K(self, lvl):
+        K = np.zeros(9, np.float32)
+        Ki = np.zeros(9, np.float32)
+        self._ck(lib.sdso_level_K(self._h, lvl, _ptr(K, _fp), _ptr(Ki, _fp)))
+        return K.reshape(3, 3), Ki.reshape(3, 3)
+
+    # -- A1
+    def frame_create(self):
+        fid = C.c_int()
+        self._ck(lib.sdso_frame_create(self._h, C.byref(fid)))
+        return fid.value
+
+    def frame_release(self, fid):
+        self._ck(lib.sdso_frame_release(self._h, fid))
+
+    def make_images(self, fid, image, exposure=1.0, use_hcalib=True):
+        img = _f32(image)
+        assert img.size == self.w * self.h
+        self._ck(lib.sdso_make_images(self._h, fid, img.ctypes.data, float(exposure), int(use_hcalib)))
+
+    def make_images_ptr(self, fid, host_ptr, exposure=1.0, use_hcalib=True):
+        self._ck(lib.sdso_make_images(self._h, fid, C.c_void_p(host_ptr), float(exposure), int(use_hcalib)))
+
+    def make_images_device(self, fid, dev_ptr, exposure=1.0, use_hcalib=True):
+        self._ck(lib.sdso_make_images_device(self._h, fid, C.c_void_p(dev_ptr), float(exposure), int(use_hcalib)))
+
+    def frame_download(self, fid, lvl):
+        w, h = self.level_size(lvl)
+        dI = np.zeros((h, w, 3), np.float32)
+        ag = np.zeros((h, w), np.float32)
+        self._ck(lib.sdso_frame_download(self._h, fid, lvl, _ptr(dI, _fp), _ptr(ag, _fp)))
+        return dI, ag
+
+    def interp33(self, fid, lvl, xy, bilin=False):
+        xy = _f32(xy).reshape(-1, 2)
+        out = np.zeros((xy.shape[0], 3), np.float32)
+        self._ck(lib.sdso_interp33(self._h, fid, lvl, _ptr(xy, _fp), xy.shape[0], _ptr(out, _fp), int(bilin)))
+        return out
+
+    # -- A3/A4
+    def tracker_make_k(self, K):
+        Kc = _f32(K)
+        self._ck(lib.sdso_tracker_make_k(self._h, _ptr(Kc, _fp)))
+
+    def tracker_set_ref(self, fid, uvidw, aff=(0.0, 0.0)):
+        p = _f32(uvidw).reshape(-1, 4)
+        a = _f64(aff)
+        self._ck(lib.sdso_tracker_set_ref(self._h, fid, _ptr(p, _fp), p.shape[0], _ptr(a, _dp)))
+
+    def tracker_set_pc(self, fid, lvl, u, v, idepth, color, aff=(0.0, 0.0)):
+        u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
+        a = _f64(aff)
+        self._ck(lib.sdso_tracker_set_pc(self._h, fid, lvl, u.size, _ptr(u, _fp), _ptr(v, _fp), _ptr(idepth, _fp),
+                                         _ptr(color, _fp), _ptr(a, _dp)))
+
+    def tracker_get_pc(self, lvl):
+        w, h = self.level_size(lvl)
+        cap = w * h
+        u, v, idp, col = (np.zeros(cap, np.float32) for _ in range(4))
+        n = C.c_int()
+        self._ck(lib.sdso_tracker_get_pc(self._h, lvl, C.byref(n), _ptr(u, _fp), _ptr(v, _fp), _ptr(idp, _fp), _ptr(col, _fp)))
+        n = n.value
+        return u[:n].copy(), v[:n].copy(), idp[:n].copy(), col[:n].copy()
+
+    # -- A5/A6
+    def calc_res_gs(self, new_fid, lvl, T, aff, cutoff, want_warped=True):
+        T = _f64(T).reshape(12)
+        aff = _f64(aff)
+        rs, H, b = np.zeros(6), np.zeros(64), np.zeros(8)
+        wn = C.c_int()
+        w, h = self.level_size(lvl)
+        warped = np.zeros(8 * (w * h + 4), np.float32) if want_warped else None
+        self._ck(lib.sdso_calc_res_gs(self._h, new_fid, lvl, _ptr(T, _dp), _ptr(aff, _dp), float(cutoff), _ptr(rs, _dp),
+                                      _ptr(H, _dp), _ptr(b, _dp), C.byref(wn), _ptr(warped, _fp) if want_warped else None))
+        out = dict(rs=rs, H=H.reshape(8, 8), b=b, warped_n=wn.value)
+        if want_warped:
+            out["warped"] = warped[:8 * wn.value].reshape(8, wn.value).copy()
+        return out
+
+    # -- A7
+    def track(self, new_fid, T, aff, coarsest, min_res_for_abort, variant=VARIANT_SSE):
+        T = _f64(T).reshape(12).copy()
+        aff = _f64(aff).copy()
+        mr = _f64(min_res_for_abort)
+        lr, fl = np.zeros(5), np.zeros(3)
+        it = np.zeros(5, np.int32)
+        ok = C.c_int()
+        self._ck(lib.sdso_track(self._h, new_fid, _ptr(T, _dp), _ptr(aff, _dp), coarsest, _ptr(mr, _dp), variant,
+                                _ptr(lr, _dp), _ptr(fl, _dp), _ptr(it, _ip), C.byref(ok)))
+        return dict(T=T.reshape(3, 4), aff=aff, lastResiduals=lr, flow=fl, iterations=it, ok=bool(ok.value))
+
+    def track_enqueue(self, new_fids, T, aff, coarsest, min_res_for_abort, variant=VARIANT_SSE):
+        nb = len(new_fids)
+        f = np.ascontiguousarray(new_fids, dtype=np.int32)
+        T = _f64(T).reshape(nb, 12)
+        aff = _f64(aff).reshape(nb, 2)
+        mr = _f64(min_res_for_abort).reshape(nb, 5)
+        self._ck(lib.sdso_track_enqueue(self._h, nb, _ptr(f, _ip), _ptr(T, _dp), _ptr(aff, _dp), coarsest, _ptr(mr, _dp), variant))
+
+    def track_collect(self, nb):
+        T, aff, lr, fl = np.zeros((nb, 12)), np.zeros((nb, 2)), np.zeros((nb, 5)), np.zeros((nb, 3))
+        it, ok = np.zeros((nb, 5), np.int32), np.zeros(nb, np.int32)
+        ev = C.c_uint64()
+        self._ck(lib.sdso_track_collect(self._h, nb, _ptr(T, _dp), _ptr(aff, _dp), _ptr(lr, _dp), _ptr(fl, _dp), _ptr(it, _ip),
+                                        _ptr(ok, _ip), C.byref(ev)))
+        return dict(T=T.reshape(nb, 3, 4), aff=aff, lastResiduals=lr, flow=fl, iterations=it, ok=ok.astype(bool), evals=int(ev.value))

@@ -1,0 +1,242 @@
+// Context, frame arena, A1 entry points of the C ABI (include/sdso_b200.h).
+#include "ctx.h"
+#include <cstring>
+#include <cmath>
+
+namespace sdso {
+
+int set_gamma_table(sdso_ctx* ctx, const float B[256]);
+
+void inverse3f(const float m[9], float out[9]) {
+  // cofactor(i,j) over cyclic indices; inverse(j,i) = cofactor(i,j) * (1/det); det expanded along column 0
+  auto cof = [&](int i, int j) -> float {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+  };
+  float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  float det = (c00 * m[0] + c10 * m[3]) + c20 * m[6];
+  float invdet = 1.0f / det;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) out[j * 3 + i] = cof(i, j) * invdet;
+}
+
+// util/globalCalib.cpp:48-108 (decide_levels) and CoarseTracker::makeK (CoarseTracker.cpp:108-136)
+void HostCalib::set(int w0, int h0, float fx0, float fy0, float cx0, float cy0, bool decide_levels) {
+  if (decide_levels) {
+    int wl = w0, hl = h0;
+    levels = 1;
+    while (wl % 2 == 0 && hl % 2 == 0 && wl * hl > 5000 && levels < kPyrLevels) { wl /= 2; hl /= 2; levels++; }
+  }
+  w[0] = w0; h[0] = h0; fx[0] = fx0; fy[0] = fy0; cx[0] = cx0; cy[0] = cy0;
+  for (int l = 1; l < kPyrLevels; l++) {
+    w[l] = w0 >> l; h[l] = h0 >> l;
+    fx[l] = (float)(fx[l - 1] * 0.5);
+    fy[l] = (float)(fy[l - 1] * 0.5);
+    cx[l] = (float)((cx[0] + 0.5) / ((int)1 << l) - 0.5);
+    cy[l] = (float)((cy[0] + 0.5) / ((int)1 << l) - 0.5);
+  }
+  for (int l = 0; l < kPyrLevels; l++) {
+    float Kl[9] = {fx[l], 0.f, cx[l], 0.f, fy[l], cy[l], 0.f, 0.f, 1.f};
+    memcpy(K[l], Kl, sizeof(Kl));
+    inverse3f(K[l], Ki[l]);
+  }
+}
+
+}  // namespace sdso
+
+using namespace sdso;
+
+extern "C" {
+
+void sdso_default_settings(sdso_settings* s) {
+  if (!s) return;
+  s->huberTH = 9;
+  s->coarseCutoffTH = 20;
+  s->outlierTH = 12 * 12;
+  s->outlierTHSumComponent = 50 * 50;
+  s->overallEnergyTHWeight = 1;
+  s->maxPixSearch = 0.027f;
+  s->minTraceTestRadius = 2;
+  s->trace_stepsize = 1.0f;
+  s->trace_GNIterations = 3;
+  s->trace_GNThreshold = 0.1f;
+  s->trace_extraSlackOnTH = 1.2f;
+  s->trace_slackInterval = 1.5f;
+  s->trace_minImprovementFactor = 2;
+  s->affineOptModeA = 0;
+  s->affineOptModeB = 0;
+  s->gammaWeightsPixelSelect = 1;
+  s->g2o_stop_flag_persists = 1;
+  s->cluster_size = 0;
+  s->block_threads = 0;
+}
+
+int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {
+  if (!out || !K || w < 16 || h < 16) return SDSO_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SDSO_E_NODEVICE;  // no CPU fallback
+  if (device < 0 || device >= ndev) return SDSO_E_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return SDSO_E_NODEVICE;
+  sdso_ctx* c = new sdso_ctx();
+  c->device = device;
+  if (settings) c->S = *settings; else sdso_default_settings(&c->S);
+  c->G.set(w, h, K[0], K[1], K[2], K[3], true);
+  c->baseline = baseline;
+  c->tex_total = 0;
+  for (int l = 0; l < c->G.levels; l++) c->tex_total += (size_t)c->G.w[l] * c->G.h[l];
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return SDSO_E_CUDA; }
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaMallocHost(&c->staging, (size_t)w * h * sizeof(float)) != cudaSuccess) { delete c; return SDSO_E_NOMEM; }
+  float B[256];
+  for (int i = 0; i < 256; i++) B[i] = (float)i;
+  int rc = set_gamma_table(c, B);
+  if (rc == SDSO_OK) rc = tracker_create(c);
+  if (rc == SDSO_OK) rc = ba_create(c);
+  if (rc == SDSO_OK) rc = trace_create(c);
+  if (rc != SDSO_OK) { sdso_ctx_destroy(c); return rc; }
+  *out = c;
+  return SDSO_OK;
+}
+
+void sdso_ctx_destroy(sdso_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  trace_destroy(ctx);
+  ba_destroy(ctx);
+  tracker_destroy(ctx);
+  for (auto& f : ctx->frames) {
+    if (f.tex[0]) cudaFree(f.tex[0]);
+    if (f.image) cudaFree(f.image);
+  }
+  if (ctx->staging) cudaFreeHost(ctx->staging);
+  delete ctx;
+}
+
+const char* sdso_last_error(const sdso_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sdso_set_stream(sdso_ctx* ctx, void* s) {
+  if (!ctx) return SDSO_E_INVALID;
+  ctx->stream = (cudaStream_t)s;
+  return SDSO_OK;
+}
+int sdso_synchronize(sdso_ctx* ctx) {
+  if (!ctx) return SDSO_E_INVALID;
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDSO_OK;
+}
+int sdso_pyr_levels(const sdso_ctx* ctx) { return ctx ? ctx->G.levels : SDSO_E_INVALID; }
+int sdso_level_size(const sdso_ctx* ctx, int lvl, int* w, int* h) {
+  if (!ctx || lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
+  if (w) *w = ctx->G.w[lvl];
+  if (h) *h = ctx->G.h[lvl];
+  return SDSO_OK;
+}
+int sdso_level_K(const sdso_ctx* ctx, int lvl, float K[9], float Ki[9]) {
+  if (!ctx || lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
+  if (K) memcpy(K, ctx->G.K[lvl], 9 * sizeof(float));
+  if (Ki) memcpy(Ki, ctx->G.Ki[lvl], 9 * sizeof(float));
+  return SDSO_OK;
+}
+uint64_t sdso_launch_count(const sdso_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sdso_set_gamma(sdso_ctx* ctx, const float B[256]) {
+  if (!ctx || !B) return SDSO_E_INVALID;
+  return set_gamma_table(ctx, B);
+}
+
+int sdso_frame_create(sdso_ctx* ctx, int* frame_id) {
+  if (!ctx || !frame_id) return SDSO_E_INVALID;
+  int id = -1;
+  for (size_t i = 0; i < ctx->frames.size(); i++) if (!ctx->frames[i].in_use) { id = (int)i; break; }
+  if (id < 0) {
+    Frame f;
+    float4* base = nullptr;
+    SDSO_CUDA(ctx, cudaMalloc(&base, ctx->tex_total * sizeof(float4)));
+    cudaError_t e = cudaMalloc(&f.image, ctx->tex_total * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(base); return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(e)); }
+    size_t off = 0;
+    for (int l = 0; l < ctx->G.levels; l++) { f.tex[l] = base + off; off += (size_t)ctx->G.w[l] * ctx->G.h[l]; }
+    ctx->frames.push_back(f);
+    id = (int)ctx->frames.size() - 1;
+  }
+  ctx->frames[id].in_use = true;
+  ctx->frames[id].valid = false;
+  *frame_id = id;
+  return SDSO_OK;
+}
+
+int sdso_frame_release(sdso_ctx* ctx, int frame_id) {
+  if (!ctx || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
+  ctx->frames[frame_id].in_use = false;  // device memory is kept for reuse
+  ctx->frames[frame_id].valid = false;
+  return SDSO_OK;
+}
+
+int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float ab_exposure, int use_hcalib) {
+  if (!ctx || !host_image || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
+  Frame& f = ctx->frames[frame_id];
+  const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
+  SDSO_CUDA(ctx, cudaMemcpyAsync(f.image, host_image, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  f.ab_exposure = ab_exposure;
+  int rc = make_images_launch(ctx, f, f.image, use_hcalib != 0);
+  if (rc) return rc;
+  f.valid = true;
+  return SDSO_OK;
+}
+
+int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_image, float ab_exposure, int use_hcalib) {
+  if (!ctx || !device_image || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
+  Frame& f = ctx->frames[frame_id];
+  const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
+  if (device_image != f.image)
+    SDSO_CUDA(ctx, cudaMemcpyAsync(f.image, device_image, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  f.ab_exposure = ab_exposure;
+  int rc = make_images_launch(ctx, f, f.image, use_hcalib != 0);
+  if (rc) return rc;
+  f.valid = true;
+  return SDSO_OK;
+}
+
+int sdso_frame_download(sdso_ctx* ctx, int frame_id, int lvl, float* dI3, float* absgrad) {
+  if (!ctx || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
+  if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
+  const size_t n = (size_t)ctx->G.w[lvl] * ctx->G.h[lvl];
+  std::vector<float4> tmp(n);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->frames[frame_id].tex[lvl], n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; i++) {
+    if (dI3) { dI3[3 * i] = tmp[i].x; dI3[3 * i + 1] = tmp[i].y; dI3[3 * i + 2] = tmp[i].z; }
+    if (absgrad) absgrad[i] = tmp[i].w;
+  }
+  return SDSO_OK;
+}
+
+}  // extern "C"
+
+namespace sdso {
+__global__ void interp_kernel(const float4* tex, int width, const float2* xy, int n, float3* out, int bilin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 p = xy[i];
+  out[i] = bilin ? interp33BiLin(tex, p.x, p.y, width) : interp33(tex, p.x, p.y, width);
+}
+}  // namespace sdso
+
+extern "C" int sdso_interp33(sdso_ctx* ctx, int frame_id, int lvl, const float* xy, int n, float* out3, int bilin_variant) {
+  if (!ctx || !xy || !out3 || n < 0 || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
+  if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
+  if (n == 0) return SDSO_OK;
+  float2* dxy = nullptr; float3* dout = nullptr;
+  SDSO_CUDA(ctx, cudaMalloc(&dxy, n * sizeof(float2)));
+  SDSO_CUDA(ctx, cudaMalloc(&dout, n * sizeof(float3)));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(dxy, xy, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+  sdso::interp_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->frames[frame_id].tex[lvl], ctx->G.w[lvl], dxy, n, dout, bilin_variant);
+  ctx->launches++;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(out3, dout, n * sizeof(float3), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dxy); cudaFree(dout);
+  return SDSO_OK;
+}

@@ -1,0 +1,94 @@
+// Context of the B200 hot path: calibration pyramid, device arenas, stream, settings.
+// Replaces the reference's process-wide globals (util/globalCalib.cpp:33-46, util/settings.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include "../../include/sdso_b200.h"
+#include "common.cuh"
+
+namespace sdso {
+
+struct Frame {
+  bool in_use = false;
+  float4* tex[kPyrLevels] = {nullptr};  // one allocation, level pointers into it
+  float* image = nullptr;               // level-0 intensity plane (the uploaded image)
+  float ab_exposure = 1.0f;
+  bool valid = false;
+};
+
+struct HostCalib {  // per level, float, as util/globalCalib.cpp:48-108 computes them
+  int levels = 0;
+  int w[kPyrLevels], h[kPyrLevels];
+  float fx[kPyrLevels], fy[kPyrLevels], cx[kPyrLevels], cy[kPyrLevels];
+  float K[kPyrLevels][9], Ki[kPyrLevels][9];
+  void set(int w0, int h0, float fx0, float fy0, float cx0, float cy0, bool decide_levels);
+};
+
+struct TrackerState;  // tracker.cu
+struct BAState;       // ba.cu
+struct TraceState;    // trace.cu
+
+}  // namespace sdso
+
+struct sdso_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  sdso_settings S;
+  sdso::HostCalib G;   // initial calibration == the reference's globals wG,hG,KG,...
+  float baseline = 0;
+  std::vector<sdso::Frame> frames;
+  size_t tex_total = 0;  // float4 texels per frame over all levels
+  float* staging = nullptr;  // pinned host staging for image upload
+  sdso::TrackerState* tracker = nullptr;
+  sdso::BAState* ba = nullptr;
+  sdso::TraceState* trace = nullptr;
+  uint64_t launches = 0;
+  int num_sms = 0;
+  std::string err;
+};
+
+namespace sdso {
+
+inline int fail(sdso_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define SDSO_CUDA(ctx, expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      return sdso::fail(ctx, SDSO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    }                                                                                              \
+  } while (0)
+
+#define SDSO_CHECK_LAUNCH(ctx)                                                                     \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return sdso::fail(ctx, SDSO_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// 3x3 float inverse by cofactors * (1/det), the same arithmetic Eigen's Matrix3f::inverse() performs,
+// so K^-1 matches the reference's KiG / Ki bit for bit.
+void inverse3f(const float m[9], float out[9]);
+
+// host-side SE3 helpers in double (row-major 3x4)
+void se3_exp(const double a[6], double T[12]);
+void se3_mul(const double A[12], const double B[12], double C[12]);
+void se3_inv(const double A[12], double B[12]);
+
+// make_images.cu
+int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib);
+// tracker.cu
+int tracker_create(sdso_ctx* ctx);
+void tracker_destroy(sdso_ctx* ctx);
+// ba.cu / trace.cu
+int ba_create(sdso_ctx* ctx);
+void ba_destroy(sdso_ctx* ctx);
+int trace_create(sdso_ctx* ctx);
+void trace_destroy(sdso_ctx* ctx);
+
+}  // namespace sdso

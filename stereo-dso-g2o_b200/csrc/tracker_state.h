@@ -1,0 +1,32 @@
+// Host-side state of the device CoarseTracker (shared by tracker.cu and tracker_ref.cu).
+#pragma once
+#include "ctx.h"
+
+namespace sdso {
+
+struct TrackProblem;
+
+struct TrackerState {
+  HostCalib K;  // tracker's own pyramid of intrinsics (makeK from the optimised HCalib)
+  float4* pc[kPyrLevels] = {nullptr};
+  int pc_n[kPyrLevels] = {0};
+  int pc_cap[kPyrLevels] = {0};
+  int ref_frame = -1;
+  double ref_aff[2] = {0, 0};
+  bool have_ref = false;
+  TrackProblem* d_problems = nullptr;
+  TrackProblem* h_problems = nullptr;  // pinned
+  int max_problems = 16;
+  float* d_dump = nullptr;
+  size_t dump_cap = 0;
+  int last_nb = 0;
+  // A4 scratch
+  float* idepth[kPyrLevels] = {nullptr};
+  float* wsum[kPyrLevels] = {nullptr};
+  float* wsum_bak[kPyrLevels] = {nullptr};
+  int* scan_tmp = nullptr;
+  int* d_counts = nullptr;
+};
+
+
+}  // namespace sdso

@@ -1,0 +1,146 @@
+"""A3-A7 parity on the GPU through the C ABI against the oracle (SSE path of CoarseTracker)."""
+import numpy as np
+import pytest
+import oracle_py as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4  # north_star tolerance for residuals, Hessians, increments
+
+
+def rot_angle(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1) / 2
+    return float(np.arccos(np.clip(c, -1, 1)))
+
+
+@pytest.fixture(scope="module")
+def pair(pkg, frames):
+    ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE)
+    orc = O.Oracle(synth.W, synth.H, synth.K4, synth.BASELINE)
+    ids = {}
+    for k in (0, 1, 2):
+        g, o = ctx.frame_create(), orc.frame_new()
+        ctx.make_images(g, frames[k][0])
+        orc.make_images(o, frames[k][0])
+        ids[k] = (g, o)
+    rng = np.random.default_rng(1)
+    pts = synth.pick_points(rng, frames[0][1], 2000)
+    ctx.tracker_set_ref(ids[0][0], pts, (0.0, 0.0))
+    orc.tracker_set_ref(ids[0][1], pts, (0.0, 0.0))
+    yield ctx, orc, ids, pts
+    ctx.close()
+
+
+def test_template_bit_exact(pair):
+    """makeCoarseDepthL0 STEP1-5 (CoarseTracker.cpp:350-533): counts, raster order and values."""
+    ctx, orc, ids, pts = pair
+    for lvl in range(orc.levels):
+        g = ctx.tracker_get_pc(lvl)
+        o = orc.tracker_get_pc(lvl)
+        assert g[0].size == o[0].size, f"pc_n level {lvl}"
+        for a, b, name in zip(g, o, ("u", "v", "idepth", "color")):
+            assert np.array_equal(a, b), f"pc_{name} level {lvl}"
+
+
+def test_template_with_colliding_splats_counts(pair, pkg, frames):
+    """Two splats on one pixel: integer outputs (counts, positions) still exact; sums agree to rounding."""
+    ctx, orc, ids, pts = pair
+    p2 = np.concatenate([pts[:500], pts[:500] * np.array([1, 1, 1.1, 0.5], np.float32)])
+    c2 = pkg.Context(synth.W, synth.H, synth.K4)
+    g = c2.frame_create()
+    c2.make_images(g, frames[0][0])
+    c2.tracker_set_ref(g, p2)
+    o2 = O.Oracle(synth.W, synth.H, synth.K4)
+    o = o2.frame_new()
+    o2.make_images(o, frames[0][0])
+    o2.tracker_set_ref(o, p2)
+    for lvl in range(o2.levels):
+        a, b = c2.tracker_get_pc(lvl), o2.tracker_get_pc(lvl)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.allclose(a[2], b[2], rtol=1e-6)
+    c2.close()
+
+
+@pytest.mark.parametrize("lvl", [0, 1, 2, 3, 4])
+def test_calc_res_and_gs(pair, lvl):
+    """calcRes (:600-792, SSE body) + calcGSSSE (:537-596): per-residual buffers bit-exact, counts exact, H/b rel 1e-4."""
+    ctx, orc, ids, pts = pair
+    Ttrue = synth.T_rel(synth.camera_pose(0), synth.camera_pose(1))
+    rng = np.random.default_rng(10 + lvl)
+    T = synth.perturb_T(Ttrue, rng, 0.05, np.deg2rad(0.5))
+    aff = (0.02, -1.5)
+    g = ctx.calc_res_gs(ids[1][0], lvl, T, aff, 20.0)
+    o = orc.calc_res_gs(ids[1][1], lvl, T, aff, 20.0)
+    assert g["warped_n"] == o["warped_n"] and g["warped_n"] % 4 == 0
+    assert g["rs"][1] == o["rs"][1]                 # numTermsInE
+    assert np.array_equal(g["warped"], o["warped"]), "buf_warped_* must be bit-exact"
+    assert np.allclose(g["rs"], o["rs"], rtol=REL, atol=0, equal_nan=True)
+    scale_H = np.abs(o["H"]).max()
+    assert np.abs(g["H"] - o["H"]).max() <= REL * scale_H
+    assert np.allclose(g["H"], o["H"], rtol=REL, atol=REL * 1e-3 * scale_H)
+    assert np.allclose(g["b"], o["b"], rtol=REL, atol=REL * np.abs(o["b"]).max())
+
+
+def test_calc_res_saturation_and_oob(pair):
+    """A pose far from the truth: many saturated / out-of-border residuals; counters must still agree exactly."""
+    ctx, orc, ids, pts = pair
+    T = np.eye(4)[:3].copy()
+    T[:, 3] = [0.8, -0.3, 2.5]
+    for cutoff in (20.0, 40.0):
+        g = ctx.calc_res_gs(ids[1][0], 0, T, (0.0, 0.0), cutoff)
+        o = orc.calc_res_gs(ids[1][1], 0, T, (0.0, 0.0), cutoff)
+        assert g["warped_n"] == o["warped_n"]
+        assert g["rs"][1] == o["rs"][1]
+        assert np.allclose(g["rs"], o["rs"], rtol=REL, equal_nan=True)
+        assert np.array_equal(g["warped"], o["warped"])
+
+
+@pytest.mark.parametrize("new_k,init", [(1, "identity"), (1, "perturbed"), (2, "identity")])
+def test_track_sse_matches_oracle(pair, new_k, init):
+    """trackNewestCoarse, SSE path (:827-1069): final pose within 1e-4 m / 1e-5 rad of the oracle, same verdict."""
+    ctx, orc, ids, pts = pair
+    Ttrue = synth.T_rel(synth.camera_pose(0), synth.camera_pose(new_k))
+    T0 = np.eye(4)[:3] if init == "identity" else synth.perturb_T(Ttrue, np.random.default_rng(3), 0.05, np.deg2rad(0.5))
+    mr = [np.nan] * 5
+    g = ctx.track(ids[new_k][0], T0, (0.0, 0.0), ctx.levels - 1, mr, pkg_variant_sse())
+    o = orc.track(ids[new_k][1], T0, (0.0, 0.0), orc.levels - 1, mr, 0)
+    assert g["ok"] == o["ok"]
+    assert np.abs(g["T"][:, 3] - o["T"][:, 3]).max() < 1e-4
+    assert rot_angle(g["T"][:, :3], o["T"][:, :3]) < 1e-5
+    assert np.allclose(g["aff"], o["aff"], rtol=1e-3, atol=1e-3)
+    assert np.allclose(g["lastResiduals"], o["lastResiduals"], rtol=1e-3)
+    assert np.allclose(g["flow"], o["flow"], rtol=REL)
+    # and both are close to the ground truth motion
+    assert np.abs(g["T"][:, 3] - Ttrue[:, 3]).max() < 5e-3
+
+
+def pkg_variant_sse():
+    return 0
+
+
+def test_track_abort_on_min_res(pair):
+    """lastResiduals[lvl] > 1.5*minResForAbort[lvl] returns false and leaves the pose untouched (:1032)."""
+    ctx, orc, ids, pts = pair
+    T0 = np.eye(4)[:3]
+    mr = [1e-3] * 5
+    g = ctx.track(ids[1][0], T0, (0.0, 0.0), ctx.levels - 1, mr, 0)
+    o = orc.track(ids[1][1], T0, (0.0, 0.0), orc.levels - 1, mr, 0)
+    assert g["ok"] is False and o["ok"] is False
+    assert np.array_equal(g["T"], T0)
+    assert np.isnan(g["lastResiduals"][0]) and np.isfinite(g["lastResiduals"][4])
+
+
+def test_track_batch_equals_single(pair):
+    """Hypotheses tracked in one launch (one cluster each) give the same result as separate launches."""
+    ctx, orc, ids, pts = pair
+    Ttrue = synth.T_rel(synth.camera_pose(0), synth.camera_pose(1))
+    rng = np.random.default_rng(4)
+    Ts = [np.eye(4)[:3]] + [synth.perturb_T(Ttrue, rng, 0.05, np.deg2rad(0.5)) for _ in range(4)]
+    singles = [ctx.track(ids[1][0], T, (0.0, 0.0), ctx.levels - 1, [np.nan] * 5, 0) for T in Ts]
+    ctx.track_enqueue([ids[1][0]] * 5, np.stack(Ts), np.zeros((5, 2)), ctx.levels - 1, np.full((5, 5), np.nan), 0)
+    b = ctx.track_collect(5)
+    for k in range(5):
+        assert np.array_equal(b["T"][k], singles[k]["T"])  # deterministic: bit-identical
+        assert b["ok"][k] == singles[k]["ok"]
+    assert b["evals"] > 0
