@@ -85,6 +85,14 @@ int sdso_level_size(const sdso_ctx* ctx, int lvl, int* w, int* h);
 int sdso_level_K(const sdso_ctx* ctx, int lvl, float K[9], float Ki[9]);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t sdso_launch_count(const sdso_ctx* ctx);
+/* CUDA-event timing of the hot launches on the context's stream: enable, run, then read the summed
+ * durations (ms) and launch counts of the track kernel and of the makeImages kernel pair since the
+ * last read. Used by bench.py for the roofline figure; off by default. */
+int sdso_profile_enable(sdso_ctx* ctx, int on);
+int sdso_profile_read(sdso_ctx* ctx, double* track_ms, int* track_launches, double* images_ms, int* images_launches);
+/* CalibHessian::B (FullSystem/HessianBlocks.h:352): photometric response table used by getBGradOnly
+ * in makeImages; identity (B[i]=i) unless set. */
+int sdso_set_gamma(sdso_ctx* ctx, const float B[256]);
 
 /* ---- A1: FrameHessian::makeImages (FullSystem/HessianBlocks.cpp:141-203) ------------------------
  * A frame is a device-resident pyramid: per level float4{I,dx,dy,absSquaredGrad} (the reference's

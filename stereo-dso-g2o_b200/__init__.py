@@ -82,6 +82,10 @@ lib.sdso_tracker_get_pc.argtypes = [C.c_void_p, C.c_int, _ip, _fp, _fp, _fp, _fp
 lib.sdso_calc_res_gs.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_float, _dp, _dp, _dp, _ip, _fp]
 lib.sdso_track.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp, _ip, _ip]
 lib.sdso_track_enqueue.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_int, _dp, C.c_int]
+lib.sdso_edge_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _ip, _dp, _dp]
+lib.sdso_profile_enable.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_profile_read.argtypes = [C.c_void_p, _dp, _ip, _dp, _ip]
+lib.sdso_set_gamma.argtypes = [C.c_void_p, _fp]
 lib.sdso_track_collect.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip, C.POINTER(C.c_uint64)]
 
 
@@ -211,6 +215,29 @@ class Context:
         if want_warped:
             out["warped"] = warped[:8 * wn.value].reshape(8, wn.value).copy()
         return out
+
+    # -- E1
+    def edge_eval(self, new_fid, lvl, T_select, T_pose, photo):
+        Ts, Tp, ph = _f64(T_select).reshape(12), _f64(T_pose).reshape(12), _f64(photo)
+        w, h = self.level_size(lvl)
+        err, J = np.zeros(w * h), np.zeros((w * h, 8))
+        n = C.c_int()
+        self._ck(lib.sdso_edge_eval(self._h, new_fid, lvl, _ptr(Ts, _dp), _ptr(Tp, _dp), _ptr(ph, _dp), C.byref(n), _ptr(err, _dp), _ptr(J, _dp)))
+        return err[:n.value].copy(), J[:n.value].copy()
+
+    def profile_enable(self, on=True):
+        self._ck(lib.sdso_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        t, m = C.c_double(), C.c_double()
+        nt, nm = C.c_int(), C.c_int()
+        self._ck(lib.sdso_profile_read(self._h, C.byref(t), C.byref(nt), C.byref(m), C.byref(nm)))
+        return dict(track_ms=t.value, track_launches=nt.value, images_ms=m.value, images_launches=nm.value)
+
+    def set_gamma(self, B):
+        B = _f32(B)
+        assert B.size == 256
+        self._ck(lib.sdso_set_gamma(self._h, _ptr(B, _fp)))
 
     # -- A7
     def track(self, new_fid, T, aff, coarsest, min_res_for_abort, variant=VARIANT_SSE):

@@ -42,11 +42,52 @@ void HostCalib::set(int w0, int h0, float fx0, float fy0, float cx0, float cy0, 
   }
 }
 
+// which: 0 = track kernel, 1 = makeImages kernels
+void prof_begin(sdso_ctx* ctx, int which) {
+  if (!ctx->profile) return;
+  auto& v = which == 0 ? ctx->ev_track : ctx->ev_images;
+  size_t& used = which == 0 ? ctx->ev_track_used : ctx->ev_images_used;
+  if (used == v.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    v.push_back({a, b});
+  }
+  cudaEventRecord(v[used].first, ctx->stream);
+}
+void prof_end(sdso_ctx* ctx, int which) {
+  if (!ctx->profile) return;
+  auto& v = which == 0 ? ctx->ev_track : ctx->ev_images;
+  size_t& used = which == 0 ? ctx->ev_track_used : ctx->ev_images_used;
+  cudaEventRecord(v[used].second, ctx->stream);
+  used++;
+}
+
 }  // namespace sdso
 
 using namespace sdso;
 
 extern "C" {
+
+int sdso_profile_enable(sdso_ctx* ctx, int on) {
+  if (!ctx) return SDSO_E_INVALID;
+  ctx->profile = on != 0;
+  ctx->ev_track_used = ctx->ev_images_used = 0;
+  return SDSO_OK;
+}
+
+int sdso_profile_read(sdso_ctx* ctx, double* track_ms, int* track_launches, double* images_ms, int* images_launches) {
+  if (!ctx) return SDSO_E_INVALID;
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double t = 0, m = 0;
+  for (size_t i = 0; i < ctx->ev_track_used; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_track[i].first, ctx->ev_track[i].second); t += ms; }
+  for (size_t i = 0; i < ctx->ev_images_used; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_images[i].first, ctx->ev_images[i].second); m += ms; }
+  if (track_ms) *track_ms = t;
+  if (track_launches) *track_launches = (int)ctx->ev_track_used;
+  if (images_ms) *images_ms = m;
+  if (images_launches) *images_launches = (int)ctx->ev_images_used;
+  ctx->ev_track_used = ctx->ev_images_used = 0;
+  return SDSO_OK;
+}
 
 void sdso_default_settings(sdso_settings* s) {
   if (!s) return;
@@ -112,6 +153,8 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
     if (f.image) cudaFree(f.image);
   }
   if (ctx->staging) cudaFreeHost(ctx->staging);
+  for (auto& e : ctx->ev_track) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : ctx->ev_images) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete ctx;
 }
 

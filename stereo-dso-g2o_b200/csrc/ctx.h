@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include <utility>
 #include <cstdio>
 #include "../../include/sdso_b200.h"
 #include "common.cuh"
@@ -45,6 +46,10 @@ struct sdso_ctx {
   sdso::BAState* ba = nullptr;
   sdso::TraceState* trace = nullptr;
   uint64_t launches = 0;
+  // optional CUDA-event profiling of the two hot launches (bench.py roofline); see sdso_profile_*
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_track, ev_images;
+  size_t ev_track_used = 0, ev_images_used = 0;
   int num_sms = 0;
   std::string err;
 };
@@ -80,6 +85,9 @@ void se3_exp(const double a[6], double T[12]);
 void se3_mul(const double A[12], const double B[12], double C[12]);
 void se3_inv(const double A[12], double B[12]);
 
+// profiling helpers (ctx.cu)
+void prof_begin(sdso_ctx* ctx, int which);
+void prof_end(sdso_ctx* ctx, int which);
 // make_images.cu
 int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib);
 // tracker.cu

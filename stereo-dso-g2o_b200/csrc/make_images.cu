@@ -122,6 +122,7 @@ int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use
     for (int l = 1; l < P.levels; l++) { P.I[l] = p; p += (size_t)P.w[l] * P.h[l]; }
   }
   P.use_gamma = (use_hcalib && ctx->S.gammaWeightsPixelSelect == 1) ? 1 : 0;
+  prof_begin(ctx, 1);
   if (P.levels > 1) {
     dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile);
     pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(P);
@@ -135,6 +136,7 @@ int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use
     gradient_kernel<<<blocks, 256, 0, ctx->stream>>>(P);
     SDSO_CHECK_LAUNCH(ctx);
   }
+  prof_end(ctx, 1);
   return SDSO_OK;
 }
 

@@ -68,6 +68,7 @@ struct TrackParams {
   int eval_lvl;
   float eval_cutoff;
   float* dump;          // mode 1: per-point records [9][n] (valid,idepth,u,v,dx,dy,residual,weight,refColor) or null
+  double* dump_d;       // mode 2: per-point records [10][n] (flag, err, J[8]) or null
   float ref_exposure;
   double ref_aff[2];    // lastRef_aff_g2l
   float huberTH, coarseCutoffTH;
@@ -177,19 +178,31 @@ struct __align__(16) TrackSmem {
   LMState lm;
   EvalConst ec;
   float partial[2][kAcc];  // this CTA's block-reduced sums, double-buffered by evaluation parity
+  double partial_d[2];     // one extra channel summed in double (robust chi2 of the g2o path)
+  double warp_d[32];
   // followed by float red[kAcc * blockDim.x]
 };
 
 __device__ __forceinline__ float* smem_red(TrackSmem* sm) { return reinterpret_cast<float*>(sm + 1); }
 
 // Block + cluster reduction of per-thread accumulators; result (identical in every CTA) -> out[kAcc]
-__device__ void reduce_all(float (&acc)[kAcc], TrackSmem* sm, int& parity, cg::cluster_group& cluster, double* out) {
+__device__ void reduce_all(float (&acc)[kAcc], TrackSmem* sm, int& parity, cg::cluster_group& cluster, double* out,
+                           double dacc = 0.0, double* dout = nullptr) {
   float* red = smem_red(sm);
   const int BT = blockDim.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = BT >> 5;
 #pragma unroll
   for (int k = 0; k < kAcc; k++) red[k * BT + tid] = acc[k];
+  if (dout) {
+    double dv = warp_sum(dacc);
+    if (lane == 0) sm->warp_d[warp] = dv;
+  }
   __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nw = BT >> 5;
+  if (dout && tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < nw; w++) s += sm->warp_d[w];
+    sm->partial_d[parity] = s;
+  }
   for (int k = warp; k < kAcc; k += nw) {
     float s = 0.f;
     for (int j = lane; j < BT; j += 32) s += red[k * BT + j];
@@ -205,6 +218,11 @@ __device__ void reduce_all(float (&acc)[kAcc], TrackSmem* sm, int& parity, cg::c
       s += (double)rs->partial[parity][tid];
     }
     out[tid] = s;
+  }
+  if (dout && tid == kAcc) {
+    double s = 0.0;
+    for (unsigned r = 0; r < C; r++) s += cluster.map_shared_rank(sm, r)->partial_d[parity];
+    *dout = s;
   }
   parity ^= 1;
   __syncthreads();
@@ -396,7 +414,7 @@ __device__ void lm_step_sse(const TrackParams& P, LMState& lm) {
 }
 
 // ================================================================================================
-__global__ void __launch_bounds__(512, 1) track_kernel(TrackParams P) {
+__global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -540,6 +558,8 @@ __global__ void __launch_bounds__(512, 1) track_kernel(TrackParams P) {
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
+#include "tracker_g2o.cuh"
+
 // ================================================================================================
 // host side
 int tracker_create(sdso_ctx* ctx) {
@@ -575,6 +595,7 @@ void tracker_destroy(sdso_ctx* ctx) {
   if (t->d_problems) cudaFree(t->d_problems);
   if (t->h_problems) cudaFreeHost(t->h_problems);
   if (t->d_dump) cudaFree(t->d_dump);
+  for (int l = 0; l < kPyrLevels; l++) { if (t->edge_flag[l]) cudaFree(t->edge_flag[l]); if (t->edge_err[l]) cudaFree(t->edge_err[l]); }
   delete t;
   ctx->tracker = nullptr;
 }
@@ -599,14 +620,18 @@ static void fill_params(sdso_ctx* ctx, TrackParams& P) {
   P.problems = t->d_problems;
 }
 
-static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb) {
+static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   int C = ctx->S.cluster_size > 0 ? ctx->S.cluster_size : 8;
   int BT = ctx->S.block_threads > 0 ? ctx->S.block_threads : 256;
+  if (BT > 256 || BT < 64 || (BT & 31)) return fail(ctx, SDSO_E_INVALID, "block_threads must be a multiple of 32 in [64,256]");
+  if (C < 1 || C > 16) return fail(ctx, SDSO_E_INVALID, "cluster_size must be in [1,16]");
   size_t smem = sizeof(TrackSmem) + (size_t)kAcc * BT * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -618,8 +643,29 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel, P));
+  if (g2o) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_g2o_kernel, P));
+  else SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel, P));
   ctx->launches++;
+  return SDSO_OK;
+}
+
+// per-problem, per-level edge flags / errors of the g2o path
+static int ensure_edge_scratch(sdso_ctx* ctx, TrackParams& P, int nb) {
+  TrackerState* t = ctx->tracker;
+  for (int l = 0; l < ctx->G.levels; l++) {
+    int stride = (t->pc_n[l] + 63) & ~63;
+    if (stride < 64) stride = 64;
+    size_t need = (size_t)stride * nb;
+    if (need > t->edge_cap[l]) {
+      if (t->edge_flag[l]) cudaFree(t->edge_flag[l]);
+      if (t->edge_err[l]) cudaFree(t->edge_err[l]);
+      t->edge_flag[l] = nullptr; t->edge_err[l] = nullptr; t->edge_cap[l] = 0;
+      SDSO_CUDA(ctx, cudaMalloc(&t->edge_flag[l], need));
+      SDSO_CUDA(ctx, cudaMalloc(&t->edge_err[l], need * sizeof(double)));
+      t->edge_cap[l] = need;
+    }
+    P.edge_flag[l] = t->edge_flag[l]; P.edge_err[l] = t->edge_err[l]; P.edge_stride[l] = stride;
+  }
   return SDSO_OK;
 }
 
@@ -702,7 +748,7 @@ int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNe
   for (int l = 0; l < ctx->G.levels; l++) hp.tex[l] = ctx->frames[new_frame].tex[l];
   hp.exposure_new = ctx->frames[new_frame].ab_exposure;
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
-  rc = launch_track(ctx, P, 1);
+  rc = launch_track(ctx, P, 1, false);
   if (rc) return rc;
   SDSO_CUDA(ctx, cudaMemcpyAsync(&hp, t->d_problems, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<float> hd;
@@ -730,6 +776,53 @@ int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNe
   return SDSO_OK;
 }
 
+int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[12], const double T_pose[12], const double photo[2],
+                   int* n_out, double* err, double* J8) {
+  if (!ctx || !T_select || !T_pose || !photo || !n_out) return SDSO_E_INVALID;
+  TrackerState* t = ctx->tracker;
+  if (!t->have_ref) return fail(ctx, SDSO_E_STATE, "edge evaluation before setCoarseTrackingRef");
+  if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
+  int rc = check_frame(ctx, new_frame);
+  if (rc) return rc;
+  TrackParams P;
+  fill_params(ctx, P);
+  P.mode = 2; P.eval_lvl = lvl; P.eval_cutoff = 1e30f; P.variant = SDSO_VARIANT_G2O;
+  rc = ensure_edge_scratch(ctx, P, 1);
+  if (rc) return rc;
+  const int n = t->pc_n[lvl];
+  size_t need = (size_t)10 * (n > 0 ? n : 1) * sizeof(double);
+  if (need > t->dump_cap) {
+    if (t->d_dump) cudaFree(t->d_dump);
+    t->d_dump = nullptr; t->dump_cap = 0;
+    SDSO_CUDA(ctx, cudaMalloc(&t->d_dump, need));
+    t->dump_cap = need;
+  }
+  P.dump_d = reinterpret_cast<double*>(t->d_dump);
+  TrackProblem& hp = t->h_problems[0];
+  memset(&hp, 0, sizeof(hp));
+  memcpy(hp.T, T_select, sizeof(hp.T));
+  memcpy(hp.T_out, T_pose, sizeof(hp.T_out));
+  hp.aff_out[0] = photo[0]; hp.aff_out[1] = photo[1];
+  for (int l = 0; l < ctx->G.levels; l++) hp.tex[l] = ctx->frames[new_frame].tex[l];
+  hp.exposure_new = ctx->frames[new_frame].ab_exposure;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_track(ctx, P, 1, true);
+  if (rc) return rc;
+  std::vector<double> hd((size_t)10 * n);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(hd.data(), t->d_dump, hd.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    if (hd[i] != 0.0) {
+      if (err) err[k] = hd[(size_t)n + i];
+      if (J8) for (int a = 0; a < 8; a++) J8[(size_t)8 * k + a] = hd[(size_t)(2 + a) * n + i];
+      k++;
+    }
+  }
+  *n_out = k;
+  return SDSO_OK;
+}
+
 int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const double* T_in, const double* aff_in, int coarsest_lvl,
                        const double* minResForAbort, int variant) {
   if (!ctx || nb <= 0 || !new_frames || !T_in || !aff_in || !minResForAbort) return SDSO_E_INVALID;
@@ -738,10 +831,10 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
   if (nb > t->max_problems) return fail(ctx, SDSO_E_INVALID, "too many problems in one batch");
   if (coarsest_lvl < 0 || coarsest_lvl >= ctx->G.levels || coarsest_lvl >= 5) return fail(ctx, SDSO_E_INVALID, "coarsest_lvl out of range");
   if (variant != SDSO_VARIANT_SSE && variant != SDSO_VARIANT_G2O) return SDSO_E_INVALID;
-  if (variant == SDSO_VARIANT_G2O) return fail(ctx, SDSO_E_INVALID, "g2o tracking variant not built in this revision");
   TrackParams P;
   fill_params(ctx, P);
   P.mode = 0; P.coarsest = coarsest_lvl; P.variant = variant;
+  if (variant == SDSO_VARIANT_G2O) { int rc = ensure_edge_scratch(ctx, P, nb); if (rc) return rc; }
   for (int k = 0; k < nb; k++) {
     int rc = check_frame(ctx, new_frames[k]);
     if (rc) return rc;
@@ -754,8 +847,10 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
     hp.exposure_new = ctx->frames[new_frames[k]].ab_exposure;
   }
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, t->h_problems, nb * sizeof(TrackProblem), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = launch_track(ctx, P, nb);
+  prof_begin(ctx, 0);
+  int rc = launch_track(ctx, P, nb, variant == SDSO_VARIANT_G2O);
   if (rc) return rc;
+  prof_end(ctx, 0);
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->h_problems, t->d_problems, nb * sizeof(TrackProblem), cudaMemcpyDeviceToHost, ctx->stream));
   t->last_nb = nb;
   return SDSO_OK;

