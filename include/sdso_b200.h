@@ -66,6 +66,7 @@ typedef struct sdso_settings {
   int32_t g2o_stop_flag_persists;   /* SURVEY.md Appendix C open point (1); default 1 */
   int32_t cluster_size;             /* thread-block cluster size of the persistent kernels (0 = default 8) */
   int32_t block_threads;            /* threads per CTA of the persistent kernels (0 = default 256) */
+  int32_t gather_batch;             /* points gathered per thread before the arithmetic: 1, 2 or 4 (0 = default) */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);
@@ -90,6 +91,9 @@ uint64_t sdso_launch_count(const sdso_ctx* ctx);
  * last read. Used by bench.py for the roofline figure; off by default. */
 int sdso_profile_enable(sdso_ctx* ctx, int on);
 int sdso_profile_read(sdso_ctx* ctx, double* track_ms, int* track_launches, double* images_ms, int* images_launches);
+/* with profiling enabled: SM-clock cycles spent per phase inside the last collected track launch
+ * ([0] serial LM step, [1] point loop, [2] block reduction, [3] cluster barrier + final sum, [4] bookkeeping) */
+int sdso_track_phase_cycles(sdso_ctx* ctx, long long cyc[16]);
 /* CalibHessian::B (FullSystem/HessianBlocks.h:352): photometric response table used by getBGradOnly
  * in makeImages; identity (B[i]=i) unless set. */
 int sdso_set_gamma(sdso_ctx* ctx, const float B[256]);

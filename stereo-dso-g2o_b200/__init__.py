@@ -31,7 +31,7 @@ class Settings(C.Structure):
         ("trace_GNThreshold", C.c_float), ("trace_extraSlackOnTH", C.c_float), ("trace_slackInterval", C.c_float),
         ("trace_minImprovementFactor", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
         ("gammaWeightsPixelSelect", C.c_int32), ("g2o_stop_flag_persists", C.c_int32), ("cluster_size", C.c_int32),
-        ("block_threads", C.c_int32),
+        ("block_threads", C.c_int32), ("gather_batch", C.c_int32),
     ]
 
 
@@ -86,6 +86,7 @@ lib.sdso_edge_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _ip,
 lib.sdso_profile_enable.argtypes = [C.c_void_p, C.c_int]
 lib.sdso_profile_read.argtypes = [C.c_void_p, _dp, _ip, _dp, _ip]
 lib.sdso_set_gamma.argtypes = [C.c_void_p, _fp]
+lib.sdso_track_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
 lib.sdso_track_collect.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _ip, C.POINTER(C.c_uint64)]
 
 
@@ -233,6 +234,11 @@ class Context:
         nt, nm = C.c_int(), C.c_int()
         self._ck(lib.sdso_profile_read(self._h, C.byref(t), C.byref(nt), C.byref(m), C.byref(nm)))
         return dict(track_ms=t.value, track_launches=nt.value, images_ms=m.value, images_launches=nm.value)
+
+    def track_phase_cycles(self):
+        c = (C.c_longlong * 16)()
+        self._ck(lib.sdso_track_phase_cycles(self._h, c))
+        return list(c)
 
     def set_gamma(self, B):
         B = _f32(B)

@@ -110,6 +110,7 @@ void sdso_default_settings(sdso_settings* s) {
   s->g2o_stop_flag_persists = 1;
   s->cluster_size = 0;
   s->block_threads = 0;
+  s->gather_batch = 0;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {

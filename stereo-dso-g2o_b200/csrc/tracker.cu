@@ -57,6 +57,7 @@ struct TrackProblem {  // one per cluster, in global memory
   double b[8];
   int warped_n;
   int pad1;
+  long long cyc[16];  // optional phase timing (clock64 of rank 0 / thread 0), see TrackParams::timing
 };
 
 struct TrackParams {
@@ -74,6 +75,7 @@ struct TrackParams {
   float huberTH, coarseCutoffTH;
   float affineOptModeA, affineOptModeB;
   int g2o_stop_persists;
+  int timing;
   TrackProblem* problems;
   // g2o variant scratch: per level edge flags/errors for each problem
   unsigned char* edge_flag[kPyrLevels];  // [problem][n_l]
@@ -101,44 +103,82 @@ struct LMState {  // lives in shared memory of every CTA (identical content ever
   double affn[2];
   double H[64], b[8];
   double inc[8];
-  double total[kAcc];
-  double totalNew[kAcc];
+  double total[kAcc];     // totals in double (g2o path, operator-level outputs)
+  float totf[kAcc];       // totals of the accepted state (SSE path; float: the block partials are float anyway)
   float lambda;
-  int flag;
+  int small;              // !(inc.norm() > 1e-3) of the last LM step (:1019)
 };
 
 // ---- small double helpers (device) -------------------------------------------------------------
-__device__ void d_mat3_mul(const double* A, const double* B, double* C) {
+__device__ __forceinline__ void d_mat3_mul(const double (&A)[9], const double (&B)[9], double (&C)[9]) {
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = 0; c < 3; c++) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
 }
 
-// exp(a) * T   with a = [upsilon; omega]   (thirdparty/Sophus/sophus/se3.hpp:407-428; left-multiplicative
-// update as CoarseTracker.cpp:978 / dso_g2o_vertex.cpp:17)
-__device__ void d_se3_exp_mul(const double a[6], const double* R, const double* t, double* Ro, double* to) {
-  const double wx = a[3], wy = a[4], wz = a[5];
-  const double th2 = wx * wx + wy * wy + wz * wz;
+// 1/x to ~1e-14 relative without the IEEE division sequence: float seed + one Newton step in double.
+// Falls back to the division outside the float range.
+__device__ __forceinline__ double fast_rcp(double x) {
+  const double ax = fabs(x);
+  if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+  float rf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));  // 1 ulp seed; an IEEE float division costs ~85 cycles here
+  double r = (double)rf;
+  r = fma(r, fma(-x, r, 1.0), r);  // 1e-7 -> 1e-14: far below the float precision of the accumulated H
+  return r;
+}
+
+// closed-form coefficients for |theta| >= 0.25 (rare on this path): kept out of line to bound code size
+__device__ __noinline__ void se3_coeffs_general(double th2, double* A, double* B, double* C) {
   const double th = sqrt(th2);
-  double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  *A = sn / th; *B = (1.0 - cs) / th2; *C = (th - sn) / (th2 * th);
+}
+
+// exp(a) * T   with a = [upsilon; omega]   (thirdparty/Sophus/sophus/se3.hpp:407-428; left-multiplicative
+// update as CoarseTracker.cpp:978 / dso_g2o_vertex.cpp:17). R = I + A W + B W^2, V = I + B W + C W^2 with
+// A = sin(t)/t, B = (1-cos t)/t^2, C = (t-sin t)/t^3; for t < 0.25 the three are evaluated by their Taylor
+// series in t^2 (truncation < 1e-20), which needs no sqrt / sincos / division. Fully unrolled: registers only.
+__device__ __forceinline__ void d_se3_exp_mul(const double (&a)[8], const double* Rin, const double* tin, double (&Ro)[9], double (&to)[3]) {
+  double R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) R[i] = Rin[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) t[i] = tin[i];
+  const double wx = a[3], wy = a[4], wz = a[5];
+  const double x = wx * wx + wy * wy + wz * wz;
+  const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
   double O2[9];
   d_mat3_mul(O, O, O2);
-  double A, B, C;  // R = I + A O + B O2 ; V = I + B O + C O2
-  if (th < 1e-10) { A = 1.0; B = 0.5; C = 1.0 / 6.0; }
-  else { A = sin(th) / th; B = (1.0 - cos(th)) / th2; C = (th - sin(th)) / (th2 * th); }
+  double A, B, C;
+  if (x < 0.0625) {
+    // sum_k (-1)^k x^k / (2k+1)!, /(2k+2)!, /(2k+3)!   (Horner, k = 7..0)
+    A = -1.0 / 1307674368000.0; B = -1.0 / 20922789888000.0; C = -1.0 / 355687428096000.0;
+    A = fma(A, x, 1.0 / 6227020800.0);  B = fma(B, x, 1.0 / 87178291200.0);  C = fma(C, x, 1.0 / 1307674368000.0);
+    A = fma(A, x, -1.0 / 39916800.0);   B = fma(B, x, -1.0 / 479001600.0);   C = fma(C, x, -1.0 / 6227020800.0);
+    A = fma(A, x, 1.0 / 362880.0);      B = fma(B, x, 1.0 / 3628800.0);      C = fma(C, x, 1.0 / 39916800.0);
+    A = fma(A, x, -1.0 / 5040.0);       B = fma(B, x, -1.0 / 40320.0);       C = fma(C, x, -1.0 / 362880.0);
+    A = fma(A, x, 1.0 / 120.0);         B = fma(B, x, 1.0 / 720.0);          C = fma(C, x, 1.0 / 5040.0);
+    A = fma(A, x, -1.0 / 6.0);          B = fma(B, x, -1.0 / 24.0);          C = fma(C, x, -1.0 / 120.0);
+    A = fma(A, x, 1.0);                 B = fma(B, x, 0.5);                  C = fma(C, x, 1.0 / 6.0);
+  } else {
+    se3_coeffs_general(x, &A, &B, &C);
+  }
   double Re[9], V[9];
+#pragma unroll
   for (int i = 0; i < 9; i++) {
-    double I = (i % 4 == 0) ? 1.0 : 0.0;
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
     Re[i] = I + A * O[i] + B * O2[i];
     V[i] = I + B * O[i] + C * O2[i];
   }
   double te[3];
+#pragma unroll
   for (int r = 0; r < 3; r++) te[r] = V[r * 3] * a[0] + V[r * 3 + 1] * a[1] + V[r * 3 + 2] * a[2];
-  double Rt[9];
-  d_mat3_mul(Re, R, Rt);
-  double tn[3];
-  for (int r = 0; r < 3; r++) tn[r] = Re[r * 3] * t[0] + Re[r * 3 + 1] * t[1] + Re[r * 3 + 2] * t[2] + te[r];
-  for (int i = 0; i < 9; i++) Ro[i] = Rt[i];
-  for (int i = 0; i < 3; i++) to[i] = tn[i];
+  d_mat3_mul(Re, R, Ro);
+#pragma unroll
+  for (int r = 0; r < 3; r++) to[r] = Re[r * 3] * t[0] + Re[r * 3 + 1] * t[1] + Re[r * 3 + 2] * t[2] + te[r];
 }
 
 // LDLT solve (no pivoting; the systems on this path are SPD after damping). Returns false on breakdown.
@@ -174,157 +214,329 @@ __device__ __forceinline__ void d_aff_from_to(float expF, float expT, double aF,
 }
 
 // ---- shared memory layout ------------------------------------------------------------------------
+constexpr int kAccPad = 64;    // accumulator registers per thread (kAcc used, padded to a power of two)
+constexpr int kMaxCluster = 16;
+constexpr int kMaxWarps = 8;   // 256 threads per CTA
+
 struct __align__(16) TrackSmem {
   LMState lm;
   EvalConst ec;
-  float partial[2][kAcc];  // this CTA's block-reduced sums, double-buffered by evaluation parity
-  double partial_d[2];     // one extra channel summed in double (robust chi2 of the g2o path)
-  double warp_d[32];
-  // followed by float red[kAcc * blockDim.x]
+  float wpart[kMaxWarps][kAccPad];           // per-warp sums of this CTA
+  float gather[2][kMaxCluster][kAccPad];     // [parity][source CTA][k]: every CTA PUSHES its sums into every peer
+  double gather_d[2][kMaxCluster];           // same for the one channel that is summed in double
+  double warp_d[kMaxWarps];
+  double total_d;
+  unsigned long long bar[2];                 // mbarriers of the two exchange buffers
 };
 
-__device__ __forceinline__ float* smem_red(TrackSmem* sm) { return reinterpret_cast<float*>(sm + 1); }
+struct PhaseTimer {  // phase breakdown of the persistent kernel, enabled by TrackParams::timing
+  long long last = 0;
+  long long* cyc = nullptr;
+  __device__ __forceinline__ void start(long long* c) { cyc = c; last = clock64(); }
+  __device__ __forceinline__ void tick(int k) {
+    if (cyc) { long long now = clock64(); cyc[k] += now - last; last = now; }
+  }
+};
 
-// Block + cluster reduction of per-thread accumulators; result (identical in every CTA) -> out[kAcc]
-__device__ void reduce_all(float (&acc)[kAcc], TrackSmem* sm, int& parity, cg::cluster_group& cluster, double* out,
-                           double dacc = 0.0, double* dout = nullptr) {
-  float* red = smem_red(sm);
-  const int BT = blockDim.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, nw = BT >> 5;
-#pragma unroll
-  for (int k = 0; k < kAcc; k++) red[k * BT + tid] = acc[k];
-  if (dout) {
+// Register-transposing warp reduction: 64 values x 32 lanes -> lane L ends with the warp sums of
+// indices 2L and 2L+1 in a[0], a[1]. 62 shuffles instead of 64 x 5, no shared memory.
+#define SDSO_RSTAGE(O, N)                                                  \
+  _Pragma("unroll") for (int j = 0; j < N; j++) {                          \
+    const bool up = (lane & O) != 0;                                       \
+    const float keep = up ? a[j + N] : a[j];                               \
+    const float send = up ? a[j] : a[j + N];                               \
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, O);                   \
+  }
+__device__ __forceinline__ void warp_reduce_transpose64(float (&a)[kAccPad], int lane) {
+  SDSO_RSTAGE(16, 32)
+  SDSO_RSTAGE(8, 16)
+  SDSO_RSTAGE(4, 8)
+  SDSO_RSTAGE(2, 4)
+  SDSO_RSTAGE(1, 2)
+}
+#undef SDSO_RSTAGE
+
+// ---- DSMEM exchange primitives (inline PTX; sm_90+ cluster features) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// asynchronous remote shared-memory store that signals the destination CTA's mbarrier with the byte count
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_b64(uint32_t raddr, unsigned long long v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(v), "r"(rbar) : "memory");
+}
+
+struct Exchange {  // per-thread bookkeeping of the double-buffered exchange
+  int parity = 0;         // which buffer the next exchange uses
+  unsigned phases = 0;    // bit p = phase parity the next wait on bar[p] expects
+};
+
+// Block reduction + all-to-all exchange inside the cluster WITHOUT a cluster barrier: every CTA pushes its 64
+// block sums (+ one double) into every peer with st.async, each destination's mbarrier counts the bytes, and
+// every thread waits on its own CTA's mbarrier only (acquire at CTA scope: L1 stays warm, no CCTL.IVALL).
+// Returns the buffer index p; sm->gather[p][r][k], r < C, is then valid. Double-buffered: a CTA can start
+// pushing exchange n+2 only after every peer has pushed n+1, i.e. after every peer finished reading n.
+template <bool WITH_D>
+__device__ __forceinline__ int reduce_exchange(float (&acc)[kAccPad], TrackSmem* sm, Exchange& ex, unsigned C, unsigned rank, double dacc,
+                                               PhaseTimer* tm = nullptr) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int p = ex.parity;
+  warp_reduce_transpose64(acc, lane);
+  *reinterpret_cast<float2*>(&sm->wpart[warp][2 * lane]) = make_float2(acc[0], acc[1]);
+  if (WITH_D) {  // double-precision ops are slow on this part: only the g2o path pays for the extra channel
     double dv = warp_sum(dacc);
     if (lane == 0) sm->warp_d[warp] = dv;
   }
   __syncthreads();
-  if (dout && tid == 0) {
+  if (tid < kAccPad) {
+    float s = 0.f;
+    for (int w = 0; w < nw; w++) s += sm->wpart[w][tid];
+    const uint32_t dst = smem_u32(&sm->gather[p][rank][tid]), bar = smem_u32(&sm->bar[p]);
+    for (unsigned r = 0; r < C; r++) st_async_b32(mapa_u32(dst, r), __float_as_uint(s), mapa_u32(bar, r));
+  } else if (WITH_D && tid == kAccPad) {
     double s = 0.0;
     for (int w = 0; w < nw; w++) s += sm->warp_d[w];
-    sm->partial_d[parity] = s;
+    const uint32_t dst = smem_u32(&sm->gather_d[p][rank]), bar = smem_u32(&sm->bar[p]);
+    for (unsigned r = 0; r < C; r++) st_async_b64(mapa_u32(dst, r), (unsigned long long)__double_as_longlong(s), mapa_u32(bar, r));
+  } else if (tid == kAccPad + 32) {
+    mbar_arrive_expect_tx(&sm->bar[p], C * (kAccPad * 4 + (WITH_D ? 8 : 0)));
   }
-  for (int k = warp; k < kAcc; k += nw) {
-    float s = 0.f;
-    for (int j = lane; j < BT; j += 32) s += red[k * BT + j];
-    s = warp_sum(s);
-    if (lane == 0) sm->partial[parity][k] = s;
-  }
-  cluster.sync();  // partials of all CTAs visible (release/acquire at cluster scope)
-  const unsigned C = cluster.num_blocks();
-  if (tid < kAcc) {
-    double s = 0.0;
-    for (unsigned r = 0; r < C; r++) {
-      const TrackSmem* rs = cluster.map_shared_rank(sm, r);
-      s += (double)rs->partial[parity][tid];
-    }
-    out[tid] = s;
-  }
-  if (dout && tid == kAcc) {
-    double s = 0.0;
-    for (unsigned r = 0; r < C; r++) s += cluster.map_shared_rank(sm, r)->partial_d[parity];
-    *dout = s;
-  }
-  parity ^= 1;
+  if (tm) tm->tick(2);
+  mbar_wait(&sm->bar[p], (ex.phases >> p) & 1u);
+  ex.phases ^= (1u << p);
+  ex.parity ^= 1;
+  if (tm) tm->tick(3);
+  return p;
+}
+
+__device__ __forceinline__ double gather_sum(const TrackSmem* sm, int p, unsigned C, int k) {
+  double s = 0.0;
+#pragma unroll 1
+  for (unsigned r = 0; r < C; r++) s += (double)sm->gather[p][r][k];  // fixed order
+  return s;
+}
+__device__ __forceinline__ float gather_sumf(const TrackSmem* sm, int p, unsigned C, int k) {
+  float s0 = 0.f, s1 = 0.f;  // two interleaved chains, fixed order: even ranks, odd ranks
+#pragma unroll 1
+  for (unsigned r = 0; r + 1 < C; r += 2) { s0 += sm->gather[p][r][k]; s1 += sm->gather[p][r + 1][k]; }
+  if (C & 1) s0 += sm->gather[p][C - 1][k];
+  return s0 + s1;
+}
+__device__ __forceinline__ double gather_sum_d(const TrackSmem* sm, int p, unsigned C) {
+  double s = 0.0;
+#pragma unroll 1
+  for (unsigned r = 0; r < C; r++) s += sm->gather_d[p][r];
+  return s;
+}
+
+// Convenience form: exchange, then the totals (bit-identical in every CTA: fixed summation order) -> out[kAcc]
+// in shared memory, visible to the whole CTA on return.
+__device__ void reduce_all(float (&acc)[kAccPad], TrackSmem* sm, Exchange& ex, cg::cluster_group& cluster, double* out,
+                           double dacc = 0.0, double* dout = nullptr, PhaseTimer* tm = nullptr) {
+  const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
+  const int p = reduce_exchange<true>(acc, sm, ex, C, rank, dacc, tm);
+  const int tid = threadIdx.x;
+  if (tid < kAcc) out[tid] = gather_sum(sm, p, C, tid);
+  if (dout) *dout = gather_sum_d(sm, p, C);
   __syncthreads();
 }
 
+// 8x8 SPD solve by one warp: lane l (mod 8) owns row l of the augmented matrix [A | rhs] in registers.
+// Elimination without pivoting (the damped systems on this path are SPD); all lanes end with x[0..7].
+// pd = every pivot was finite and > 0 (what a Cholesky factorisation needs to succeed).
+__device__ __forceinline__ void warp_solve8(double (&row)[9], int lane, double (&x)[8], bool& pd) {
+  const int l = lane & 7;
+  double pinv[8];
+  pd = true;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    double pk[9];
+#pragma unroll
+    for (int j = k; j < 9; j++) pk[j] = __shfl_sync(0xffffffffu, row[j], k);
+    pd = pd && (pk[k] > 0) && isfinite(pk[k]);
+    const double inv = fast_rcp(pk[k]);
+    pinv[k] = inv;
+    if (l > k) {
+      const double f = row[k] * inv;
+#pragma unroll
+      for (int j = k + 1; j < 9; j++) row[j] -= f * pk[j];
+    }
+  }
+#pragma unroll
+  for (int k = 7; k >= 0; k--) {
+    const double xk = __shfl_sync(0xffffffffu, row[8] * pinv[k], k);
+    x[k] = xk;
+    if (l < k) row[8] -= row[k] * xk;
+  }
+}
+
 // ---- SSE-path evaluation: calcRes (:645-773) + calcGSSSE (:537-596) fused over this CTA's points ----
+// Points are processed in batches of U per thread: all point records first, then all 4xU texel gathers,
+// then the arithmetic, so up to 4U independent 16-byte loads are in flight per thread.
+template <int U>
 __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex,
-                                const EvalConst& ec, float (&acc)[kAcc], unsigned& evals, int gtid, int gthreads,
+                                const EvalConst& ec, float (&acc)[kAccPad], unsigned& evals, int gtid, int gthreads,
                                 float* dump) {
 #pragma unroll
-  for (int k = 0; k < kAcc; k++) acc[k] = 0.f;
+  for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
   const float fxl = L.fx, fyl = L.fy, cxl = L.cx, cyl = L.cy;
-  const int wl = L.w, hl = L.h;
+  const int wl = L.w, hl = L.h, n = L.n;
   const float huberTH = P.huberTH;
   const float4* __restrict__ pc = L.pc;
-  for (int i = gtid; i < L.n; i += gthreads) {
-    const float4 p = __ldg(pc + i);
-    const float x = p.x, y = p.y, id = p.z, refColor = p.w;
-    float pt[3];
+  float RKi[9], tt[3];
 #pragma unroll
-    for (int r = 0; r < 3; r++) pt[r] = (ec.RKi[r * 3 + 0] * x + ec.RKi[r * 3 + 1] * y + ec.RKi[r * 3 + 2]) + ec.t[r] * id;
-    const float u = pt[0] / pt[2], v = pt[1] / pt[2];
-    const float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
-    const float new_idepth = id / pt[2];
-    evals++;
-    if (lvl == 0 && (i % 32) == 0) {  // flow indicators :662-693
-      float ptT[3], ptT2[3], pt3[3];
+  for (int k = 0; k < 9; k++) RKi[k] = ec.RKi[k];
 #pragma unroll
-      for (int r = 0; r < 3; r++) {
-        float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
-        ptT[r] = kp + ec.t[r] * id;
-        ptT2[r] = kp - ec.t[r] * id;
-        pt3[r] = (ec.RKi[r * 3 + 0] * x + ec.RKi[r * 3 + 1] * y + ec.RKi[r * 3 + 2]) - ec.t[r] * id;
-      }
-      float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
-      float KuT = fxl * uT + cxl, KvT = fyl * vT + cyl;
-      float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
-      float KuT2 = fxl * uT2 + cxl, KvT2 = fyl * vT2 + cyl;
-      float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
-      float Ku3 = fxl * u3 + cxl, Kv3 = fyl * v3 + cyl;
-      acc[A_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-      acc[A_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-      acc[A_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-      acc[A_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-      acc[A_SN] += 2.f;
+  for (int k = 0; k < 3; k++) tt[k] = ec.t[k];
+  const float affLL0 = ec.affLL[0], affLL1 = ec.affLL[1], cutoff = ec.cutoff, maxEnergy = ec.maxEnergy, ea = ec.a, eb0 = ec.b0;
+
+  for (int base = gtid; base < n; base += gthreads * U) {
+    float4 p[U];
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+      const int i = base + q * gthreads;
+      p[q] = (i < n) ? __ldg(pc + i) : make_float4(0.f, 0.f, 1.f, 0.f);
     }
-    bool valid = false;
-    float hitx = 0.f, hity = 0.f, hitz = 0.f, residual = 0.f, hw = 0.f;
-    if (Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0) {  // :696
-      const float3 hit = interp33(tex, Ku, Kv, wl);
-      if (isfinite(hit.x)) {
-        hitx = hit.x; hity = hit.y; hitz = hit.z;
-        residual = hit.x - (ec.affLL[0] * refColor + ec.affLL[1]);
-        const float ar = fabsf(residual);
-        hw = ar < huberTH ? 1.f : huberTH / ar;
-        if (ar > ec.cutoff) {
-          acc[A_E] += ec.maxEnergy; acc[A_NE] += 1.f; acc[A_NSAT] += 1.f;
-        } else {
-          acc[A_E] += hw * residual * residual * (2 - hw);
-          acc[A_NE] += 1.f; acc[A_NW] += 1.f;
-          valid = true;
+    float uu[U], vv[U], Kuu[U], Kvv[U], nid[U];
+    bool inb[U];
+    float4 t00[U], t10[U], t01[U], t11[U];
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+      const int i = base + q * gthreads;
+      const float x = p[q].x, y = p[q].y, id = p[q].z;
+      float pt[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) pt[r] = (RKi[r * 3 + 0] * x + RKi[r * 3 + 1] * y + RKi[r * 3 + 2]) + tt[r] * id;
+      const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+      const float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+      const float new_idepth = id / pt[2];
+      uu[q] = u; vv[q] = v; Kuu[q] = Ku; Kvv[q] = Kv; nid[q] = new_idepth;
+      if (i < n) {
+        evals++;
+        if (lvl == 0 && (i % 32) == 0) {  // flow indicators :662-693
+          float ptT[3], ptT2[3], pt3[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
+            ptT[r] = kp + tt[r] * id;
+            ptT2[r] = kp - tt[r] * id;
+            pt3[r] = (RKi[r * 3 + 0] * x + RKi[r * 3 + 1] * y + RKi[r * 3 + 2]) - tt[r] * id;
+          }
+          float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
+          float KuT = fxl * uT + cxl, KvT = fyl * vT + cyl;
+          float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
+          float KuT2 = fxl * uT2 + cxl, KvT2 = fyl * vT2 + cyl;
+          float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
+          float Ku3 = fxl * u3 + cxl, Kv3 = fyl * v3 + cyl;
+          acc[A_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+          acc[A_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+          acc[A_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+          acc[A_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+          acc[A_SN] += 2.f;
         }
       }
-    }
-    if (valid) {
-      // calcGSSSE :553-581
-      const float dx = hity * fxl, dy = hitz * fyl;
-      float J[9];
-      J[0] = new_idepth * dx;
-      J[1] = new_idepth * dy;
-      J[2] = 0.f - new_idepth * (u * dx + v * dy);
-      J[3] = 0.f - ((u * v) * dx + dy * (1.f + v * v));
-      J[4] = (u * v) * dy + dx * (1.f + u * u);
-      J[5] = u * dy - v * dx;
-      J[6] = ec.a * (ec.b0 - refColor);
-      J[7] = -1.f;
-      J[8] = residual;
-      int idx = 0;
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        const float Jw = J[r] * hw;
-#pragma unroll
-        for (int c = r; c < 9; c++) { acc[A_H + idx] = __fmaf_rn(Jw, J[c], acc[A_H + idx]); idx++; }
+      inb[q] = (i < n) && (Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0);  // :696
+      if (inb[q]) {
+        const float4* bp = tex + (int)Ku + (int)Kv * wl;
+        t00[q] = __ldg(bp); t10[q] = __ldg(bp + 1); t01[q] = __ldg(bp + wl); t11[q] = __ldg(bp + 1 + wl);
       }
     }
-    if (dump) {
-      const int n = L.n;
-      dump[0 * n + i] = valid ? 1.f : 0.f;
-      dump[1 * n + i] = new_idepth; dump[2 * n + i] = u; dump[3 * n + i] = v;
-      dump[4 * n + i] = hity; dump[5 * n + i] = hitz; dump[6 * n + i] = residual;
-      dump[7 * n + i] = hw; dump[8 * n + i] = refColor;
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+      const int i = base + q * gthreads;
+      const float refColor = p[q].w;
+      bool valid = false;
+      float hity = 0.f, hitz = 0.f, residual = 0.f, hw = 0.f;
+      if (inb[q]) {
+        // getInterpolatedElement33 (util/globalFuncs.h:73-86), weights and sum order as written there
+        const float Ku = Kuu[q], Kv = Kvv[q];
+        const int ix = (int)Ku, iy = (int)Kv;
+        const float dx = Ku - ix, dy = Kv - iy;
+        const float dxdy = dx * dy;
+        const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+        const float hitx = w11 * t11[q].x + w01 * t01[q].x + w10 * t10[q].x + w00 * t00[q].x;
+        hity = w11 * t11[q].y + w01 * t01[q].y + w10 * t10[q].y + w00 * t00[q].y;
+        hitz = w11 * t11[q].z + w01 * t01[q].z + w10 * t10[q].z + w00 * t00[q].z;
+        if (isfinite(hitx)) {
+          residual = hitx - (affLL0 * refColor + affLL1);
+          const float ar = fabsf(residual);
+          hw = ar < huberTH ? 1.f : huberTH / ar;
+          if (ar > cutoff) {
+            acc[A_E] += maxEnergy; acc[A_NE] += 1.f; acc[A_NSAT] += 1.f;
+          } else {
+            acc[A_E] += hw * residual * residual * (2 - hw);
+            acc[A_NE] += 1.f; acc[A_NW] += 1.f;
+            valid = true;
+          }
+        }
+      }
+      if (valid) {
+        // calcGSSSE :553-581
+        const float u = uu[q], v = vv[q], id = nid[q];
+        const float dx = hity * fxl, dy = hitz * fyl;
+        float J[9];
+        J[0] = id * dx;
+        J[1] = id * dy;
+        J[2] = 0.f - id * (u * dx + v * dy);
+        J[3] = 0.f - ((u * v) * dx + dy * (1.f + v * v));
+        J[4] = (u * v) * dy + dx * (1.f + u * u);
+        J[5] = u * dy - v * dx;
+        J[6] = ea * (eb0 - refColor);
+        J[7] = -1.f;
+        J[8] = residual;
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          const float Jw = J[r] * hw;
+#pragma unroll
+          for (int c = r; c < 9; c++) { acc[A_H + idx] = __fmaf_rn(Jw, J[c], acc[A_H + idx]); idx++; }
+        }
+      }
+      if (dump && i < n) {
+        dump[0 * n + i] = valid ? 1.f : 0.f;
+        dump[1 * n + i] = nid[q]; dump[2 * n + i] = uu[q]; dump[3 * n + i] = vv[q];
+        dump[4 * n + i] = hity; dump[5 * n + i] = hitz; dump[6 * n + i] = residual;
+        dump[7 * n + i] = hw; dump[8 * n + i] = refColor;
+      }
     }
   }
 }
 
-// thread 0: per-evaluation constants for the SSE path (calcRes :617-621, calcGSSSE :540-544)
+// per-evaluation constants for the SSE path (calcRes :617-621, calcGSSSE :540-544); called by ONE thread
 __device__ void make_eval_const_sse(const TrackParams& P, const TrackLevel& L, const TrackProblem& prob, const double* R,
                                     const double* t, const double* aff, float cutoff, EvalConst& ec) {
   float Rf[9];
+#pragma unroll
   for (int i = 0; i < 9; i++) Rf[i] = (float)R[i];
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = 0; c < 3; c++) ec.RKi[r * 3 + c] = Rf[r * 3 + 0] * L.Ki[0 * 3 + c] + Rf[r * 3 + 1] * L.Ki[1 * 3 + c] + Rf[r * 3 + 2] * L.Ki[2 * 3 + c];
+#pragma unroll
   for (int i = 0; i < 3; i++) ec.t[i] = (float)t[i];
   double ab[2];
   d_aff_from_to(P.ref_exposure, prob.exposure_new, P.ref_aff[0], P.ref_aff[1], aff[0], aff[1], ab);
@@ -335,8 +547,9 @@ __device__ void make_eval_const_sse(const TrackParams& P, const TrackLevel& L, c
   ec.maxEnergy = 2 * P.huberTH * cutoff - P.huberTH * P.huberTH;
 }
 
-// H (8x8), b from the 45 accumulated entries: calcGSSSE :582-595
-__device__ void finish_gs(const double* total, double* H, double* b) {
+// H (8x8), b from the 45 accumulated entries: calcGSSSE :582-595 (used by the operator-level entry)
+template <typename T>
+__device__ void finish_gs(const T* total, double* H, double* b) {
   const int nw = (int)total[A_NW];
   const int n = (nw + 3) & ~3;  // buf_warped_n is padded to a multiple of 4 (:763-773)
   const float invn = 1.0f / n;
@@ -351,7 +564,8 @@ __device__ void finish_gs(const double* total, double* H, double* b) {
   }
 }
 
-__device__ void rs_from_total(const double* total, double rs[6]) {
+template <typename T>
+__device__ void rs_from_total(const T* total, double rs[6]) {
   // CoarseTracker.cpp:783-789 (float arithmetic as written)
   const float E = (float)total[A_E];
   const int numTermsInE = (int)total[A_NE];
@@ -365,55 +579,203 @@ __device__ void rs_from_total(const double* total, double rs[6]) {
   rs[5] = numSaturated / (float)numTermsInE;
 }
 
-// thread 0: one LM step of the SSE path (commented block CoarseTracker.cpp:929-979) -> trial state
-__device__ void lm_step_sse(const TrackParams& P, LMState& lm) {
-  double Hl[64];
-  for (int i = 0; i < 64; i++) Hl[i] = lm.H[i];
-  for (int i = 0; i < 8; i++) Hl[i * 8 + i] *= (1 + lm.lambda);
-  double nb[8];
-  for (int i = 0; i < 8; i++) nb[i] = -lm.b[i];
-  double inc[8];
-  const bool fixA = P.affineOptModeA < 0, fixB = P.affineOptModeB < 0;
-  if (!fixA && !fixB) {
-    d_ldlt_solve<8>(8, Hl, 8, nb, inc);
-  } else if (fixA && fixB) {
-    d_ldlt_solve<8>(6, Hl, 8, nb, inc);
-    inc[6] = inc[7] = 0;
-  } else if (!fixA && fixB) {
-    d_ldlt_solve<8>(7, Hl, 8, nb, inc);
-    inc[7] = 0;
-  } else {  // fix a, optimise b: stitch row/col 7 into 6 (:947-964)
-    double Hs[64], bs[8];
-    for (int i = 0; i < 64; i++) Hs[i] = Hl[i];
-    for (int i = 0; i < 8; i++) bs[i] = lm.b[i];
-    for (int r = 0; r < 8; r++) Hs[r * 8 + 6] = Hs[r * 8 + 7];
-    for (int c = 0; c < 8; c++) Hs[6 * 8 + c] = Hs[7 * 8 + c];
-    bs[6] = bs[7];
-    double nbs[8], is[8];
-    for (int i = 0; i < 8; i++) nbs[i] = -bs[i];
-    d_ldlt_solve<8>(7, Hs, 8, nbs, is);
-    for (int i = 0; i < 6; i++) inc[i] = is[i];
-    inc[6] = 0; inc[7] = is[6];
-  }
-  float extrapFac = 1;
-  const float lambdaExtrapolationLimit = 0.001f;
-  if (lm.lambda < lambdaExtrapolationLimit) extrapFac = sqrt(sqrt(lambdaExtrapolationLimit / lm.lambda));
-  for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
-  for (int i = 0; i < 8; i++) lm.inc[i] = inc[i];
-  double s[8];
-  for (int i = 0; i < 8; i++) s[i] = inc[i];
-  for (int i = 0; i < 3; i++) s[i] *= SCALE_XI_ROT;
-  for (int i = 3; i < 6; i++) s[i] *= SCALE_XI_TRANS;
-  s[6] *= SCALE_A; s[7] *= SCALE_B;
-  double sum = 0;
-  for (int i = 0; i < 8; i++) sum += s[i];
-  if (!isfinite(sum)) for (int i = 0; i < 8; i++) s[i] = 0;
-  d_se3_exp_mul(s, lm.R, lm.t, lm.Rn, lm.tn);
-  lm.affn[0] = lm.aff[0] + s[6];
-  lm.affn[1] = lm.aff[1] + s[7];
+__device__ __forceinline__ int tri9(int r, int c) {  // index of (r,c), r<=c, in the row-major upper triangle of a 9x9
+  return r * 9 - (r * (r - 1)) / 2 + (c - r);
 }
 
-// ================================================================================================
+// 8x8 SPD solve, Gauss-Jordan over one warp with the matrix spread over all 32 lanes: lane = 4*r + q holds
+// a[r][q], a[r][q+4] and (a copy of) the right-hand side a[r][8]. Each pivot step is 5 shuffles, one
+// reciprocal and 3 FMAs per lane and the dependency chain per step is ~100 cycles (a single warp issues
+// dependent instructions every ~5 cycles, so instruction COUNT and chain length are what matters here).
+// No pivoting: the damped systems on this path are SPD. All lanes end with x[0..7].
+__device__ __forceinline__ void warp_solve8_gj(double e0, double e1, double e2, int lane, double (&x)[8], bool& pd) {
+  const int r = lane >> 2, q = lane & 3;
+  pd = true;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int kq = k & 3, src = k * 4 + q;
+    const double pk0 = __shfl_sync(0xffffffffu, e0, src), pk1 = __shfl_sync(0xffffffffu, e1, src), pk2 = __shfl_sync(0xffffffffu, e2, src);
+    const double mine = (k >> 2) ? e1 : e0;  // slot that holds column k (compile-time choice)
+    const double piv = __shfl_sync(0xffffffffu, mine, k * 4 + kq);
+    const double ark = __shfl_sync(0xffffffffu, mine, (lane & ~3) + kq);
+    pd = pd && (piv > 0) && isfinite(piv);
+    const double f = ark * fast_rcp(piv);
+    if (r != k) { e0 = fma(-f, pk0, e0); e1 = fma(-f, pk1, e1); e2 = fma(-f, pk2, e2); }
+  }
+  const double dsel = (r >> 2) ? e1 : e0;
+  const double d = __shfl_sync(0xffffffffu, dsel, r * 4 + (r & 3));
+  const double xr = e2 * fast_rcp(d);
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = __shfl_sync(0xffffffffu, xr, i * 4);
+}
+
+// exp(x) in double for the affine brightness factor: |x| < 0.5 uses a 15-term Horner (truncation 2e-17)
+// instead of the library routine (~160 cycles); both round to the same float except in measure-zero cases.
+__device__ __forceinline__ double d_exp_small(double x) {
+  if (!(fabs(x) < 0.5)) return exp(x);
+  double r = 1.0 / 1307674368000.0;
+  r = fma(r, x, 1.0 / 87178291200.0);
+  r = fma(r, x, 1.0 / 6227020800.0);
+  r = fma(r, x, 1.0 / 479001600.0);
+  r = fma(r, x, 1.0 / 39916800.0);
+  r = fma(r, x, 1.0 / 3628800.0);
+  r = fma(r, x, 1.0 / 362880.0);
+  r = fma(r, x, 1.0 / 40320.0);
+  r = fma(r, x, 1.0 / 5040.0);
+  r = fma(r, x, 1.0 / 720.0);
+  r = fma(r, x, 1.0 / 120.0);
+  r = fma(r, x, 1.0 / 24.0);
+  r = fma(r, x, 1.0 / 6.0);
+  r = fma(r, x, 0.5);
+  r = fma(r, x, 1.0);
+  r = fma(r, x, 1.0);
+  return r;
+}
+
+// Prologue of every evaluation, executed by warps 0 and 1 (the others wait at the CTA barrier):
+//   warp 0, ITER stage : one LM step of the SSE path (commented block CoarseTracker.cpp:929-979): rows of
+//                        Hl = H (diag*(1+lambda)) | -b straight from the accepted-state sums (calcGSSSE :582-595
+//                        folded in), warp solve, scaled increment -> shared memory, then the trial pose
+//                        exp(inc)*T lane-parallel (lane i < 9 owns entry (i/3, i%3) of the 3x3 blocks);
+//   warp 0, any stage  : R*Ki and t of the evaluated pose (calcRes :617-618);
+//   warp 1             : after warp 0 published the increment (named barrier), the brightness transfer
+//                        (calcRes :621, calcGSSSE :543-544) of the evaluated affine state.
+__device__ __forceinline__ void eval_prologue(const TrackParams& P, const TrackLevel& L, const TrackProblem& prob, LMState& lm, EvalConst& ec,
+                                              float cutoff, bool trial, int tid, long long* cyc) {
+  const int lane = tid & 31;
+  if (tid < 32) {
+    long long c0 = cyc ? clock64() : 0;
+    const int e = lane < 9 ? lane : 0, er = e / 3, ecn = e % 3;
+    double Rn_e, tn_e;
+    if (trial) {
+      const int r = lane >> 2, q = lane & 3;
+      const float* tot = lm.totf;
+      const int nwv = (int)tot[A_NW];
+      const int n = (nwv + 3) & ~3;
+      const float invn = 1.0f / n;
+      // H(r,c) = acc * (1/n) * sc[c] * sc[r], sc = {1,1,1,.5,.5,.5,10,1000} (:584-595, names swapped as written there)
+      const double scr = (r < 3) ? (double)SCALE_XI_ROT : (r < 6 ? (double)SCALE_XI_TRANS : (r == 6 ? (double)SCALE_A : (double)SCALE_B));
+      const double sc0 = (q < 3) ? (double)SCALE_XI_ROT : (double)SCALE_XI_TRANS;                                  // column q
+      const double sc1 = (q < 2) ? (double)SCALE_XI_TRANS : (q == 2 ? (double)SCALE_A : (double)SCALE_B);          // column q+4
+      const double f1 = (double)invn * scr;
+      const int c0i = q, c1i = q + 4;
+      double e0 = (double)tot[A_H + tri9(r < c0i ? r : c0i, r < c0i ? c0i : r)] * (f1 * sc0);
+      double e1 = (double)tot[A_H + tri9(r < c1i ? r : c1i, r < c1i ? c1i : r)] * (f1 * sc1);
+      double e2 = -((double)tot[A_H + tri9(r, 8)] * f1);
+      const float onePlusLambda = 1 + lm.lambda;
+      if (c0i == r) e0 *= onePlusLambda;
+      if (c1i == r) e1 *= onePlusLambda;
+      // fixed affine parameters (:937-964): decouple the fixed unknown(s); the reduced solves are identical
+      if (P.affineOptModeA < 0) { if (r == 6) { e0 = 0; e1 = (c1i == 6) ? 1.0 : 0.0; e2 = 0; } else if (c1i == 6) e1 = 0; }
+      if (P.affineOptModeB < 0) { if (r == 7) { e0 = 0; e1 = (c1i == 7) ? 1.0 : 0.0; e2 = 0; } else if (c1i == 7) e1 = 0; }
+      double inc[8];
+      bool pd;
+      if (cyc) { long long c1 = clock64(); cyc[6] += c1 - c0; c0 = c1; }
+      warp_solve8_gj(e0, e1, e2, lane, inc, pd);
+      if (cyc) { long long c1 = clock64(); cyc[7] += c1 - c0; c0 = c1; }
+      const float lambdaExtrapolationLimit = 0.001f;
+      if (lm.lambda < lambdaExtrapolationLimit) {
+        const float extrapFac = sqrt(sqrt(lambdaExtrapolationLimit / lm.lambda));
+#pragma unroll
+        for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+      }
+      // incScaled (:969-976); SCALE_XI_ROT == 1
+      double s[8];
+#pragma unroll
+      for (int i = 0; i < 3; i++) s[i] = inc[i];
+#pragma unroll
+      for (int i = 3; i < 6; i++) s[i] = inc[i] * SCALE_XI_TRANS;
+      s[6] = inc[6] * SCALE_A; s[7] = inc[7] * SCALE_B;
+      bool fin = true;
+#pragma unroll
+      for (int i = 0; i < 8; i++) fin = fin && isfinite(s[i]);  // !isfinite(incScaled.sum()) -> setZero
+      if (!fin) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = 0;
+      }
+      // publish what warp 1 and the break test need
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) if (i == (lane & 7)) { const float v = (float)inc[i]; sq = v * v; }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      if (lane == 0) { lm.affn[0] = lm.aff[0] + s[6]; lm.affn[1] = lm.aff[1] + s[7]; lm.small = !(sq > 1e-6f) ? 1 : 0; }
+      asm volatile("bar.arrive 1, 64;" ::: "memory");  // warp 1 may start the brightness transfer
+      if (cyc) { long long c1 = clock64(); cyc[8] += c1 - c0; c0 = c1; }
+      // ---- trial pose = exp(s[0:6]) * T, lane-parallel ----
+      const double wx = s[3], wy = s[4], wz = s[5];
+      const double x = fma(wx, wx, fma(wy, wy, wz * wz));
+      double A, B, Cc;
+      if (x < 0.0625) {
+        A = -1.0 / 1307674368000.0; B = -1.0 / 20922789888000.0; Cc = -1.0 / 355687428096000.0;
+        A = fma(A, x, 1.0 / 6227020800.0);  B = fma(B, x, 1.0 / 87178291200.0);  Cc = fma(Cc, x, 1.0 / 1307674368000.0);
+        A = fma(A, x, -1.0 / 39916800.0);   B = fma(B, x, -1.0 / 479001600.0);   Cc = fma(Cc, x, -1.0 / 6227020800.0);
+        A = fma(A, x, 1.0 / 362880.0);      B = fma(B, x, 1.0 / 3628800.0);      Cc = fma(Cc, x, 1.0 / 39916800.0);
+        A = fma(A, x, -1.0 / 5040.0);       B = fma(B, x, -1.0 / 40320.0);       Cc = fma(Cc, x, -1.0 / 362880.0);
+        A = fma(A, x, 1.0 / 120.0);         B = fma(B, x, 1.0 / 720.0);          Cc = fma(Cc, x, 1.0 / 5040.0);
+        A = fma(A, x, -1.0 / 6.0);          B = fma(B, x, -1.0 / 24.0);          Cc = fma(Cc, x, -1.0 / 120.0);
+        A = fma(A, x, 1.0);                 B = fma(B, x, 0.5);                  Cc = fma(Cc, x, 1.0 / 6.0);
+      } else {
+        se3_coeffs_general(x, &A, &B, &Cc);
+      }
+      // entry (er, ecn) of W = hat(w) and of W^2 = w w^T - |w|^2 I
+      const double wr = er == 0 ? wx : (er == 1 ? wy : wz), wc = ecn == 0 ? wx : (ecn == 1 ? wy : wz);
+      double Oe = 0.0;
+      if (e == 1) Oe = -wz; else if (e == 2) Oe = wy; else if (e == 3) Oe = wz; else if (e == 5) Oe = -wx; else if (e == 6) Oe = -wy; else if (e == 7) Oe = wx;
+      const double ident = (er == ecn) ? 1.0 : 0.0;
+      const double O2e = fma(wr, wc, -(ident * x));
+      const double Re_e = fma(B, O2e, fma(A, Oe, ident));   // exp(W)
+      const double V_e = fma(Cc, O2e, fma(B, Oe, ident));   // V
+      // te = V * upsilon, to = Re * t + te, Ro = Re * R : row er of Re / V lives in lanes 3*er .. 3*er+2
+      const double up = ecn == 0 ? s[0] : (ecn == 1 ? s[1] : s[2]);
+      const double vte = fma(Re_e, lm.t[ecn], V_e * up);  // lane (er,k): Re[er][k]*t[k] + V[er][k]*u[k]
+      const int base = 3 * er;
+      tn_e = __shfl_sync(0xffffffffu, vte, base) + __shfl_sync(0xffffffffu, vte, base + 1) + __shfl_sync(0xffffffffu, vte, base + 2);
+      const double Re0 = __shfl_sync(0xffffffffu, Re_e, base), Re1 = __shfl_sync(0xffffffffu, Re_e, base + 1), Re2 = __shfl_sync(0xffffffffu, Re_e, base + 2);
+      Rn_e = fma(Re0, lm.R[ecn], fma(Re1, lm.R[3 + ecn], Re2 * lm.R[6 + ecn]));  // (Re*R)[er][ecn]
+      if (lane < 9) lm.Rn[lane] = Rn_e;
+      if (lane < 9 && ecn == 0) lm.tn[er] = tn_e;
+      if (cyc) { long long c1 = clock64(); cyc[9] += c1 - c0; c0 = c1; }
+    } else {
+      asm volatile("bar.arrive 1, 64;" ::: "memory");
+      Rn_e = lm.R[e];
+      tn_e = lm.t[er];
+    }
+    // R*Ki and t in float (calcRes :617-618): lane (r,c) needs row r of R
+    const float Rf = (float)Rn_e;
+    const int base = 3 * er;
+    const float R0 = __shfl_sync(0xffffffffu, Rf, base), R1 = __shfl_sync(0xffffffffu, Rf, base + 1), R2 = __shfl_sync(0xffffffffu, Rf, base + 2);
+    if (lane < 9) {
+      ec.RKi[lane] = R0 * L.Ki[ecn] + R1 * L.Ki[3 + ecn] + R2 * L.Ki[6 + ecn];
+      if (ecn == 0) ec.t[er] = (float)tn_e;
+    }
+    if (cyc) { long long c1 = clock64(); cyc[10] += c1 - c0; c0 = c1; }
+  } else if (tid < 64) {
+    asm volatile("bar.sync 1, 64;" ::: "memory");  // warp 0 has published lm.affn (trial) / nothing to wait for otherwise
+    if (lane == 0) {
+      // AffLight::fromToVecExposure (util/NumType.h:159-170)
+      const double a0 = trial ? lm.affn[0] : lm.aff[0], b0 = trial ? lm.affn[1] : lm.aff[1];
+      float eF = P.ref_exposure, eT = prob.exposure_new;
+      if (eF == 0 || eT == 0) { eT = eF = 1; }
+      double a = d_exp_small(a0 - P.ref_aff[0]) * eT;
+      if (eF != 1.0f) a = a / eF;
+      const double b = b0 - a * P.ref_aff[1];
+      ec.affLL[0] = (float)a; ec.affLL[1] = (float)b;
+      ec.a = (float)a;
+      ec.b0 = (float)P.ref_aff[1];
+      ec.cutoff = cutoff;
+      ec.maxEnergy = 2 * P.huberTH * cutoff - P.huberTH * P.huberTH;
+    }
+  }
+}
+
+// The kernel is written as ONE loop with a single eval + exchange site (stages below): the persistent
+// kernel walks through its code once per evaluation with only 8 warps per SM, so instruction fetch is on
+// the critical path and every duplicated inlined copy of the evaluation costs real time.
+enum { ST_LEVEL_INIT = 0, ST_CUTOFF_REPEAT = 1, ST_ITER = 2 };
+
+template <int kU>  // gather batch per thread
 __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
@@ -424,105 +786,121 @@ __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
   const int tid = threadIdx.x;
   const int gtid = rank * blockDim.x + tid, gthreads = C * blockDim.x;
   LMState& lm = sm->lm;
-  float acc[kAcc];
+  float acc[kAccPad];
   unsigned evals = 0;
-  int parity = 0;
+  Exchange ex;
 
   if (tid == 0) {
     for (int i = 0; i < 9; i++) lm.R[i] = prob.T[(i / 3) * 4 + (i % 3)];
     for (int i = 0; i < 3; i++) lm.t[i] = prob.T[i * 4 + 3];
     lm.aff[0] = prob.aff[0]; lm.aff[1] = prob.aff[1];
+    mbar_init(&sm->bar[0], 1); mbar_init(&sm->bar[1], 1);
+    mbar_fence_init();
+  }
+  cluster.sync();  // barriers initialised and every CTA of the cluster resident before any DSMEM push
+
+  // phase timers accumulate in SHARED memory (a global read-modify-write per tick would cost more than the phases)
+  __shared__ long long s_cyc[16];
+  if (tid < 16) s_cyc[tid] = 0;
+  __syncthreads();
+  PhaseTimer tm;
+  if (P.timing && P.mode == 0 && rank == 0 && tid == 0) tm.start(s_cyc);
+  const bool single = (P.mode == 1);  // operator-level entry: one fused calcRes + calcGSSSE at eval_lvl
+  bool haveRepeated = false, aborted = false;
+  int lvl = single ? P.eval_lvl : P.coarsest;
+  int stage = ST_LEVEL_INIT, iteration = 0;
+  float levelCutoffRepeat = 1;
+  float meanOld = 0;
+
+  // per-level results live in shared memory (dynamic indexing by level would otherwise go to local memory)
+  __shared__ double s_lastRes[5];
+  __shared__ double s_flow[3];
+  __shared__ int s_iters[5];
+  if (tid < 5) { s_lastRes[tid] = NAN; s_iters[tid] = 0; }
+  if (tid < 3) s_flow[tid] = 1000;
+  __syncthreads();
+
+  while (true) {
+    const TrackLevel& L = P.L[lvl];
+    const float cutoff = single ? P.eval_cutoff : P.coarseCutoffTH * levelCutoffRepeat;
+    // ---- prologue: constants of this evaluation (warp 0) ----
+    if (tid < 64) {
+      eval_prologue(P, L, prob, lm, sm->ec, cutoff, stage == ST_ITER, tid, tm.cyc);
+      if (tid == 0 && stage == ST_LEVEL_INIT) lm.lambda = 0.01f;
+      tm.tick(11);
+    }
+    __syncthreads();
+    tm.tick(0);
+    // ---- the evaluation + the exchange: the only instance of this code in the kernel ----
+    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr);
+    tm.tick(1);
+    const int pb = reduce_exchange<false>(acc, sm, ex, C, rank, 0.0, &tm);
+    const float sumE = gather_sumf(sm, pb, C, A_E), sumNE = gather_sumf(sm, pb, C, A_NE);
+
+    // ---- epilogue ----
+    if (stage != ST_ITER) {
+      if (tid < kAcc) lm.totf[tid] = gather_sumf(sm, pb, C, tid);
+      if (single) {
+        __syncthreads();
+        if (rank == 0 && tid == 0) {
+          rs_from_total(lm.totf, prob.rs);
+          finish_gs(lm.totf, prob.H, prob.b);
+          const int nw = (int)lm.totf[A_NW];
+          prob.warped_n = (nw + 3) & ~3;
+        }
+        break;
+      }
+      // rs[5] = numSaturated / numTermsInE (:789); cutoff doubling while > 60 % saturated (:897-904)
+      const float sat = (int)gather_sumf(sm, pb, C, A_NSAT) / (float)(int)sumNE;
+      __syncthreads();
+      if (sat > 0.6 && levelCutoffRepeat < 50) { levelCutoffRepeat *= 2; stage = ST_CUTOFF_REPEAT; continue; }
+      meanOld = sumE / sumNE;  // resOld[0] / resOld[1]  (float: the sums carry float precision)
+      stage = ST_ITER; iteration = 0;
+      tm.tick(5);
+      continue;
+    }
+
+    // ST_ITER: accept / reject (:989-1019)
+    const int maxIt = lvl == 0 ? 10 : (lvl == 1 ? 20 : 50);  // {10,20,50,50,50} (:861)
+    const float meanNew = sumE / sumNE;
+    const bool accept = meanNew < meanOld;
+    const bool small = lm.small != 0;  // !(inc.norm() > 1e-3)
+    __syncthreads();  // everyone has read the LM state before it is mutated
+    if (accept) {
+      meanOld = meanNew;
+      if (tid < kAcc) lm.totf[tid] = gather_sumf(sm, pb, C, tid);  // sums of the accepted state (calcGSSSE at :996)
+      if (tid >= 64 && tid < 73) lm.R[tid - 64] = lm.Rn[tid - 64];
+      if (tid >= 73 && tid < 76) lm.t[tid - 73] = lm.tn[tid - 73];
+      if (tid >= 76 && tid < 78) lm.aff[tid - 76] = lm.affn[tid - 76];
+      if (tid == 78) lm.lambda *= 0.5f;
+    } else if (tid == 0) {
+      lm.lambda *= 4;
+      if (lm.lambda < 0.001f) lm.lambda = 0.001f;
+    }
+    iteration++;
+    __syncthreads();
+    tm.tick(4);
+    if (!small && iteration < maxIt) continue;
+
+    // ---- level finished (:1026-1041) ----
+    double rsOld[6];
+    rs_from_total(lm.totf, rsOld);  // resOld of the accepted state
+    const double lr = sqrtf((float)(rsOld[0] / rsOld[1]));  // :1028
+    if (tid == 0) {
+      s_lastRes[lvl] = lr; s_iters[lvl] += iteration;
+      s_flow[0] = rsOld[2]; s_flow[1] = rsOld[3]; s_flow[2] = rsOld[4];
+    }
+    if (lr > 1.5 * prob.minResForAbort[lvl]) { aborted = true; break; }
+    if (levelCutoffRepeat > 1 && !haveRepeated) { haveRepeated = true; }  // repeat this level once (:1036-1040)
+    else lvl--;
+    if (lvl < 0) break;
+    levelCutoffRepeat = 1;
+    stage = ST_LEVEL_INIT;
   }
   __syncthreads();
 
-  if (P.mode == 1) {  // ---- single fused calcRes + calcGSSSE (operator-level entry) ----
-    const int lvl = P.eval_lvl;
-    const TrackLevel& L = P.L[lvl];
-    if (tid == 0) make_eval_const_sse(P, L, prob, lm.R, lm.t, lm.aff, P.eval_cutoff, sm->ec);
-    __syncthreads();
-    eval_points_sse(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, P.dump);
-    reduce_all(acc, sm, parity, cluster, lm.total);
-    if (rank == 0 && tid == 0) {
-      rs_from_total(lm.total, prob.rs);
-      finish_gs(lm.total, prob.H, prob.b);
-      const int nw = (int)lm.total[A_NW];
-      prob.warped_n = (nw + 3) & ~3;
-    }
-    cluster.sync();
-    return;
-  }
-
-  // ---- full coarse-to-fine tracking, SSE path (CoarseTracker.cpp:827-1069, commented control flow) ----
-  const int maxIterations[5] = {10, 20, 50, 50, 50};
-  bool haveRepeated = false;
-  double lastRes[5] = {NAN, NAN, NAN, NAN, NAN};
-  double flow[3] = {1000, 1000, 1000};
-  int iters[5] = {0, 0, 0, 0, 0};
-  bool aborted = false;
-
-  for (int lvl = P.coarsest; lvl >= 0 && !aborted; lvl--) {
-    const TrackLevel& L = P.L[lvl];
-    const float4* tex = prob.tex[lvl];
-    float levelCutoffRepeat = 1;
-    // resOld = calcRes(...)
-    if (tid == 0) make_eval_const_sse(P, L, prob, lm.R, lm.t, lm.aff, P.coarseCutoffTH * levelCutoffRepeat, sm->ec);
-    __syncthreads();
-    eval_points_sse(P, L, lvl, tex, sm->ec, acc, evals, gtid, gthreads, nullptr);
-    reduce_all(acc, sm, parity, cluster, lm.total);
-    double rsOld[6];
-    rs_from_total(lm.total, rsOld);
-    while (rsOld[5] > 0.6 && levelCutoffRepeat < 50) {  // :897-904
-      levelCutoffRepeat *= 2;
-      __syncthreads();
-      if (tid == 0) make_eval_const_sse(P, L, prob, lm.R, lm.t, lm.aff, P.coarseCutoffTH * levelCutoffRepeat, sm->ec);
-      __syncthreads();
-      eval_points_sse(P, L, lvl, tex, sm->ec, acc, evals, gtid, gthreads, nullptr);
-      reduce_all(acc, sm, parity, cluster, lm.total);
-      rs_from_total(lm.total, rsOld);
-    }
-    if (tid == 0) { finish_gs(lm.total, lm.H, lm.b); lm.lambda = 0.01f; }
-    __syncthreads();
-
-    for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
-      iters[lvl]++;
-      if (tid == 0) {
-        lm_step_sse(P, lm);
-        make_eval_const_sse(P, L, prob, lm.Rn, lm.tn, lm.affn, P.coarseCutoffTH * levelCutoffRepeat, sm->ec);
-      }
-      __syncthreads();
-      eval_points_sse(P, L, lvl, tex, sm->ec, acc, evals, gtid, gthreads, nullptr);
-      reduce_all(acc, sm, parity, cluster, lm.totalNew);
-      double rsNew[6];
-      rs_from_total(lm.totalNew, rsNew);
-      const bool accept = (rsNew[0] / rsNew[1]) < (rsOld[0] / rsOld[1]);  // :989
-      double nrm = 0;
-      for (int i = 0; i < 8; i++) nrm += lm.inc[i] * lm.inc[i];
-      nrm = sqrt(nrm);
-      __syncthreads();  // everyone has read lm.inc / totals before thread 0 mutates the state
-      if (accept) {
-        for (int i = 0; i < 6; i++) rsOld[i] = rsNew[i];
-        if (tid == 0) {
-          finish_gs(lm.totalNew, lm.H, lm.b);
-          for (int i = 0; i < 9; i++) lm.R[i] = lm.Rn[i];
-          for (int i = 0; i < 3; i++) lm.t[i] = lm.tn[i];
-          lm.aff[0] = lm.affn[0]; lm.aff[1] = lm.affn[1];
-          lm.lambda *= 0.5f;
-        }
-      } else if (tid == 0) {
-        lm.lambda *= 4;
-        if (lm.lambda < 0.001f) lm.lambda = 0.001f;
-      }
-      __syncthreads();
-      if (!(nrm > 1e-3)) break;  // :1019
-    }
-    lastRes[lvl] = sqrtf((float)(rsOld[0] / rsOld[1]));  // :1028
-    flow[0] = rsOld[2]; flow[1] = rsOld[3]; flow[2] = rsOld[4];
-    if (lastRes[lvl] > 1.5 * prob.minResForAbort[lvl]) { aborted = true; break; }
-    if (levelCutoffRepeat > 1 && !haveRepeated) { lvl++; haveRepeated = true; }
-  }
-
   // outputs (:1044-1068)
-  if (rank == 0 && tid == 0) {
+  if (!single && rank == 0 && tid == 0) {
     bool ok = !aborted;
     double aout[2] = {lm.aff[0], lm.aff[1]};
     if (ok) {
@@ -545,9 +923,10 @@ __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
       for (int i = 0; i < 12; i++) prob.T_out[i] = prob.T[i];
       prob.aff_out[0] = prob.aff[0]; prob.aff_out[1] = prob.aff[1];
     }
-    for (int i = 0; i < 5; i++) { prob.lastResiduals[i] = lastRes[i]; prob.iterations[i] = iters[i]; }
-    for (int i = 0; i < 3; i++) prob.flow[i] = flow[i];
+    for (int i = 0; i < 5; i++) { prob.lastResiduals[i] = s_lastRes[i]; prob.iterations[i] = s_iters[i]; }
+    for (int i = 0; i < 3; i++) prob.flow[i] = s_flow[i];
     prob.ok = ok ? 1 : 0;
+    for (int i = 0; i < 16; i++) prob.cyc[i] = s_cyc[i];
   }
   // evals: integer sum, order-independent
   {
@@ -555,7 +934,7 @@ __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((tid & 31) == 0) atomicAdd(&prob.evals, (unsigned long long)e);
   }
-  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+  cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
 #include "tracker_g2o.cuh"
@@ -617,20 +996,21 @@ static void fill_params(sdso_ctx* ctx, TrackParams& P) {
   P.huberTH = ctx->S.huberTH; P.coarseCutoffTH = ctx->S.coarseCutoffTH;
   P.affineOptModeA = ctx->S.affineOptModeA; P.affineOptModeB = ctx->S.affineOptModeB;
   P.g2o_stop_persists = ctx->S.g2o_stop_flag_persists;
+  P.timing = ctx->profile ? 1 : 0;
   P.problems = t->d_problems;
 }
 
 static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   int C = ctx->S.cluster_size > 0 ? ctx->S.cluster_size : 8;
   int BT = ctx->S.block_threads > 0 ? ctx->S.block_threads : 256;
-  if (BT > 256 || BT < 64 || (BT & 31)) return fail(ctx, SDSO_E_INVALID, "block_threads must be a multiple of 32 in [64,256]");
+  if (BT > 256 || BT < 128 || (BT & 31)) return fail(ctx, SDSO_E_INVALID, "block_threads must be a multiple of 32 in [128,256]");
   if (C < 1 || C > 16) return fail(ctx, SDSO_E_INVALID, "cluster_size must be in [1,16]");
-  size_t smem = sizeof(TrackSmem) + (size_t)kAcc * BT * sizeof(float);
+  size_t smem = sizeof(TrackSmem);
   static bool attr_set = false;
   if (!attr_set) {
-    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
@@ -644,7 +1024,13 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   if (g2o) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_g2o_kernel, P));
-  else SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel, P));
+  else {
+    const int U = ctx->S.gather_batch > 0 ? ctx->S.gather_batch : 2;
+    if (U == 1) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<1>, P));
+    else if (U == 2) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<2>, P));
+    else if (U == 4) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<4>, P));
+    else return fail(ctx, SDSO_E_INVALID, "gather_batch must be 1, 2 or 4");
+  }
   ctx->launches++;
   return SDSO_OK;
 }
@@ -872,6 +1258,7 @@ int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, do
     if (iterations) memcpy(iterations + 5 * k, hp.iterations, sizeof(hp.iterations));
     if (ok) ok[k] = hp.ok;
     ev += hp.evals;
+    for (int i = 0; i < 16; i++) t->last_cyc[i] = (k == 0 ? 0 : t->last_cyc[i]) + hp.cyc[i];
   }
   if (evals) *evals = ev;
   return SDSO_OK;
@@ -892,3 +1279,11 @@ int sdso_track(sdso_ctx* ctx, int new_frame, double T_io[12], double aff_io[2], 
 }
 
 }  // extern "C"
+
+// phase cycles (clock64 on rank 0 / thread 0) of the last collected track launch, when profiling is enabled:
+// [0] serial LM step, [1] point loop, [2] block reduction, [3] cluster barrier + final sum, [4] accept/reject bookkeeping
+extern "C" int sdso_track_phase_cycles(sdso_ctx* ctx, long long cyc[16]) {
+  if (!ctx || !cyc) return SDSO_E_INVALID;
+  for (int i = 0; i < 16; i++) cyc[i] = ctx->tracker->last_cyc[i];
+  return SDSO_OK;
+}

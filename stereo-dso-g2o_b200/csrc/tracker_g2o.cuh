@@ -33,10 +33,10 @@ __device__ __forceinline__ void d_huber(double e2, double delta, double& rho0, d
 // MODE 2: computeActiveErrors + buildSystem (linearizeOplus + constructQuadraticForm)
 template <int MODE>
 __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex, const G2OConst& gc,
-                                unsigned char* __restrict__ flag, double* __restrict__ eerr, float (&acc)[kAcc], double& chi,
+                                unsigned char* __restrict__ flag, double* __restrict__ eerr, float (&acc)[kAccPad], double& chi,
                                 unsigned& evals, int gtid, int gthreads, double* dump) {
 #pragma unroll
-  for (int k = 0; k < kAcc; k++) acc[k] = 0.f;
+  for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
   chi = 0.0;
   const int wl = L.w, hl = L.h;
   const double delta = P.huberTH;
@@ -220,10 +220,10 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
   TrackProblem& prob = P.problems[prob_id];
   const int tid = threadIdx.x;
   const int gtid = rank * blockDim.x + tid, gthreads = C * blockDim.x;
-  float acc[kAcc];
+  float acc[kAccPad];
   double chi = 0.0, chiTot = 0.0;
   unsigned evals = 0;
-  int parity = 0;
+  Exchange parity;
   double* tot = sm->lm.total;
 
   if (tid == 0) {
@@ -231,8 +231,10 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
     for (int i = 0; i < 3; i++) gs.t[i] = gs.tsel[i] = prob.T[i * 4 + 3];
     gs.photo[0] = prob.aff[0]; gs.photo[1] = prob.aff[1];
     gs.forceStop = 0; gs.totalEdges = 0; gs.lastChi = 0;
+    mbar_init(&sm->bar[0], 1); mbar_init(&sm->bar[1], 1);
+    mbar_fence_init();
   }
-  __syncthreads();
+  cluster.sync();
 
   if (P.mode == 2) {  // ---- operator-level E1 evaluation: edges selected at T (prob.T), evaluated at (T_out, aff_out) ----
     const int lvl = P.eval_lvl;
@@ -309,8 +311,9 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
             for (int i = 0; i < 8; i++) Hl[i * 8 + i] += gs.lambda;  // additive damping
             for (int i = 0; i < 8; i++) gs.x[i] = 0;
             gs.ok2 = d_llt_solve8(Hl, gs.b, gs.x) ? 1 : 0;
-            double Rn[9], tn[3];
-            d_se3_exp_mul(gs.x, gs.R, gs.t, Rn, tn);  // oplus (dso_g2o_vertex.cpp:15-18)
+            double Rn[9], tn[3], xs[8];
+            for (int i = 0; i < 8; i++) xs[i] = gs.x[i];
+            d_se3_exp_mul(xs, gs.R, gs.t, Rn, tn);  // oplus (dso_g2o_vertex.cpp:15-18)
             for (int i = 0; i < 9; i++) gs.R[i] = Rn[i];
             for (int i = 0; i < 3; i++) gs.t[i] = tn[i];
             gs.photo[0] += gs.x[6]; gs.photo[1] += gs.x[7];  // (:30-40)

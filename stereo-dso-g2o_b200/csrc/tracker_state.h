@@ -20,6 +20,7 @@ struct TrackerState {
   float* d_dump = nullptr;
   size_t dump_cap = 0;
   int last_nb = 0;
+  long long last_cyc[16] = {0};
   unsigned char* edge_flag[kPyrLevels] = {nullptr};
   double* edge_err[kPyrLevels] = {nullptr};
   size_t edge_cap[kPyrLevels] = {0};
