@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_common.hpp).
 // C entry points for ctypes (tests/, smoke(), bench.py cpu_baseline / --impl reference).
 #include "oracle_core.hpp"
+#include "oracle_ba.hpp"
 #include <memory>
 
 using namespace orc;
@@ -12,6 +13,7 @@ struct Ctx {
   CalibHessian HCalib;
   std::vector<std::unique_ptr<Frame>> frames;
   CoarseTracker tracker;
+  BAWindow ba;
 };
 }  // namespace
 
@@ -139,4 +141,177 @@ void orc_se3_mul(const double A[12], const double B[12], double C[12]) { (SE3::f
 void orc_se3_inv(const double A[12], double B[12]) { SE3::fromMat34(A).inverse().toMat34(B); }
 void orc_ldlt_solve(int n, const double* A, const double* b, double* x) { ldlt_solve(n, A, b, x); }
 
+}  // extern "C"
+
+// ---- D1: ImmaturePoint constructor (ImmaturePoint.cpp:33-88): colour, weights, gradH of the 8-pixel pattern ----
+extern "C" int orc_immature_init(void* p, int fid, float u, float v, float* color8, float* weights8, float* gradH4, float* energyTH) {
+  Ctx* c = (Ctx*)p;
+  const float* dI = c->frames[fid]->dIp[0].data();
+  float gradH[4] = {0, 0, 0, 0};
+  for (int idx = 0; idx < patternNum; idx++) {
+    int dx = patternP[idx][0], dy = patternP[idx][1];
+    float ptc[3];
+    getInterpolatedElement33BiLin(dI, u + dx, v + dy, c->G.w[0], ptc);
+    color8[idx] = ptc[0];
+    if (!std::isfinite(color8[idx])) { *energyTH = NAN; return 0; }
+    gradH[0] += ptc[1] * ptc[1]; gradH[1] += ptc[1] * ptc[2]; gradH[2] += ptc[2] * ptc[1]; gradH[3] += ptc[2] * ptc[2];
+    weights8[idx] = sqrtf(c->S.outlierTHSumComponent / (c->S.outlierTHSumComponent + (ptc[1] * ptc[1] + ptc[2] * ptc[2])));
+  }
+  for (int i = 0; i < 4; i++) gradH4[i] = gradH[i];
+  float e = patternNum * c->S.outlierTH;
+  e *= c->S.overallEnergyTHWeight * c->S.overallEnergyTHWeight;
+  *energyTH = e;
+  return 1;
+}
+
+// ---- windowed BA (SSE path) -------------------------------------------------------------------------
+extern "C" {
+void orc_ba_reset(void* p) {
+  Ctx* c = (Ctx*)p;
+  c->ba = BAWindow();
+  c->ba.G = &c->G; c->ba.S = c->S; c->ba.HCalib = c->HCalib;
+}
+void orc_ba_set_calib_delta(void* p, const double d[4]) { Ctx* c = (Ctx*)p; for (int i = 0; i < 4; i++) c->ba.HCalib.value_minus_value_zero[i] = d[i]; }
+int orc_ba_add_frame(void* p, int fid, const double T_w2c[12], double a, double b, int frameID) {
+  Ctx* c = (Ctx*)p;
+  BAFrame f; f.img = c->frames[fid].get(); f.frameID = frameID;
+  f.setEvalPT_scaled(SE3::fromMat34(T_w2c), a, b);
+  // EFFrame::takeData -> FrameHessian::getPrior (HessianBlocks.h:246-268)
+  for (int i = 0; i < 8; i++) f.prior[i] = 0;
+  if (frameID == 0) {
+    for (int i = 0; i < 3; i++) f.prior[i] = c->S.initialTransPrior;
+    for (int i = 3; i < 6; i++) f.prior[i] = c->S.initialRotPrior;
+    f.prior[6] = c->S.initialAffAPrior; f.prior[7] = c->S.initialAffBPrior;
+  } else {
+    f.prior[6] = c->S.affineOptModeA < 0 ? c->S.initialAffAPrior : c->S.affineOptModeA;
+    f.prior[7] = c->S.affineOptModeB < 0 ? c->S.initialAffBPrior : c->S.affineOptModeB;
+  }
+  c->ba.frames.push_back(f);
+  return (int)c->ba.frames.size() - 1;
+}
+void orc_ba_set_state(void* p, int idx, const double state[10]) { ((Ctx*)p)->ba.frames[idx].setState(state); }
+void orc_ba_set_energy_th(void* p, int idx, float th) { ((Ctx*)p)->ba.frames[idx].frameEnergyTH = th; }
+int orc_ba_add_point(void* p, int host, float u, float v, float idepth, float idepth_zero, const float* color8, const float* weights8, int hasDepthPrior) {
+  Ctx* c = (Ctx*)p;
+  BAPoint q; q.host = host; q.u = u; q.v = v;
+  q.idepth = idepth; q.idepth_scaled = SCALE_IDEPTH * idepth;
+  q.idepth_zero = idepth_zero; q.idepth_zero_scaled = SCALE_IDEPTH * idepth_zero;
+  for (int i = 0; i < 8; i++) { q.color[i] = color8[i]; q.weights[i] = weights8[i]; }
+  q.hasDepthPrior = hasDepthPrior != 0;
+  q.priorF = q.hasDepthPrior ? c->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0;  // EFPoint::takeData
+  q.deltaF = q.idepth - q.idepth_zero;
+  c->ba.points.push_back(q);
+  return (int)c->ba.points.size() - 1;
+}
+int orc_ba_add_residual(void* p, int pidx, int target) {
+  Ctx* c = (Ctx*)p;
+  BARes r; r.point = pidx; r.host = c->ba.points[pidx].host; r.target = target;
+  r.state_state = RS_IN; r.state_NewState = RS_OUTLIER; r.state_energy = 0;  // resetOOB (Residuals.h:107-115)
+  memset(&r.J, 0, sizeof(r.J)); memset(&r.efJ, 0, sizeof(r.efJ));
+  c->ba.res.push_back(r);
+  c->ba.points[pidx].residuals.push_back((int)c->ba.res.size() - 1);
+  return (int)c->ba.res.size() - 1;
+}
+void orc_ba_set_point_flag(void* p, int pidx, int flag) { ((Ctx*)p)->ba.points[pidx].stateFlag = flag; }
+void orc_ba_prepare(void* p) {
+  Ctx* c = (Ctx*)p;
+  c->ba.setPrecalcValues(); c->ba.setAdjointsF(); c->ba.setDeltaF(); c->ba.getNullspaces();
+}
+int orc_ba_counts(void* p, int* nframes, int* npoints, int* nres) {
+  Ctx* c = (Ctx*)p; *nframes = c->ba.n(); *npoints = (int)c->ba.points.size(); *nres = (int)c->ba.res.size(); return c->ba.dim();
+}
+void orc_ba_precalc(void* p, int h, int t, float* out /*50*/) {
+  Ctx* c = (Ctx*)p; const FrameFramePrecalc& q = c->ba.precalc[(size_t)h * c->ba.n() + t];
+  int k = 0;
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_KRKiTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RKiTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RTll_0[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_tTll[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_KtTll[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_tTll_0[i];
+  out[k++] = q.PRE_aff_mode[0]; out[k++] = q.PRE_aff_mode[1]; out[k++] = q.PRE_b0_mode; out[k++] = q.distanceLL;
+}
+void orc_ba_adjoints(void* p, double* adHost, double* adTarget, float* adHTdeltaF) {
+  Ctx* c = (Ctx*)p;
+  if (adHost) memcpy(adHost, c->ba.adHost.data(), c->ba.adHost.size() * sizeof(double));
+  if (adTarget) memcpy(adTarget, c->ba.adTarget.data(), c->ba.adTarget.size() * sizeof(double));
+  if (adHTdeltaF) memcpy(adHTdeltaF, c->ba.adHTdeltaF.data(), c->ba.adHTdeltaF.size() * sizeof(float));
+}
+double orc_ba_linearize_all(void* p, int fix) { return ((Ctx*)p)->ba.linearizeAll(fix != 0); }
+void orc_ba_apply_res(void* p, int copy) { Ctx* c = (Ctx*)p; for (auto& r : c->ba.res) c->ba.applyRes(r, copy != 0); }
+void orc_ba_fix_linearization(void* p, int ridx) { Ctx* c = (Ctx*)p; c->ba.fixLinearizationF(c->ba.res[ridx]); }
+// per residual: state_NewState, state_state, NewEnergy, NewEnergyWithOutlier, isActive, J (74 floats: candidate J if which==0, EF J if which==1), JpJdF, centerProjectedTo
+void orc_ba_get_res(void* p, int which, int* newState, int* state, double* newEnergy, double* newEnergyWO, int* active, float* J74, float* JpJdF8, float* center3, float* resToZero8) {
+  Ctx* c = (Ctx*)p;
+  for (size_t i = 0; i < c->ba.res.size(); i++) {
+    const BARes& r = c->ba.res[i];
+    if (newState) newState[i] = r.state_NewState;
+    if (state) state[i] = r.state_state;
+    if (newEnergy) newEnergy[i] = r.state_NewEnergy;
+    if (newEnergyWO) newEnergyWO[i] = r.state_NewEnergyWithOutlier;
+    if (active) active[i] = r.isActive() ? 1 : 0;
+    if (J74) memcpy(J74 + 74 * i, which == 0 ? &r.J : &r.efJ, 74 * sizeof(float));
+    if (JpJdF8) memcpy(JpJdF8 + 8 * i, r.JpJdF, 8 * sizeof(float));
+    if (center3) memcpy(center3 + 3 * i, r.centerProjectedTo, 3 * sizeof(float));
+    if (resToZero8) memcpy(resToZero8 + 8 * i, r.res_toZeroF, 8 * sizeof(float));
+  }
+}
+// per point: Hdd_accAF, bd_accAF, Hcd_accAF[4], Hdd_accLF, bd_accLF, Hcd_accLF[4], HdiF, bdSumF, step, priorF, deltaF (16 floats)
+void orc_ba_get_points(void* p, float* out16) {
+  Ctx* c = (Ctx*)p;
+  for (size_t i = 0; i < c->ba.points.size(); i++) {
+    const BAPoint& q = c->ba.points[i]; float* o = out16 + 16 * i;
+    o[0] = q.Hdd_accAF; o[1] = q.bd_accAF; for (int k = 0; k < 4; k++) o[2 + k] = q.Hcd_accAF[k];
+    o[6] = q.Hdd_accLF; o[7] = q.bd_accLF; for (int k = 0; k < 4; k++) o[8 + k] = q.Hcd_accLF[k];
+    o[12] = q.HdiF; o[13] = q.bdSumF; o[14] = q.step; o[15] = q.priorF;
+  }
+}
+void orc_ba_accumulate_top(void* p, int mode, int usePrior, double* H, double* b, float* blocks) {
+  Ctx* c = (Ctx*)p; std::vector<double> Hv, bv;
+  c->ba.accumulateTop(mode, Hv, bv, usePrior != 0);
+  memcpy(H, Hv.data(), Hv.size() * sizeof(double)); memcpy(b, bv.data(), bv.size() * sizeof(double));
+  if (blocks) memcpy(blocks, c->ba.lastTopBlocks.data(), c->ba.lastTopBlocks.size() * sizeof(float));
+}
+void orc_ba_accumulate_sc(void* p, int shift, double* H, double* b) {
+  Ctx* c = (Ctx*)p; std::vector<double> Hv, bv;
+  c->ba.accumulateSC(shift != 0, Hv, bv);
+  memcpy(H, Hv.data(), Hv.size() * sizeof(double)); memcpy(b, bv.data(), bv.size() * sizeof(double));
+}
+void orc_ba_solve(void* p, int iteration, double lambda, double* x, double* Hfinal, double* bfinal) {
+  Ctx* c = (Ctx*)p; std::vector<double> xv, Hf, bf;
+  c->ba.solveSystemF(iteration, lambda, xv, &Hf, &bf);
+  memcpy(x, xv.data(), xv.size() * sizeof(double));
+  if (Hfinal) memcpy(Hfinal, Hf.data(), Hf.size() * sizeof(double));
+  if (bfinal) memcpy(bfinal, bf.data(), bf.size() * sizeof(double));
+}
+void orc_ba_resubstitute(void* p, const double* x, double* frame_steps, double* calib_step) {
+  Ctx* c = (Ctx*)p; std::vector<double> xv(x, x + c->ba.dim());
+  c->ba.resubstituteF(xv, frame_steps, calib_step);
+}
+void orc_ba_set_marg_prior(void* p, const double* HM, const double* bM) {
+  Ctx* c = (Ctx*)p; int d = c->ba.dim();
+  c->ba.HM.assign(HM, HM + (size_t)d * d); c->ba.bM.assign(bM, bM + d);
+}
+void orc_ba_get_marg_prior(void* p, double* HM, double* bM) {
+  Ctx* c = (Ctx*)p;
+  memcpy(HM, c->ba.HM.data(), c->ba.HM.size() * sizeof(double)); memcpy(bM, c->ba.bM.data(), c->ba.bM.size() * sizeof(double));
+}
+void orc_ba_marginalize_points(void* p) { ((Ctx*)p)->ba.marginalizePointsF(); }
+void orc_ba_marginalize_frame(void* p, int idx) { ((Ctx*)p)->ba.marginalizeFrame(idx); }
+void orc_ba_orthogonalize(void* p, double* b, double* H) {
+  Ctx* c = (Ctx*)p; int d = c->ba.dim();
+  std::vector<double> bv, Hv;
+  if (b) bv.assign(b, b + d);
+  if (H) Hv.assign(H, H + (size_t)d * d);
+  c->ba.orthogonalize(b ? &bv : nullptr, H ? &Hv : nullptr);
+  if (b) memcpy(b, bv.data(), d * sizeof(double));
+  if (H) memcpy(H, Hv.data(), (size_t)d * d * sizeof(double));
+}
+double orc_ba_energies(void* p, double* lenergy) { Ctx* c = (Ctx*)p; if (lenergy) *lenergy = c->ba.calcLEnergyF(); return c->ba.calcMEnergyF(); }
+void orc_ba_nullspaces(void* p, double* N /* dim x 7, row-major */) {
+  Ctx* c = (Ctx*)p; int d = c->ba.dim();
+  for (int i = 0; i < 6; i++) for (int r = 0; r < d; r++) N[(size_t)r * 7 + i] = c->ba.lastNullspaces_pose[i][r];
+  for (int r = 0; r < d; r++) N[(size_t)r * 7 + 6] = c->ba.lastNullspaces_scale[0][r];
+}
 }  // extern "C"
