@@ -67,6 +67,16 @@ typedef struct sdso_settings {
   int32_t cluster_size;             /* thread-block cluster size of the persistent kernels (0 = default 8) */
   int32_t block_threads;            /* threads per CTA of the persistent kernels (0 = default 256) */
   int32_t gather_batch;             /* points gathered per thread before the arithmetic: 1, 2 or 4 (0 = default) */
+  /* windowed BA (util/settings.cpp:42-52,76) */
+  float idepthFixPrior;             /* :42 */
+  float idepthFixPriorMargFac;      /* :43 */
+  float initialRotPrior;            /* :44 */
+  float initialTransPrior;          /* :45 */
+  float initialAffBPrior;           /* :46 */
+  float initialAffAPrior;           /* :47 */
+  float initialCalibHessian;        /* :48 */
+  float margWeightFac;              /* :76 */
+  double solverModeDelta;           /* :52 */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);
@@ -158,6 +168,55 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
                        int coarsest_lvl, const double* minResForAbort, int variant);
 int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, double* lastResiduals,
                        double* flowIndicators, int* iterations, int* ok, uint64_t* evals /* nullable, total */);
+
+/* ---- B1-B12: windowed bundle adjustment, SSE path (Residuals.cpp, OptimizationBackend/*) ----------------
+ * The window is uploaded once as SoA arenas (frames, points, residuals); every operator below runs on the
+ * device. Indices: frames 0..n-1 in insertion order (= EFFrame::idx), points 0..P-1 in the reference's
+ * allPoints order (EnergyFunctional.cpp:1003-1016), residuals 0..R-1 in the order given to
+ * sdso_ba_set_residuals (per point = PointHessian::residuals order). Matrices are dense row-major doubles of
+ * dimension dim = 4 + 8 n (CPARS + 8 per frame), as EnergyFunctional assembles them. */
+int sdso_ba_reset(sdso_ctx* ctx);
+/* CalibHessian::value_scaledf {fxl,fyl,cxl,cyl} (HessianBlocks.h:300-340) and value_minus_value_zero (nullable = 0) */
+int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_value_zero[4]);
+/* FrameHessian::setEvalPT_scaled(worldToCam, aff_g2l) + EFFrame::takeData (HessianBlocks.h:223-268); frame_id = a
+ * pyramid built by sdso_make_images; frameID == 0 receives the gauge priors */
+int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], double a, double b, int frameID, int* idx_out);
+int sdso_ba_set_state(sdso_ctx* ctx, int idx, const double state[10]);     /* FrameHessian::setState (HessianBlocks.h:177-199) */
+int sdso_ba_set_energy_th(sdso_ctx* ctx, int idx, float frameEnergyTH);    /* FrameHessian::frameEnergyTH */
+/* PointHessian / EFPoint fields: host frame idx, u, v, idepth, idepth_zero, color[8], weights[8], hasDepthPrior */
+int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, const float* v, const float* idepth,
+                       const float* idepth_zero, const float* color8, const float* weights8, const unsigned char* has_prior);
+int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* target);  /* PointFrameResidual(point, host, target) + resetOOB */
+int sdso_ba_set_point_flags(sdso_ctx* ctx, const unsigned char* flags);    /* EFPointStatus per point (0 GOOD, 1 MARGINALIZE, 2 DROP) */
+/* FullSystem::setPrecalcValues (FullSystem.cpp:1633-1644): FrameFramePrecalc::set for all pairs (HessianBlocks.cpp:206-242),
+ * EnergyFunctional::setAdjointsF (EnergyFunctional.cpp:41-119), setDeltaF (:173-207), getNullspaces (FullSystemOptimize.cpp:1087-1147) */
+int sdso_ba_prepare(sdso_ctx* ctx);
+int sdso_ba_counts(sdso_ctx* ctx, int* n, int* P, int* R, int* dim);
+int sdso_ba_get_precalc(sdso_ctx* ctx, int h, int t, float out[49]);
+int sdso_ba_get_adjoints(sdso_ctx* ctx, double* adHost, double* adTarget, float* adHTdeltaF);  /* [n*n][64], [n*n][64], [n*n][8]; index h + t*n */
+int sdso_ba_nullspaces(sdso_ctx* ctx, double* N /* dim x 7 row-major */);
+/* FullSystem::linearizeAll(fixLinearization) (FullSystemOptimize.cpp:142-203): PointFrameResidual::linearize
+ * (Residuals.cpp:83-336) over the active residuals, summed energy; fix != 0 also applies applyRes(true) */
+int sdso_ba_linearize_all(sdso_ctx* ctx, int fix, double* energy);
+int sdso_ba_apply_res(sdso_ctx* ctx, int copy_jacobians);                 /* PointFrameResidual::applyRes (Residuals.cpp:367-385) */
+/* EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:96-123) for the listed residuals (rids == NULL: all active) */
+int sdso_ba_fix_linearization(sdso_ctx* ctx, int count, const int* rids);
+int sdso_ba_get_res(sdso_ctx* ctx, int which /* 0 candidate J, 1 EFResidual::J */, int* newState, int* state, double* newEnergy,
+                    double* newEnergyWithOutlier, int* active, int* linearized, float* J74, float* JpJdF8, float* center3, float* resToZero8);
+int sdso_ba_get_points(sdso_ctx* ctx, float* out16);
+/* AccumulatedTopHessianSSE::addPoint<mode> over all points + stitchDouble (AccumulatedTopHessian.cpp:36-193, 265-337);
+ * blocks (nullable) = the n*n 13x13 float accumulators, index h + t*n */
+int sdso_ba_accumulate_top(sdso_ctx* ctx, int mode, int use_prior, double* H, double* b, float* blocks);
+/* AccumulatedSCHessianSSE::addPoint over all points + stitchDouble (AccumulatedSCHessian.cpp:34-195) */
+int sdso_ba_accumulate_sc(sdso_ctx* ctx, int shift_prior_to_zero, double* H, double* b);
+/* EnergyFunctional::solveSystemF(iteration, lambda, HCalib) (EnergyFunctional.cpp:838-995) incl. resubstituteF_MT;
+ * x = the solved increment (before the sign flip of resubstitute), Hfinal/bfinal (nullable) = the damped reduced system */
+int sdso_ba_solve(sdso_ctx* ctx, int iteration, double lambda, double* x, double* Hfinal, double* bfinal);
+/* EnergyFunctional::resubstituteF_MT (:272-341) for a given x (NULL: the last solve's); frame_steps [n][10], calib_step [4];
+ * point steps are read with sdso_ba_get_points */
+int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, double* calib_step);
+int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM);   /* EnergyFunctional::HM, bM */
+int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,9 @@ class Settings(C.Structure):
         ("trace_minImprovementFactor", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
         ("gammaWeightsPixelSelect", C.c_int32), ("g2o_stop_flag_persists", C.c_int32), ("cluster_size", C.c_int32),
         ("block_threads", C.c_int32), ("gather_batch", C.c_int32),
+        ("idepthFixPrior", C.c_float), ("idepthFixPriorMargFac", C.c_float), ("initialRotPrior", C.c_float),
+        ("initialTransPrior", C.c_float), ("initialAffBPrior", C.c_float), ("initialAffAPrior", C.c_float),
+        ("initialCalibHessian", C.c_float), ("margWeightFac", C.c_float), ("solverModeDelta", C.c_double),
     ]
 
 
@@ -272,3 +275,174 @@ class Context:
         self._ck(lib.sdso_track_collect(self._h, nb, _ptr(T, _dp), _ptr(aff, _dp), _ptr(lr, _dp), _ptr(fl, _dp), _ptr(it, _ip),
                                         _ptr(ok, _ip), C.byref(ev)))
         return dict(T=T.reshape(nb, 3, 4), aff=aff, lastResiduals=lr, flow=fl, iterations=it, ok=ok.astype(bool), evals=int(ev.value))
+
+
+# ---------------------------------------------------------------------------------------------------
+# B1-B12: windowed bundle adjustment (EnergyFunctional / PointFrameResidual operator surface)
+_u8p = C.POINTER(C.c_ubyte)
+lib.sdso_ba_reset.argtypes = [C.c_void_p]
+lib.sdso_ba_set_calib.argtypes = [C.c_void_p, _fp, _dp]
+lib.sdso_ba_add_frame.argtypes = [C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, C.c_int, _ip]
+lib.sdso_ba_set_state.argtypes = [C.c_void_p, C.c_int, _dp]
+lib.sdso_ba_set_energy_th.argtypes = [C.c_void_p, C.c_int, C.c_float]
+lib.sdso_ba_set_points.argtypes = [C.c_void_p, C.c_int, _ip, _fp, _fp, _fp, _fp, _fp, _fp, _u8p]
+lib.sdso_ba_set_residuals.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+lib.sdso_ba_set_point_flags.argtypes = [C.c_void_p, _u8p]
+lib.sdso_ba_prepare.argtypes = [C.c_void_p]
+lib.sdso_ba_counts.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip]
+lib.sdso_ba_get_precalc.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp]
+lib.sdso_ba_get_adjoints.argtypes = [C.c_void_p, _dp, _dp, _fp]
+lib.sdso_ba_nullspaces.argtypes = [C.c_void_p, _dp]
+lib.sdso_ba_linearize_all.argtypes = [C.c_void_p, C.c_int, _dp]
+lib.sdso_ba_apply_res.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_ba_fix_linearization.argtypes = [C.c_void_p, C.c_int, _ip]
+lib.sdso_ba_get_res.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _ip, _ip, _fp, _fp, _fp, _fp]
+lib.sdso_ba_get_points.argtypes = [C.c_void_p, _fp]
+lib.sdso_ba_accumulate_top.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _fp]
+lib.sdso_ba_accumulate_sc.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+lib.sdso_ba_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, _dp, _dp]
+lib.sdso_ba_resubstitute.argtypes = [C.c_void_p, _dp, _dp, _dp]
+lib.sdso_ba_set_marg_prior.argtypes = [C.c_void_p, _dp, _dp]
+lib.sdso_ba_get_marg_prior.argtypes = [C.c_void_p, _dp, _dp]
+
+
+class Window:
+    """The sliding window of one Context: index-based mirror of EnergyFunctional + PointFrameResidual
+    (frames / points / residuals as integer ids)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = ctx._h
+        self._ck = ctx._ck
+        self._ck(lib.sdso_ba_reset(self.h))
+
+    def set_calib(self, K, delta=None):
+        Kc = _f32(K)
+        d = _f64(delta) if delta is not None else None
+        self._ck(lib.sdso_ba_set_calib(self.h, _ptr(Kc, _fp), _ptr(d, _dp) if d is not None else None))
+
+    def add_frame(self, fid, T_w2c, a=0.0, b=0.0, frameID=1):
+        T = _f64(T_w2c).reshape(12)
+        idx = C.c_int()
+        self._ck(lib.sdso_ba_add_frame(self.h, fid, _ptr(T, _dp), a, b, frameID, C.byref(idx)))
+        return idx.value
+
+    def set_state(self, idx, state10):
+        s = _f64(state10)
+        self._ck(lib.sdso_ba_set_state(self.h, idx, _ptr(s, _dp)))
+
+    def set_energy_th(self, idx, th):
+        self._ck(lib.sdso_ba_set_energy_th(self.h, idx, float(th)))
+
+    def set_points(self, host, u, v, idepth, idepth_zero, color8, weights8, has_prior):
+        host = np.ascontiguousarray(host, np.int32)
+        u, v, idepth, idepth_zero = _f32(u), _f32(v), _f32(idepth), _f32(idepth_zero)
+        c, w = _f32(color8).reshape(-1, 8), _f32(weights8).reshape(-1, 8)
+        hp = np.ascontiguousarray(has_prior, np.uint8)
+        self._ck(lib.sdso_ba_set_points(self.h, host.size, _ptr(host, _ip), _ptr(u, _fp), _ptr(v, _fp), _ptr(idepth, _fp),
+                                        _ptr(idepth_zero, _fp), _ptr(c, _fp), _ptr(w, _fp), _ptr(hp, _u8p)))
+
+    def set_residuals(self, point, target):
+        p, t = np.ascontiguousarray(point, np.int32), np.ascontiguousarray(target, np.int32)
+        self._ck(lib.sdso_ba_set_residuals(self.h, p.size, _ptr(p, _ip), _ptr(t, _ip)))
+
+    def set_point_flags(self, flags):
+        f = np.ascontiguousarray(flags, np.uint8)
+        self._ck(lib.sdso_ba_set_point_flags(self.h, _ptr(f, _u8p)))
+
+    def prepare(self):
+        self._ck(lib.sdso_ba_prepare(self.h))
+
+    def counts(self):
+        n, P, R, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib.sdso_ba_counts(self.h, C.byref(n), C.byref(P), C.byref(R), C.byref(d)))
+        return dict(frames=n.value, points=P.value, res=R.value, dim=d.value)
+
+    def precalc(self, h, t):
+        out = np.zeros(49, np.float32)
+        self._ck(lib.sdso_ba_get_precalc(self.h, h, t, _ptr(out, _fp)))
+        return out
+
+    def adjoints(self):
+        n = self.counts()["frames"]
+        ah, at, d = np.zeros((n * n, 8, 8)), np.zeros((n * n, 8, 8)), np.zeros((n * n, 8), np.float32)
+        self._ck(lib.sdso_ba_get_adjoints(self.h, _ptr(ah, _dp), _ptr(at, _dp), _ptr(d, _fp)))
+        return ah, at, d
+
+    def nullspaces(self):
+        N = np.zeros((self.counts()["dim"], 7))
+        self._ck(lib.sdso_ba_nullspaces(self.h, _ptr(N, _dp)))
+        return N
+
+    def linearize_all(self, fix=False):
+        e = C.c_double()
+        self._ck(lib.sdso_ba_linearize_all(self.h, int(fix), C.byref(e)))
+        return e.value
+
+    def linearize_all_async(self, fix=False):
+        self._ck(lib.sdso_ba_linearize_all(self.h, int(fix), None))
+
+    def apply_res(self, copy=True):
+        self._ck(lib.sdso_ba_apply_res(self.h, int(copy)))
+
+    def fix_linearization(self, rids=None):
+        if rids is None:
+            self._ck(lib.sdso_ba_fix_linearization(self.h, 0, None))
+        else:
+            r = np.ascontiguousarray(rids, np.int32)
+            self._ck(lib.sdso_ba_fix_linearization(self.h, r.size, _ptr(r, _ip)))
+
+    def get_res(self, which=0):
+        R = self.counts()["res"]
+        ns, st, ac, li = (np.zeros(R, np.int32) for _ in range(4))
+        ne, nw = np.zeros(R), np.zeros(R)
+        J, jp, ce, rz = np.zeros((R, 74), np.float32), np.zeros((R, 8), np.float32), np.zeros((R, 3), np.float32), np.zeros((R, 8), np.float32)
+        self._ck(lib.sdso_ba_get_res(self.h, which, _ptr(ns, _ip), _ptr(st, _ip), _ptr(ne, _dp), _ptr(nw, _dp), _ptr(ac, _ip), _ptr(li, _ip),
+                                     _ptr(J, _fp), _ptr(jp, _fp), _ptr(ce, _fp), _ptr(rz, _fp)))
+        return dict(newState=ns, state=st, newEnergy=ne, newEnergyWithOutlier=nw, active=ac, linearized=li, J=J, JpJdF=jp, center=ce, res_toZero=rz)
+
+    def get_points(self):
+        P = self.counts()["points"]
+        o = np.zeros((P, 16), np.float32)
+        self._ck(lib.sdso_ba_get_points(self.h, _ptr(o, _fp)))
+        return dict(Hdd_A=o[:, 0], bd_A=o[:, 1], Hcd_A=o[:, 2:6], Hdd_L=o[:, 6], bd_L=o[:, 7], Hcd_L=o[:, 8:12], HdiF=o[:, 12], bdSumF=o[:, 13],
+                    step=o[:, 14], priorF=o[:, 15])
+
+    def accumulate_top(self, mode, use_prior):
+        c = self.counts()
+        d, n = c["dim"], c["frames"]
+        H, b, blk = np.zeros((d, d)), np.zeros(d), np.zeros((n * n, 13, 13), np.float32)
+        self._ck(lib.sdso_ba_accumulate_top(self.h, mode, int(use_prior), _ptr(H, _dp), _ptr(b, _dp), _ptr(blk, _fp)))
+        return H, b, blk
+
+    def accumulate_sc(self, shift=True):
+        d = self.counts()["dim"]
+        H, b = np.zeros((d, d)), np.zeros(d)
+        self._ck(lib.sdso_ba_accumulate_sc(self.h, int(shift), _ptr(H, _dp), _ptr(b, _dp)))
+        return H, b
+
+    def solve(self, iteration, lam=1e-5):
+        d = self.counts()["dim"]
+        x, H, b = np.zeros(d), np.zeros((d, d)), np.zeros(d)
+        self._ck(lib.sdso_ba_solve(self.h, iteration, lam, _ptr(x, _dp), _ptr(H, _dp), _ptr(b, _dp)))
+        return x, H, b
+
+    def solve_async(self, iteration, lam=1e-5):
+        self._ck(lib.sdso_ba_solve(self.h, iteration, lam, None, None, None))
+
+    def resubstitute(self, x=None):
+        n = self.counts()["frames"]
+        xs = _f64(x) if x is not None else None
+        fs, cs = np.zeros((n, 10)), np.zeros(4)
+        self._ck(lib.sdso_ba_resubstitute(self.h, _ptr(xs, _dp) if xs is not None else None, _ptr(fs, _dp), _ptr(cs, _dp)))
+        return fs, cs
+
+    def set_marg_prior(self, HM, bM):
+        HM, bM = _f64(HM), _f64(bM)
+        self._ck(lib.sdso_ba_set_marg_prior(self.h, _ptr(HM, _dp), _ptr(bM, _dp)))
+
+    def get_marg_prior(self):
+        d = self.counts()["dim"]
+        HM, bM = np.zeros((d, d)), np.zeros(d)
+        self._ck(lib.sdso_ba_get_marg_prior(self.h, _ptr(HM, _dp), _ptr(bM, _dp)))
+        return HM, bM

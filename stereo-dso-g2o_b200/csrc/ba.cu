@@ -1,7 +1,733 @@
-// Windowed bundle adjustment on the device (B1-B12, E2). Filled in by ba_*.cu; this file owns the state.
-#include "ctx.h"
+// Windowed bundle adjustment on the device — host side of B1-B12 (SSE path of the reference):
+// window upload (SoA arenas, residuals stored sorted by (host,target)), the O(n^2) double-precision
+// bookkeeping the reference also does on the host (FrameFramePrecalc::set, setAdjointsF, setDeltaF,
+// nullspaces), and the C-ABI entry points that launch the kernels of ba_kernels.cuh.
+#include "ba_kernels.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 namespace sdso {
-struct BAState { int dummy = 0; };
-int ba_create(sdso_ctx* ctx) { ctx->ba = new BAState(); return SDSO_OK; }
-void ba_destroy(sdso_ctx* ctx) { delete ctx->ba; ctx->ba = nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t grow(T*& p, size_t n) {
+  if (p) cudaFree(p);
+  p = nullptr;
+  return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+}
+#define BA_ALLOC(ptr, n) SDSO_CUDA(ctx, grow(ptr, n))
+
+static void free_all(BAState* b) {
+  void* ptrs[] = {b->d_tex0, b->d_frameTH, b->d_precalc, b->d_adHost, b->d_adTarget, b->d_adHostF, b->d_adTargetF, b->d_adHTdeltaF, b->d_cDeltaF,
+                  b->d_fprior, b->d_p_host, b->d_p_u, b->d_p_v, b->d_p_idepth, b->d_p_idepth_zero, b->d_p_color, b->d_p_weights, b->d_p_priorF,
+                  b->d_p_deltaF, b->d_p_res_begin, b->d_slot_of, b->d_p_acc, b->d_p_flag, b->d_p_res_list, b->d_s_point, b->d_s_key, b->d_s_state,
+                  b->d_s_newstate, b->d_s_flags, b->d_s_sel, b->d_s_energy, b->d_J, b->d_s_rtz, b->d_s_JpJd, b->d_s_center, b->d_s_psum,
+                  b->d_slot2rid, b->d_rid2slot, b->d_chunks, b->d_key_chunk_begin, b->d_tpart, b->d_dpart, b->d_pblockpart, b->d_G, b->d_Gf,
+                  b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list};
+  for (void* p : ptrs) if (p) cudaFree(p);
+}
+
+int ba_create(sdso_ctx* ctx) {
+  BAState* b = new BAState();
+  ctx->ba = b;
+  const int F = kMaxFrames, F2 = F * F, dmax = kCPARS + 8 * F;
+  BA_ALLOC(b->d_tex0, F); BA_ALLOC(b->d_frameTH, F); BA_ALLOC(b->d_precalc, F2);
+  BA_ALLOC(b->d_adHost, F2 * 64); BA_ALLOC(b->d_adTarget, F2 * 64); BA_ALLOC(b->d_adHostF, F2 * 64); BA_ALLOC(b->d_adTargetF, F2 * 64);
+  BA_ALLOC(b->d_adHTdeltaF, F2 * 8); BA_ALLOC(b->d_cDeltaF, 4); BA_ALLOC(b->d_fprior, F * 24);
+  BA_ALLOC(b->d_G, F2 * 169 + F2); BA_ALLOC(b->d_Gf, F2 * 169);
+  BA_ALLOC(b->d_D, (size_t)F2 * F * 65); BA_ALLOC(b->d_E, F2 * 40); BA_ALLOC(b->d_Hcc, 20);
+  BA_ALLOC(b->d_U, (size_t)F2 * F * 64); BA_ALLOC(b->d_V, (size_t)F2 * F * 64);
+  b->sys_stride = (size_t)dmax * dmax + dmax;
+  BA_ALLOC(b->d_sys, b->sys_stride * SYS_NUM);
+  SDSO_CUDA(ctx, cudaMemset(b->d_sys, 0, b->sys_stride * SYS_NUM * sizeof(double)));
+  BA_ALLOC(b->d_scalars, 16); BA_ALLOC(b->d_counter, 1); BA_ALLOC(b->d_N, dmax * 7); BA_ALLOC(b->d_xAd, F2 * 8);
+  SDSO_CUDA(ctx, cudaMemset(b->d_counter, 0, sizeof(unsigned)));
+  return SDSO_OK;
+}
+void ba_destroy(sdso_ctx* ctx) {
+  if (!ctx->ba) return;
+  free_all(ctx->ba);
+  delete ctx->ba;
+  ctx->ba = nullptr;
+}
+
+static BAView view(BAState* b) {
+  BAView v;
+  v.n = b->n; v.P = b->P; v.R = b->R; v.capP = b->capP; v.capR = b->capR; v.c = b->calib;
+  v.tex0 = b->d_tex0; v.frameTH = b->d_frameTH; v.precalc = b->d_precalc;
+  v.adHost = b->d_adHost; v.adTarget = b->d_adTarget; v.adHostF = b->d_adHostF; v.adTargetF = b->d_adTargetF;
+  v.adHTdeltaF = b->d_adHTdeltaF; v.cDeltaF = b->d_cDeltaF; v.fprior = b->d_fprior;
+  v.p_host = b->d_p_host; v.p_u = b->d_p_u; v.p_v = b->d_p_v; v.p_idepth = b->d_p_idepth; v.p_idepth_zero = b->d_p_idepth_zero;
+  v.p_color = b->d_p_color; v.p_weights = b->d_p_weights; v.p_priorF = b->d_p_priorF; v.p_deltaF = b->d_p_deltaF;
+  v.p_res_begin = b->d_p_res_begin; v.p_res_list = b->d_p_res_list; v.slot_of = b->d_slot_of; v.p_acc = b->d_p_acc; v.p_flag = b->d_p_flag;
+  v.s_point = b->d_s_point; v.s_key = b->d_s_key; v.s_state = b->d_s_state; v.s_newstate = b->d_s_newstate; v.s_flags = b->d_s_flags; v.s_sel = b->d_s_sel;
+  v.s_energy = b->d_s_energy; v.J = b->d_J; v.s_rtz = b->d_s_rtz; v.s_JpJd = b->d_s_JpJd; v.s_center = b->d_s_center; v.s_psum = b->d_s_psum;
+  v.chunks = b->d_chunks; v.nchunks = b->nchunks; v.key_chunk_begin = b->d_key_chunk_begin;
+  v.tpart = b->d_tpart; v.dpart = b->d_dpart; v.pblockpart = b->d_pblockpart;
+  v.G = b->d_G; v.Gf = b->d_Gf; v.D = b->d_D; v.E = b->d_E; v.Hcc = b->d_Hcc; v.U = b->d_U; v.V = b->d_V;
+  v.energy_part = b->d_energy_part; v.scalars = b->d_scalars; v.counter = b->d_counter;
+  return v;
+}
+
+static inline double* sysH(BAState* b, int which) { return b->d_sys + b->sys_stride * which; }
+static inline double* sysb(BAState* b, int which) { const int dm = kCPARS + 8 * kMaxFrames; return b->d_sys + b->sys_stride * which + (size_t)dm * dm; }
+
+// ---- FrameHessian state handling (HessianBlocks.h:177-231, HessianBlocks.cpp:78-123) ----------------
+static void frame_update_pre(HostBAFrame& f) {
+  double E[12];
+  se3_exp(f.state_scaled, E);
+  se3_mul(E, f.T_eval, f.T_w2c);
+  se3_inv(f.T_w2c, f.T_c2w);
+}
+static void frame_set_state(HostBAFrame& f, const double s[10]) {
+  for (int i = 0; i < 10; i++) f.state[i] = s[i];
+  for (int i = 0; i < 3; i++) f.state_scaled[i] = SCALE_XI_TRANS * f.state[i];
+  for (int i = 3; i < 6; i++) f.state_scaled[i] = SCALE_XI_ROT * f.state[i];
+  f.state_scaled[6] = SCALE_A * f.state[6]; f.state_scaled[7] = SCALE_B * f.state[7];
+  f.state_scaled[8] = SCALE_A * f.state[8]; f.state_scaled[9] = SCALE_B * f.state[9];
+  frame_update_pre(f);
+}
+static void frame_set_state_scaled(HostBAFrame& f, const double s[10]) {
+  for (int i = 0; i < 10; i++) f.state_scaled[i] = s[i];
+  for (int i = 0; i < 3; i++) f.state[i] = (1.0f / SCALE_XI_TRANS) * f.state_scaled[i];
+  for (int i = 3; i < 6; i++) f.state[i] = (1.0f / SCALE_XI_ROT) * f.state_scaled[i];
+  f.state[6] = (1.0f / SCALE_A) * f.state_scaled[6]; f.state[7] = (1.0f / SCALE_B) * f.state_scaled[7];
+  f.state[8] = (1.0f / SCALE_A) * f.state_scaled[8]; f.state[9] = (1.0f / SCALE_B) * f.state_scaled[9];
+  frame_update_pre(f);
+}
+static void frame_set_state_zero(HostBAFrame& f) {
+  for (int i = 0; i < 10; i++) f.state_zero[i] = f.state[i];
+  double inv0[12];
+  se3_inv(f.T_eval, inv0);
+  for (int i = 0; i < 6; i++) {  // numeric derivative of log(T exp(eps) T^-1) (HessianBlocks.cpp:83-93)
+    double eps[6] = {0, 0, 0, 0, 0, 0}, Ep[12], Em[12], Pp[12], Pm[12], lp[6], lm[6];
+    eps[i] = 1e-3; se3_exp(eps, Ep);
+    eps[i] = -1e-3; se3_exp(eps, Em);
+    se3_mul(f.T_eval, Ep, Pp); se3_mul(Pp, inv0, Pp);
+    se3_mul(f.T_eval, Em, Pm); se3_mul(Pm, inv0, Pm);
+    se3_log(Pp, lp); se3_log(Pm, lm);
+    for (int r = 0; r < 6; r++) f.ns_pose[r * 6 + i] = (lp[r] - lm[r]) / (2e-3);
+  }
+  double Pp[12], Pm[12], lp[6], lm[6];
+  memcpy(Pp, f.T_eval, sizeof(Pp)); memcpy(Pm, f.T_eval, sizeof(Pm));
+  for (int k = 0; k < 3; k++) { Pp[k * 4 + 3] *= 1.00001; Pm[k * 4 + 3] /= 1.00001; }
+  se3_mul(Pp, inv0, Pp); se3_mul(Pm, inv0, Pm);
+  se3_log(Pp, lp); se3_log(Pm, lm);
+  for (int r = 0; r < 6; r++) f.ns_scale[r] = (lp[r] - lm[r]) / (2e-3);
+}
+
+static void aff_from_to(float eF, float eT, double aF, double bF, double aT, double bT, double out[2]) {  // NumType.h:159-170
+  if (eF == 0 || eT == 0) { eT = eF = 1; }
+  const double a = std::exp(aT - aF) * eT / eF;
+  out[0] = a; out[1] = bT - a * bF;
+}
+static void mat33f_mul(const float A[9], const float B[9], float C[9]) {
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r * 3 + c] = A[r * 3 + 0] * B[0 * 3 + c] + A[r * 3 + 1] * B[1 * 3 + c] + A[r * 3 + 2] * B[2 * 3 + c];
+}
+
+// FrameFramePrecalc::set for all pairs (HessianBlocks.cpp:206-242), setAdjointsF (EnergyFunctional.cpp:41-119),
+// setDeltaF (:173-207), getNullspaces (FullSystemOptimize.cpp:1087-1147); uploads the results.
+static int prepare_window(sdso_ctx* ctx) {
+  BAState* b = ctx->ba;
+  const int n = b->n;
+  const sdso_settings& S = ctx->S;
+  std::vector<PrecalcDev> pre((size_t)n * n);
+  std::vector<double> adH((size_t)n * n * 64, 0.0), adT((size_t)n * n * 64, 0.0);
+  std::vector<float> adHF((size_t)n * n * 64), adTF((size_t)n * n * 64), adHTd((size_t)n * n * 8);
+  const BACalib& c = b->calib;
+  const float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
+  float Kinv[9];
+  inverse3f(K, Kinv);
+  for (int h = 0; h < n; h++) for (int t = 0; t < n; t++) {
+    const HostBAFrame& host = b->frames[h]; const HostBAFrame& target = b->frames[t];
+    PrecalcDev& p = pre[(size_t)h * n + t];
+    memset(&p, 0, sizeof(p));
+    double hinv[12], l0[12], l[12];
+    se3_inv(host.T_eval, hinv);
+    se3_mul(target.T_eval, hinv, l0);
+    se3_mul(target.T_w2c, host.T_c2w, l);
+    for (int r = 0; r < 3; r++) {
+      for (int q = 0; q < 3; q++) { p.PRE_RTll_0[r * 3 + q] = (float)l0[r * 4 + q]; p.PRE_RTll[r * 3 + q] = (float)l[r * 4 + q]; }
+      p.PRE_tTll_0[r] = (float)l0[r * 4 + 3]; p.PRE_tTll[r] = (float)l[r * 4 + 3];
+    }
+    p.distanceLL = (float)std::sqrt(l[3] * l[3] + l[7] * l[7] + l[11] * l[11]);
+    float KR[9];
+    mat33f_mul(K, p.PRE_RTll, KR);
+    mat33f_mul(KR, Kinv, p.PRE_KRKiTll);
+    mat33f_mul(p.PRE_RTll, Kinv, p.PRE_RKiTll);
+    for (int r = 0; r < 3; r++) p.PRE_KtTll[r] = K[r * 3] * p.PRE_tTll[0] + K[r * 3 + 1] * p.PRE_tTll[1] + K[r * 3 + 2] * p.PRE_tTll[2];
+    double ab[2];
+    aff_from_to(host.ab_exposure, target.ab_exposure, host.state_scaled[6], host.state_scaled[7], target.state_scaled[6], target.state_scaled[7], ab);
+    p.PRE_aff_mode[0] = (float)ab[0]; p.PRE_aff_mode[1] = (float)ab[1];
+    p.PRE_b0_mode = (float)(host.state_zero[7] * SCALE_B);
+    // adjoints at the evaluation point
+    double Adj[36], AH[64] = {0}, AT[64] = {0};
+    se3_adj(l0, Adj);
+    for (int i = 0; i < 8; i++) { AH[i * 8 + i] = 1; AT[i * 8 + i] = 1; }
+    for (int r = 0; r < 6; r++) for (int q = 0; q < 6; q++) AH[r * 8 + q] = -Adj[q * 6 + r];
+    double ab0[2];
+    aff_from_to(host.ab_exposure, target.ab_exposure, host.state_zero[6] * SCALE_A, host.state_zero[7] * SCALE_B, target.state_zero[6] * SCALE_A,
+                target.state_zero[7] * SCALE_B, ab0);
+    const float affLL0 = (float)ab0[0];
+    AT[6 * 8 + 6] = -affLL0; AT[7 * 8 + 7] = -1;
+    AH[6 * 8 + 6] = affLL0; AH[7 * 8 + 7] = affLL0;
+    const double rs[8] = {SCALE_XI_TRANS, SCALE_XI_TRANS, SCALE_XI_TRANS, SCALE_XI_ROT, SCALE_XI_ROT, SCALE_XI_ROT, SCALE_A, SCALE_B};
+    for (int r = 0; r < 8; r++) for (int q = 0; q < 8; q++) { AH[r * 8 + q] *= rs[r]; AT[r * 8 + q] *= rs[r]; }
+    const size_t o = ((size_t)h + (size_t)t * n) * 64;
+    for (int i = 0; i < 64; i++) { adH[o + i] = AH[i]; adT[o + i] = AT[i]; adHF[o + i] = (float)AH[i]; adTF[o + i] = (float)AT[i]; }
+  }
+  for (int i = 0; i < 4; i++) b->cPrior[i] = S.initialCalibHessian;
+  // setDeltaF
+  std::vector<double> fpr((size_t)kMaxFrames * 24, 0.0);
+  for (int h = 0; h < n; h++) {
+    HostBAFrame& f = b->frames[h];
+    for (int i = 0; i < 8; i++) { f.delta[i] = f.state[i] - f.state_zero[i]; f.delta_prior[i] = f.state[i]; }
+    for (int i = 0; i < 8; i++) { fpr[h * 24 + i] = f.prior[i]; fpr[h * 24 + 8 + i] = f.delta_prior[i]; fpr[h * 24 + 16 + i] = f.delta[i]; }
+  }
+  for (int h = 0; h < n; h++) for (int t = 0; t < n; t++) {
+    const size_t idx = (size_t)h + (size_t)t * n;
+    float dh[8], dt[8];
+    for (int i = 0; i < 8; i++) { dh[i] = (float)(b->frames[h].state[i] - b->frames[h].state_zero[i]); dt[i] = (float)(b->frames[t].state[i] - b->frames[t].state_zero[i]); }
+    for (int j = 0; j < 8; j++) {
+      float a = 0, bb = 0;
+      for (int i = 0; i < 8; i++) a += dh[i] * adHF[idx * 64 + i * 8 + j];
+      for (int i = 0; i < 8; i++) bb += dt[i] * adTF[idx * 64 + i * 8 + j];
+      adHTd[idx * 8 + j] = a + bb;
+    }
+  }
+  float cDeltaF[4];
+  for (int i = 0; i < 4; i++) cDeltaF[i] = (float)b->calib_delta[i];
+  // nullspaces: 6 pose + 1 scale vectors over the frames (calibration rows are zero)
+  const int d = b->dim();
+  std::vector<double> N((size_t)d * 7, 0.0);
+  for (int f = 0; f < n; f++) for (int r = 0; r < 6; r++) {
+    const double sc = (r < 3) ? (1.0f / SCALE_XI_TRANS) : (1.0f / SCALE_XI_ROT);
+    for (int i = 0; i < 6; i++) N[(size_t)(kCPARS + f * 8 + r) * 7 + i] = b->frames[f].ns_pose[r * 6 + i] * sc;
+    N[(size_t)(kCPARS + f * 8 + r) * 7 + 6] = b->frames[f].ns_scale[r] * sc;
+  }
+  b->h_N = N;
+  // per-frame device pointers and thresholds
+  std::vector<const float4*> tex(kMaxFrames, nullptr);
+  std::vector<float> th(kMaxFrames, 0.f);
+  for (int h = 0; h < n; h++) { tex[h] = ctx->frames[b->frames[h].frame_id].tex[0]; th[h] = b->frames[h].frameEnergyTH; }
+  b->h_pre = pre; b->h_adH = adH; b->h_adT = adT; b->h_adHTd = adHTd;
+  cudaStream_t st = ctx->stream;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_precalc, pre.data(), pre.size() * sizeof(PrecalcDev), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adHost, adH.data(), adH.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adTarget, adT.data(), adT.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adHostF, adHF.data(), adHF.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adTargetF, adTF.data(), adTF.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adHTdeltaF, adHTd.data(), adHTd.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_cDeltaF, cDeltaF, sizeof(cDeltaF), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_fprior, fpr.data(), fpr.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_N, N.data(), N.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_tex0, tex.data(), tex.size() * sizeof(float4*), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_frameTH, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  // deltaF of the points follows idepth - idepth_zero (EFPoint::takeData / setDeltaF :196-204): device side
+  b->prepared = true;
+  return SDSO_OK;
+}
+
+__global__ void ba_point_delta_kernel(int P, const float* idepth, const float* idepth_zero, float* deltaF) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) deltaF[p] = idepth[p] - idepth_zero[p];
+}
+
+// ---- launches ---------------------------------------------------------------------------------------------
+static int launch_top(sdso_ctx* ctx, int mode, int which, bool usePrior) {
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  const int d = b->dim(), n = b->n;
+  if (b->nchunks > 0) { ba_top_kernel<<<b->nchunks, kChunk, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
+  ba_top_finish_kernel<<<n * n, 192, 0, ctx->stream>>>(v); SDSO_CHECK_LAUNCH(ctx);
+  if (b->P > 0) { ba_point_sums_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
+  double* dc = nullptr;
+  // cPrior lives at scalars[8..11]
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_scalars + 8, b->cPrior, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  dc = b->d_scalars + 8;
+  ba_stitch_top_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, which), sysb(b, which), usePrior ? 1 : 0, dc);
+  SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+static int launch_sc(sdso_ctx* ctx, bool shift, int which) {
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  const int d = b->dim(), n = b->n;
+  ba_sc_point_kernel<<<std::max(b->pblocks, 1), 128, 0, ctx->stream>>>(v, shift ? 1 : 0); SDSO_CHECK_LAUNCH(ctx);
+  if (b->nchunks > 0) { ba_sc_pair_kernel<<<dim3(b->nchunks, n + 1), kChunk, 0, ctx->stream>>>(v, shift ? 1 : 0); SDSO_CHECK_LAUNCH(ctx); }
+  ba_sc_finish_kernel<<<dim3(n * n, n + 1), 96, 0, ctx->stream>>>(v, b->pblocks); SDSO_CHECK_LAUNCH(ctx);
+  ba_sc_uv_kernel<<<n * n * n, 64, 0, ctx->stream>>>(v); SDSO_CHECK_LAUNCH(ctx);
+  ba_stitch_sc_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, which), sysb(b, which)); SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+static int download_sys(sdso_ctx* ctx, int which, double* H, double* bv) {
+  BAState* b = ctx->ba;
+  const int d = b->dim();
+  if (H) SDSO_CUDA(ctx, cudaMemcpyAsync(H, sysH(b, which), (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (bv) SDSO_CUDA(ctx, cudaMemcpyAsync(bv, sysb(b, which), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDSO_OK;
+}
+
+static int launch_solve(sdso_ctx* ctx, int iteration, double lambda) {
+  BAState* b = ctx->ba;
+  const int d = b->dim();
+  int rc = launch_top(ctx, 0, SYS_A, false);               // accumulateAF_MT (EnergyFunctional.cpp:857)
+  if (!rc) rc = launch_top(ctx, 1, SYS_L, true);           // accumulateLF_MT (:863)
+  if (!rc) rc = launch_sc(ctx, true, SYS_SC);              // accumulateSCF_MT (:866)
+  if (rc) return rc;
+  SolveParams S;
+  S.n = b->n; S.d = d; S.iteration = iteration; S.have_M = b->have_M ? 1 : 0;
+  S.lambda = 1e-5;  // SOLVER_FIX_LAMBDA (:844-846): setting_solverMode fixes lambda regardless of the argument
+  (void)lambda;
+  S.solverModeDelta = ctx->S.solverModeDelta;
+  S.HA = sysH(b, SYS_A); S.bA = sysb(b, SYS_A); S.HL = sysH(b, SYS_L); S.bL = sysb(b, SYS_L); S.Hsc = sysH(b, SYS_SC); S.bsc = sysb(b, SYS_SC);
+  S.HM = sysH(b, SYS_M); S.bM = sysb(b, SYS_M);
+  S.fprior = b->d_fprior; S.cDeltaF = b->d_cDeltaF; S.N = b->d_N;
+  S.HF = sysH(b, SYS_FINAL); S.bF = sysb(b, SYS_FINAL); S.x = sysb(b, SYS_X);
+  const size_t smem = ((size_t)d * d + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  ba_solve_kernel<<<1, 256, smem, ctx->stream>>>(S);
+  SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+static int launch_resub(sdso_ctx* ctx, const double* d_x) {
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  const int n = b->n;
+  ba_xad_kernel<<<(n * n * 8 + 127) / 128, 128, 0, ctx->stream>>>(v, d_x, b->d_xAd); SDSO_CHECK_LAUNCH(ctx);
+  if (b->P > 0) { ba_resub_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, d_x, b->d_xAd); SDSO_CHECK_LAUNCH(ctx); }
+  return SDSO_OK;
+}
+
 }  // namespace sdso
+
+using namespace sdso;
+
+#define BA_CHECK(ctx)                                                  \
+  if (!(ctx) || !(ctx)->ba) return SDSO_E_INVALID;                     \
+  BAState* b = (ctx)->ba;                                              \
+  (void)b;
+#define BA_PREPARED(ctx)                                               \
+  BA_CHECK(ctx)                                                        \
+  if (!b->prepared) return fail(ctx, SDSO_E_STATE, "sdso_ba_prepare has not been called for this window");
+
+extern "C" {
+
+int sdso_ba_reset(sdso_ctx* ctx) {
+  BA_CHECK(ctx)
+  b->n = b->P = b->R = 0;
+  b->frames.clear();
+  b->prepared = false;
+  b->have_M = false;
+  for (int i = 0; i < 4; i++) b->calib_delta[i] = 0;
+  // default calibration = the context's initial one
+  const float K[4] = {ctx->G.fx[0], ctx->G.fy[0], ctx->G.cx[0], ctx->G.cy[0]};
+  return sdso_ba_set_calib(ctx, K, nullptr);
+}
+
+int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_value_zero[4]) {
+  BA_CHECK(ctx)
+  if (!K) return SDSO_E_INVALID;
+  BACalib& c = b->calib;
+  c.fxl = K[0]; c.fyl = K[1]; c.cxl = K[2]; c.cyl = K[3];
+  c.fxli = 1.0f / c.fxl; c.fyli = 1.0f / c.fyl; c.cxli = -c.cxl / c.fxl; c.cyli = -c.cyl / c.fyl;  // HessianBlocks.h:320-323
+  c.w0 = ctx->G.w[0]; c.h0 = ctx->G.h[0];
+  c.wM3G = (float)(c.w0 - 3); c.hM3G = (float)(c.h0 - 3);
+  c.huberTH = ctx->S.huberTH; c.outlierTHSumComponent = ctx->S.outlierTHSumComponent;
+  c.affineOptModeA = ctx->S.affineOptModeA; c.affineOptModeB = ctx->S.affineOptModeB;
+  if (value_minus_value_zero) for (int i = 0; i < 4; i++) b->calib_delta[i] = value_minus_value_zero[i];
+  b->prepared = false;
+  return SDSO_OK;
+}
+
+int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], double a, double bb, int frameID, int* idx_out) {
+  BA_CHECK(ctx)
+  if (!T_w2c || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
+  if (b->n >= kMaxFrames) return fail(ctx, SDSO_E_INVALID, "window is full (kMaxFrames)");
+  HostBAFrame f;
+  f.frame_id = frame_id; f.frameID = frameID; f.ab_exposure = ctx->frames[frame_id].ab_exposure;
+  memcpy(f.T_eval, T_w2c, sizeof(f.T_eval));
+  const double init[10] = {0, 0, 0, 0, 0, 0, a, bb, 0, 0};  // setEvalPT_scaled (HessianBlocks.h:223-231)
+  frame_set_state_scaled(f, init);
+  frame_set_state_zero(f);
+  // EFFrame::takeData -> FrameHessian::getPrior (HessianBlocks.h:246-268)
+  const sdso_settings& S = ctx->S;
+  for (int i = 0; i < 8; i++) f.prior[i] = 0;
+  if (frameID == 0) {
+    for (int i = 0; i < 3; i++) f.prior[i] = S.initialTransPrior;
+    for (int i = 3; i < 6; i++) f.prior[i] = S.initialRotPrior;
+    f.prior[6] = S.initialAffAPrior; f.prior[7] = S.initialAffBPrior;
+  } else {
+    f.prior[6] = S.affineOptModeA < 0 ? S.initialAffAPrior : S.affineOptModeA;
+    f.prior[7] = S.affineOptModeB < 0 ? S.initialAffBPrior : S.affineOptModeB;
+  }
+  b->frames.push_back(f);
+  b->n = (int)b->frames.size();
+  b->prepared = false;
+  if (idx_out) *idx_out = b->n - 1;
+  return SDSO_OK;
+}
+
+int sdso_ba_set_state(sdso_ctx* ctx, int idx, const double state[10]) {
+  BA_CHECK(ctx)
+  if (idx < 0 || idx >= b->n || !state) return SDSO_E_INVALID;
+  frame_set_state(b->frames[idx], state);
+  b->prepared = false;
+  return SDSO_OK;
+}
+
+int sdso_ba_set_energy_th(sdso_ctx* ctx, int idx, float th) {
+  BA_CHECK(ctx)
+  if (idx < 0 || idx >= b->n) return SDSO_E_INVALID;
+  b->frames[idx].frameEnergyTH = th;
+  b->prepared = false;
+  return SDSO_OK;
+}
+
+int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
+                       const float* color8, const float* weights8, const unsigned char* has_prior) {
+  BA_CHECK(ctx)
+  if (P < 0 || (P > 0 && (!host || !u || !v || !idepth || !idepth_zero || !color8 || !weights8))) return SDSO_E_INVALID;
+  for (int i = 0; i < P; i++) if (host[i] < 0 || host[i] >= b->n) return fail(ctx, SDSO_E_INVALID, "point host index out of range (add the frames first)");
+  if (P > b->capP) {
+    const int cap = std::max(P, 1024);
+    BA_ALLOC(b->d_p_host, cap); BA_ALLOC(b->d_p_u, cap); BA_ALLOC(b->d_p_v, cap); BA_ALLOC(b->d_p_idepth, cap); BA_ALLOC(b->d_p_idepth_zero, cap);
+    BA_ALLOC(b->d_p_color, 2 * (size_t)cap); BA_ALLOC(b->d_p_weights, 2 * (size_t)cap); BA_ALLOC(b->d_p_priorF, cap); BA_ALLOC(b->d_p_deltaF, cap);
+    BA_ALLOC(b->d_p_res_begin, cap + 1); BA_ALLOC(b->d_slot_of, (size_t)cap * kMaxFrames); BA_ALLOC(b->d_p_acc, 16 * (size_t)cap);
+    BA_ALLOC(b->d_p_flag, cap);
+    const int pb = (cap + 127) / 128;
+    BA_ALLOC(b->d_pblockpart, (size_t)pb * 32);
+    b->capP = cap;
+  }
+  b->P = P;
+  b->pblocks = (P + 127) / 128;
+  b->h_p_host.assign(host, host + P);
+  std::vector<float> prior(P);
+  for (int i = 0; i < P; i++) prior[i] = (has_prior && has_prior[i]) ? ctx->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0.f;  // EFPoint::takeData
+  cudaStream_t st = ctx->stream;
+  const size_t fb = (size_t)P * sizeof(float);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_host, host, P * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_u, u, fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_v, v, fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_idepth, idepth, fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_idepth_zero, idepth_zero, fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_color, color8, 8 * fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_weights, weights8, 8 * fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_priorF, prior.data(), fb, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_p_acc, 0, 16 * (size_t)b->capP * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_p_flag, 0, (size_t)b->capP, st));
+  if (P > 0) { ba_point_delta_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, b->d_p_idepth, b->d_p_idepth_zero, b->d_p_deltaF); SDSO_CHECK_LAUNCH(ctx); }
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  b->R = 0;
+  b->prepared = false;
+  return SDSO_OK;
+}
+
+int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* target) {
+  BA_CHECK(ctx)
+  if (R < 0 || (R > 0 && (!point || !target))) return SDSO_E_INVALID;
+  const int n = b->n, P = b->P;
+  for (int i = 0; i < R; i++) if (point[i] < 0 || point[i] >= P || target[i] < 0 || target[i] >= n) return fail(ctx, SDSO_E_INVALID, "residual index out of range");
+  // stable sort by key = host + target*n  (slot order)
+  std::vector<int> key(R), order(R);
+  for (int i = 0; i < R; i++) { key[i] = b->h_p_host[point[i]] + target[i] * n; order[i] = i; }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return key[a] < key[c]; });
+  b->h_slot2rid = order;
+  b->h_rid2slot.assign(R, 0);
+  for (int s = 0; s < R; s++) b->h_rid2slot[order[s]] = s;
+  b->h_r_point.assign(point, point + R); b->h_r_target.assign(target, target + R);
+  std::vector<int> s_point(R), s_key(R), seg(n * n + 1, 0);
+  for (int s = 0; s < R; s++) { s_point[s] = point[order[s]]; s_key[s] = key[order[s]]; seg[s_key[s] + 1]++; }
+  for (int k = 0; k < n * n; k++) seg[k + 1] += seg[k];
+  b->h_seg_begin = seg;
+  // chunks of <= kChunk slots, never crossing a key boundary
+  b->h_chunks.clear();
+  std::vector<int> kcb(n * n + 1, 0);
+  for (int k = 0; k < n * n; k++) {
+    kcb[k] = (int)b->h_chunks.size();
+    for (int s0 = seg[k]; s0 < seg[k + 1]; s0 += kChunk) b->h_chunks.push_back(Chunk{k, s0, std::min(s0 + kChunk, seg[k + 1]), 0});
+  }
+  kcb[n * n] = (int)b->h_chunks.size();
+  b->nchunks = (int)b->h_chunks.size();
+  // CSR point -> slots in residualsAll (= caller) order, and the (point,target) -> slot table
+  std::vector<int> begin(P + 1, 0), list(R), slot_of((size_t)std::max(P, 1) * n, -1);
+  for (int i = 0; i < R; i++) begin[point[i] + 1]++;
+  for (int p = 0; p < P; p++) begin[p + 1] += begin[p];
+  std::vector<int> fill(begin.begin(), begin.end() - 1);
+  for (int i = 0; i < R; i++) {
+    list[fill[point[i]]++] = b->h_rid2slot[i];
+    int& so = slot_of[(size_t)point[i] * n + target[i]];
+    if (so >= 0) return fail(ctx, SDSO_E_INVALID, "two residuals of one point towards the same target");
+    so = b->h_rid2slot[i];
+  }
+  if (R > b->capR) {
+    const int cap = std::max(R, 4096);
+    BA_ALLOC(b->d_p_res_list, cap); BA_ALLOC(b->d_s_point, cap); BA_ALLOC(b->d_s_key, cap);
+    BA_ALLOC(b->d_s_state, cap); BA_ALLOC(b->d_s_newstate, cap); BA_ALLOC(b->d_s_flags, cap); BA_ALLOC(b->d_s_sel, cap);
+    BA_ALLOC(b->d_s_energy, 3 * (size_t)cap); BA_ALLOC(b->d_J, 2 * (size_t)kJ * cap); BA_ALLOC(b->d_s_rtz, 8 * (size_t)cap);
+    BA_ALLOC(b->d_s_JpJd, 8 * (size_t)cap); BA_ALLOC(b->d_s_center, 3 * (size_t)cap); BA_ALLOC(b->d_s_psum, 6 * (size_t)cap);
+    BA_ALLOC(b->d_slot2rid, cap); BA_ALLOC(b->d_rid2slot, cap); BA_ALLOC(b->d_list, cap);
+    BA_ALLOC(b->d_energy_part, (size_t)(cap + 127) / 128);
+    b->capR = cap;
+  }
+  if (b->nchunks > b->capChunks) {
+    const int cap = b->nchunks + 64;
+    BA_ALLOC(b->d_chunks, cap); BA_ALLOC(b->d_tpart, (size_t)cap * kTopVals); BA_ALLOC(b->d_dpart, (size_t)cap * (kMaxFrames + 1) * 65);
+    b->capChunks = cap;
+  }
+  if (!b->d_key_chunk_begin) BA_ALLOC(b->d_key_chunk_begin, kMaxFrames * kMaxFrames + 1);
+  b->R = R;
+  cudaStream_t st = ctx->stream;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_s_point, s_point.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_s_key, s_key.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_res_list, list.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_res_begin, begin.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_slot_of, slot_of.data(), (size_t)P * n * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_slot2rid, b->h_slot2rid.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_rid2slot, b->h_rid2slot.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_chunks, b->h_chunks.data(), b->nchunks * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_key_chunk_begin, kcb.data(), kcb.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  // resetOOB (Residuals.h:107-115): state IN, new state OUTLIER, energy 0; EFResidual: not linearised, not active
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_state, RS_IN, b->capR, st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_newstate, RS_OUTLIER, b->capR, st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_flags, 0, b->capR, st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_sel, 0, b->capR, st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_energy, 0, 3 * (size_t)b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_J, 0, 2 * (size_t)kJ * b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_rtz, 0, 8 * (size_t)b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_JpJd, 0, 8 * (size_t)b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_center, 0, 3 * (size_t)b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaMemsetAsync(b->d_s_psum, 0, 6 * (size_t)b->capR * sizeof(float), st));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  return SDSO_OK;
+}
+
+int sdso_ba_set_point_flags(sdso_ctx* ctx, const unsigned char* flags) {
+  BA_CHECK(ctx)
+  if (!flags) return SDSO_E_INVALID;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_flag, flags, b->P, cudaMemcpyHostToDevice, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDSO_OK;
+}
+
+int sdso_ba_prepare(sdso_ctx* ctx) {
+  BA_CHECK(ctx)
+  if (b->n < 1) return fail(ctx, SDSO_E_STATE, "no frames in the window");
+  return prepare_window(ctx);
+}
+
+int sdso_ba_counts(sdso_ctx* ctx, int* n, int* P, int* R, int* dim) {
+  BA_CHECK(ctx)
+  if (n) *n = b->n;
+  if (P) *P = b->P;
+  if (R) *R = b->R;
+  if (dim) *dim = b->dim();
+  return SDSO_OK;
+}
+
+int sdso_ba_get_precalc(sdso_ctx* ctx, int h, int t, float out[49]) {
+  BA_PREPARED(ctx)
+  if (h < 0 || t < 0 || h >= b->n || t >= b->n || !out) return SDSO_E_INVALID;
+  const PrecalcDev& q = b->h_pre[(size_t)h * b->n + t];
+  int k = 0;
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_KRKiTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RKiTll[i];
+  for (int i = 0; i < 9; i++) out[k++] = q.PRE_RTll_0[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_tTll[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_KtTll[i];
+  for (int i = 0; i < 3; i++) out[k++] = q.PRE_tTll_0[i];
+  out[k++] = q.PRE_aff_mode[0]; out[k++] = q.PRE_aff_mode[1]; out[k++] = q.PRE_b0_mode; out[k++] = q.distanceLL;
+  return SDSO_OK;
+}
+
+int sdso_ba_get_adjoints(sdso_ctx* ctx, double* adHost, double* adTarget, float* adHTdeltaF) {
+  BA_PREPARED(ctx)
+  if (adHost) memcpy(adHost, b->h_adH.data(), b->h_adH.size() * sizeof(double));
+  if (adTarget) memcpy(adTarget, b->h_adT.data(), b->h_adT.size() * sizeof(double));
+  if (adHTdeltaF) memcpy(adHTdeltaF, b->h_adHTd.data(), b->h_adHTd.size() * sizeof(float));
+  return SDSO_OK;
+}
+
+int sdso_ba_nullspaces(sdso_ctx* ctx, double* N) {
+  BA_PREPARED(ctx)
+  if (!N) return SDSO_E_INVALID;
+  memcpy(N, b->h_N.data(), b->h_N.size() * sizeof(double));
+  return SDSO_OK;
+}
+
+int sdso_ba_linearize_all(sdso_ctx* ctx, int fix, double* energy) {
+  BA_PREPARED(ctx)
+  double e = 0;
+  if (b->R > 0) {
+    BAView v = view(b);
+    ba_linearize_kernel<<<(b->R + 127) / 128, 128, 0, ctx->stream>>>(v, fix);
+    SDSO_CHECK_LAUNCH(ctx);
+    if (energy) {
+      SDSO_CUDA(ctx, cudaMemcpyAsync(&e, b->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  if (energy) *energy = e;
+  return SDSO_OK;
+}
+
+int sdso_ba_apply_res(sdso_ctx* ctx, int copy_jacobians) {
+  BA_PREPARED(ctx)
+  if (b->R == 0) return SDSO_OK;
+  BAView v = view(b);
+  ba_apply_res_kernel<<<(b->R + 127) / 128, 128, 0, ctx->stream>>>(v, copy_jacobians);
+  SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+int sdso_ba_fix_linearization(sdso_ctx* ctx, int count, const int* rids) {
+  BA_PREPARED(ctx)
+  BAView v = view(b);
+  if (!rids) {
+    if (b->R == 0) return SDSO_OK;
+    ba_fixlin_kernel<<<(b->R + 127) / 128, 128, 0, ctx->stream>>>(v, nullptr, b->R);
+    SDSO_CHECK_LAUNCH(ctx);
+    return SDSO_OK;
+  }
+  if (count <= 0) return SDSO_OK;
+  std::vector<int> slots(count);
+  for (int i = 0; i < count; i++) {
+    if (rids[i] < 0 || rids[i] >= b->R) return SDSO_E_INVALID;
+    slots[i] = b->h_rid2slot[rids[i]];
+  }
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_list, slots.data(), count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ba_fixlin_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(v, b->d_list, count);
+  SDSO_CHECK_LAUNCH(ctx);
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDSO_OK;
+}
+
+// Readback in the CALLER's residual order. which: 0 = candidate J (PointFrameResidual::J), 1 = EFResidual::J.
+int sdso_ba_get_res(sdso_ctx* ctx, int which, int* newState, int* state, double* newEnergy, double* newEnergyWO, int* active, int* linearized,
+                    float* J74, float* JpJdF8, float* center3, float* resToZero8) {
+  BA_PREPARED(ctx)
+  const int R = b->R;
+  const size_t cR = b->capR;
+  if (R == 0) return SDSO_OK;
+  std::vector<unsigned char> st(R), ns(R), fl(R), sel(R);
+  std::vector<float> en(3 * cR);
+  cudaStream_t s = ctx->stream;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(st.data(), b->d_s_state, R, cudaMemcpyDeviceToHost, s));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(ns.data(), b->d_s_newstate, R, cudaMemcpyDeviceToHost, s));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(fl.data(), b->d_s_flags, R, cudaMemcpyDeviceToHost, s));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(sel.data(), b->d_s_sel, R, cudaMemcpyDeviceToHost, s));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(en.data(), b->d_s_energy, 3 * cR * sizeof(float), cudaMemcpyDeviceToHost, s));
+  std::vector<float> J, jp, ce, rz;
+  if (J74) { J.resize(2 * (size_t)kJ * cR); SDSO_CUDA(ctx, cudaMemcpyAsync(J.data(), b->d_J, J.size() * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+  if (JpJdF8) { jp.resize(8 * cR); SDSO_CUDA(ctx, cudaMemcpyAsync(jp.data(), b->d_s_JpJd, jp.size() * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+  if (center3) { ce.resize(3 * cR); SDSO_CUDA(ctx, cudaMemcpyAsync(ce.data(), b->d_s_center, ce.size() * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+  if (resToZero8) { rz.resize(8 * cR); SDSO_CUDA(ctx, cudaMemcpyAsync(rz.data(), b->d_s_rtz, rz.size() * sizeof(float), cudaMemcpyDeviceToHost, s)); }
+  SDSO_CUDA(ctx, cudaStreamSynchronize(s));
+  for (int rid = 0; rid < R; rid++) {
+    const int sl = b->h_rid2slot[rid];
+    if (newState) newState[rid] = ns[sl];
+    if (state) state[rid] = st[sl];
+    if (newEnergy) newEnergy[rid] = en[cR + sl];
+    if (newEnergyWO) newEnergyWO[rid] = en[2 * cR + sl];
+    if (active) active[rid] = (fl[sl] & RF_ACTIVE) ? 1 : 0;
+    if (linearized) linearized[rid] = (fl[sl] & RF_LINEARIZED) ? 1 : 0;
+    if (J74) { const int buf = which == 0 ? (sel[sl] ^ 1) : sel[sl]; for (int k = 0; k < kJ; k++) J74[(size_t)rid * kJ + k] = J[((size_t)buf * kJ + k) * cR + sl]; }
+    if (JpJdF8) for (int k = 0; k < 8; k++) JpJdF8[(size_t)rid * 8 + k] = jp[k * cR + sl];
+    if (center3) for (int k = 0; k < 3; k++) center3[(size_t)rid * 3 + k] = ce[k * cR + sl];
+    if (resToZero8) for (int k = 0; k < 8; k++) resToZero8[(size_t)rid * 8 + k] = rz[k * cR + sl];
+  }
+  return SDSO_OK;
+}
+
+// per point: Hdd_accAF, bd_accAF, Hcd_accAF[4], Hdd_accLF, bd_accLF, Hcd_accLF[4], HdiF, bdSumF, step, priorF (16 floats)
+int sdso_ba_get_points(sdso_ctx* ctx, float* out16) {
+  BA_PREPARED(ctx)
+  if (!out16) return SDSO_E_INVALID;
+  const int P = b->P;
+  const size_t cP = b->capP;
+  if (P == 0) return SDSO_OK;
+  std::vector<float> acc(16 * cP), pr(P);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(acc.data(), b->d_p_acc, acc.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(pr.data(), b->d_p_priorF, P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < P; p++) {
+    for (int k = 0; k < 15; k++) out16[(size_t)p * 16 + k] = acc[k * cP + p];
+    out16[(size_t)p * 16 + 15] = pr[p];
+  }
+  return SDSO_OK;
+}
+
+int sdso_ba_accumulate_top(sdso_ctx* ctx, int mode, int use_prior, double* H, double* bv, float* blocks) {
+  BA_PREPARED(ctx)
+  if (mode < 0 || mode > 2) return SDSO_E_INVALID;
+  int rc = launch_top(ctx, mode, SYS_TMP, use_prior != 0);
+  if (rc) return rc;
+  if (blocks) SDSO_CUDA(ctx, cudaMemcpyAsync(blocks, b->d_Gf, (size_t)b->n * b->n * 169 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  return download_sys(ctx, SYS_TMP, H, bv);
+}
+
+int sdso_ba_accumulate_sc(sdso_ctx* ctx, int shift_prior_to_zero, double* H, double* bv) {
+  BA_PREPARED(ctx)
+  int rc = launch_sc(ctx, shift_prior_to_zero != 0, SYS_TMP);
+  if (rc) return rc;
+  return download_sys(ctx, SYS_TMP, H, bv);
+}
+
+int sdso_ba_solve(sdso_ctx* ctx, int iteration, double lambda, double* x, double* Hfinal, double* bfinal) {
+  BA_PREPARED(ctx)
+  int rc = launch_solve(ctx, iteration, lambda);
+  if (rc) return rc;
+  rc = launch_resub(ctx, sysb(b, SYS_X));  // solveSystemF ends with resubstituteF_MT (:989)
+  if (rc) return rc;
+  const int d = b->dim();
+  if (x) SDSO_CUDA(ctx, cudaMemcpyAsync(x, sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return download_sys(ctx, SYS_FINAL, Hfinal, bfinal);
+}
+
+int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, double* calib_step) {
+  BA_PREPARED(ctx)
+  const int d = b->dim(), n = b->n;
+  std::vector<double> xv(d);
+  if (x) {
+    SDSO_CUDA(ctx, cudaMemcpyAsync(sysb(b, SYS_X), x, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(xv.data(), x, d * sizeof(double));
+  } else {
+    SDSO_CUDA(ctx, cudaMemcpyAsync(xv.data(), sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  int rc = launch_resub(ctx, sysb(b, SYS_X));
+  if (rc) return rc;
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (calib_step) for (int i = 0; i < 4; i++) calib_step[i] = -xv[i];  // HCalib->step = -x.head<CPARS>() (:280)
+  if (frame_steps) for (int h = 0; h < n; h++) {
+    for (int i = 0; i < 8; i++) frame_steps[h * 10 + i] = -xv[kCPARS + 8 * h + i];
+    frame_steps[h * 10 + 8] = frame_steps[h * 10 + 9] = 0;
+  }
+  return SDSO_OK;
+}
+
+int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
+  BA_CHECK(ctx)
+  if (!HM || !bM) return SDSO_E_INVALID;
+  const int d = b->dim();
+  SDSO_CUDA(ctx, cudaMemcpyAsync(sysH(b, SYS_M), HM, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(sysb(b, SYS_M), bM, d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  b->have_M = true;
+  return SDSO_OK;
+}
+
+int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM) {
+  BA_CHECK(ctx)
+  return download_sys(ctx, SYS_M, HM, bM);
+}
+
+}  // extern "C"

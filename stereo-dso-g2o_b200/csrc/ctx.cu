@@ -111,6 +111,15 @@ void sdso_default_settings(sdso_settings* s) {
   s->cluster_size = 0;
   s->block_threads = 0;
   s->gather_batch = 0;
+  s->idepthFixPrior = 50 * 50;
+  s->idepthFixPriorMargFac = 600 * 600;
+  s->initialRotPrior = 1e11f;
+  s->initialTransPrior = 1e10f;
+  s->initialAffBPrior = 1e14f;
+  s->initialAffAPrior = 1e14f;
+  s->initialCalibHessian = 5e9f;
+  s->margWeightFac = 0.5f * 0.5f;
+  s->solverModeDelta = 0.00001;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {

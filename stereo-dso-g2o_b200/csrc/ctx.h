@@ -84,6 +84,8 @@ void inverse3f(const float m[9], float out[9]);
 void se3_exp(const double a[6], double T[12]);
 void se3_mul(const double A[12], const double B[12], double C[12]);
 void se3_inv(const double A[12], double B[12]);
+void se3_log(const double T[12], double a[6]);
+void se3_adj(const double T[12], double Ad[36]);  // 6x6 row-major
 
 // profiling helpers (ctx.cu)
 void prof_begin(sdso_ctx* ctx, int which);

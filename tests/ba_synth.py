@@ -62,3 +62,27 @@ def fill_oracle(win, orc, OBA, immature_init):
             ba.add_residual(pi, t)
     ba.prepare()
     return ba, fids, cw
+
+
+def fill_device(win, ctx, Window, cw):
+    """Build the device-side window from the same data (colour/weights `cw` as produced by the D1 operator)."""
+    fids = []
+    for f in win["frames"]:
+        fid = ctx.frame_create()
+        ctx.make_images(fid, f["image"])
+        fids.append(fid)
+    W = Window(ctx)
+    for k, f in enumerate(win["frames"]):
+        idx = W.add_frame(fids[k], f["T_w2c"], f["a"], f["b"], f["frameID"])
+        W.set_state(idx, f["state"])
+        W.set_energy_th(idx, f["energyTH"])
+    pts = win["points"]
+    W.set_points([p["host"] for p in pts], [p["u"] for p in pts], [p["v"] for p in pts], [p["idepth"] for p in pts],
+                 [p["idepth_zero"] for p in pts], np.stack([c for c, _ in cw]), np.stack([w for _, w in cw]), [p["has_prior"] for p in pts])
+    rp, rt = [], []
+    for pi, p in enumerate(pts):
+        for t in p["targets"]:
+            rp.append(pi); rt.append(t)
+    W.set_residuals(rp, rt)
+    W.prepare()
+    return W, fids
