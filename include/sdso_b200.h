@@ -218,6 +218,29 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM);   /* EnergyFunctional::HM, bM */
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM);
 
+/* ---- D1-D3, E3: immature points — constructor, temporal and static-stereo epipolar search ------------------------
+ * One record per ImmaturePoint (FullSystem/ImmaturePoint.h:59-114): the fields the constructor, traceOn and
+ * traceStereo read or write. Records are caller-owned host memory, updated in place. */
+typedef struct sdso_immature_point {
+  float u, v;
+  float idepth_min, idepth_max;
+  float quality, energyTH;
+  float color[8], weights[8], gradH[4];                  /* gradH row-major 2x2 */
+  float u_stereo, v_stereo, idepth_min_stereo, idepth_max_stereo, idepth_stereo;
+  float lastTraceUV[2], lastTracePixelInterval;
+  int32_t lastTraceStatus;                               /* ImmaturePointStatus (ImmaturePoint.h:50-56): 0 GOOD 1 OOB 2 OUTLIER 3 SKIPPED 4 BADCONDITION 5 UNINITIALIZED */
+  int32_t bestIdx, numSteps;                             /* diagnostics of the last discrete search (-1 / 0 if it did not run) */
+} sdso_immature_point;
+/* ImmaturePoint::ImmaturePoint(u, v, host, ...) (ImmaturePoint.cpp:33-88) for n pixel positions uv[n][2]; ok[i] = 0 where the
+ * constructor bailed out on a non-finite colour (energyTH = NaN). Also sets u_stereo=u, v_stereo=v, idepth_*_stereo = (0, NaN)
+ * as every caller does (FullSystem.cpp:582-585). */
+int sdso_immature_init(sdso_ctx* ctx, int host_frame, int n, const float* uv, sdso_immature_point* out, int* ok /* nullable */);
+/* ImmaturePoint::traceOn(frame, hostToFrame_KRKi, hostToFrame_Kt, hostToFrame_affine, HCalib) (ImmaturePoint.cpp:459-828) */
+int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[3], const float aff[2], int n,
+                  sdso_immature_point* pts, int* status /* nullable */);
+/* ImmaturePoint::traceStereo(frame, K, mode_right) (ImmaturePoint.cpp:94-451); baseline = the context's */
+int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, sdso_immature_point* pts, int* status /* nullable */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 // C entry points for ctypes (tests/, smoke(), bench.py cpu_baseline / --impl reference).
 #include "oracle_core.hpp"
 #include "oracle_ba.hpp"
+#include "oracle_trace.hpp"
 #include <memory>
 
 using namespace orc;
@@ -313,5 +314,22 @@ void orc_ba_nullspaces(void* p, double* N /* dim x 7, row-major */) {
   Ctx* c = (Ctx*)p; int d = c->ba.dim();
   for (int i = 0; i < 6; i++) for (int r = 0; r < d; r++) N[(size_t)r * 7 + i] = c->ba.lastNullspaces_pose[i][r];
   for (int r = 0; r < d; r++) N[(size_t)r * 7 + 6] = c->ba.lastNullspaces_scale[0][r];
+}
+}  // extern "C"
+
+// ---- D1-D3 on arrays of ImmaturePoint records (oracle/oracle_trace.hpp) ---------------------------------------
+extern "C" {
+int orc_immature_record_size() { return (int)sizeof(ImmaturePoint); }
+void orc_immature_init_batch(void* p, int fid, int n, const float* uv, ImmaturePoint* out, int* ok) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) ok[i] = immatureInit(c->G, c->S, *c->frames[fid], uv[2 * i], uv[2 * i + 1], out[i]) ? 1 : 0;
+}
+void orc_trace_on(void* p, int fid, const float KRKi[9], const float Kt[3], const float aff[2], int n, ImmaturePoint* pts, int* status) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) status[i] = traceOn(c->G, c->S, pts[i], *c->frames[fid], KRKi, Kt, aff);
+}
+void orc_trace_stereo(void* p, int fid, const float K[9], int mode_right, int n, ImmaturePoint* pts, int* status) {
+  Ctx* c = (Ctx*)p;
+  for (int i = 0; i < n; i++) status[i] = traceStereo(c->G, c->S, pts[i], *c->frames[fid], K, mode_right != 0);
 }
 }  // extern "C"

@@ -446,3 +446,48 @@ class Window:
         HM, bM = np.zeros((d, d)), np.zeros(d)
         self._ck(lib.sdso_ba_get_marg_prior(self.h, _ptr(HM, _dp), _ptr(bM, _dp)))
         return HM, bM
+
+
+# ---------------------------------------------------------------------------------------------------
+# D1-D3: immature points (ImmaturePoint constructor, traceOn, traceStereo)
+IMMATURE_DTYPE = np.dtype([
+    ("u", "f4"), ("v", "f4"), ("idepth_min", "f4"), ("idepth_max", "f4"), ("quality", "f4"), ("energyTH", "f4"),
+    ("color", "f4", 8), ("weights", "f4", 8), ("gradH", "f4", 4),
+    ("u_stereo", "f4"), ("v_stereo", "f4"), ("idepth_min_stereo", "f4"), ("idepth_max_stereo", "f4"), ("idepth_stereo", "f4"),
+    ("lastTraceUV", "f4", 2), ("lastTracePixelInterval", "f4"),
+    ("lastTraceStatus", "i4"), ("bestIdx", "i4"), ("numSteps", "i4")])
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+lib.sdso_immature_init.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, C.c_void_p, _ip]
+lib.sdso_trace_on.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, C.c_int, C.c_void_p, _ip]
+lib.sdso_trace_stereo.argtypes = [C.c_void_p, C.c_int, _fp, C.c_int, C.c_int, C.c_void_p, _ip]
+
+
+def _immature_init(self, host_fid, uv):
+    uv = _f32(uv).reshape(-1, 2)
+    n = uv.shape[0]
+    pts = np.zeros(n, IMMATURE_DTYPE)
+    ok = np.zeros(n, np.int32)
+    self._ck(lib.sdso_immature_init(self._h, host_fid, n, _ptr(uv, _fp), pts.ctypes.data, _ptr(ok, _ip)))
+    return pts, ok.astype(bool)
+
+
+def _trace_on(self, fid, KRKi, Kt, aff, pts):
+    """In-place update of the records; returns the status array."""
+    assert pts.dtype == IMMATURE_DTYPE and pts.flags["C_CONTIGUOUS"]
+    K_, t_, a_ = _f32(KRKi).reshape(9), _f32(Kt).reshape(3), _f32(aff).reshape(2)
+    st = np.zeros(pts.size, np.int32)
+    self._ck(lib.sdso_trace_on(self._h, fid, _ptr(K_, _fp), _ptr(t_, _fp), _ptr(a_, _fp), pts.size, pts.ctypes.data, _ptr(st, _ip)))
+    return st
+
+
+def _trace_stereo(self, fid, K, mode_right, pts):
+    assert pts.dtype == IMMATURE_DTYPE and pts.flags["C_CONTIGUOUS"]
+    K_ = _f32(K).reshape(9)
+    st = np.zeros(pts.size, np.int32)
+    self._ck(lib.sdso_trace_stereo(self._h, fid, _ptr(K_, _fp), int(mode_right), pts.size, pts.ctypes.data, _ptr(st, _ip)))
+    return st
+
+
+Context.immature_init = _immature_init
+Context.trace_on = _trace_on
+Context.trace_stereo = _trace_stereo
