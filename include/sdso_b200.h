@@ -218,6 +218,22 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM);   /* EnergyFunctional::HM, bM */
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM);
 
+/* ---- point-sharded windowed BA over 2/4/8 GPUs ------------------------------------------------------
+ * Every rank holds all keyframe pyramids and a contiguous block of the allPoints order with its residuals. Per LM
+ * iteration: sdso_ba_linearize_all (local) -> sdso_ba_assemble (local partial damped system; priors and HM on rank 0)
+ * -> sdso_ba_allreduce (ONE NCCL allreduce of (4+8n)^2+(4+8n)+1 doubles over NVLink) -> sdso_ba_solve_assembled (every rank
+ * solves redundantly and back-substitutes its own points). The reference's only reduce is the per-thread accumulator sum
+ * of stitchDoubleInternal (AccumulatedTopHessian.cpp:299-308); this is its multi-GPU analogue. */
+int sdso_shard_range(int npoints, int rank, int nranks, int* begin, int* end);  /* contiguous block of allPoints owned by rank */
+int sdso_ba_set_shard(sdso_ctx* ctx, int rank, int nranks);
+int sdso_ba_assemble(sdso_ctx* ctx, void** device_system /* nullable */, int* count /* nullable */);
+int sdso_ba_allreduce(sdso_ctx* ctx, double* energy_out /* nullable: summed linearisation energy (synchronises) */);
+int sdso_ba_solve_assembled(sdso_ctx* ctx, int iteration, double* x, double* Hfinal, double* bfinal);
+int sdso_nccl_unique_id(unsigned char id[128]);                 /* ncclGetUniqueId, to be broadcast by the host's rendezvous */
+int sdso_nccl_init(sdso_ctx* ctx, int rank, int nranks, const unsigned char id[128]);
+int sdso_nccl_destroy(sdso_ctx* ctx);
+int sdso_allreduce_f64(sdso_ctx* ctx, void* device_buffer, int count);  /* in-place sum on the context's stream */
+
 /* ---- D1-D3, E3: immature points — constructor, temporal and static-stereo epipolar search ------------------------
  * One record per ImmaturePoint (FullSystem/ImmaturePoint.h:59-114): the fields the constructor, traceOn and
  * traceStereo read or write. Records are caller-owned host memory, updated in place. */

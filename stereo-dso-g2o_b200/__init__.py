@@ -491,3 +491,72 @@ def _trace_stereo(self, fid, K, mode_right, pts):
 Context.immature_init = _immature_init
 Context.trace_on = _trace_on
 Context.trace_stereo = _trace_stereo
+
+
+# ---------------------------------------------------------------------------------------------------
+# point-sharded windowed BA
+lib.sdso_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip]
+lib.sdso_ba_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+lib.sdso_ba_assemble.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _ip]
+lib.sdso_ba_allreduce.argtypes = [C.c_void_p, _dp]
+lib.sdso_ba_solve_assembled.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+lib.sdso_nccl_unique_id.argtypes = [C.c_void_p]
+lib.sdso_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.sdso_nccl_destroy.argtypes = [C.c_void_p]
+lib.sdso_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+
+
+def shard_range(npoints, rank, nranks):
+    b, e = C.c_int(), C.c_int()
+    rc = lib.sdso_shard_range(npoints, rank, nranks, C.byref(b), C.byref(e))
+    if rc != OK:
+        raise SdsoError(f"sdso_shard_range({npoints}, {rank}, {nranks}) -> {rc}")
+    return b.value, e.value
+
+
+def nccl_unique_id():
+    buf = (C.c_ubyte * 128)()
+    rc = lib.sdso_nccl_unique_id(buf)
+    if rc != OK:
+        raise SdsoError(f"sdso_nccl_unique_id -> {rc} (NCCL not loadable)")
+    return bytes(buf)
+
+
+def _nccl_init(self, rank, nranks, uid):
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+    self._ck(lib.sdso_nccl_init(self._h, rank, nranks, buf))
+
+
+Context.nccl_init = _nccl_init
+
+
+def _w_set_shard(self, rank, nranks):
+    self._ck(lib.sdso_ba_set_shard(self.h, rank, nranks))
+
+
+def _w_assemble(self):
+    ptr, cnt = C.c_void_p(), C.c_int()
+    self._ck(lib.sdso_ba_assemble(self.h, C.byref(ptr), C.byref(cnt)))
+    return ptr.value, cnt.value
+
+
+def _w_allreduce(self, want_energy=False):
+    e = C.c_double()
+    self._ck(lib.sdso_ba_allreduce(self.h, C.byref(e) if want_energy else None))
+    return e.value if want_energy else None
+
+
+def _w_solve_assembled(self, iteration, want=True):
+    d = self.counts()["dim"]
+    if not want:
+        self._ck(lib.sdso_ba_solve_assembled(self.h, iteration, None, None, None))
+        return None
+    x, H, b = np.zeros(d), np.zeros((d, d)), np.zeros(d)
+    self._ck(lib.sdso_ba_solve_assembled(self.h, iteration, _ptr(x, _dp), _ptr(H, _dp), _ptr(b, _dp)))
+    return x, H, b
+
+
+Window.set_shard = _w_set_shard
+Window.assemble = _w_assemble
+Window.allreduce = _w_allreduce
+Window.solve_assembled = _w_solve_assembled

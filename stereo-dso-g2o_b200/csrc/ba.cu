@@ -38,7 +38,7 @@ int ba_create(sdso_ctx* ctx) {
   BA_ALLOC(b->d_G, F2 * 169 + F2); BA_ALLOC(b->d_Gf, F2 * 169);
   BA_ALLOC(b->d_D, (size_t)F2 * F * 65); BA_ALLOC(b->d_E, F2 * 40); BA_ALLOC(b->d_Hcc, 20);
   BA_ALLOC(b->d_U, (size_t)F2 * F * 64); BA_ALLOC(b->d_V, (size_t)F2 * F * 64);
-  b->sys_stride = (size_t)dmax * dmax + dmax;
+  b->sys_stride = (size_t)dmax * dmax + dmax + 8;
   BA_ALLOC(b->d_sys, b->sys_stride * SYS_NUM);
   SDSO_CUDA(ctx, cudaMemset(b->d_sys, 0, b->sys_stride * SYS_NUM * sizeof(double)));
   BA_ALLOC(b->d_scalars, 16); BA_ALLOC(b->d_counter, 1); BA_ALLOC(b->d_N, dmax * 7); BA_ALLOC(b->d_xAd, F2 * 8);
@@ -71,7 +71,8 @@ static BAView view(BAState* b) {
 }
 
 static inline double* sysH(BAState* b, int which) { return b->d_sys + b->sys_stride * which; }
-static inline double* sysb(BAState* b, int which) { const int dm = kCPARS + 8 * kMaxFrames; return b->d_sys + b->sys_stride * which + (size_t)dm * dm; }
+// b follows H contiguously ((4+8n)^2 + (4+8n) doubles): one buffer per (H,b) pair, so a shard's partial system is ONE allreduce
+static inline double* sysb(BAState* b, int which) { const int d = b->dim(); return b->d_sys + b->sys_stride * which + (size_t)d * d; }
 
 // ---- FrameHessian state handling (HessianBlocks.h:177-231, HessianBlocks.cpp:78-123) ----------------
 static void frame_update_pre(HostBAFrame& f) {
@@ -267,34 +268,59 @@ static int launch_sc(sdso_ctx* ctx, bool shift, int which) {
 static int download_sys(sdso_ctx* ctx, int which, double* H, double* bv) {
   BAState* b = ctx->ba;
   const int d = b->dim();
+  if (!H && !bv) return SDSO_OK;  // nothing to return: stay asynchronous
   if (H) SDSO_CUDA(ctx, cudaMemcpyAsync(H, sysH(b, which), (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (bv) SDSO_CUDA(ctx, cudaMemcpyAsync(bv, sysb(b, which), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SDSO_OK;
 }
 
-static int launch_solve(sdso_ctx* ctx, int iteration, double lambda) {
+static void fill_solve_params(sdso_ctx* ctx, SolveParams& S, int iteration) {
   BAState* b = ctx->ba;
-  const int d = b->dim();
-  int rc = launch_top(ctx, 0, SYS_A, false);               // accumulateAF_MT (EnergyFunctional.cpp:857)
-  if (!rc) rc = launch_top(ctx, 1, SYS_L, true);           // accumulateLF_MT (:863)
-  if (!rc) rc = launch_sc(ctx, true, SYS_SC);              // accumulateSCF_MT (:866)
-  if (rc) return rc;
-  SolveParams S;
-  S.n = b->n; S.d = d; S.iteration = iteration; S.have_M = b->have_M ? 1 : 0;
-  S.lambda = 1e-5;  // SOLVER_FIX_LAMBDA (:844-846): setting_solverMode fixes lambda regardless of the argument
-  (void)lambda;
+  S.n = b->n; S.d = b->dim(); S.iteration = iteration;
+  S.have_M = (b->have_M && b->shard_rank == 0) ? 1 : 0;  // HM / bM enter once (rank 0 of a sharded window)
+  S.lambda = 1e-5;  // SOLVER_FIX_LAMBDA (EnergyFunctional.cpp:844-846): setting_solverMode fixes lambda regardless of the argument
   S.solverModeDelta = ctx->S.solverModeDelta;
   S.HA = sysH(b, SYS_A); S.bA = sysb(b, SYS_A); S.HL = sysH(b, SYS_L); S.bL = sysb(b, SYS_L); S.Hsc = sysH(b, SYS_SC); S.bsc = sysb(b, SYS_SC);
   S.HM = sysH(b, SYS_M); S.bM = sysb(b, SYS_M);
   S.fprior = b->d_fprior; S.cDeltaF = b->d_cDeltaF; S.N = b->d_N;
   S.HF = sysH(b, SYS_FINAL); S.bF = sysb(b, SYS_FINAL); S.x = sysb(b, SYS_X);
+}
+
+// accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT (EnergyFunctional.cpp:857-866) over this rank's points, then the
+// (partial) damped reduced system into SYS_FINAL
+static int launch_assemble(sdso_ctx* ctx) {
+  BAState* b = ctx->ba;
+  const int d = b->dim();
+  int rc = launch_top(ctx, 0, SYS_A, false);
+  if (!rc) rc = launch_top(ctx, 1, SYS_L, b->shard_rank == 0);  // priors enter once
+  if (!rc) rc = launch_sc(ctx, true, SYS_SC);
+  if (rc) return rc;
+  SolveParams S;
+  fill_solve_params(ctx, S, 0);
+  ba_assemble_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(S);
+  SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+static int launch_factor_solve(sdso_ctx* ctx, int iteration) {
+  BAState* b = ctx->ba;
+  const int d = b->dim();
+  SolveParams S;
+  fill_solve_params(ctx, S, iteration);
   const size_t smem = ((size_t)d * d + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   ba_solve_kernel<<<1, 256, smem, ctx->stream>>>(S);
   SDSO_CHECK_LAUNCH(ctx);
   return SDSO_OK;
+}
+
+static int launch_solve(sdso_ctx* ctx, int iteration, double lambda) {
+  (void)lambda;
+  int rc = launch_assemble(ctx);
+  if (!rc) rc = launch_factor_solve(ctx, iteration);
+  return rc;
 }
 
 static int launch_resub(sdso_ctx* ctx, const double* d_x) {
@@ -326,6 +352,7 @@ int sdso_ba_reset(sdso_ctx* ctx) {
   b->frames.clear();
   b->prepared = false;
   b->have_M = false;
+  b->shard_rank = 0; b->shard_n = 1;
   for (int i = 0; i < 4; i++) b->calib_delta[i] = 0;
   // default calibration = the context's initial one
   const float K[4] = {ctx->G.fx[0], ctx->G.fy[0], ctx->G.cx[0], ctx->G.cy[0]};
@@ -712,6 +739,49 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
     frame_steps[h * 10 + 8] = frame_steps[h * 10 + 9] = 0;
   }
   return SDSO_OK;
+}
+
+/* ---- point-sharded windows ---- */
+int sdso_ba_set_shard(sdso_ctx* ctx, int rank, int nranks) {
+  BA_CHECK(ctx)
+  if (nranks < 1 || rank < 0 || rank >= nranks) return SDSO_E_INVALID;
+  b->shard_rank = rank; b->shard_n = nranks;
+  return SDSO_OK;
+}
+
+int sdso_ba_assemble(sdso_ctx* ctx, void** device_system, int* count) {
+  BA_PREPARED(ctx)
+  int rc = launch_assemble(ctx);
+  if (rc) return rc;
+  const int d = b->dim();
+  if (device_system) *device_system = sysH(b, SYS_FINAL);
+  if (count) *count = d * d + d;
+  return SDSO_OK;
+}
+
+// one NCCL allreduce of the partial system [(4+8n)^2 + (4+8n)] plus the linearisation energy (scalars[0]) appended to it
+int sdso_ba_allreduce(sdso_ctx* ctx, double* energy_out) {
+  BA_PREPARED(ctx)
+  const int d = b->dim();
+  double* buf = sysH(b, SYS_FINAL);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(buf + (size_t)d * d + d, b->d_scalars, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  int rc = sdso_allreduce_f64(ctx, buf, d * d + d + 1);
+  if (rc) return rc;
+  if (energy_out) {
+    SDSO_CUDA(ctx, cudaMemcpyAsync(energy_out, buf + (size_t)d * d + d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SDSO_OK;
+}
+
+int sdso_ba_solve_assembled(sdso_ctx* ctx, int iteration, double* x, double* Hfinal, double* bfinal) {
+  BA_PREPARED(ctx)
+  int rc = launch_factor_solve(ctx, iteration);
+  if (!rc) rc = launch_resub(ctx, sysb(b, SYS_X));
+  if (rc) return rc;
+  const int d = b->dim();
+  if (x) SDSO_CUDA(ctx, cudaMemcpyAsync(x, sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return download_sys(ctx, SYS_FINAL, Hfinal, bfinal);
 }
 
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {

@@ -706,7 +706,7 @@ __global__ void ba_stitch_sc_kernel(BAView B, double* H, double* bvec) {
   H[e] = s;
 }
 
-// ---- B8: assemble + damp + Schur + scaled pivoted LDLT (+ orthogonalisation) in ONE CTA ------------------------
+// ---- B8: assemble (elementwise) then scaled diagonal-pivoted LDLT (+ orthogonalisation) in ONE CTA ----------------
 struct SolveParams {
   int n, d, iteration, have_M;
   double lambda, solverModeDelta;
@@ -716,6 +716,37 @@ struct SolveParams {
   const double* N;   // d x 7 nullspace columns (row-major) or null
   double* HF; double* bF; double* x;
 };
+
+// HFinal = HL + HM + HA, diag *= (1 + lambda), -= H_sc / (1 + lambda); bFinal = bL + (bM + HM delta) + bA - b_sc
+// (EnergyFunctional.cpp:869-918). Linear in the per-point contributions, so a rank that holds a shard of the points
+// produces a PARTIAL (HFinal, bFinal) here (have_M and the priors only on one rank) and the shards are summed by one
+// allreduce before ba_solve_kernel.
+__global__ void ba_assemble_kernel(SolveParams S) {
+  const int d = S.d;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d * d + d) return;
+  const double lam = S.lambda;
+  if (e >= d * d) {
+    const int i = e - d * d;
+    double bm = 0;
+    if (S.have_M) {
+      double s = 0;
+      for (int c = 0; c < d; c++) {
+        const double dl = c < 4 ? (double)S.cDeltaF[c] : S.fprior[((c - 4) / 8) * 24 + 16 + (c - 4) % 8];
+        s += S.HM[(size_t)i * d + c] * dl;
+      }
+      bm = S.bM[i] + s;
+    }
+    S.bF[i] = S.bL[i] + bm + S.bA[i] - S.bsc[i];
+    return;
+  }
+  const int r = e / d, c = e % d;
+  const double f = (double)(1.0f) / (1 + lam);
+  double v = S.HL[e] + (S.have_M ? S.HM[e] : 0.0) + S.HA[e];
+  if (r == c) v *= (1 + lam);
+  v -= S.Hsc[e] * f;
+  S.HF[e] = v;
+}
 
 // x -= N (N^T N)^+ N^T x  (orthogonalize(&x, 0), EnergyFunctional.cpp:775-835), run by one CTA; scratch in shared memory
 __device__ void ortho_vec(const double* __restrict__ Nraw, int d, int m, double delta, double* x, double* sN /* d*m */, double* sw /* >= 3*m*m+4*m */) {
@@ -777,24 +808,8 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   double* scr = delta + d;        // d*7 + 256
   __shared__ int perm[kCPARS + 8 * kMaxFrames];
   __shared__ int piv;
-  // delta = [cDeltaF ; frame deltas]
-  for (int i = tid; i < d; i += nt) delta[i] = i < 4 ? (double)S.cDeltaF[i] : S.fprior[((i - 4) / 8) * 24 + 16 + (i - 4) % 8];
-  __syncthreads();
-  const double lam = S.lambda;
-  const double f = (double)(1.0f) / (1 + lam);
-  for (int i = tid; i < d; i += nt) {
-    double bm = 0;
-    if (S.have_M) { double s = 0; for (int c = 0; c < d; c++) s += S.HM[(size_t)i * d + c] * delta[c]; bm = S.bM[i] + s; }
-    const double v = S.bL[i] + bm + S.bA[i] - S.bsc[i];
-    S.bF[i] = v; bs[i] = v;
-  }
-  for (int e = tid; e < d * d; e += nt) {
-    const int r = e / d, c = e % d;
-    double v = S.HL[e] + (S.have_M ? S.HM[e] : 0.0) + S.HA[e];
-    if (r == c) v *= (1 + lam);
-    v -= S.Hsc[e] * f;
-    S.HF[e] = v; M[e] = v;
-  }
+  for (int i = tid; i < d; i += nt) bs[i] = S.bF[i];
+  for (int e = tid; e < d * d; e += nt) M[e] = S.HF[e];
   __syncthreads();
   for (int i = tid; i < d; i += nt) { sv[i] = 1.0 / sqrt(M[i * d + i] + 10); perm[i] = i; }
   __syncthreads();

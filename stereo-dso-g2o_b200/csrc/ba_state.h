@@ -116,6 +116,7 @@ struct BAState {
   double* d_N = nullptr;                  // [d][7] nullspace columns (6 pose + 1 scale)
   float* d_xAd = nullptr;                 // [n*n][8]
   int* d_list = nullptr;                  // scratch slot list
+  int shard_rank = 0, shard_n = 1;        // point-sharded window: priors and HM enter on rank 0 only
   bool have_M = false;                    // HM/bM (marginalisation prior) present in SYS_M
   std::vector<double> h_N, h_adH, h_adT;
   std::vector<float> h_adHTd;

@@ -155,6 +155,7 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  collective_destroy(ctx);
   trace_destroy(ctx);
   ba_destroy(ctx);
   tracker_destroy(ctx);

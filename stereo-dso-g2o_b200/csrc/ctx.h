@@ -51,6 +51,8 @@ struct sdso_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_track, ev_images;
   size_t ev_track_used = 0, ev_images_used = 0;
   int num_sms = 0;
+  void* nccl_comm = nullptr;  // ncclComm_t of the sharded-BA allreduce (collective.cu), null unless sdso_nccl_init ran
+  int nccl_rank = 0, nccl_nranks = 1;
   std::string err;
 };
 
@@ -98,6 +100,7 @@ void tracker_destroy(sdso_ctx* ctx);
 // ba.cu / trace.cu
 int ba_create(sdso_ctx* ctx);
 void ba_destroy(sdso_ctx* ctx);
+void collective_destroy(sdso_ctx* ctx);
 int trace_create(sdso_ctx* ctx);
 void trace_destroy(sdso_ctx* ctx);
 

@@ -86,3 +86,10 @@ def fill_device(win, ctx, Window, cw):
     W.set_residuals(rp, rt)
     W.prepare()
     return W, fids
+
+
+def shard_window(win, begin, end):
+    """The sub-window a rank owns under point sharding: all frames, points [begin, end) of allPoints."""
+    out = dict(win)
+    out["points"] = win["points"][begin:end]
+    return out
