@@ -36,7 +36,7 @@ int ba_create(sdso_ctx* ctx) {
   BA_ALLOC(b->d_adHost, F2 * 64); BA_ALLOC(b->d_adTarget, F2 * 64); BA_ALLOC(b->d_adHostF, F2 * 64); BA_ALLOC(b->d_adTargetF, F2 * 64);
   BA_ALLOC(b->d_adHTdeltaF, F2 * 8); BA_ALLOC(b->d_cDeltaF, 4); BA_ALLOC(b->d_fprior, F * 24);
   BA_ALLOC(b->d_G, F2 * 169 + F2); BA_ALLOC(b->d_Gf, F2 * 169);
-  BA_ALLOC(b->d_D, (size_t)F2 * F * 65); BA_ALLOC(b->d_E, F2 * 40); BA_ALLOC(b->d_Hcc, 20);
+  BA_ALLOC(b->d_D, (size_t)F2 * F * 65); BA_ALLOC(b->d_E, F2 * 40 * 3); BA_ALLOC(b->d_Hcc, 20);
   BA_ALLOC(b->d_U, (size_t)F2 * F * 64); BA_ALLOC(b->d_V, (size_t)F2 * F * 64);
   b->sys_stride = (size_t)dmax * dmax + dmax + 8;
   BA_ALLOC(b->d_sys, b->sys_stride * SYS_NUM);
@@ -208,6 +208,52 @@ static int prepare_window(sdso_ctx* ctx) {
     N[(size_t)(kCPARS + f * 8 + r) * 7 + 6] = b->frames[f].ns_scale[r] * sc;
   }
   b->h_N = N;
+  // Orthonormal basis of span(N) restricted to singular values > solverModeDelta * max (EnergyFunctional::orthogonalize,
+  // EnergyFunctional.cpp:775-835): columns are normalised, the SVD comes from the Jacobi eigen-decomposition of N^T N.
+  std::vector<double> Q((size_t)d * 7, 0.0);
+  int nrank = 0;
+  {
+    const int m = 7;
+    std::vector<double> Nn((size_t)d * m);
+    for (int i = 0; i < m; i++) {
+      double nrm = 0;
+      for (int r = 0; r < d; r++) nrm += N[(size_t)r * m + i] * N[(size_t)r * m + i];
+      nrm = std::sqrt(nrm);
+      for (int r = 0; r < d; r++) Nn[(size_t)r * m + i] = N[(size_t)r * m + i] / nrm;
+    }
+    double G[49], V[49];
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) {
+      double sacc = 0;
+      for (int r = 0; r < d; r++) sacc += Nn[(size_t)r * m + i] * Nn[(size_t)r * m + j];
+      G[i * m + j] = sacc; V[i * m + j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 60; sweep++) {
+      double off = 0;
+      for (int i = 0; i < m; i++) for (int j = i + 1; j < m; j++) off += G[i * m + j] * G[i * m + j];
+      if (off < 1e-300) break;
+      for (int p = 0; p < m; p++) for (int q = p + 1; q < m; q++) {
+        if (std::fabs(G[p * m + q]) < 1e-300) continue;
+        const double theta = (G[q * m + q] - G[p * m + p]) / (2 * G[p * m + q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        const double cc = 1 / std::sqrt(t * t + 1), ss = t * cc;
+        for (int k = 0; k < m; k++) { const double x = G[k * m + p], y = G[k * m + q]; G[k * m + p] = cc * x - ss * y; G[k * m + q] = ss * x + cc * y; }
+        for (int k = 0; k < m; k++) { const double x = G[p * m + k], y = G[q * m + k]; G[p * m + k] = cc * x - ss * y; G[q * m + k] = ss * x + cc * y; }
+        for (int k = 0; k < m; k++) { const double x = V[k * m + p], y = V[k * m + q]; V[k * m + p] = cc * x - ss * y; V[k * m + q] = ss * x + cc * y; }
+      }
+    }
+    double mx = 0, sv[7];
+    for (int i = 0; i < m; i++) { sv[i] = std::sqrt(std::max(G[i * m + i], 0.0)); mx = std::max(mx, sv[i]); }
+    for (int i = 0; i < m; i++) {
+      if (!(sv[i] > S.solverModeDelta * mx)) continue;
+      for (int r = 0; r < d; r++) {
+        double nv = 0;
+        for (int j = 0; j < m; j++) nv += Nn[(size_t)r * m + j] * V[j * m + i];
+        Q[(size_t)r * 7 + nrank] = nv / sv[i];
+      }
+      nrank++;
+    }
+  }
+  b->nrank = nrank;
   // per-frame device pointers and thresholds
   std::vector<const float4*> tex(kMaxFrames, nullptr);
   std::vector<float> th(kMaxFrames, 0.f);
@@ -222,7 +268,7 @@ static int prepare_window(sdso_ctx* ctx) {
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_adHTdeltaF, adHTd.data(), adHTd.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_cDeltaF, cDeltaF, sizeof(cDeltaF), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_fprior, fpr.data(), fpr.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_N, N.data(), N.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_N, Q.data(), Q.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_tex0, tex.data(), tex.size() * sizeof(float4*), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_frameTH, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaStreamSynchronize(st));  // the host vectors above go out of scope
@@ -242,13 +288,16 @@ static int launch_top(sdso_ctx* ctx, int mode, int which, bool usePrior) {
   BAView v = view(b);
   const int d = b->dim(), n = b->n;
   if (b->nchunks > 0) { ba_top_kernel<<<b->nchunks, kChunk, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
-  ba_top_finish_kernel<<<n * n, 192, 0, ctx->stream>>>(v); SDSO_CHECK_LAUNCH(ctx);
+  // W/Z/Wc/Zc scratch lives in the U/V arenas (the Schur stitch, which owns them, runs after both top stitches)
+  double* Wm = b->d_U; double* Zm = b->d_U + (size_t)n * n * 64; double* Wc = b->d_V; double* Zc = b->d_V + (size_t)n * n * 40;
+  ba_top_finish_kernel<<<n * n, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc); SDSO_CHECK_LAUNCH(ctx);
   if (b->P > 0) { ba_point_sums_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
   double* dc = nullptr;
   // cPrior lives at scalars[8..11]
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_scalars + 8, b->cPrior, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   dc = b->d_scalars + 8;
-  ba_stitch_top_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, which), sysb(b, which), usePrior ? 1 : 0, dc);
+  ba_stitch_top_kernel<<<n * n + 1, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc, sysH(b, which), sysb(b, which), usePrior ? 1 : 0, dc);
+  (void)d;
   SDSO_CHECK_LAUNCH(ctx);
   return SDSO_OK;
 }
@@ -259,9 +308,10 @@ static int launch_sc(sdso_ctx* ctx, bool shift, int which) {
   const int d = b->dim(), n = b->n;
   ba_sc_point_kernel<<<std::max(b->pblocks, 1), 128, 0, ctx->stream>>>(v, shift ? 1 : 0); SDSO_CHECK_LAUNCH(ctx);
   if (b->nchunks > 0) { ba_sc_pair_kernel<<<dim3(b->nchunks, n + 1), kChunk, 0, ctx->stream>>>(v, shift ? 1 : 0); SDSO_CHECK_LAUNCH(ctx); }
-  ba_sc_finish_kernel<<<dim3(n * n, n + 1), 96, 0, ctx->stream>>>(v, b->pblocks); SDSO_CHECK_LAUNCH(ctx);
-  ba_sc_uv_kernel<<<n * n * n, 64, 0, ctx->stream>>>(v); SDSO_CHECK_LAUNCH(ctx);
-  ba_stitch_sc_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, which), sysb(b, which)); SDSO_CHECK_LAUNCH(ctx);
+  double* Uc = b->d_E + (size_t)kMaxFrames * kMaxFrames * 40; double* Vc = Uc + (size_t)kMaxFrames * kMaxFrames * 40;
+  ba_sc_finish_kernel<<<dim3(n * n, n + 1), 96, 0, ctx->stream>>>(v, b->pblocks, Uc, Vc); SDSO_CHECK_LAUNCH(ctx);
+  ba_stitch_sc_kernel<<<n * n + 1, 256, 0, ctx->stream>>>(v, Uc, Vc, sysH(b, which), sysb(b, which)); SDSO_CHECK_LAUNCH(ctx);
+  (void)d;
   return SDSO_OK;
 }
 
@@ -283,7 +333,7 @@ static void fill_solve_params(sdso_ctx* ctx, SolveParams& S, int iteration) {
   S.solverModeDelta = ctx->S.solverModeDelta;
   S.HA = sysH(b, SYS_A); S.bA = sysb(b, SYS_A); S.HL = sysH(b, SYS_L); S.bL = sysb(b, SYS_L); S.Hsc = sysH(b, SYS_SC); S.bsc = sysb(b, SYS_SC);
   S.HM = sysH(b, SYS_M); S.bM = sysb(b, SYS_M);
-  S.fprior = b->d_fprior; S.cDeltaF = b->d_cDeltaF; S.N = b->d_N;
+  S.fprior = b->d_fprior; S.cDeltaF = b->d_cDeltaF; S.N = b->d_N; S.nrank = b->nrank;
   S.HF = sysH(b, SYS_FINAL); S.bF = sysb(b, SYS_FINAL); S.x = sysb(b, SYS_X);
 }
 
@@ -308,7 +358,7 @@ static int launch_factor_solve(sdso_ctx* ctx, int iteration) {
   const int d = b->dim();
   SolveParams S;
   fill_solve_params(ctx, S, iteration);
-  const size_t smem = ((size_t)d * d + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
+  const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   ba_solve_kernel<<<1, 256, smem, ctx->stream>>>(S);

@@ -394,27 +394,49 @@ __global__ void __launch_bounds__(kChunk) ba_top_kernel(BAView B, int mode) {
   }
 }
 
-// fixed-order sum of the chunk partials of one key, expanded to the 13x13 block AccumulatorApprox::finish builds
-__global__ void ba_top_finish_kernel(BAView B) {
+// Fixed-order sum of the chunk partials of one key, expanded to the 13x13 block AccumulatorApprox::finish builds, then the
+// first half of the adjoint stitch for this key: W = adHost*A88, Z = adTarget*A88 (8x8) and Wc = adHost*[A8C | b8],
+// Zc = adTarget*[A8C | b8] (8x5), all in double (AccumulatedTopHessian.cpp:299-322). grid = n*n keys, 256 threads.
+__global__ void __launch_bounds__(256) ba_top_finish_kernel(BAView B, double* W, double* Z, double* Wc, double* Zc) {
   __shared__ float v[kTopVals];
-  const int key = blockIdx.x;
-  if (threadIdx.x < kTopVals) {
+  __shared__ double Gs[169];
+  const int key = blockIdx.x, tid = threadIdx.x;
+  if (tid < kTopVals) {
     float t = 0;
-    for (int c = B.key_chunk_begin[key]; c < B.key_chunk_begin[key + 1]; c++) t += B.tpart[(size_t)c * kTopVals + threadIdx.x];
-    v[threadIdx.x] = t;
+    for (int c = B.key_chunk_begin[key]; c < B.key_chunk_begin[key + 1]; c++) t += B.tpart[(size_t)c * kTopVals + tid];
+    v[tid] = t;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 169; e += blockDim.x) {
-    int r = e / 13, c = e % 13;
+  if (tid < 169) {
+    int r = tid / 13, c = tid % 13;
     if (r > c) { const int q = r; r = c; c = q; }
     float val;
     if (c < 10) val = v[r * 10 - (r * (r - 1)) / 2 + (c - r)];
     else if (r < 10) val = v[55 + 3 * r + (c - 10)];
     else { const int rr = r - 10, cc = c - 10; val = v[85 + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5))]; }
-    B.Gf[(size_t)key * 169 + e] = val;
-    B.G[(size_t)key * 169 + e] = (double)val;
+    B.Gf[(size_t)key * 169 + tid] = val;
+    B.G[(size_t)key * 169 + tid] = (double)val;
+    Gs[tid] = (double)val;
   }
-  if (threadIdx.x == 0) B.G[(size_t)B.n * B.n * 169 + key] = (double)v[91];  // acc.num of this key
+  if (tid == 0) B.G[(size_t)B.n * B.n * 169 + key] = (double)v[91];  // acc.num of this key
+  __syncthreads();
+  const double* AH = B.adHost + (size_t)key * 64; const double* AT = B.adTarget + (size_t)key * 64;
+  if (tid < 128) {
+    const int e = tid & 63, i = e >> 3, j = e & 7;
+    const double* A = (tid < 64) ? AH : AT;
+    double sacc = 0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) sacc += A[i * 8 + p] * Gs[(4 + p) * 13 + 4 + j];
+    ((tid < 64) ? W : Z)[(size_t)key * 64 + e] = sacc;
+  } else if (tid < 128 + 80) {
+    const int q = tid - 128, e = q % 40, i = e / 5, c = e % 5;
+    const double* A = (q < 40) ? AH : AT;
+    const int col = (c < 4) ? c : 12;
+    double sacc = 0;
+#pragma unroll
+    for (int p = 0; p < 8; p++) sacc += A[i * 8 + p] * Gs[(4 + p) * 13 + col];
+    ((q < 40) ? Wc : Zc)[(size_t)key * 40 + e] = sacc;
+  }
 }
 
 // per-point tail: sums of its residuals' terms in residualsAll order
@@ -546,164 +568,140 @@ __global__ void __launch_bounds__(kChunk) ba_sc_pair_kernel(BAView B, int shiftP
   }
 }
 
-// grid = (n*n keys, n+1): D[key][t2] (64 + count), E/EB[key]; block (0,0) also sums accHcc / accbc
-__global__ void ba_sc_finish_kernel(BAView B, int pblocks) {
+// grid = (n*n keys, n+1), 96 threads. Fixed-order sums of the chunk partials: D[key][t2] (64 + count), E/EB[key]; then the
+// first half of the adjoint stitch: U = adHost[key]*D, V = adTarget[key]*D (t2 < n) or Uc/Vc = ad*[E | EB] (t2 == n).
+// Block (0,0) also sums accHcc / accbc (AccumulatedSCHessian.cpp:106-195).
+__global__ void __launch_bounds__(96) ba_sc_finish_kernel(BAView B, int pblocks, double* Uc, double* Vc) {
+  __shared__ double Ds[65];
   const int key = blockIdx.x, t2 = blockIdx.y, e = threadIdx.x;
   const int n = B.n;
   if (e < 65) {
     float t = 0;
     for (int c = B.key_chunk_begin[key]; c < B.key_chunk_begin[key + 1]; c++) t += B.dpart[((size_t)c * (n + 1) + t2) * 65 + e];
+    Ds[e] = (double)t;
     if (t2 < n) B.D[((size_t)key * n + t2) * 65 + e] = (double)t;
     else if (e < 40) B.E[(size_t)key * 40 + e] = (double)t;
   }
-  if (key == 0 && t2 == 0 && e < 20) {
+  if (key == 0 && t2 == 0 && e >= 65 && e < 85) {
     float t = 0;
-    for (int b = 0; b < pblocks; b++) t += B.pblockpart[(size_t)b * 32 + e];
-    B.Hcc[e] = (double)t;
+    for (int b = 0; b < pblocks; b++) t += B.pblockpart[(size_t)b * 32 + (e - 65)];
+    B.Hcc[e - 65] = (double)t;
   }
-}
-
-// ---- B5: stitch. One thread per element of the (4+8n)^2 matrix and of b -------------------------------------
-__device__ __forceinline__ double quad88(const double* A, int i, const double* G, int goff_r, int goff_c, const double* Bm, int j) {
-  // sum_pq A[i,p] * G[(goff_r+p)*13 + goff_c+q] * Bm[j,q]
-  double s = 0;
-#pragma unroll
-  for (int p = 0; p < 8; p++) {
-    double in = 0;
-#pragma unroll
-    for (int q = 0; q < 8; q++) in += G[(goff_r + p) * 13 + goff_c + q] * Bm[j * 8 + q];
-    s += A[i * 8 + p] * in;
-  }
-  return s;
-}
-
-__global__ void ba_stitch_top_kernel(BAView B, double* H, double* bvec, int usePrior, const double* cPrior) {
-  const int n = B.n, d = kCPARS + 8 * n;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d * d + d) return;
-  const double* G = B.G;
-  if (e >= d * d) {  // b
-    const int r = e - d * d;
-    double s = 0;
-    if (r < 4) {
-      for (int k = 0; k < n * n; k++) s += G[(size_t)k * 169 + r * 13 + 12];
-      if (usePrior) s += cPrior[r] * (double)B.cDeltaF[r];
-    } else {
-      const int a = (r - 4) / 8, i = (r - 4) % 8;
-      for (int o = 0; o < n; o++) {
-        const int kh = a + o * n, kt = o + a * n;  // keys with host a / with target a
-        const double* AH = B.adHost + (size_t)kh * 64; const double* AT = B.adTarget + (size_t)kt * 64;
-        for (int q = 0; q < 8; q++) {
-          s += AH[i * 8 + q] * G[(size_t)kh * 169 + (4 + q) * 13 + 12];
-          s += AT[i * 8 + q] * G[(size_t)kt * 169 + (4 + q) * 13 + 12];
-        }
-      }
-      if (usePrior) s += B.fprior[a * 24 + i] * B.fprior[a * 24 + 8 + i];
-    }
-    bvec[r] = s;
-    return;
-  }
-  int r = e / d, c = e % d;
-  double s = 0;
-  if (r < 4 && c < 4) {
-    for (int k = 0; k < n * n; k++) s += G[(size_t)k * 169 + r * 13 + c];
-    if (usePrior && r == c) s += cPrior[r];
-  } else if (r < 4 || c < 4) {
-    if (r < 4) { const int q = r; r = c; c = q; }  // H[0:4, hIdx] = H[hIdx, 0:4]^T
-    const int a = (r - 4) / 8, i = (r - 4) % 8;
-    for (int o = 0; o < n; o++) {
-      const int kh = a + o * n, kt = o + a * n;
-      const double* AH = B.adHost + (size_t)kh * 64; const double* AT = B.adTarget + (size_t)kt * 64;
-      for (int q = 0; q < 8; q++) {
-        s += AH[i * 8 + q] * G[(size_t)kh * 169 + (4 + q) * 13 + c];
-        s += AT[i * 8 + q] * G[(size_t)kt * 169 + (4 + q) * 13 + c];
-      }
-    }
-  } else {
-    const int a = (r - 4) / 8, i = (r - 4) % 8, b = (c - 4) / 8, j = (c - 4) % 8;
-    if (a != b) {
-      const int k1 = a + b * n, k2 = b + a * n;
-      s = quad88(B.adHost + (size_t)k1 * 64, i, G + (size_t)k1 * 169, 4, 4, B.adTarget + (size_t)k1 * 64, j) +
-          quad88(B.adHost + (size_t)k2 * 64, j, G + (size_t)k2 * 169, 4, 4, B.adTarget + (size_t)k2 * 64, i);
-    } else {
-      for (int o = 0; o < n; o++) {
-        const int kh = a + o * n, kt = o + a * n;
-        s += quad88(B.adHost + (size_t)kh * 64, i, G + (size_t)kh * 169, 4, 4, B.adHost + (size_t)kh * 64, j);
-        s += quad88(B.adTarget + (size_t)kt * 64, i, G + (size_t)kt * 169, 4, 4, B.adTarget + (size_t)kt * 64, j);
-      }
-      const int kd = a + a * n;
-      s += quad88(B.adHost + (size_t)kd * 64, i, G + (size_t)kd * 169, 4, 4, B.adTarget + (size_t)kd * 64, j);
-      if (usePrior && i == j) s += B.fprior[a * 24 + i];
-    }
-  }
-  H[e] = s;
-}
-
-// ---- B7: U = adHost[key] * D[key][k], V = adTarget[key] * D[key][k]; grid = n*n*n, 64 threads ---------------
-__global__ void ba_sc_uv_kernel(BAView B) {
-  const int blk = blockIdx.x;  // key * n + k
-  const int key = blk / B.n;
-  const int i = threadIdx.x / 8, j = threadIdx.x % 8;
-  const double* Dm = B.D + (size_t)blk * 65;
+  __syncthreads();
   const double* AH = B.adHost + (size_t)key * 64; const double* AT = B.adTarget + (size_t)key * 64;
-  double u = 0, v = 0;
+  if (t2 < n) {
+    if (e < 64) {
+      const int i = e >> 3, j = e & 7;
+      double u = 0, v = 0;
 #pragma unroll
-  for (int q = 0; q < 8; q++) { u += AH[i * 8 + q] * Dm[q * 8 + j]; v += AT[i * 8 + q] * Dm[q * 8 + j]; }
-  B.U[(size_t)blk * 64 + threadIdx.x] = u;
-  B.V[(size_t)blk * 64 + threadIdx.x] = v;
+      for (int q = 0; q < 8; q++) { u += AH[i * 8 + q] * Ds[q * 8 + j]; v += AT[i * 8 + q] * Ds[q * 8 + j]; }
+      B.U[((size_t)key * n + t2) * 64 + e] = u;
+      B.V[((size_t)key * n + t2) * 64 + e] = v;
+    }
+  } else if (e < 40) {
+    const int i = e / 5, c = e % 5;  // c < 4: E column, c == 4: EB
+    double u = 0, v = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { const double x = (c < 4) ? Ds[q * 4 + c] : Ds[32 + q]; u += AH[i * 8 + q] * x; v += AT[i * 8 + q] * x; }
+    Uc[(size_t)key * 40 + e] = u;
+    Vc[(size_t)key * 40 + e] = v;
+  }
 }
 
-__device__ __forceinline__ double rowdot8(const double* X, int i, const double* Bm, int j) {
+__device__ __forceinline__ double rowdot8(const double* __restrict__ X, int i, const double* __restrict__ Bm, int j) {
   double s = 0;
 #pragma unroll
   for (int q = 0; q < 8; q++) s += X[i * 8 + q] * Bm[j * 8 + q];
   return s;
 }
 
-__global__ void ba_stitch_sc_kernel(BAView B, double* H, double* bvec) {
-  const int n = B.n, d = kCPARS + 8 * n, n2 = n * n;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d * d + d) return;
-  if (e >= d * d) {
-    const int r = e - d * d;
+// ---- B5: second half of the top stitch + symmetrisation. grid = n*n 8x8 frame blocks + 1 (calibration rows/cols and b),
+// 256 threads = 64 elements x 4 term groups; the groups are summed in fixed order ----------------------------------------
+__global__ void __launch_bounds__(256) ba_stitch_top_kernel(BAView B, const double* W, const double* Z, const double* Wc, const double* Zc,
+                                                            double* H, double* bvec, int usePrior, const double* cPrior) {
+  __shared__ double red[4][64];
+  const int n = B.n, d = kCPARS + 8 * n, tid = threadIdx.x;
+  if ((int)blockIdx.x < n * n) {
+    const int a = blockIdx.x % n, b = blockIdx.x / n;
+    const int e = tid & 63, g = tid >> 6, i = e >> 3, j = e & 7;
     double s = 0;
-    if (r < 4) s = B.Hcc[16 + r];
-    else {
-      const int a = (r - 4) / 8, i = (r - 4) % 8;
-      for (int o = 0; o < n; o++) {
-        const int kh = a + o * n, kt = o + a * n;
-        const double* AH = B.adHost + (size_t)kh * 64; const double* AT = B.adTarget + (size_t)kt * 64;
-        for (int q = 0; q < 8; q++) { s += AH[i * 8 + q] * B.E[(size_t)kh * 40 + 32 + q]; s += AT[i * 8 + q] * B.E[(size_t)kt * 40 + 32 + q]; }
+    if (a != b) {  // M[a,b] + M[b,a]^T with M[h,t] = AH A88 AT^T of key (h,t)
+      const int k1 = a + b * n, k2 = b + a * n;
+      if (g == 0) s = rowdot8(W + (size_t)k1 * 64, i, B.adTarget + (size_t)k1 * 64, j);
+      if (g == 1) s = rowdot8(W + (size_t)k2 * 64, j, B.adTarget + (size_t)k2 * 64, i);
+    } else {
+      for (int t = g; t < 2 * n + 1; t += 4) {
+        if (t < n) { const int kh = a + t * n; s += rowdot8(W + (size_t)kh * 64, i, B.adHost + (size_t)kh * 64, j); }
+        else if (t < 2 * n) { const int kt = (t - n) + a * n; s += rowdot8(Z + (size_t)kt * 64, i, B.adTarget + (size_t)kt * 64, j); }
+        else { const int kd = a + a * n; s += rowdot8(W + (size_t)kd * 64, i, B.adTarget + (size_t)kd * 64, j); }
       }
     }
-    bvec[r] = s;
+    red[g][e] = s;
+    __syncthreads();
+    if (g == 0) {
+      double t = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+      if (usePrior && a == b && i == j) t += B.fprior[a * 24 + i];
+      H[(size_t)(4 + 8 * a + i) * d + 4 + 8 * b + j] = t;
+    }
     return;
   }
-  int r = e / d, c = e % d;
-  double s = 0;
-  if (r < 4 && c < 4) s = B.Hcc[r * 4 + c];
-  else if (r < 4 || c < 4) {
-    if (r < 4) { const int q = r; r = c; c = q; }
-    const int a = (r - 4) / 8, i = (r - 4) % 8;
-    for (int o = 0; o < n; o++) {
-      const int kh = a + o * n, kt = o + a * n;
-      const double* AH = B.adHost + (size_t)kh * 64; const double* AT = B.adTarget + (size_t)kt * 64;
-      for (int q = 0; q < 8; q++) { s += AH[i * 8 + q] * B.E[(size_t)kh * 40 + q * 4 + c]; s += AT[i * 8 + q] * B.E[(size_t)kt * 40 + q * 4 + c]; }
-    }
-  } else {
-    const int a = (r - 4) / 8, i = (r - 4) % 8, b = (c - 4) / 8, j = (c - 4) % 8;
-    // H[jIdx,kIdx] += AT_ij D_ijk AT_ik^T  : (j=a, k=b), all hosts o
-    for (int o = 0; o < n; o++) s += rowdot8(B.V + ((size_t)(o + n * a) * n + b) * 64, i, B.adTarget + (size_t)(o + n * b) * 64, j);
-    // H[jIdx,iIdx] += AT_ij D_ijk AH_ik^T  : (j=a, host=b), all k
-    for (int k = 0; k < n; k++) s += rowdot8(B.V + ((size_t)(b + n * a) * n + k) * 64, i, B.adHost + (size_t)(b + n * k) * 64, j);
-    // H[iIdx,kIdx] += AH_ij D_ijk AT_ik^T  : (host=a, k=b), all j
-    for (int o = 0; o < n; o++) s += rowdot8(B.U + ((size_t)(a + n * o) * n + b) * 64, i, B.adTarget + (size_t)(a + n * b) * 64, j);
-    if (a == b)  // H[iIdx,iIdx] += AH_ij D_ijk AH_ik^T : all j, k
-      for (int o = 0; o < n; o++)
-        for (int k = 0; k < n; k++) s += rowdot8(B.U + ((size_t)(a + n * o) * n + k) * 64, i, B.adHost + (size_t)(a + n * k) * 64, j);
-    (void)n2;
+  // calibration block, calibration rows/columns, and b
+  for (int idx = tid; idx < 8 * n * 5; idx += blockDim.x) {
+    const int r = idx / 5, c = idx % 5, a = r / 8, i = r % 8;
+    double s = 0;
+    for (int o = 0; o < n; o++) s += Wc[(size_t)(a + o * n) * 40 + i * 5 + c] + Zc[(size_t)(o + a * n) * 40 + i * 5 + c];
+    if (c < 4) { H[(size_t)(4 + r) * d + c] = s; H[(size_t)c * d + 4 + r] = s; }
+    else { if (usePrior) s += B.fprior[a * 24 + i] * B.fprior[a * 24 + 8 + i]; bvec[4 + r] = s; }
   }
-  H[e] = s;
+  for (int idx = tid; idx < 20; idx += blockDim.x) {
+    const int r = idx / 5, c = idx % 5;
+    double s = 0;
+    for (int k = 0; k < n * n; k++) s += B.G[(size_t)k * 169 + r * 13 + (c < 4 ? c : 12)];
+    if (c < 4) { if (usePrior && r == c) s += cPrior[r]; H[(size_t)r * d + c] = s; }
+    else { if (usePrior) s += cPrior[r] * (double)B.cDeltaF[r]; bvec[r] = s; }
+  }
+}
+
+// ---- B7: second half of the Schur stitch, same decomposition --------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_stitch_sc_kernel(BAView B, const double* Uc, const double* Vc, double* H, double* bvec) {
+  __shared__ double red[4][64];
+  const int n = B.n, d = kCPARS + 8 * n, tid = threadIdx.x;
+  if ((int)blockIdx.x < n * n) {
+    const int a = blockIdx.x % n, b = blockIdx.x / n;
+    const int e = tid & 63, g = tid >> 6, i = e >> 3, j = e & 7;
+    const int nterms = 3 * n + (a == b ? n * n : 0);
+    double s = 0;
+    for (int t = g; t < nterms; t += 4) {
+      if (t < n) {             // H[jIdx,kIdx] += AT_ij D_ijk AT_ik^T : (j=a, k=b), host o
+        const int o = t;
+        s += rowdot8(B.V + ((size_t)(o + n * a) * n + b) * 64, i, B.adTarget + (size_t)(o + n * b) * 64, j);
+      } else if (t < 2 * n) {  // H[jIdx,iIdx] += AT_ij D_ijk AH_ik^T : (j=a, host=b), target k
+        const int k = t - n;
+        s += rowdot8(B.V + ((size_t)(b + n * a) * n + k) * 64, i, B.adHost + (size_t)(b + n * k) * 64, j);
+      } else if (t < 3 * n) {  // H[iIdx,kIdx] += AH_ij D_ijk AT_ik^T : (host=a, k=b), target o
+        const int o = t - 2 * n;
+        s += rowdot8(B.U + ((size_t)(a + n * o) * n + b) * 64, i, B.adTarget + (size_t)(a + n * b) * 64, j);
+      } else {                 // H[iIdx,iIdx] += AH_ij D_ijk AH_ik^T : all (j,k)
+        const int q = t - 3 * n, o = q / n, k = q % n;
+        s += rowdot8(B.U + ((size_t)(a + n * o) * n + k) * 64, i, B.adHost + (size_t)(a + n * k) * 64, j);
+      }
+    }
+    red[g][e] = s;
+    __syncthreads();
+    if (g == 0) H[(size_t)(4 + 8 * a + i) * d + 4 + 8 * b + j] = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+    return;
+  }
+  for (int idx = tid; idx < 8 * n * 5; idx += blockDim.x) {
+    const int r = idx / 5, c = idx % 5, a = r / 8, i = r % 8;
+    double s = 0;
+    for (int o = 0; o < n; o++) s += Uc[(size_t)(a + o * n) * 40 + i * 5 + c] + Vc[(size_t)(o + a * n) * 40 + i * 5 + c];
+    if (c < 4) { H[(size_t)(4 + r) * d + c] = s; H[(size_t)c * d + 4 + r] = s; }
+    else bvec[4 + r] = s;
+  }
+  for (int idx = tid; idx < 20; idx += blockDim.x) {
+    if (idx < 16) H[(size_t)(idx / 4) * d + idx % 4] = B.Hcc[idx];
+    else bvec[idx - 16] = B.Hcc[idx];
+  }
 }
 
 // ---- B8: assemble (elementwise) then scaled diagonal-pivoted LDLT (+ orthogonalisation) in ONE CTA ----------------
@@ -713,7 +711,8 @@ struct SolveParams {
   const double* HA; const double* bA; const double* HL; const double* bL; const double* Hsc; const double* bsc;
   const double* HM; const double* bM;
   const double* fprior; const float* cDeltaF;
-  const double* N;   // d x 7 nullspace columns (row-major) or null
+  const double* N;   // d x 7 (row-major): orthonormal basis of the gauge nullspace in the first nrank columns, or null
+  int nrank;
   double* HF; double* bF; double* x;
 };
 
@@ -748,49 +747,21 @@ __global__ void ba_assemble_kernel(SolveParams S) {
   S.HF[e] = v;
 }
 
-// x -= N (N^T N)^+ N^T x  (orthogonalize(&x, 0), EnergyFunctional.cpp:775-835), run by one CTA; scratch in shared memory
-__device__ void ortho_vec(const double* __restrict__ Nraw, int d, int m, double delta, double* x, double* sN /* d*m */, double* sw /* >= 3*m*m+4*m */) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  double* G = sw; double* Vv = sw + m * m; double* wv = Vv + m * m; double* coef = wv + m; double* nrm = coef + m;
-  if (tid < m) { double s = 0; for (int r = 0; r < d; r++) s += Nraw[r * m + tid] * Nraw[r * m + tid]; nrm[tid] = sqrt(s); }
-  __syncthreads();
-  for (int e = tid; e < d * m; e += nt) sN[e] = Nraw[e] / nrm[e % m];
-  __syncthreads();
-  if (tid < m * m) { const int i = tid / m, j = tid % m; double s = 0; for (int r = 0; r < d; r++) s += sN[r * m + i] * sN[r * m + j]; G[tid] = s; Vv[tid] = (i == j) ? 1.0 : 0.0; }
-  __syncthreads();
-  if (tid == 0) {  // cyclic Jacobi on the m x m Gram matrix (m = 7)
-    for (int sweep = 0; sweep < 60; sweep++) {
-      double off = 0;
-      for (int i = 0; i < m; i++) for (int j = i + 1; j < m; j++) off += G[i * m + j] * G[i * m + j];
-      if (off < 1e-300) break;
-      for (int p = 0; p < m; p++) for (int q = p + 1; q < m; q++) {
-        if (fabs(G[p * m + q]) < 1e-300) continue;
-        const double theta = (G[q * m + q] - G[p * m + p]) / (2 * G[p * m + q]);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-        const double c = 1 / sqrt(t * t + 1), s = t * c;
-        for (int k = 0; k < m; k++) { const double a = G[k * m + p], b = G[k * m + q]; G[k * m + p] = c * a - s * b; G[k * m + q] = s * a + c * b; }
-        for (int k = 0; k < m; k++) { const double a = G[p * m + k], b = G[q * m + k]; G[p * m + k] = c * a - s * b; G[q * m + k] = s * a + c * b; }
-        for (int k = 0; k < m; k++) { const double a = Vv[k * m + p], b = Vv[k * m + q]; Vv[k * m + p] = c * a - s * b; Vv[k * m + q] = s * a + c * b; }
-      }
-    }
-    double mx = 0;
-    for (int i = 0; i < m; i++) { wv[i] = sqrt(fmax(G[i * m + i], 0.0)); mx = fmax(mx, wv[i]); }
-    for (int i = 0; i < m; i++) if (!(wv[i] > delta * mx)) wv[i] = 0;  // dropped singular values
-  }
-  __syncthreads();
-  // coef_i = (U_i . x) / sigma_i with U_i = N v_i / sigma_i  ->  x -= sum_i (N v_i) * (v_i^T N^T x) / sigma_i^2
-  if (tid < m) {
+// x -= Q Q^T x with Q (d x rank, orthonormal columns) = the left singular vectors of the 7 normalised nullspace vectors whose
+// singular value exceeds solverModeDelta * max — i.e. orthogonalize(&x, 0) (EnergyFunctional.cpp:775-835). The basis depends
+// only on the evaluation points, so it is computed once per window on the host (sdso_ba_prepare) instead of per solve.
+__device__ void ortho_vec(const double* __restrict__ Q, int d, int rank, double* x, double* coef /* >= 8 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < rank) {
     double s = 0;
-    if (wv[tid] > 0) {
-      for (int r = 0; r < d; r++) { double nv = 0; for (int j = 0; j < m; j++) nv += sN[r * m + j] * Vv[j * m + tid]; s += nv * x[r]; }
-      s /= (wv[tid] * wv[tid]);
-    }
-    coef[tid] = s;
+    for (int r = lane; r < d; r += 32) s += Q[r * 7 + warp] * x[r];
+    s = warp_sum(s);
+    if (lane == 0) coef[warp] = s;
   }
   __syncthreads();
-  for (int r = tid; r < d; r += nt) {
+  for (int r = threadIdx.x; r < d; r += blockDim.x) {
     double sub = 0;
-    for (int i = 0; i < m; i++) { if (coef[i] == 0) continue; double nv = 0; for (int j = 0; j < m; j++) nv += sN[r * m + j] * Vv[j * m + i]; sub += nv * coef[i]; }
+    for (int i = 0; i < rank; i++) sub += Q[r * 7 + i] * coef[i];
     x[r] -= sub;
   }
   __syncthreads();
@@ -799,68 +770,93 @@ __device__ void ortho_vec(const double* __restrict__ Nraw, int d, int m, double 
 __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   extern __shared__ double sm[];
   const int d = S.d, tid = threadIdx.x, nt = blockDim.x;
-  double* M = sm;                 // d*d
-  double* bs = M + d * d;         // d
+  const int ld = d | 1;           // odd leading dimension: column walks hit distinct banks
+  double* M = sm;                 // d*ld
+  double* bs = M + d * ld;        // d
   double* sv = bs + d;            // d  SVecI
   double* dg = sv + d;            // d  D of LDLT
   double* y = dg + d;             // d
-  double* delta = y + d;          // d
-  double* scr = delta + d;        // d*7 + 256
+  double* lcol = y + d;           // d  current L column
+  double* scr = lcol + d;         // d*7 + 256
   __shared__ int perm[kCPARS + 8 * kMaxFrames];
   __shared__ int piv;
-  for (int i = tid; i < d; i += nt) bs[i] = S.bF[i];
-  for (int e = tid; e < d * d; e += nt) M[e] = S.HF[e];
+  __shared__ double pivval;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 tiling of the trailing update
+  for (int i = tid; i < d; i += nt) { bs[i] = S.bF[i]; sv[i] = 1.0 / sqrt(S.HF[(size_t)i * d + i] + 10); perm[i] = i; }
   __syncthreads();
-  for (int i = tid; i < d; i += nt) { sv[i] = 1.0 / sqrt(M[i * d + i] + 10); perm[i] = i; }
-  __syncthreads();
-  for (int e = tid; e < d * d; e += nt) M[e] = sv[e / d] * M[e] * sv[e % d];
+  for (int r = ty; r < d; r += 16)
+    for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
   for (int i = tid; i < d; i += nt) bs[i] = sv[i] * bs[i];
   __syncthreads();
   // diagonal-pivoted LDLT (the strategy of Eigen::LDLT, which EnergyFunctional.cpp:976 calls)
   for (int k = 0; k < d; k++) {
-    if (tid == 0) {
-      int p = k; double best = fabs(M[k * d + k]);
-      for (int i = k + 1; i < d; i++) { const double v = fabs(M[i * d + i]); if (v > best) { best = v; p = i; } }
-      piv = p;
-      if (p != k) { const int q = perm[k]; perm[k] = perm[p]; perm[p] = q; }
+    if (warp == 0) {  // arg max |M_ii|, i >= k, lowest index on ties
+      double best = -1.0; int p = k;
+      for (int i = k + lane; i < d; i += 32) { const double v = fabs(M[i * ld + i]); if (v > best) { best = v; p = i; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, p, o);
+        if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+      }
+      if (lane == 0) {
+        piv = p; pivval = M[p * ld + p];
+        if (p != k) { const int q = perm[k]; perm[k] = perm[p]; perm[p] = q; }
+      }
     }
     __syncthreads();
     const int p = piv;
-    if (p != k) {
-      for (int j = tid; j < d; j += nt) { const double a = M[k * d + j]; M[k * d + j] = M[p * d + j]; M[p * d + j] = a; }
-      __syncthreads();
-      for (int j = tid; j < d; j += nt) { const double a = M[j * d + k]; M[j * d + k] = M[j * d + p]; M[j * d + p] = a; }
-      __syncthreads();
+    // Symmetric swap of k and p fused with the scaling of column k, one phase: thread j owns (k,j),(p,j),(j,k),(j,p); the thread
+    // with j == p owns the 2x2 corner. Only the lower triangle (and the diagonal) is kept current from here on.
+    const double dk = pivval;
+    const bool singular = (dk == 0.0 || !isfinite(dk));
+    for (int j = tid; j < d; j += nt) {
+      if (j == k) continue;
+      if (j == p) {  // (p != k here) corner: new (k,k) = old (p,p), new (p,p) = old (k,k), new (p,k) = old (k,p) = old (p,k)
+        const double akk = M[k * ld + k], apk = M[p * ld + k];
+        M[k * ld + k] = dk; M[p * ld + p] = akk;
+        const double l = singular ? 0.0 : apk / dk;
+        M[p * ld + k] = l; lcol[p] = l;
+        continue;
+      }
+      // lower-triangle accessors: L(a,b) lives at M[max][min]
+      if (p != k) {
+        double* ek = (j < k) ? &M[k * ld + j] : &M[j * ld + k];
+        double* ep = (j < p) ? &M[p * ld + j] : &M[j * ld + p];
+        const double t = *ek; *ek = *ep; *ep = t;
+      }
+      if (j > k) { const double l = singular ? 0.0 : M[j * ld + k] / dk; M[j * ld + k] = l; lcol[j] = l; }
     }
-    const double dk = M[k * d + k];
-    __syncthreads();
     if (tid == 0) dg[k] = dk;
-    if (dk == 0.0 || !isfinite(dk)) { for (int i = k + 1 + tid; i < d; i += nt) M[i * d + k] = 0; __syncthreads(); continue; }
-    for (int i = k + 1 + tid; i < d; i += nt) M[i * d + k] /= dk;
     __syncthreads();
-    const int rem = d - k - 1;
-    for (int e = tid; e < rem * rem; e += nt) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j <= i) M[i * d + j] -= M[i * d + k] * dk * M[j * d + k];
-    }
-    __syncthreads();
-    for (int e = tid; e < rem * rem; e += nt) {
-      const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-      if (j > i) M[i * d + j] = M[j * d + i];
+    if (!singular) {
+      for (int i = k + 1 + ty; i < d; i += 16)
+        for (int j = k + 1 + tx; j <= i; j += 16) M[i * ld + j] -= lcol[i] * dk * lcol[j];
     }
     __syncthreads();
   }
-  if (tid == 0) {
-    for (int i = 0; i < d; i++) y[i] = bs[perm[i]];
-    for (int i = 0; i < d; i++) { double v = y[i]; for (int j = 0; j < i; j++) v -= M[i * d + j] * y[j]; y[i] = v; }
-    for (int i = 0; i < d; i++) y[i] = (dg[i] != 0.0) ? y[i] / dg[i] : 0.0;
-    for (int i = d - 1; i >= 0; i--) { double v = y[i]; for (int j = i + 1; j < d; j++) v -= M[j * d + i] * y[j]; y[i] = v; }
-    for (int i = 0; i < d; i++) bs[perm[i]] = y[i];
+  if (warp == 0) {  // triangular solves, column oriented, one warp
+    for (int i = lane; i < d; i += 32) y[i] = bs[perm[i]];
+    __syncwarp();
+    for (int i = 0; i < d; i++) {
+      const double yi = y[i];
+      for (int j = i + 1 + lane; j < d; j += 32) y[j] -= M[j * ld + i] * yi;
+      __syncwarp();
+    }
+    for (int i = lane; i < d; i += 32) y[i] = (dg[i] != 0.0) ? y[i] / dg[i] : 0.0;
+    __syncwarp();
+    for (int i = d - 1; i >= 0; i--) {
+      const double yi = y[i];
+      for (int j = lane; j < i; j += 32) y[j] -= M[i * ld + j] * yi;
+      __syncwarp();
+    }
+    for (int i = lane; i < d; i += 32) bs[perm[i]] = y[i];
   }
   __syncthreads();
   for (int i = tid; i < d; i += nt) bs[i] *= sv[i];
   __syncthreads();
-  if (S.iteration >= 2 && S.N) ortho_vec(S.N, d, 7, S.solverModeDelta, bs, M, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
+  if (S.iteration >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
   for (int i = tid; i < d; i += nt) S.x[i] = bs[i];
 }
 

@@ -113,7 +113,8 @@ struct BAState {
   double* d_energy_part = nullptr;        // per-block energy partials
   double* d_scalars = nullptr;            // [16]
   unsigned int* d_counter = nullptr;
-  double* d_N = nullptr;                  // [d][7] nullspace columns (6 pose + 1 scale)
+  double* d_N = nullptr;                  // [d][7] orthonormal basis of the gauge nullspace (first nrank columns)
+  int nrank = 0;
   float* d_xAd = nullptr;                 // [n*n][8]
   int* d_list = nullptr;                  // scratch slot list
   int shard_rank = 0, shard_n = 1;        // point-sharded window: priors and HM enter on rank 0 only
