@@ -120,6 +120,16 @@ int sdso_frame_release(sdso_ctx* ctx, int frame_id);
 int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float ab_exposure, int use_hcalib);
 /* same, image already on the device (device pointer, w*h floats) */
 int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_image, float ab_exposure, int use_hcalib);
+/* Batched forms (nb <= 32 frames, ONE pyramid launch + ONE gradient launch for all of them). src_u8 != 0: the sources are
+ * 8-bit grey images; the widening to float — PhotometricUndistorter::processFrame in mode=1 (util/Undistort.cpp:222-260,
+ * no response / vignette calibration) — is fused into the pyramid kernel, which cuts the H2D bytes by 4.
+ *   sdso_upload_images_async : H2D of the sources on the context's copy stream (returns at once; overlaps running kernels)
+ *   sdso_make_images_uploaded: the compute stream waits for those copies, then builds the nb pyramids
+ *   sdso_make_images_batch_device: sources already in device memory */
+int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* host_images, int src_u8);
+int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const float* ab_exposure /* nullable: 1 */, int use_hcalib);
+int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* device_images, int src_u8,
+                                  const float* ab_exposure /* nullable: 1 */, int use_hcalib);
 /* read back level lvl: dI3 = w_l*h_l*3 floats AoS {I,dx,dy} (the reference's layout), absgrad = w_l*h_l */
 int sdso_frame_download(sdso_ctx* ctx, int frame_id, int lvl, float* dI3 /* nullable */, float* absgrad /* nullable */);
 /* getInterpolatedElement33 / 33BiLin (util/globalFuncs.h:73-86, 160-184) at n points of level lvl */
@@ -163,6 +173,12 @@ int sdso_track(sdso_ctx* ctx, int new_frame, double T_io[12], double aff_io[2], 
 int sdso_track_batch(sdso_ctx* ctx, int nb, const int* new_frames, double* T_io, double* aff_io, int coarsest_lvl,
                      const double* minResForAbort, int variant, double* lastResiduals, double* flowIndicators,
                      int* iterations, int* ok);
+/* Several reference keyframes at once (independent sequences sharing one GPU): sdso_tracker_select_ref switches the slot that
+ * sdso_tracker_set_ref / set_pc / get_pc / calc_res_gs operate on; sdso_track_enqueue_multi tracks problem k against the
+ * template of slot ref_slots[k] (NULL: the current slot for all), one cluster per problem, ONE launch. */
+int sdso_tracker_select_ref(sdso_ctx* ctx, int slot);
+int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const int* new_frames, const double* T_in, const double* aff_in,
+                             int coarsest_lvl, const double* minResForAbort, int variant);
 /* async pair used by bench.py so that CUDA events bracket the kernels without host syncs */
 int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const double* T_in, const double* aff_in,
                        int coarsest_lvl, const double* minResForAbort, int variant);

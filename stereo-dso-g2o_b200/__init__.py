@@ -560,3 +560,54 @@ Window.set_shard = _w_set_shard
 Window.assemble = _w_assemble
 Window.allreduce = _w_allreduce
 Window.solve_assembled = _w_solve_assembled
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched makeImages (uint8 / float sources, asynchronous upload) and multi-reference tracking
+_vpp = C.POINTER(C.c_void_p)
+lib.sdso_upload_images_async.argtypes = [C.c_void_p, C.c_int, _ip, _vpp, C.c_int]
+lib.sdso_make_images_uploaded.argtypes = [C.c_void_p, C.c_int, _ip, _fp, C.c_int]
+lib.sdso_make_images_batch_device.argtypes = [C.c_void_p, C.c_int, _ip, _vpp, C.c_int, _fp, C.c_int]
+lib.sdso_tracker_select_ref.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_track_enqueue_multi.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int]
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def _upload_images_async(self, fids, host_ptrs, u8=False):
+    f = np.ascontiguousarray(fids, dtype=np.int32)
+    self._ck(lib.sdso_upload_images_async(self._h, f.size, _ptr(f, _ip), _ptr_array(host_ptrs), int(u8)))
+
+
+def _make_images_uploaded(self, fids, use_hcalib=True):
+    f = np.ascontiguousarray(fids, dtype=np.int32)
+    self._ck(lib.sdso_make_images_uploaded(self._h, f.size, _ptr(f, _ip), None, int(use_hcalib)))
+
+
+def _make_images_batch_device(self, fids, dev_ptrs, u8=False, use_hcalib=True):
+    f = np.ascontiguousarray(fids, dtype=np.int32)
+    self._ck(lib.sdso_make_images_batch_device(self._h, f.size, _ptr(f, _ip), _ptr_array(dev_ptrs), int(u8), None, int(use_hcalib)))
+
+
+def _tracker_select_ref(self, slot):
+    self._ck(lib.sdso_tracker_select_ref(self._h, int(slot)))
+
+
+def _track_enqueue_multi(self, ref_slots, new_fids, T, aff, coarsest, min_res_for_abort, variant=VARIANT_SSE):
+    nb = len(new_fids)
+    f = np.ascontiguousarray(new_fids, dtype=np.int32)
+    r = np.ascontiguousarray(ref_slots, dtype=np.int32) if ref_slots is not None else None
+    T = _f64(T).reshape(nb, 12)
+    aff = _f64(aff).reshape(nb, 2)
+    mr = _f64(min_res_for_abort).reshape(nb, 5)
+    self._ck(lib.sdso_track_enqueue_multi(self._h, nb, _ptr(r, _ip) if r is not None else None, _ptr(f, _ip), _ptr(T, _dp), _ptr(aff, _dp),
+                                          coarsest, _ptr(mr, _dp), variant))
+
+
+Context.upload_images_async = _upload_images_async
+Context.make_images_uploaded = _make_images_uploaded
+Context.make_images_batch_device = _make_images_batch_device
+Context.tracker_select_ref = _tracker_select_ref
+Context.track_enqueue_multi = _track_enqueue_multi

@@ -162,8 +162,11 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   for (auto& f : ctx->frames) {
     if (f.tex[0]) cudaFree(f.tex[0]);
     if (f.image) cudaFree(f.image);
+    if (f.src8) cudaFree(f.src8);
+    if (f.uploaded) cudaEventDestroy(f.uploaded);
   }
   if (ctx->staging) cudaFreeHost(ctx->staging);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->ev_track) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : ctx->ev_images) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   delete ctx;
@@ -245,12 +248,78 @@ int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_ima
   if (!ctx || !device_image || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
   Frame& f = ctx->frames[frame_id];
   const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
-  if (device_image != f.image)
-    SDSO_CUDA(ctx, cudaMemcpyAsync(f.image, device_image, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  (void)n;  // the pyramid kernel copies an external level-0 image into the frame's own intensity plane
   f.ab_exposure = ab_exposure;
-  int rc = make_images_launch(ctx, f, f.image, use_hcalib != 0);
+  int rc = make_images_launch(ctx, f, device_image, use_hcalib != 0);
   if (rc) return rc;
   f.valid = true;
+  return SDSO_OK;
+}
+
+static int check_batch(sdso_ctx* ctx, int nb, const int* frame_ids) {
+  if (!ctx || nb < 0 || nb > 32 || (nb > 0 && !frame_ids)) return SDSO_E_INVALID;
+  for (int i = 0; i < nb; i++)
+    if (frame_ids[i] < 0 || frame_ids[i] >= (int)ctx->frames.size() || !ctx->frames[frame_ids[i]].in_use) return SDSO_E_INVALID;
+  return SDSO_OK;
+}
+
+// Asynchronous H2D upload of nb source images (float32 or uint8, w*h each, ideally pinned) on the context's copy stream.
+// Returns immediately; sdso_make_images_uploaded makes the compute stream wait for exactly these copies.
+int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* host_images, int src_u8) {
+  int rc = check_batch(ctx, nb, frame_ids);
+  if (rc) return rc;
+  if (nb > 0 && !host_images) return SDSO_E_INVALID;
+  if (!ctx->copy_stream) SDSO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
+  for (int i = 0; i < nb; i++) {
+    Frame& f = ctx->frames[frame_ids[i]];
+    if (!f.uploaded) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+    if (src_u8) {
+      if (!f.src8) SDSO_CUDA(ctx, cudaMalloc(&f.src8, n));
+      SDSO_CUDA(ctx, cudaMemcpyAsync(f.src8, host_images[i], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+      SDSO_CUDA(ctx, cudaMemcpyAsync(f.image, host_images[i], n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    f.pending_u8 = src_u8 ? 1 : 0;
+    f.valid = false;
+  }
+  // one event for the whole batch is enough: copies on one stream complete in order
+  if (nb > 0) SDSO_CUDA(ctx, cudaEventRecord(ctx->frames[frame_ids[nb - 1]].uploaded, ctx->copy_stream));
+  return SDSO_OK;
+}
+
+// makeImages of nb frames whose sources were uploaded with sdso_upload_images_async: ONE pyramid + ONE gradient launch.
+int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const float* ab_exposure, int use_hcalib) {
+  int rc = check_batch(ctx, nb, frame_ids);
+  if (rc) return rc;
+  if (nb == 0) return SDSO_OK;
+  Frame* fr[32]; const void* src[32];
+  const int u8 = ctx->frames[frame_ids[0]].pending_u8;
+  for (int i = 0; i < nb; i++) {
+    Frame& f = ctx->frames[frame_ids[i]];
+    if (f.pending_u8 < 0 || f.pending_u8 != u8) return fail(ctx, SDSO_E_STATE, "make_images_uploaded: frame has no pending upload (or mixed source formats)");
+    fr[i] = &f; src[i] = u8 ? (const void*)f.src8 : (const void*)f.image;
+    f.ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f;
+  }
+  SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[frame_ids[nb - 1]].uploaded, 0));
+  rc = make_images_batch_launch(ctx, nb, fr, src, u8 != 0, use_hcalib != 0);
+  if (rc) return rc;
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
+  return SDSO_OK;
+}
+
+// makeImages of nb frames from images already on the device (float32 or uint8): ONE pyramid + ONE gradient launch.
+int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* device_images, int src_u8,
+                                  const float* ab_exposure, int use_hcalib) {
+  int rc = check_batch(ctx, nb, frame_ids);
+  if (rc) return rc;
+  if (nb == 0) return SDSO_OK;
+  if (!device_images) return SDSO_E_INVALID;
+  Frame* fr[32];
+  for (int i = 0; i < nb; i++) { fr[i] = &ctx->frames[frame_ids[i]]; fr[i]->ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f; }
+  rc = make_images_batch_launch(ctx, nb, fr, device_images, src_u8 != 0, use_hcalib != 0);
+  if (rc) return rc;
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
   return SDSO_OK;
 }
 

@@ -17,6 +17,9 @@ struct Frame {
   float* image = nullptr;               // level-0 intensity plane (the uploaded image)
   float ab_exposure = 1.0f;
   bool valid = false;
+  unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (allocated on first use)
+  cudaEvent_t uploaded = nullptr;       // recorded on the copy stream after the asynchronous upload of this frame's source
+  int pending_u8 = -1;                  // source format of the pending upload: -1 none, 0 float (in `image`), 1 uint8 (in `src8`)
 };
 
 struct HostCalib {  // per level, float, as util/globalCalib.cpp:48-108 computes them
@@ -42,6 +45,7 @@ struct sdso_ctx {
   std::vector<sdso::Frame> frames;
   size_t tex_total = 0;  // float4 texels per frame over all levels
   float* staging = nullptr;  // pinned host staging for image upload
+  cudaStream_t copy_stream = nullptr;  // H2D uploads that overlap the kernels of the previous step (sdso_upload_images_async)
   sdso::TrackerState* tracker = nullptr;
   sdso::BAState* ba = nullptr;
   sdso::TraceState* trace = nullptr;
@@ -94,6 +98,7 @@ void prof_begin(sdso_ctx* ctx, int which);
 void prof_end(sdso_ctx* ctx, int which);
 // make_images.cu
 int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib);
+int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const void* const* srcs, bool src_u8, bool use_hcalib);
 // tracker.cu
 int tracker_create(sdso_ctx* ctx);
 void tracker_destroy(sdso_ctx* ctx);

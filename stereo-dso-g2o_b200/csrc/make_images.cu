@@ -13,20 +13,26 @@
 
 namespace sdso {
 
-struct PyrParams {
+constexpr int kMaxBatch = 32;  // images per launch (blockIdx.z)
+
+struct PyrGeom {  // identical for every frame of a context
   int levels;
   int w[kPyrLevels], h[kPyrLevels];
-  float* I[kPyrLevels];     // intensity planes (I[0] = input image)
-  float4* tex[kPyrLevels];  // output texels
-  int px_offset[kPyrLevels + 1];  // prefix sum of w_l*h_l
+  int px_offset[kPyrLevels + 1];  // prefix sum of w_l*h_l: level l of a frame lives at base + px_offset[l]
   int use_gamma;
+  int src_u8;                     // source images are 8-bit (PhotometricUndistorter::processFrame in mode 1 = plain widening, Undistort.cpp:222-260)
+};
+struct PyrBatch {
+  const void* src[kMaxBatch];     // level-0 source (float or uint8), device memory
+  float* img[kMaxBatch];          // per-frame intensity planes, all levels (level 0 = the float image)
+  float4* tex[kMaxBatch];         // per-frame texels, all levels
 };
 
 __device__ float g_Bgamma[256];  // CalibHessian::B (HessianBlocks.h:352), identity unless sdso_set_gamma
 
 constexpr int kTile = 64;
 
-__global__ void __launch_bounds__(256) pyr_down_kernel(PyrParams P) {
+__global__ void __launch_bounds__(256) pyr_down_kernel(PyrGeom P, PyrBatch B) {
   // level-1 tile 32x32, level-2 16x16, ... in shared memory
   __shared__ float s1[32][33];
   __shared__ float s2[16][17];
@@ -35,11 +41,38 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(PyrParams P) {
   __shared__ float s5[2][3];
   const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;  // level-0 origin of this tile
   const int tid = threadIdx.x;
-  const float* __restrict__ I0 = P.I[0];
-  const int w0 = P.w[0];
+  const int w0 = P.w[0], h0 = P.h[0];
+  float* __restrict__ base = B.img[blockIdx.z];
+  const float* __restrict__ I0 = P.src_u8 ? base : (const float*)B.src[blockIdx.z];
+  if (P.src_u8 || (const float*)B.src[blockIdx.z] != base) {
+    // widen / copy the level-0 tile into the frame's own intensity plane (read again by the gradient kernel and the epipolar search)
+    if (P.src_u8) {
+      const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
+      for (int k = tid; k < kTile * kTile / 4; k += 256) {
+        const int lx = (k & 15) * 4, ly = k >> 4;
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (y < h0 && x < w0) {
+          const size_t o = x + (size_t)y * w0;
+          if (x + 3 < w0 && (o & 3) == 0) {
+            const uchar4 v = *reinterpret_cast<const uchar4*>(S8 + o);
+            *reinterpret_cast<float4*>(base + o) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+          } else {
+            for (int q = 0; q < 4 && x + q < w0; q++) base[o + q] = (float)S8[o + q];
+          }
+        }
+      }
+    } else {
+      const float* __restrict__ SF = (const float*)B.src[blockIdx.z];
+      for (int k = tid; k < kTile * kTile; k += 256) {
+        const int x = tx0 + (k & 63), y = ty0 + (k >> 6);
+        if (y < h0 && x < w0) base[x + (size_t)y * w0] = SF[x + (size_t)y * w0];
+      }
+    }
+    __syncthreads();  // level 1 below reads this CTA's own tile only
+  }
   if (P.levels > 1) {
     const int w1 = P.w[1], h1 = P.h[1];
-    float* __restrict__ O = P.I[1];
+    float* __restrict__ O = base + P.px_offset[1];
     for (int k = tid; k < 32 * 32; k += 256) {
       int lx = k & 31, ly = k >> 5;
       int x = (tx0 >> 1) + lx, y = (ty0 >> 1) + ly;
@@ -57,12 +90,13 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(PyrParams P) {
 #define SDSO_DOWN(LVL, SRC, DST, N)                                                          \
   if (P.levels > LVL) {                                                                      \
     const int wl = P.w[LVL], hl = P.h[LVL];                                                  \
+    float* __restrict__ Ol = base + P.px_offset[LVL];                                        \
     for (int k = tid; k < N * N; k += 256) {                                                 \
       int lx = k % N, ly = k / N;                                                            \
       int x = (tx0 >> LVL) + lx, y = (ty0 >> LVL) + ly;                                      \
       float v = 0.25f * (((SRC[2 * ly][2 * lx] + SRC[2 * ly][2 * lx + 1]) + SRC[2 * ly + 1][2 * lx]) + SRC[2 * ly + 1][2 * lx + 1]); \
       DST[ly][lx] = v;                                                                       \
-      if (x < wl && y < hl) P.I[LVL][x + (size_t)y * wl] = v;                                \
+      if (x < wl && y < hl) Ol[x + (size_t)y * wl] = v;                                      \
     }                                                                                        \
   }                                                                                          \
   __syncthreads();
@@ -73,15 +107,17 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(PyrParams P) {
 #undef SDSO_DOWN
 }
 
-__global__ void __launch_bounds__(256) gradient_kernel(PyrParams P) {
+__global__ void __launch_bounds__(256) gradient_kernel(PyrGeom P, PyrBatch B) {
   const int total = P.px_offset[P.levels];
+  const float* __restrict__ Ibase = B.img[blockIdx.z];
+  float4* __restrict__ Tbase = B.tex[blockIdx.z];
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
     int lvl = 0;
 #pragma unroll
     for (int l = 1; l < kPyrLevels; l++) if (l < P.levels && g >= P.px_offset[l]) lvl = l;
     const int idx = g - P.px_offset[lvl];
     const int wl = P.w[lvl], hl = P.h[lvl];
-    const float* __restrict__ I = P.I[lvl];
+    const float* __restrict__ I = Ibase + P.px_offset[lvl];
     const float c = I[idx];
     float dx = 0.f, dy = 0.f, ag = 0.f;
     if (idx >= wl && idx < wl * (hl - 1)) {
@@ -99,45 +135,51 @@ __global__ void __launch_bounds__(256) gradient_kernel(PyrParams P) {
         ag *= gw * gw;
       }
     }
-    P.tex[lvl][idx] = make_float4(c, dx, dy, ag);
+    Tbase[g] = make_float4(c, dx, dy, ag);
   }
 }
 
-int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib) {
-  PyrParams P;
+// nb frames, one launch pair. srcs[i]: device pointer to the level-0 source of frames[i] (float, or uint8 when src_u8).
+int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const void* const* srcs, bool src_u8, bool use_hcalib) {
+  if (nb <= 0) return SDSO_OK;
+  if (nb > kMaxBatch) return fail(ctx, SDSO_E_INVALID, "make_images batch larger than 32");
+  PyrGeom P;
   P.levels = ctx->G.levels;
   int off = 0;
-  for (int l = 0; l < P.levels; l++) {
-    P.w[l] = ctx->G.w[l]; P.h[l] = ctx->G.h[l];
-    P.tex[l] = f.tex[l];
+  for (int l = 0; l < kPyrLevels; l++) {
+    P.w[l] = l < P.levels ? ctx->G.w[l] : 0; P.h[l] = l < P.levels ? ctx->G.h[l] : 0;
     P.px_offset[l] = off;
     off += P.w[l] * P.h[l];
   }
-  P.px_offset[P.levels] = off;
-  for (int l = P.levels; l < kPyrLevels; l++) { P.w[l] = P.h[l] = 0; P.tex[l] = nullptr; P.I[l] = nullptr; P.px_offset[l + 1] = off; }
-  P.I[0] = const_cast<float*>(dev_image);
-  // coarser intensity planes live behind the level-0 plane in the frame's image buffer
-  {
-    float* p = f.image + (size_t)P.w[0] * P.h[0];
-    for (int l = 1; l < P.levels; l++) { P.I[l] = p; p += (size_t)P.w[l] * P.h[l]; }
-  }
+  P.px_offset[kPyrLevels] = off;
+  for (int l = P.levels; l <= kPyrLevels; l++) P.px_offset[l] = off;
   P.use_gamma = (use_hcalib && ctx->S.gammaWeightsPixelSelect == 1) ? 1 : 0;
+  P.src_u8 = src_u8 ? 1 : 0;
+  PyrBatch B;
+  for (int i = 0; i < kMaxBatch; i++) { B.src[i] = nullptr; B.img[i] = nullptr; B.tex[i] = nullptr; }
+  for (int i = 0; i < nb; i++) { B.src[i] = srcs[i]; B.img[i] = frames[i]->image; B.tex[i] = frames[i]->tex[0]; }
   prof_begin(ctx, 1);
-  if (P.levels > 1) {
-    dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile);
-    pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+  {
+    dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile, nb);
+    pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(P, B);
     SDSO_CHECK_LAUNCH(ctx);
   }
   {
-    int total = off;
-    int blocks = (total + 255) / 256;
-    int cap = ctx->num_sms * 8;
+    int blocks = (off + 255) / 256;
+    int cap = (ctx->num_sms * 8 + nb - 1) / nb;
+    if (cap < 64) cap = 64;
     if (blocks > cap) blocks = cap;
-    gradient_kernel<<<blocks, 256, 0, ctx->stream>>>(P);
+    gradient_kernel<<<dim3(blocks, 1, nb), 256, 0, ctx->stream>>>(P, B);
     SDSO_CHECK_LAUNCH(ctx);
   }
   prof_end(ctx, 1);
   return SDSO_OK;
+}
+
+int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib) {
+  Frame* fp = &f;
+  const void* src = dev_image;
+  return make_images_batch_launch(ctx, 1, &fp, &src, false, use_hcalib);
 }
 
 int set_gamma_table(sdso_ctx* ctx, const float B[256]) {

@@ -42,7 +42,10 @@ struct TrackProblem {  // one per cluster, in global memory
   double minResForAbort[5];
   const float4* tex[kPyrLevels];  // new frame pyramid
   float exposure_new;
-  int pad0;
+  float ref_exposure;             // per-problem reference keyframe: independent sequences of one launch track against their own templates
+  const float4* pc[kPyrLevels];   // {u, v, idepth, color} per level of that reference (CoarseTracker.h:117-121 fused)
+  int pc_n[kPyrLevels];
+  double ref_aff[2];              // lastRef_aff_g2l
   // outputs
   double T_out[12];
   double aff_out[2];
@@ -400,13 +403,12 @@ __device__ __forceinline__ void warp_solve8(double (&row)[9], int lane, double (
 template <int U>
 __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex,
                                 const EvalConst& ec, float (&acc)[kAccPad], unsigned& evals, int gtid, int gthreads,
-                                float* dump) {
+                                float* dump, const float4* __restrict__ pc, const int n) {
 #pragma unroll
   for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
   const float fxl = L.fx, fyl = L.fy, cxl = L.cx, cyl = L.cy;
-  const int wl = L.w, hl = L.h, n = L.n;
+  const int wl = L.w, hl = L.h;
   const float huberTH = P.huberTH;
-  const float4* __restrict__ pc = L.pc;
   float RKi[9], tt[3];
 #pragma unroll
   for (int k = 0; k < 9; k++) RKi[k] = ec.RKi[k];
@@ -539,10 +541,10 @@ __device__ void make_eval_const_sse(const TrackParams& P, const TrackLevel& L, c
 #pragma unroll
   for (int i = 0; i < 3; i++) ec.t[i] = (float)t[i];
   double ab[2];
-  d_aff_from_to(P.ref_exposure, prob.exposure_new, P.ref_aff[0], P.ref_aff[1], aff[0], aff[1], ab);
+  d_aff_from_to(prob.ref_exposure, prob.exposure_new, prob.ref_aff[0], prob.ref_aff[1], aff[0], aff[1], ab);
   ec.affLL[0] = (float)ab[0]; ec.affLL[1] = (float)ab[1];
   ec.a = (float)ab[0];
-  ec.b0 = (float)P.ref_aff[1];
+  ec.b0 = (float)prob.ref_aff[1];
   ec.cutoff = cutoff;
   ec.maxEnergy = 2 * P.huberTH * cutoff - P.huberTH * P.huberTH;
 }
@@ -756,14 +758,14 @@ __device__ __forceinline__ void eval_prologue(const TrackParams& P, const TrackL
     if (lane == 0) {
       // AffLight::fromToVecExposure (util/NumType.h:159-170)
       const double a0 = trial ? lm.affn[0] : lm.aff[0], b0 = trial ? lm.affn[1] : lm.aff[1];
-      float eF = P.ref_exposure, eT = prob.exposure_new;
+      float eF = prob.ref_exposure, eT = prob.exposure_new;
       if (eF == 0 || eT == 0) { eT = eF = 1; }
-      double a = d_exp_small(a0 - P.ref_aff[0]) * eT;
+      double a = d_exp_small(a0 - prob.ref_aff[0]) * eT;
       if (eF != 1.0f) a = a / eF;
-      const double b = b0 - a * P.ref_aff[1];
+      const double b = b0 - a * prob.ref_aff[1];
       ec.affLL[0] = (float)a; ec.affLL[1] = (float)b;
       ec.a = (float)a;
-      ec.b0 = (float)P.ref_aff[1];
+      ec.b0 = (float)prob.ref_aff[1];
       ec.cutoff = cutoff;
       ec.maxEnergy = 2 * P.huberTH * cutoff - P.huberTH * P.huberTH;
     }
@@ -832,7 +834,7 @@ __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
     __syncthreads();
     tm.tick(0);
     // ---- the evaluation + the exchange: the only instance of this code in the kernel ----
-    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr);
+    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl]);
     tm.tick(1);
     const int pb = reduce_exchange<false>(acc, sm, ex, C, rank, 0.0, &tm);
     const float sumE = gather_sumf(sm, pb, C, A_E), sumNE = gather_sumf(sm, pb, C, A_NE);
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
     }
     if (ok) {
       double rel[2];
-      d_aff_from_to(P.ref_exposure, prob.exposure_new, P.ref_aff[0], P.ref_aff[1], aout[0], aout[1], rel);
+      d_aff_from_to(prob.ref_exposure, prob.exposure_new, prob.ref_aff[0], prob.ref_aff[1], aout[0], aout[1], rel);
       const float r0 = (float)rel[0], r1 = (float)rel[1];
       if ((P.affineOptModeA == 0 && (fabsf(logf(r0)) > 1.5)) || (P.affineOptModeB == 0 && (fabsf(r1) > 200))) ok = false;
     }
@@ -974,6 +976,8 @@ void tracker_destroy(sdso_ctx* ctx) {
   if (t->d_problems) cudaFree(t->d_problems);
   if (t->h_problems) cudaFreeHost(t->h_problems);
   if (t->d_dump) cudaFree(t->d_dump);
+  for (size_t k = 0; k < t->saved.size(); k++)
+    if ((int)k != t->cur_slot) for (int l = 0; l < kPyrLevels; l++) if (t->saved[k].pc[l]) cudaFree(t->saved[k].pc[l]);
   for (int l = 0; l < kPyrLevels; l++) { if (t->edge_flag[l]) cudaFree(t->edge_flag[l]); if (t->edge_err[l]) cudaFree(t->edge_err[l]); }
   delete t;
   ctx->tracker = nullptr;
@@ -998,6 +1002,26 @@ static void fill_params(sdso_ctx* ctx, TrackParams& P) {
   P.g2o_stop_persists = ctx->S.g2o_stop_flag_persists;
   P.timing = ctx->profile ? 1 : 0;
   P.problems = t->d_problems;
+}
+
+// reference slot `slot` as a RefSlot view (the current slot lives in the TrackerState members)
+static RefSlot slot_view(const TrackerState* t, int slot) {
+  if (slot == t->cur_slot || slot < 0) {
+    RefSlot r;
+    for (int l = 0; l < kPyrLevels; l++) { r.pc[l] = t->pc[l]; r.pc_n[l] = t->pc_n[l]; r.pc_cap[l] = t->pc_cap[l]; }
+    r.ref_frame = t->ref_frame; r.ref_aff[0] = t->ref_aff[0]; r.ref_aff[1] = t->ref_aff[1]; r.have_ref = t->have_ref;
+    return r;
+  }
+  if (slot >= (int)t->saved.size()) return RefSlot();
+  return t->saved[slot];
+}
+static int fill_problem_ref(sdso_ctx* ctx, TrackProblem& hp, int slot) {
+  const RefSlot r = slot_view(ctx->tracker, slot);
+  if (!r.have_ref) return fail(ctx, SDSO_E_STATE, "trackNewestCoarse before setCoarseTrackingRef (reference slot is empty)");
+  for (int l = 0; l < ctx->G.levels; l++) { hp.pc[l] = r.pc[l]; hp.pc_n[l] = r.pc_n[l]; }
+  hp.ref_exposure = ctx->frames[r.ref_frame].ab_exposure;
+  hp.ref_aff[0] = r.ref_aff[0]; hp.ref_aff[1] = r.ref_aff[1];
+  return SDSO_OK;
 }
 
 static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
@@ -1133,6 +1157,8 @@ int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNe
   hp.aff[0] = aff[0]; hp.aff[1] = aff[1];
   for (int l = 0; l < ctx->G.levels; l++) hp.tex[l] = ctx->frames[new_frame].tex[l];
   hp.exposure_new = ctx->frames[new_frame].ab_exposure;
+  rc = fill_problem_ref(ctx, hp, -1);
+  if (rc) return rc;
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_track(ctx, P, 1, false);
   if (rc) return rc;
@@ -1191,6 +1217,7 @@ int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[
   hp.aff_out[0] = photo[0]; hp.aff_out[1] = photo[1];
   for (int l = 0; l < ctx->G.levels; l++) hp.tex[l] = ctx->frames[new_frame].tex[l];
   hp.exposure_new = ctx->frames[new_frame].ab_exposure;
+  { int rcr = fill_problem_ref(ctx, hp, -1); if (rcr) return rcr; }
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_track(ctx, P, 1, true);
   if (rc) return rc;
@@ -1211,9 +1238,35 @@ int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[
 
 int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const double* T_in, const double* aff_in, int coarsest_lvl,
                        const double* minResForAbort, int variant) {
+  return sdso_track_enqueue_multi(ctx, nb, nullptr, new_frames, T_in, aff_in, coarsest_lvl, minResForAbort, variant);
+}
+
+int sdso_tracker_select_ref(sdso_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= 64) return SDSO_E_INVALID;
+  TrackerState* t = ctx->tracker;
+  if (slot == t->cur_slot) return SDSO_OK;
+  const size_t need = (size_t)(slot > t->cur_slot ? slot : t->cur_slot) + 1;
+  if (t->saved.size() < need) t->saved.resize(need);
+  t->saved[t->cur_slot] = slot_view(t, t->cur_slot);  // park the current template
+  RefSlot& r = t->saved[slot];
+  for (int l = 0; l < ctx->G.levels; l++) {
+    if (!r.pc[l]) {
+      const size_t n = (size_t)ctx->G.w[l] * ctx->G.h[l];
+      SDSO_CUDA(ctx, cudaMalloc(&r.pc[l], n * sizeof(float4)));
+      r.pc_cap[l] = (int)n;
+    }
+  }
+  for (int l = 0; l < kPyrLevels; l++) { t->pc[l] = r.pc[l]; t->pc_n[l] = r.pc_n[l]; t->pc_cap[l] = r.pc_cap[l]; }
+  t->ref_frame = r.ref_frame; t->ref_aff[0] = r.ref_aff[0]; t->ref_aff[1] = r.ref_aff[1]; t->have_ref = r.have_ref;
+  t->cur_slot = slot;
+  return SDSO_OK;
+}
+
+int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const int* new_frames, const double* T_in, const double* aff_in,
+                             int coarsest_lvl, const double* minResForAbort, int variant) {
   if (!ctx || nb <= 0 || !new_frames || !T_in || !aff_in || !minResForAbort) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
-  if (!t->have_ref) return fail(ctx, SDSO_E_STATE, "trackNewestCoarse before setCoarseTrackingRef");
+  if (!ref_slots && !t->have_ref) return fail(ctx, SDSO_E_STATE, "trackNewestCoarse before setCoarseTrackingRef");
   if (nb > t->max_problems) return fail(ctx, SDSO_E_INVALID, "too many problems in one batch");
   if (coarsest_lvl < 0 || coarsest_lvl >= ctx->G.levels || coarsest_lvl >= 5) return fail(ctx, SDSO_E_INVALID, "coarsest_lvl out of range");
   if (variant != SDSO_VARIANT_SSE && variant != SDSO_VARIANT_G2O) return SDSO_E_INVALID;
@@ -1231,6 +1284,8 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
     for (int i = 0; i < 5; i++) hp.minResForAbort[i] = minResForAbort[5 * k + i];
     for (int l = 0; l < ctx->G.levels; l++) hp.tex[l] = ctx->frames[new_frames[k]].tex[l];
     hp.exposure_new = ctx->frames[new_frames[k]].ab_exposure;
+    rc = fill_problem_ref(ctx, hp, ref_slots ? ref_slots[k] : -1);
+    if (rc) return rc;
   }
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, t->h_problems, nb * sizeof(TrackProblem), cudaMemcpyHostToDevice, ctx->stream));
   prof_begin(ctx, 0);

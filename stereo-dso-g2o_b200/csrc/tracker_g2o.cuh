@@ -34,14 +34,13 @@ __device__ __forceinline__ void d_huber(double e2, double delta, double& rho0, d
 template <int MODE>
 __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex, const G2OConst& gc,
                                 unsigned char* __restrict__ flag, double* __restrict__ eerr, float (&acc)[kAccPad], double& chi,
-                                unsigned& evals, int gtid, int gthreads, double* dump) {
+                                unsigned& evals, int gtid, int gthreads, double* dump, const float4* __restrict__ pc, const int npc) {
 #pragma unroll
   for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
   chi = 0.0;
   const int wl = L.w, hl = L.h;
   const double delta = P.huberTH;
-  const float4* __restrict__ pc = L.pc;
-  for (int i = gtid; i < L.n; i += gthreads) {
+  for (int i = gtid; i < npc; i += gthreads) {
     const float4 p = __ldg(pc + i);
     const float x = p.x, y = p.y, id = p.z;
     if (MODE == 0) {
@@ -151,7 +150,7 @@ __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int l
         }
       }
       if (dump) {
-        const int n = L.n;
+        const int n = npc;
         dump[i] = 1.0;
         dump[(size_t)n + i] = err;
 #pragma unroll
@@ -171,9 +170,9 @@ __device__ void make_g2o_const(const TrackParams& P, const TrackLevel& L, const 
   for (int i = 0; i < 9; i++) gc.R[i] = R[i];
   for (int i = 0; i < 3; i++) gc.tt[i] = t[i];
   double ab[2];
-  d_aff_from_to(P.ref_exposure, prob.exposure_new, P.ref_aff[0], P.ref_aff[1], photo[0], photo[1], ab);
+  d_aff_from_to(prob.ref_exposure, prob.exposure_new, prob.ref_aff[0], prob.ref_aff[1], photo[0], photo[1], ab);
   gc.ab[0] = (float)ab[0]; gc.ab[1] = (float)ab[1];
-  gc.b0 = P.ref_aff[1];
+  gc.b0 = prob.ref_aff[1];
   gc.cutoff10 = cutoffTH * 10;
 }
 
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
       make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, Rp, tp, prob.aff_out, P.eval_cutoff, gc);
     }
     __syncthreads();
-    eval_points_g2o<0>(P, L, lvl, prob.tex[lvl], gc, flag, eerr, acc, chi, evals, gtid, gthreads, P.dump_d);
+    eval_points_g2o<0>(P, L, lvl, prob.tex[lvl], gc, flag, eerr, acc, chi, evals, gtid, gthreads, P.dump_d, prob.pc[lvl], prob.pc_n[lvl]);
     reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
     if (rank == 0 && tid == 0) prob.warped_n = (int)tot[G_NE];
     cluster.sync();
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
     // ---- calcRes: build this level's edges (:894)
     if (tid == 0) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
     __syncthreads();
-    eval_points_g2o<0>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr);
+    eval_points_g2o<0>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
     reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
     const int nEdges = (int)tot[G_NE];
     {
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
         __syncthreads();
         if (tid == 0) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
         __syncthreads();
-        eval_points_g2o<2>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr);
+        eval_points_g2o<2>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
         reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
         if (tid == 0) {
           int idx = 0;
@@ -320,7 +319,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
             make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
           }
           __syncthreads();
-          eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr);
+          eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
           reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
           if (tid == 0) {
             double tempChi = chiTot;
@@ -350,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
           __syncthreads();
         } while (gs.again);
         // postIteration(it): SparseOptimizerTerminateAction -> computeActiveErrors, gain test (1e-3, :845-848)
-        eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr);
+        eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
         reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
         if (tid == 0) {
           gs.levelChi = chiTot;
@@ -379,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
     }
     if (ok) {
       double rel[2];
-      d_aff_from_to(P.ref_exposure, prob.exposure_new, P.ref_aff[0], P.ref_aff[1], aout[0], aout[1], rel);
+      d_aff_from_to(prob.ref_exposure, prob.exposure_new, prob.ref_aff[0], prob.ref_aff[1], aout[0], aout[1], rel);
       const float r0 = (float)rel[0], r1 = (float)rel[1];
       if ((P.affineOptModeA == 0 && (fabsf(logf(r0)) > 1.5)) || (P.affineOptModeB == 0 && (fabsf(r1) > 200))) ok = false;
     }

@@ -6,6 +6,16 @@ namespace sdso {
 
 struct TrackProblem;
 
+// One reference keyframe's tracking template (the members of the same names below hold the CURRENT slot)
+struct RefSlot {
+  float4* pc[kPyrLevels] = {nullptr};
+  int pc_n[kPyrLevels] = {0};
+  int pc_cap[kPyrLevels] = {0};
+  int ref_frame = -1;
+  double ref_aff[2] = {0, 0};
+  bool have_ref = false;
+};
+
 struct TrackerState {
   HostCalib K;  // tracker's own pyramid of intrinsics (makeK from the optimised HCalib)
   float4* pc[kPyrLevels] = {nullptr};
@@ -16,7 +26,9 @@ struct TrackerState {
   bool have_ref = false;
   TrackProblem* d_problems = nullptr;
   TrackProblem* h_problems = nullptr;  // pinned
-  int max_problems = 16;
+  int max_problems = 32;
+  std::vector<RefSlot> saved;  // parked reference slots (independent sequences tracked by one launch); saved[cur_slot] is stale
+  int cur_slot = 0;
   float* d_dump = nullptr;
   size_t dump_cap = 0;
   int last_nb = 0;

@@ -1,0 +1,69 @@
+"""Batched forms of the hot path: one launch for many frames / many independent sequences must give exactly what the
+single-frame calls give (the kernels are deterministic, so equality is bitwise)."""
+import numpy as np
+import pytest
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batched_make_images_u8_and_float_equal_single(pkg, frames):
+    import torch
+    ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE)
+    imgs = [frames[0][0], frames[1][0], frames[2][0], frames["r0"][0]]
+    single = []
+    for im in imgs:
+        f = ctx.frame_create(); ctx.make_images(f, im); single.append(f)
+    # float sources resident on the device
+    dev = [torch.from_numpy(im).cuda().contiguous() for im in imgs]
+    fb = [ctx.frame_create() for _ in imgs]
+    ctx.make_images_batch_device(fb, [d.data_ptr() for d in dev], u8=False)
+    # uint8 sources uploaded asynchronously from pinned host memory (the synthetic images are quantised: exact in 8 bits)
+    host8 = [torch.from_numpy(im.astype(np.uint8)).contiguous().pin_memory() for im in imgs]
+    fu = [ctx.frame_create() for _ in imgs]
+    ctx.upload_images_async(fu, [h.data_ptr() for h in host8], u8=True)
+    ctx.make_images_uploaded(fu)
+    ctx.synchronize()
+    for k in range(len(imgs)):
+        for lvl in range(ctx.levels):
+            a, ag = ctx.frame_download(single[k], lvl)
+            b, bg = ctx.frame_download(fb[k], lvl)
+            c, cg = ctx.frame_download(fu[k], lvl)
+            assert np.array_equal(a, b) and np.array_equal(ag, bg), (k, lvl, "float batch")
+            assert np.array_equal(a, c) and np.array_equal(ag, cg), (k, lvl, "u8 batch")
+    # the epipolar search reads the frame's planar level-0 image: must be valid after a u8 build
+    uv = np.array([[100.0, 100.0], [640.5, 200.25]], np.float32)
+    p1, _ = ctx.immature_init(single[0], uv); p2, _ = ctx.immature_init(fu[0], uv)
+    assert np.array_equal(p1["color"], p2["color"])
+    ctx.close()
+
+
+def test_multi_reference_batch_equals_separate_tracking(pkg, scene, frames):
+    """Three independent 'sequences' (own reference keyframe, own template, own new frame) tracked by ONE launch."""
+    ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE)
+    fid = {k: ctx.frame_create() for k in (0, 1, 2)}
+    for k in (0, 1, 2):
+        ctx.make_images(fid[k], frames[k][0])
+    rng = np.random.default_rng(1)
+    seqs = [(0, 1), (1, 2), (0, 2)]  # (reference, new)
+    singles, T0s = [], []
+    for s, (r, nw) in enumerate(seqs):
+        ctx.tracker_select_ref(s)
+        ctx.tracker_set_ref(fid[r], synth.pick_points(rng, frames[r][1], 1500 + 100 * s), (0.0, 0.0))
+        Ttrue = synth.T_rel(synth.camera_pose(r), synth.camera_pose(nw))
+        T0 = synth.perturb_T(Ttrue, rng, 0.03, np.deg2rad(0.3))
+        T0s.append(T0)
+        singles.append(ctx.track(fid[nw], T0, (0.0, 0.0), ctx.levels - 1, [np.nan] * 5, 0))
+        assert np.abs(singles[-1]["T"][:, 3] - Ttrue[:, 3]).max() < 1e-2
+    ctx.track_enqueue_multi([0, 1, 2], [fid[nw] for _, nw in seqs], np.stack(T0s), np.zeros((3, 2)), ctx.levels - 1, np.full((3, 5), np.nan), 0)
+    b = ctx.track_collect(3)
+    for s in range(3):
+        assert np.array_equal(b["T"][s], singles[s]["T"]), s
+        assert np.array_equal(b["lastResiduals"][s], singles[s]["lastResiduals"])
+        assert b["ok"][s] == singles[s]["ok"]
+    # slots are independent: re-reading slot 0's template after touching the others
+    ctx.tracker_select_ref(0)
+    n0 = ctx.tracker_get_pc(0)[0].size
+    ctx.tracker_select_ref(2)
+    assert ctx.tracker_get_pc(0)[0].size != n0
+    ctx.close()
