@@ -120,7 +120,7 @@ int sdso_frame_release(sdso_ctx* ctx, int frame_id);
 int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float ab_exposure, int use_hcalib);
 /* same, image already on the device (device pointer, w*h floats) */
 int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_image, float ab_exposure, int use_hcalib);
-/* Batched forms (nb <= 32 frames, ONE pyramid launch + ONE gradient launch for all of them). src_u8 != 0: the sources are
+/* Batched forms (one pyramid launch + one gradient launch per 32 frames). src_u8 != 0: the sources are
  * 8-bit grey images; the widening to float — PhotometricUndistorter::processFrame in mode=1 (util/Undistort.cpp:222-260,
  * no response / vignette calibration) — is fused into the pyramid kernel, which cuts the H2D bytes by 4.
  *   sdso_upload_images_async : H2D of the sources on the context's copy stream (returns at once; overlaps running kernels)

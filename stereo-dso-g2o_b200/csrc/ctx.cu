@@ -257,7 +257,7 @@ int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_ima
 }
 
 static int check_batch(sdso_ctx* ctx, int nb, const int* frame_ids) {
-  if (!ctx || nb < 0 || nb > 32 || (nb > 0 && !frame_ids)) return SDSO_E_INVALID;
+  if (!ctx || nb < 0 || nb > 4096 || (nb > 0 && !frame_ids)) return SDSO_E_INVALID;
   for (int i = 0; i < nb; i++)
     if (frame_ids[i] < 0 || frame_ids[i] >= (int)ctx->frames.size() || !ctx->frames[frame_ids[i]].in_use) return SDSO_E_INVALID;
   return SDSO_OK;
@@ -293,7 +293,7 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
   int rc = check_batch(ctx, nb, frame_ids);
   if (rc) return rc;
   if (nb == 0) return SDSO_OK;
-  Frame* fr[32]; const void* src[32];
+  std::vector<Frame*> fr(nb); std::vector<const void*> src(nb);
   const int u8 = ctx->frames[frame_ids[0]].pending_u8;
   for (int i = 0; i < nb; i++) {
     Frame& f = ctx->frames[frame_ids[i]];
@@ -302,8 +302,10 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
     f.ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f;
   }
   SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[frame_ids[nb - 1]].uploaded, 0));
-  rc = make_images_batch_launch(ctx, nb, fr, src, u8 != 0, use_hcalib != 0);
-  if (rc) return rc;
+  for (int o = 0; o < nb; o += 32) {  // 32 frames per launch pair (kernel-parameter space)
+    rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
+    if (rc) return rc;
+  }
   for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
   return SDSO_OK;
 }
@@ -315,10 +317,12 @@ int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, c
   if (rc) return rc;
   if (nb == 0) return SDSO_OK;
   if (!device_images) return SDSO_E_INVALID;
-  Frame* fr[32];
+  std::vector<Frame*> fr(nb);
   for (int i = 0; i < nb; i++) { fr[i] = &ctx->frames[frame_ids[i]]; fr[i]->ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f; }
-  rc = make_images_batch_launch(ctx, nb, fr, device_images, src_u8 != 0, use_hcalib != 0);
-  if (rc) return rc;
+  for (int o = 0; o < nb; o += 32) {
+    rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, device_images + o, src_u8 != 0, use_hcalib != 0);
+    if (rc) return rc;
+  }
   for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
   return SDSO_OK;
 }

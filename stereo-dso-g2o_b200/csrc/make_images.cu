@@ -1,14 +1,12 @@
 // A1 — FrameHessian::makeImages (FullSystem/HessianBlocks.cpp:141-203) on the device.
 //
-// Two launches per image, both pure streaming (HBM-bound):
-//   pyr_down_kernel  : one CTA per 64x64 level-0 tile; the tile is reduced through ALL coarser levels
-//                      in shared memory (2x2 box mean, summed in the reference's order
-//                      0.25f*(((a+b)+c)+d), :172-178), so level l>0 never re-reads level l-1 from DRAM.
-//   gradient_kernel  : one thread per pixel of EVERY level (flattened index space); central
-//                      differences on the flat index with the reference's row wrap (:182-184),
-//                      non-finite -> 0, absSquaredGrad (+ gamma factor, :196-200), one coalesced
-//                      16-byte store {I,dx,dy,absSquaredGrad} per pixel.
-// Algorithmic bytes per image: read 4*W*H + write 16*sum_l(w_l*h_l)  (SURVEY.md §8d).
+// One streaming (HBM-bound) pass per batch of up to 32 images:
+//   pyr_fused_kernel : one CTA per 64x64 level-0 tile (+ halo): source (float or 8-bit) -> shared memory -> all pyramid
+//                      levels of the tile in shared memory (2x2 box mean in the reference's order 0.25f*(((a+b)+c)+d),
+//                      :172-178) -> central differences, non-finite -> 0, absSquaredGrad (+ gamma factor, :196-200) ->
+//                      one coalesced 16-byte store {I,dx,dy,absSquaredGrad} per pixel of every level + the intensity planes.
+//   pyr_wrap_kernel  : the two image columns whose flat-index difference wraps to the neighbouring row (:182-184).
+// Algorithmic bytes per image: read W*H (8-bit) or 4*W*H + write 16*sum_l(w_l*h_l) texels + 4*sum_l planes.
 #include "ctx.h"
 
 namespace sdso {
@@ -32,110 +30,133 @@ __device__ float g_Bgamma[256];  // CalibHessian::B (HessianBlocks.h:352), ident
 
 constexpr int kTile = 64;
 
-__global__ void __launch_bounds__(256) pyr_down_kernel(PyrGeom P, PyrBatch B) {
-  // level-1 tile 32x32, level-2 16x16, ... in shared memory
-  __shared__ float s1[32][33];
-  __shared__ float s2[16][17];
-  __shared__ float s3[8][9];
-  __shared__ float s4[4][5];
-  __shared__ float s5[2][3];
-  const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;  // level-0 origin of this tile
-  const int tid = threadIdx.x;
-  const int w0 = P.w[0], h0 = P.h[0];
-  float* __restrict__ base = B.img[blockIdx.z];
-  const float* __restrict__ I0 = P.src_u8 ? base : (const float*)B.src[blockIdx.z];
-  if (P.src_u8 || (const float*)B.src[blockIdx.z] != base) {
-    // widen / copy the level-0 tile into the frame's own intensity plane (read again by the gradient kernel and the epipolar search)
-    if (P.src_u8) {
-      const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
-      for (int k = tid; k < kTile * kTile / 4; k += 256) {
-        const int lx = (k & 15) * 4, ly = k >> 4;
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (y < h0 && x < w0) {
-          const size_t o = x + (size_t)y * w0;
-          if (x + 3 < w0 && (o & 3) == 0) {
-            const uchar4 v = *reinterpret_cast<const uchar4*>(S8 + o);
-            *reinterpret_cast<float4*>(base + o) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
-          } else {
-            for (int q = 0; q < 4 && x + q < w0; q++) base[o + q] = (float)S8[o + q];
-          }
-        }
-      }
-    } else {
-      const float* __restrict__ SF = (const float*)B.src[blockIdx.z];
-      for (int k = tid; k < kTile * kTile; k += 256) {
-        const int x = tx0 + (k & 63), y = ty0 + (k >> 6);
-        if (y < h0 && x < w0) base[x + (size_t)y * w0] = SF[x + (size_t)y * w0];
-      }
-    }
-    __syncthreads();  // level 1 below reads this CTA's own tile only
+// getBGradOnly factor + absSquaredGrad (HessianBlocks.cpp:190-200)
+__device__ __forceinline__ float4 make_texel(float c, float dx, float dy, int use_gamma) {
+  if (!isfinite(dx)) dx = 0.f;
+  if (!isfinite(dy)) dy = 0.f;
+  float ag = dx * dx + dy * dy;
+  if (use_gamma) {
+    int ci = (int)(c + 0.5f);  // CalibHessian::getBGradOnly (HessianBlocks.h:356-362)
+    if (ci < 5) ci = 5;
+    if (ci > 250) ci = 250;
+    const float gw = g_Bgamma[ci + 1] - g_Bgamma[ci];
+    ag *= gw * gw;
   }
-  if (P.levels > 1) {
-    const int w1 = P.w[1], h1 = P.h[1];
-    float* __restrict__ O = base + P.px_offset[1];
-    for (int k = tid; k < 32 * 32; k += 256) {
-      int lx = k & 31, ly = k >> 5;
-      int x = (tx0 >> 1) + lx, y = (ty0 >> 1) + ly;
-      float v = 0.f;
-      if (x < w1 && y < h1) {
-        const float2 top = *reinterpret_cast<const float2*>(I0 + 2 * x + (size_t)(2 * y) * w0);
-        const float2 bot = *reinterpret_cast<const float2*>(I0 + 2 * x + (size_t)(2 * y + 1) * w0);
-        v = 0.25f * (((top.x + top.y) + bot.x) + bot.y);
-        O[x + (size_t)y * w1] = v;
-      }
-      s1[ly][lx] = v;
-    }
-  }
-  __syncthreads();
-#define SDSO_DOWN(LVL, SRC, DST, N)                                                          \
-  if (P.levels > LVL) {                                                                      \
-    const int wl = P.w[LVL], hl = P.h[LVL];                                                  \
-    float* __restrict__ Ol = base + P.px_offset[LVL];                                        \
-    for (int k = tid; k < N * N; k += 256) {                                                 \
-      int lx = k % N, ly = k / N;                                                            \
-      int x = (tx0 >> LVL) + lx, y = (ty0 >> LVL) + ly;                                      \
-      float v = 0.25f * (((SRC[2 * ly][2 * lx] + SRC[2 * ly][2 * lx + 1]) + SRC[2 * ly + 1][2 * lx]) + SRC[2 * ly + 1][2 * lx + 1]); \
-      DST[ly][lx] = v;                                                                       \
-      if (x < wl && y < hl) Ol[x + (size_t)y * wl] = v;                                      \
-    }                                                                                        \
-  }                                                                                          \
-  __syncthreads();
-  SDSO_DOWN(2, s1, s2, 16)
-  SDSO_DOWN(3, s2, s3, 8)
-  SDSO_DOWN(4, s3, s4, 4)
-  SDSO_DOWN(5, s4, s5, 2)
-#undef SDSO_DOWN
+  return make_float4(c, dx, dy, ag);
 }
 
-__global__ void __launch_bounds__(256) gradient_kernel(PyrGeom P, PyrBatch B) {
-  const int total = P.px_offset[P.levels];
-  const float* __restrict__ Ibase = B.img[blockIdx.z];
-  float4* __restrict__ Tbase = B.tex[blockIdx.z];
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    int lvl = 0;
-#pragma unroll
-    for (int l = 1; l < kPyrLevels; l++) if (l < P.levels && g >= P.px_offset[l]) lvl = l;
-    const int idx = g - P.px_offset[lvl];
-    const int wl = P.w[lvl], hl = P.h[lvl];
-    const float* __restrict__ I = Ibase + P.px_offset[lvl];
-    const float c = I[idx];
-    float dx = 0.f, dy = 0.f, ag = 0.f;
-    if (idx >= wl && idx < wl * (hl - 1)) {
-      dx = 0.5f * (I[idx + 1] - I[idx - 1]);
-      dy = 0.5f * (I[idx + wl] - I[idx - wl]);
-      if (!isfinite(dx)) dx = 0.f;
-      if (!isfinite(dy)) dy = 0.f;
-      ag = dx * dx + dy * dy;
-      if (P.use_gamma) {
-        // CalibHessian::getBGradOnly (HessianBlocks.h:356-362)
-        int ci = (int)(c + 0.5f);
-        if (ci < 5) ci = 5;
-        if (ci > 250) ci = 250;
-        float gw = g_Bgamma[ci + 1] - g_Bgamma[ci];
-        ag *= gw * gw;
+// ONE pass per image: a CTA owns a 64x64 level-0 tile plus a halo of 2^(levels-1) pixels, widens / loads it into shared
+// memory once, builds every coarser level of the tile (with its halo) in shared memory, and writes the {I,dx,dy,|grad|^2}
+// texels and the intensity planes of ALL levels from there. The source is read once (the halo re-reads hit L2), nothing is
+// read back from HBM. Image columns 0 and w-1, whose horizontal difference wraps to the neighbouring row in the reference
+// (flat idx +- 1, HessianBlocks.cpp:182-184), are finished by pyr_wrap_kernel.
+__global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x;
+  const int L = P.levels;
+  const int H0 = 1 << (L - 1);              // level-0 halo
+  const int R0 = kTile + 2 * H0;            // level-0 region side
+  const int ox = blockIdx.x * kTile - H0, oy = blockIdx.y * kTile - H0;  // level-0 origin of the region
+  const int w0 = P.w[0], h0 = P.h[0];
+  float* __restrict__ base = B.img[blockIdx.z];
+  float4* __restrict__ tbase = B.tex[blockIdx.z];
+  // ---- level 0 region into shared memory (0 outside the image)
+  float* s0 = sm;
+  if (P.src_u8) {
+    const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
+    if ((w0 & 3) == 0) {
+      const int R4 = R0 >> 2;
+      for (int k = tid; k < R0 * R4; k += 256) {
+        const int ly = k / R4, lx = (k - ly * R4) * 4;
+        const int x = ox + lx, y = oy + ly;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < h0 && x >= 0 && x + 3 < w0) {
+          const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(S8 + x + (size_t)y * w0));
+          v = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+        }
+        *reinterpret_cast<float4*>(s0 + ly * R0 + lx) = v;
+      }
+    } else {
+      for (int k = tid; k < R0 * R0; k += 256) {
+        const int ly = k / R0, lx = k - ly * R0;
+        const int x = ox + lx, y = oy + ly;
+        s0[k] = (y >= 0 && y < h0 && x >= 0 && x < w0) ? (float)__ldg(S8 + x + (size_t)y * w0) : 0.f;
       }
     }
-    Tbase[g] = make_float4(c, dx, dy, ag);
+  } else {
+    const float* __restrict__ SF = (const float*)B.src[blockIdx.z];
+    for (int k = tid; k < R0 * R0; k += 256) {
+      const int ly = k / R0, lx = k - ly * R0;
+      const int x = ox + lx, y = oy + ly;
+      s0[k] = (y >= 0 && y < h0 && x >= 0 && x < w0) ? __ldg(SF + x + (size_t)y * w0) : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- coarser levels of the region: 2x2 mean in the reference's order 0.25f*(((a+b)+c)+d) (:172-178)
+  {
+    float* src = s0; int Rs = R0;
+    float* dst = s0 + R0 * R0;
+    for (int l = 1; l < L; l++) {
+      const int Rd = Rs >> 1;
+      for (int k = tid; k < Rd * Rd; k += 256) {
+        const int ly = k / Rd, lx = k - ly * Rd;
+        const float* q = src + (2 * ly) * Rs + 2 * lx;
+        dst[k] = 0.25f * (((q[0] + q[1]) + q[Rs]) + q[Rs + 1]);
+      }
+      __syncthreads();
+      src = dst; Rs = Rd; dst = dst + Rd * Rd;
+    }
+  }
+  // ---- texels + intensity planes of every level from shared memory
+  {
+    const float* src = s0; int Rs = R0;
+    for (int l = 0; l < L; l++) {
+      const int wl = P.w[l], hl = P.h[l];
+      const int T = kTile >> l, Hl = H0 >> l;           // tile side and halo at this level
+      const int tx0 = (blockIdx.x * kTile) >> l, ty0 = (blockIdx.y * kTile) >> l;
+      float* __restrict__ Il = base + P.px_offset[l];
+      float4* __restrict__ Tl = tbase + P.px_offset[l];
+      for (int k = tid; k < T * T; k += 256) {
+        const int ly = k / T, lx = k - ly * T;
+        const int x = tx0 + lx, y = ty0 + ly;
+        if (x >= wl || y >= hl) continue;
+        const float* q = src + (ly + Hl) * Rs + (lx + Hl);
+        const float c = q[0];
+        float dx = 0.f, dy = 0.f;
+        const bool inner = (y >= 1 && y < hl - 1);        // flat idx in [w, w(h-1))
+        if (inner) {
+          dx = 0.5f * (q[1] - q[-1]);                   // columns 0 and w-1 are redone by pyr_wrap_kernel
+          dy = 0.5f * (q[Rs] - q[-Rs]);
+        }
+        Il[x + (size_t)y * wl] = c;
+        Tl[x + (size_t)y * wl] = inner ? make_texel(c, dx, dy, P.use_gamma) : make_float4(c, 0.f, 0.f, 0.f);
+      }
+      src += Rs * Rs; Rs >>= 1;
+    }
+  }
+}
+
+// The reference differentiates on the flat index, so at x = 0 the left neighbour is (w-1, y-1) and at x = w-1 the right
+// neighbour is (0, y+1) (HessianBlocks.cpp:182-184). One thread per (level, row, side); reads the planes written above.
+__global__ void __launch_bounds__(128) pyr_wrap_kernel(PyrGeom P, PyrBatch B) {
+  const float* __restrict__ base = B.img[blockIdx.z];
+  float4* __restrict__ tbase = B.tex[blockIdx.z];
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int l = 0; l < P.levels; l++) {
+    const int wl = P.w[l], hl = P.h[l];
+    const int cnt = 2 * (hl - 2);
+    if (k < cnt) {
+      const int y = 1 + (k >> 1), side = k & 1;
+      const float* __restrict__ I = base + P.px_offset[l];
+      const int x = side ? wl - 1 : 0;
+      const int idx = x + y * wl;
+      const float c = I[idx];
+      const float dx = 0.5f * (I[idx + 1] - I[idx - 1]);
+      const float dy = 0.5f * (I[idx + wl] - I[idx - wl]);
+      tbase[P.px_offset[l] + idx] = make_texel(c, dx, dy, P.use_gamma);
+      return;
+    }
+    k -= cnt;
   }
 }
 
@@ -160,16 +181,17 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
   for (int i = 0; i < nb; i++) { B.src[i] = srcs[i]; B.img[i] = frames[i]->image; B.tex[i] = frames[i]->tex[0]; }
   prof_begin(ctx, 1);
   {
+    const int H0 = 1 << (P.levels - 1);
+    size_t smem = 0;
+    for (int l = 0, R = kTile + 2 * H0; l < P.levels; l++, R >>= 1) smem += (size_t)R * R * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem > smem_set) { SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile, nb);
-    pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(P, B);
+    pyr_fused_kernel<<<grid, 256, smem, ctx->stream>>>(P, B);
     SDSO_CHECK_LAUNCH(ctx);
-  }
-  {
-    int blocks = (off + 255) / 256;
-    int cap = (ctx->num_sms * 8 + nb - 1) / nb;
-    if (cap < 64) cap = 64;
-    if (blocks > cap) blocks = cap;
-    gradient_kernel<<<dim3(blocks, 1, nb), 256, 0, ctx->stream>>>(P, B);
+    int rows = 0;
+    for (int l = 0; l < P.levels; l++) rows += 2 * (P.h[l] - 2);
+    pyr_wrap_kernel<<<dim3((rows + 127) / 128, 1, nb), 128, 0, ctx->stream>>>(P, B);
     SDSO_CHECK_LAUNCH(ctx);
   }
   prof_end(ctx, 1);

@@ -777,8 +777,11 @@ __device__ __forceinline__ void eval_prologue(const TrackParams& P, const TrackL
 // the critical path and every duplicated inlined copy of the evaluation costs real time.
 enum { ST_LEVEL_INIT = 0, ST_CUTOFF_REPEAT = 1, ST_ITER = 2 };
 
-template <int kU>  // gather batch per thread
-__global__ void __launch_bounds__(256, 1) track_kernel(TrackParams P) {
+// kU = gather batch per thread. kU == 1 is compiled for two resident CTAs per SM (<= 128 registers): the throughput
+// configuration (many independent sequences, one small cluster each); kU >= 2 keeps all 255 registers for one CTA per SM,
+// the latency configuration (one sequence spread over an 8-CTA cluster).
+template <int kU>
+__global__ void __launch_bounds__(256, (kU == 1 ? 2 : 1)) track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -1242,7 +1245,7 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
 }
 
 int sdso_tracker_select_ref(sdso_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot >= 64) return SDSO_E_INVALID;
+  if (!ctx || slot < 0 || slot >= 1024) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (slot == t->cur_slot) return SDSO_OK;
   const size_t need = (size_t)(slot > t->cur_slot ? slot : t->cur_slot) + 1;
