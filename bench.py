@@ -246,15 +246,15 @@ def main():
     npx = synth.W * synth.H
     # 8-bit sources (the synthetic renderer quantises to integers, so uint8 is exact): device copies for the resident-input
     # number, pinned host copies for the end-to-end number
-    # (sequences at the same path position read the same pinned host image; on the device every sequence has its own copy)
-    hcache = {}
-    def host_img(s_, j):
-        key = (wl[s_]["pos"], j)
-        if key not in hcache:
-            hcache[key] = torch.from_numpy(wl[s_]["new_imgs"][j].astype(np.uint8)).contiguous().pin_memory()
-        return hcache[key]
-    host8 = [[host_img(s_, j) for s_ in range(S)] for j in range(POSES)]
-    dev8 = [[host8[j][s_].to(f"cuda:{dev}").contiguous() for s_ in range(S)] for j in range(POSES)]
+    # host side: one contiguous pinned ring-buffer slab [S, H, W] per step pattern j (as a camera ingest ring would hold them),
+    # so the library can move a step's sources with a single copy
+    host8 = []
+    for j in range(POSES):
+        slab = torch.empty((S, synth.H, synth.W), dtype=torch.uint8).pin_memory()
+        for s_ in range(S):
+            slab[s_].copy_(torch.from_numpy(wl[s_]["new_imgs"][j].astype(np.uint8)))
+        host8.append(slab)
+    dev8 = [host8[j].to(f"cuda:{dev}") for j in range(POSES)]
     T_init = [np.stack([wl[s_]["T_init"][j].reshape(12) for s_ in range(S)]) for j in range(POSES)]
     aff0 = np.zeros((S, 2))
     mr = np.full((S, 5), np.nan)
@@ -263,11 +263,11 @@ def main():
 
     def enqueue_device(i):
         j, fs = i % POSES, slots[i % SETS]
-        ctx.make_images_batch_device(fs, [t.data_ptr() for t in dev8[j]], u8=True)
+        ctx.make_images_batch_device(fs, [dev8[j][s_].data_ptr() for s_ in range(S)], u8=True)
         ctx.track_enqueue_multi(ref_slots, fs, T_init[j], aff0, coarsest, mr, variant)
 
     def upload(i):
-        ctx.upload_images_async(slots[i % SETS], [t.data_ptr() for t in host8[i % POSES]], u8=True)
+        ctx.upload_images_async(slots[i % SETS], [host8[i % POSES][s_].data_ptr() for s_ in range(S)], u8=True)
 
     def enqueue_host(i):
         ctx.make_images_uploaded(slots[i % SETS])
@@ -325,6 +325,19 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
+    # ---- plain H2D bandwidth of this box (one pinned copy of a whole step's sources), for context
+    big = host8[0]
+    dst = torch.empty_like(big, device=f"cuda:{dev}")
+    dst.copy_(big, non_blocking=True); torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for _ in range(5):
+        dst.copy_(big, non_blocking=True)
+    b1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs = 5 * big.numel() / (b0.elapsed_time(b1) * 1e-3) / 1e9
+    del dst
+
     # ---- single-sequence latency (one cluster on the GPU), for information
     lat_n = min(K_, 50)
     for i in range(3):
@@ -366,7 +379,7 @@ def main():
             traffic = json.load(open(tp)).get(f"track_{args.variant}_batch{S}_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    img_bytes = S * (npx * 1 + npx * 4 + 16 * 603911)  # u8 read + float plane written + texels written, per batched launch pair
+    img_bytes = 32 * (npx * 1 + 4 * 603911 + 16 * 603911)  # per launch of 32 images: u8 read + intensity planes + texels written
     # CPU baseline (rank 0, bounded sample of the same workload on all host cores)
     cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
     line = dict(
@@ -376,7 +389,8 @@ def main():
         tracked_frames_per_s=world * S * K_ / (ms_dev * 1e-3),
         evals_per_step=evals / (world * K_),
         e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=S * npx, d2h_bytes_per_step=S * (8 * (12 + 2 + 5 + 3) + 4 * 6 + 8),
-                 ms_per_step=ms_e2e / K_, tracked_frames_per_s=world * S * K_ / (ms_e2e * 1e-3)),
+                 ms_per_step=ms_e2e / K_, tracked_frames_per_s=world * S * K_ / (ms_e2e * 1e-3),
+                 h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=S * npx / (ms_e2e / K_ * 1e-3) / 1e9),
         single_sequence=dict(ms_per_frame=ms_single, tracked_frames_per_s=1e3 / ms_single,
                              note="latency of one sequence alone on the GPU in this (throughput) configuration: one CTA; the latency configuration (8-CTA cluster, gather batch 2) tracks a frame in ~0.2 ms, profiles/r1_bench_sse_first.json"),
         gpu_launches=int(launches),

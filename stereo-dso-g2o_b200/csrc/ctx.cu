@@ -162,9 +162,10 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   for (auto& f : ctx->frames) {
     if (f.tex[0]) cudaFree(f.tex[0]);
     if (f.image) cudaFree(f.image);
-    if (f.src8) cudaFree(f.src8);
+    if (f.src8 && f.src8_owned) cudaFree(f.src8);
     if (f.uploaded) cudaEventDestroy(f.uploaded);
   }
+  for (void* a : ctx->arenas) cudaFree(a);
   if (ctx->staging) cudaFreeHost(ctx->staging);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->ev_track) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -271,15 +272,37 @@ int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const 
   if (nb > 0 && !host_images) return SDSO_E_INVALID;
   if (!ctx->copy_stream) SDSO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
+  if (src_u8) {
+    // frames that have no 8-bit staging yet get slices of ONE allocation, so a batch that is also contiguous on the host
+    // (a ring buffer of camera frames) goes up as a single copy
+    int missing = 0;
+    for (int i = 0; i < nb; i++) if (!ctx->frames[frame_ids[i]].src8) missing++;
+    if (missing > 0) {
+      unsigned char* arena = nullptr;
+      SDSO_CUDA(ctx, cudaMalloc(&arena, (size_t)missing * n));
+      ctx->arenas.push_back(arena);
+      int k = 0;
+      for (int i = 0; i < nb; i++) { Frame& f = ctx->frames[frame_ids[i]]; if (!f.src8) { f.src8 = arena + (size_t)(k++) * n; f.src8_owned = false; } }
+    }
+  }
+  const size_t bytes = src_u8 ? n : n * sizeof(float);
+  for (int i = 0; i < nb;) {
+    Frame& f = ctx->frames[frame_ids[i]];
+    unsigned char* dst = src_u8 ? f.src8 : (unsigned char*)f.image;
+    const unsigned char* src = (const unsigned char*)host_images[i];
+    int run = 1;  // longest run that is contiguous on both sides
+    while (i + run < nb) {
+      Frame& g = ctx->frames[frame_ids[i + run]];
+      unsigned char* d2 = src_u8 ? g.src8 : (unsigned char*)g.image;
+      if (d2 != dst + (size_t)run * bytes || (const unsigned char*)host_images[i + run] != src + (size_t)run * bytes) break;
+      run++;
+    }
+    SDSO_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)run * bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    i += run;
+  }
   for (int i = 0; i < nb; i++) {
     Frame& f = ctx->frames[frame_ids[i]];
     if (!f.uploaded) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
-    if (src_u8) {
-      if (!f.src8) SDSO_CUDA(ctx, cudaMalloc(&f.src8, n));
-      SDSO_CUDA(ctx, cudaMemcpyAsync(f.src8, host_images[i], n, cudaMemcpyHostToDevice, ctx->copy_stream));
-    } else {
-      SDSO_CUDA(ctx, cudaMemcpyAsync(f.image, host_images[i], n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-    }
     f.pending_u8 = src_u8 ? 1 : 0;
     f.valid = false;
   }

@@ -17,7 +17,8 @@ struct Frame {
   float* image = nullptr;               // level-0 intensity plane (the uploaded image)
   float ab_exposure = 1.0f;
   bool valid = false;
-  unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (allocated on first use)
+  unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (a slice of a batch arena)
+  bool src8_owned = false;
   cudaEvent_t uploaded = nullptr;       // recorded on the copy stream after the asynchronous upload of this frame's source
   int pending_u8 = -1;                  // source format of the pending upload: -1 none, 0 float (in `image`), 1 uint8 (in `src8`)
 };
@@ -45,6 +46,7 @@ struct sdso_ctx {
   std::vector<sdso::Frame> frames;
   size_t tex_total = 0;  // float4 texels per frame over all levels
   float* staging = nullptr;  // pinned host staging for image upload
+  std::vector<void*> arenas;           // batch allocations of 8-bit staging
   cudaStream_t copy_stream = nullptr;  // H2D uploads that overlap the kernels of the previous step (sdso_upload_images_async)
   sdso::TrackerState* tracker = nullptr;
   sdso::BAState* ba = nullptr;

@@ -1007,6 +1007,23 @@ static void fill_params(sdso_ctx* ctx, TrackParams& P) {
   P.problems = t->d_problems;
 }
 
+// Problem records go to the device through a kernel that reads the pinned (UVA-mapped) host array directly, not through a
+// cudaMemcpyAsync: an H2D copy on the compute stream would queue on the same copy engine behind the bulk image upload of the
+// NEXT step (copy stream) and stall the tracker launch until that upload has finished.
+__global__ void stage_problems_kernel(const uint4* __restrict__ host_mapped, uint4* __restrict__ dev, int n16) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dev[i] = host_mapped[i];
+}
+static int stage_problems(sdso_ctx* ctx, int nb) {
+  TrackerState* t = ctx->tracker;
+  static_assert(sizeof(TrackProblem) % 16 == 0, "TrackProblem must be a multiple of 16 bytes");
+  const int n16 = (int)(nb * sizeof(TrackProblem) / 16);
+  int blocks = (n16 + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  stage_problems_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(t->h_problems), reinterpret_cast<uint4*>(t->d_problems), n16);
+  SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
 // reference slot `slot` as a RefSlot view (the current slot lives in the TrackerState members)
 static RefSlot slot_view(const TrackerState* t, int slot) {
   if (slot == t->cur_slot || slot < 0) {
@@ -1290,9 +1307,10 @@ int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const 
     rc = fill_problem_ref(ctx, hp, ref_slots ? ref_slots[k] : -1);
     if (rc) return rc;
   }
-  SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_problems, t->h_problems, nb * sizeof(TrackProblem), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = stage_problems(ctx, nb);
+  if (rc) return rc;
   prof_begin(ctx, 0);
-  int rc = launch_track(ctx, P, nb, variant == SDSO_VARIANT_G2O);
+  rc = launch_track(ctx, P, nb, variant == SDSO_VARIANT_G2O);
   if (rc) return rc;
   prof_end(ctx, 0);
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->h_problems, t->d_problems, nb * sizeof(TrackProblem), cudaMemcpyDeviceToHost, ctx->stream));
