@@ -77,6 +77,11 @@ typedef struct sdso_settings {
   float initialCalibHessian;        /* :48 */
   float margWeightFac;              /* :76 */
   double solverModeDelta;           /* :52 */
+  int32_t minOptIterations;         /* :68 */
+  float thOptIterations;            /* :69 */
+  float frameEnergyTHConstWeight;   /* :98 */
+  float frameEnergyTHN;             /* :99 */
+  float frameEnergyTHFacMedian;     /* :100 */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);
@@ -231,6 +236,15 @@ int sdso_ba_solve(sdso_ctx* ctx, int iteration, double lambda, double* x, double
 /* EnergyFunctional::resubstituteF_MT (:272-341) for a given x (NULL: the last solve's); frame_steps [n][10], calib_step [4];
  * point steps are read with sdso_ba_get_points */
 int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, double* calib_step);
+/* FullSystem::setNewFrameEnergyTH (FullSystemOptimize.cpp:98-139): exact 70 % quantile of state_NewEnergyWithOutlier over the
+ * active residuals that target the newest frame -> that frame's frameEnergyTH (applied, and returned) */
+int sdso_ba_new_frame_energy_th(sdso_ctx* ctx, float* th);
+/* FullSystem::optimize, SSE body (FullSystemOptimize.cpp:870-1042) with backupState / solveSystem / doStepFromBackup /
+ * linearizeAll / applyRes per iteration (setting_forceAceptStep = true, settings.cpp:53), then the new evaluation point of the
+ * newest frame and the final linearizeAll(true). Returns what the reference returns: sqrt(energy / (patternNum * resInA)). */
+int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iterations_done);
+/* current frame states [n][10], PRE_worldToCam [n][12], point idepths [P], calibration value_scaled [4] (each nullable) */
+int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idepth, double* calib);
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM);   /* EnergyFunctional::HM, bM */
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM);
 

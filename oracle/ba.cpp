@@ -452,6 +452,7 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
   const int nf = n(), d = dim();
   std::vector<AccumulatorApprox> acc((size_t)nf * nf);
   for (auto& a : acc) a.initialize();
+  int resInA_tmp = 0;
   for (auto& p : points) {
     if (mode == 2 && p.stateFlag != 1) continue;  // marginalizePointsF feeds only PS_MARGINALIZE points (:680-696)
     const float* dc = cDeltaF;
@@ -491,6 +492,7 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
         rr += resApprox[i] * resApprox[i];
       }
       AccumulatorApprox& a = acc[htIDX];
+      if (mode == 0) resInA_tmp++;
       a.update(rJ.Jpdc[0], rJ.Jpdxi[0], rJ.Jpdc[1], rJ.Jpdxi[1], rJ.JIdx2[0], rJ.JIdx2[1], rJ.JIdx2[3]);
       a.updateBotRight(rJ.Jab2[0], rJ.Jab2[1], Jab_r[0], rJ.Jab2[3], Jab_r[1], rr);
       a.updateTopRight(rJ.Jpdc[0], rJ.Jpdxi[0], rJ.Jpdc[1], rJ.Jpdxi[1], rJ.JabJIdx[0], rJ.JabJIdx[1], rJ.JabJIdx[2], rJ.JabJIdx[3], JI_r[0], JI_r[1]);
@@ -503,6 +505,7 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
     if (mode == 1 || mode == 2) { p.Hdd_accLF = Hdd_acc; p.bd_accLF = bd_acc; for (int k = 0; k < 4; k++) p.Hcd_accLF[k] = Hcd_acc[k]; }
     if (mode == 2) { for (int k = 0; k < 4; k++) p.Hcd_accAF[k] = 0; p.Hdd_accAF = 0; p.bd_accAF = 0; }
   }
+  if (mode == 0) resInA = resInA_tmp;
   // stitch
   H.assign((size_t)d * d, 0.0); b.assign(d, 0.0);
   lastTopBlocks.assign((size_t)nf * nf * 169, 0.f);
@@ -877,6 +880,115 @@ double BAWindow::calcLEnergyF() {
     acc += p.deltaF * p.deltaF * p.priorF;
   }
   return E + acc;
+}
+
+
+// ---- LM driver of the SSE path ---------------------------------------------------------------------------------
+void BAWindow::initCalibValue() {
+  if (calib_init) return;
+  // CalibHessian(): value_scaled = (fx,fy,cx,cy); value = SCALE_*_INVERSE * value_scaled; value_zero = value
+  calib_value[0] = (1.0f / SCALE_F) * (double)HCalib.fxl; calib_value[1] = (1.0f / SCALE_F) * (double)HCalib.fyl;
+  calib_value[2] = (1.0f / SCALE_C) * (double)HCalib.cxl; calib_value[3] = (1.0f / SCALE_C) * (double)HCalib.cyl;
+  for (int i = 0; i < 4; i++) calib_value_zero[i] = calib_value[i] - HCalib.value_minus_value_zero[i];
+  calib_init = true;
+}
+void BAWindow::setCalibValue(const double v[4]) {
+  for (int i = 0; i < 4; i++) calib_value[i] = v[i];
+  const double vs[4] = {SCALE_F * v[0], SCALE_F * v[1], SCALE_C * v[2], SCALE_C * v[3]};
+  HCalib.fxl = (float)vs[0]; HCalib.fyl = (float)vs[1]; HCalib.cxl = (float)vs[2]; HCalib.cyl = (float)vs[3];
+  HCalib.fxli = 1.0f / HCalib.fxl; HCalib.fyli = 1.0f / HCalib.fyl;
+  HCalib.cxli = -HCalib.cxl / HCalib.fxl; HCalib.cyli = -HCalib.cyl / HCalib.fyl;
+  for (int i = 0; i < 4; i++) HCalib.value_minus_value_zero[i] = calib_value[i] - calib_value_zero[i];
+}
+void BAWindow::backupState() {  // FullSystemOptimize.cpp:309-350, non-momentum branch
+  for (int i = 0; i < 4; i++) calib_backup[i] = calib_value[i];
+  for (auto& f : frames) for (int i = 0; i < 10; i++) f.state_backup[i] = f.state[i];
+  for (auto& p : points) p.idepth_backup = p.idepth;
+}
+bool BAWindow::doStepFromBackup(float stepfacC, float stepfacT, float stepfacR, float stepfacA, float stepfacD) {  // :207-305
+  float sumA = 0, sumB = 0, sumT = 0, sumR = 0, sumID = 0, numID = 0, sumNID = 0;
+  double v[4];
+  for (int i = 0; i < 4; i++) v[i] = calib_backup[i] + stepfacC * calib_step[i];
+  setCalibValue(v);
+  const double pf[10] = {stepfacT, stepfacT, stepfacT, stepfacR, stepfacR, stepfacR, stepfacA, stepfacA, stepfacA, stepfacA};
+  for (size_t h = 0; h < frames.size(); h++) {
+    BAFrame& f = frames[h];
+    double st[10];
+    for (int i = 0; i < 10; i++) st[i] = f.state_backup[i] + pf[i] * f.step[i];
+    f.setState(st);
+    sumA += f.step[6] * f.step[6];
+    sumB += f.step[7] * f.step[7];
+    sumT += f.step[0] * f.step[0] + f.step[1] * f.step[1] + f.step[2] * f.step[2];
+    sumR += f.step[3] * f.step[3] + f.step[4] * f.step[4] + f.step[5] * f.step[5];
+  }
+  for (auto& p : points) {
+    const float nv = p.idepth_backup + stepfacD * p.step;
+    p.idepth = nv; p.idepth_scaled = SCALE_IDEPTH * nv;
+    sumID += p.step * p.step;
+    sumNID += fabsf(p.idepth_backup);
+    numID++;
+    p.idepth_zero = nv; p.idepth_zero_scaled = SCALE_IDEPTH * nv;
+  }
+  sumA /= frames.size(); sumB /= frames.size(); sumR /= frames.size(); sumT /= frames.size();
+  sumID /= numID; sumNID /= numID;
+  setPrecalcValues(); setDeltaF();
+  const float th = S.thOptIterations;
+  return sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
+}
+float BAWindow::newFrameEnergyTH() {  // :98-139
+  std::vector<float> all;
+  const int newest = n() - 1;
+  for (auto& r : res) if (!r.isLinearized && r.state_NewEnergyWithOutlier >= 0 && r.target == newest) all.push_back((float)r.state_NewEnergyWithOutlier);
+  if (all.empty()) return 12 * 12 * patternNum;
+  const int nthIdx = (int)(S.frameEnergyTHN * all.size());
+  std::nth_element(all.begin(), all.begin() + nthIdx, all.end());
+  const float nthElement = sqrtf(all[nthIdx]);
+  float th = nthElement * S.frameEnergyTHFacMedian;
+  th = 26.0f * S.frameEnergyTHConstWeight + th * (1 - S.frameEnergyTHConstWeight);
+  th = th * th;
+  th *= S.overallEnergyTHWeight * S.overallEnergyTHWeight;
+  return th;
+}
+double BAWindow::optimize(int mnumOptIts, int* iterations_done) {  // :870-1042 with setting_forceAceptStep = true (settings.cpp:53)
+  initCalibValue();
+  const int nf = n();
+  if (nf < 2) return 0;
+  if (nf < 3) mnumOptIts = 20;
+  if (nf < 4) mnumOptIts = 15;
+  for (auto& r : res) if (!r.isLinearized) { r.state_NewEnergy = r.state_energy = 0; r.state_NewState = RS_OUTLIER; r.state_state = RS_IN; }  // resetOOB
+  // linearizeAll ends with setNewFrameEnergyTH() (FullSystemOptimize.cpp:163): the newest frame's threshold follows every pass
+  double lastEnergy = linearizeAll(false);
+  frames.back().frameEnergyTH = newFrameEnergyTH();
+  for (auto& r : res) if (!r.isLinearized) applyRes(r, true);
+  const double lambda = 1e-1;
+  int it = 0;
+  for (; it < mnumOptIts; it++) {
+    backupState();
+    std::vector<double> x;
+    solveSystemF(it, lambda, x, nullptr, nullptr);
+    std::vector<double> fs((size_t)nf * 10);
+    resubstituteF(x, fs.data(), calib_step);
+    for (int h = 0; h < nf; h++) for (int i = 0; i < 10; i++) frames[h].step[i] = fs[(size_t)h * 10 + i];
+    const bool canbreak = doStepFromBackup(1, 1, 1, 1, 1);
+    lastEnergy = linearizeAll(false);
+    frames.back().frameEnergyTH = newFrameEnergyTH();
+    for (auto& r : res) if (!r.isLinearized) applyRes(r, true);
+    if (canbreak && it >= S.minOptIterations) { it++; break; }
+  }
+  if (iterations_done) *iterations_done = it;
+  // new evaluation point of the newest frame (:996-1005)
+  BAFrame& nw = frames.back();
+  double nz[10] = {0, 0, 0, 0, 0, 0, nw.state[6], nw.state[7], 0, 0};
+  nw.worldToCam_evalPT = nw.PRE_worldToCam;
+  nw.setState(nz);
+  nw.setStateZero(nz);
+  setAdjointsF();
+  setPrecalcValues(); setDeltaF(); getNullspaces();
+  lastEnergy = linearizeAll(true);
+  frames.back().frameEnergyTH = newFrameEnergyTH();
+  std::vector<double> Ht, bt;
+  accumulateTop(0, Ht, bt, false);  // resInA as the last accumulateAF would report it
+  return sqrtf((float)(lastEnergy / (patternNum * std::max(resInA, 1))));
 }
 
 }  // namespace orc

@@ -240,7 +240,7 @@ void orc_ba_adjoints(void* p, double* adHost, double* adTarget, float* adHTdelta
   if (adHTdeltaF) memcpy(adHTdeltaF, c->ba.adHTdeltaF.data(), c->ba.adHTdeltaF.size() * sizeof(float));
 }
 double orc_ba_linearize_all(void* p, int fix) { return ((Ctx*)p)->ba.linearizeAll(fix != 0); }
-void orc_ba_apply_res(void* p, int copy) { Ctx* c = (Ctx*)p; for (auto& r : c->ba.res) c->ba.applyRes(r, copy != 0); }
+void orc_ba_apply_res(void* p, int copy) { Ctx* c = (Ctx*)p; for (auto& r : c->ba.res) if (!r.isLinearized) c->ba.applyRes(r, copy != 0); }  // activeResiduals only
 void orc_ba_fix_linearization(void* p, int ridx) { Ctx* c = (Ctx*)p; c->ba.fixLinearizationF(c->ba.res[ridx]); }
 // per residual: state_NewState, state_state, NewEnergy, NewEnergyWithOutlier, isActive, J (74 floats: candidate J if which==0, EF J if which==1), JpJdF, centerProjectedTo
 void orc_ba_get_res(void* p, int which, int* newState, int* state, double* newEnergy, double* newEnergyWO, int* active, float* J74, float* JpJdF8, float* center3, float* resToZero8) {
@@ -331,5 +331,20 @@ void orc_trace_on(void* p, int fid, const float KRKi[9], const float Kt[3], cons
 void orc_trace_stereo(void* p, int fid, const float K[9], int mode_right, int n, ImmaturePoint* pts, int* status) {
   Ctx* c = (Ctx*)p;
   for (int i = 0; i < n; i++) status[i] = traceStereo(c->G, c->S, pts[i], *c->frames[fid], K, mode_right != 0);
+}
+}  // extern "C"
+
+extern "C" {
+double orc_ba_optimize(void* p, int iters, int* done) { return ((Ctx*)p)->ba.optimize(iters, done); }
+float orc_ba_new_frame_energy_th(void* p) { return ((Ctx*)p)->ba.newFrameEnergyTH(); }
+// frame states [n][10], world-to-camera [n][12], point idepths [P], calibration value_scaled [4]
+void orc_ba_get_state(void* p, double* states, double* T_w2c, float* idepth, double* calib) {
+  Ctx* c = (Ctx*)p;
+  for (size_t h = 0; h < c->ba.frames.size(); h++) {
+    if (states) for (int i = 0; i < 10; i++) states[h * 10 + i] = c->ba.frames[h].state[i];
+    if (T_w2c) c->ba.frames[h].PRE_worldToCam.toMat34(T_w2c + 12 * h);
+  }
+  if (idepth) for (size_t i = 0; i < c->ba.points.size(); i++) idepth[i] = c->ba.points[i].idepth;
+  if (calib) { calib[0] = c->ba.HCalib.fxl; calib[1] = c->ba.HCalib.fyl; calib[2] = c->ba.HCalib.cxl; calib[3] = c->ba.HCalib.cyl; }
 }
 }  // extern "C"

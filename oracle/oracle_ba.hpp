@@ -43,6 +43,7 @@ struct BAFrame {  // FrameHessian + EFFrame (only what the backend reads)
   double nullspaces_affine[8]; // 4x2
   double nullspaces_scale[6];
   double prior[8] = {0}, delta_prior[8] = {0}, delta[8] = {0};  // EFFrame
+  double step[10] = {0}, state_backup[10] = {0};
   float frameEnergyTH = 8 * 8 * patternNum;
   void setState(const double s[10]);                               // HessianBlocks.h:177-199
   void setStateScaled(const double s[10]);                         // :201-215
@@ -61,7 +62,7 @@ struct BAPoint {  // PointHessian + EFPoint
   float priorF = 0, deltaF = 0;
   float bdSumF = 0, HdiF = 0, Hdd_accLF = 0, bd_accLF = 0, Hdd_accAF = 0, bd_accAF = 0;
   float Hcd_accLF[4] = {0, 0, 0, 0}, Hcd_accAF[4] = {0, 0, 0, 0};
-  float idepth_hessian = 0, step = 0;
+  float idepth_hessian = 0, step = 0, idepth_backup = 0;
   int stateFlag = 0;  // EFPointStatus: 0 GOOD, 1 MARGINALIZE, 2 DROP
   std::vector<int> residuals;  // indices into BAWindow::res (residualsAll order)
 };
@@ -119,6 +120,16 @@ struct BAWindow {
   void marginalizeFrame(int idx);                                                              // :554-660
   double calcMEnergyF();                                                                       // :344-351
   double calcLEnergyF();                                                                       // :354-442
+  // FullSystem LM driver of the SSE path (FullSystemOptimize.cpp:870-1042, 207-370, 98-139)
+  double calib_value[4] = {0, 0, 0, 0}, calib_value_zero[4] = {0, 0, 0, 0}, calib_step[4] = {0, 0, 0, 0}, calib_backup[4] = {0, 0, 0, 0};
+  bool calib_init = false;
+  int resInA = 0;
+  void initCalibValue();
+  void setCalibValue(const double v[4]);                 // CalibHessian::setValue (HessianBlocks.h:316-331)
+  void backupState();
+  bool doStepFromBackup(float stepfacC, float stepfacT, float stepfacR, float stepfacA, float stepfacD);
+  float newFrameEnergyTH();                              // setNewFrameEnergyTH value for the newest frame (:98-139)
+  double optimize(int mnumOptIts, int* iterations_done);
 };
 
 // g2o LBA edge (dso_g2o_edge.cpp:5-282), operator level

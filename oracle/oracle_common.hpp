@@ -58,6 +58,9 @@ struct Settings {
         initialAffAPrior = 1e14f, initialCalibHessian = 5e9f; // :44-48
   float margWeightFac = 0.5f * 0.5f;   // :76
   double solverModeDelta = 0.00001;    // :52
+  int maxOptIterations = 6, minOptIterations = 1;  // :67-68
+  float thOptIterations = 1.2f;        // :69
+  float frameEnergyTHConstWeight = 0.5f, frameEnergyTHN = 0.7f, frameEnergyTHFacMedian = 1.5f;  // :98-100
 };
 
 // ---- tiny dense helpers (row-major, runtime n) ---------------------------------------------

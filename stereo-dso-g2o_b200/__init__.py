@@ -35,6 +35,8 @@ class Settings(C.Structure):
         ("idepthFixPrior", C.c_float), ("idepthFixPriorMargFac", C.c_float), ("initialRotPrior", C.c_float),
         ("initialTransPrior", C.c_float), ("initialAffBPrior", C.c_float), ("initialAffAPrior", C.c_float),
         ("initialCalibHessian", C.c_float), ("margWeightFac", C.c_float), ("solverModeDelta", C.c_double),
+        ("minOptIterations", C.c_int32), ("thOptIterations", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
+        ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float),
     ]
 
 
@@ -611,3 +613,32 @@ Context.make_images_uploaded = _make_images_uploaded
 Context.make_images_batch_device = _make_images_batch_device
 Context.tracker_select_ref = _tracker_select_ref
 Context.track_enqueue_multi = _track_enqueue_multi
+
+
+lib.sdso_ba_new_frame_energy_th.argtypes = [C.c_void_p, _fp]
+lib.sdso_ba_optimize.argtypes = [C.c_void_p, C.c_int, _dp, _ip]
+lib.sdso_ba_get_state.argtypes = [C.c_void_p, _dp, _dp, _fp, _dp]
+
+
+def _w_new_frame_energy_th(self):
+    th = C.c_float()
+    self._ck(lib.sdso_ba_new_frame_energy_th(self.h, C.byref(th)))
+    return th.value
+
+
+def _w_optimize(self, iters=6):
+    r, d = C.c_double(), C.c_int()
+    self._ck(lib.sdso_ba_optimize(self.h, iters, C.byref(r), C.byref(d)))
+    return r.value, d.value
+
+
+def _w_get_state(self):
+    c = self.counts()
+    st, T, idp, cal = np.zeros((c["frames"], 10)), np.zeros((c["frames"], 3, 4)), np.zeros(c["points"], np.float32), np.zeros(4)
+    self._ck(lib.sdso_ba_get_state(self.h, _ptr(st, _dp), _ptr(T, _dp), _ptr(idp, _fp), _ptr(cal, _dp)))
+    return dict(states=st, T_w2c=T, idepth=idp, calib=cal)
+
+
+Window.new_frame_energy_th = _w_new_frame_energy_th
+Window.optimize = _w_optimize
+Window.get_state = _w_get_state

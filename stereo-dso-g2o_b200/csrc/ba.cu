@@ -21,10 +21,10 @@ static cudaError_t grow(T*& p, size_t n) {
 static void free_all(BAState* b) {
   void* ptrs[] = {b->d_tex0, b->d_frameTH, b->d_precalc, b->d_adHost, b->d_adTarget, b->d_adHostF, b->d_adTargetF, b->d_adHTdeltaF, b->d_cDeltaF,
                   b->d_fprior, b->d_p_host, b->d_p_u, b->d_p_v, b->d_p_idepth, b->d_p_idepth_zero, b->d_p_color, b->d_p_weights, b->d_p_priorF,
-                  b->d_p_deltaF, b->d_p_res_begin, b->d_slot_of, b->d_p_acc, b->d_p_flag, b->d_p_res_list, b->d_s_point, b->d_s_key, b->d_s_state,
+                  b->d_p_deltaF, b->d_p_idepth_backup, b->d_p_res_begin, b->d_slot_of, b->d_p_acc, b->d_p_flag, b->d_p_res_list, b->d_s_point, b->d_s_key, b->d_s_state,
                   b->d_s_newstate, b->d_s_flags, b->d_s_sel, b->d_s_energy, b->d_J, b->d_s_rtz, b->d_s_JpJd, b->d_s_center, b->d_s_psum,
                   b->d_slot2rid, b->d_rid2slot, b->d_chunks, b->d_key_chunk_begin, b->d_tpart, b->d_dpart, b->d_pblockpart, b->d_G, b->d_Gf,
-                  b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list};
+                  b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list, b->d_step_part};
   for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -41,8 +41,8 @@ int ba_create(sdso_ctx* ctx) {
   b->sys_stride = (size_t)dmax * dmax + dmax + 8;
   BA_ALLOC(b->d_sys, b->sys_stride * SYS_NUM);
   SDSO_CUDA(ctx, cudaMemset(b->d_sys, 0, b->sys_stride * SYS_NUM * sizeof(double)));
-  BA_ALLOC(b->d_scalars, 16); BA_ALLOC(b->d_counter, 1); BA_ALLOC(b->d_N, dmax * 7); BA_ALLOC(b->d_xAd, F2 * 8);
-  SDSO_CUDA(ctx, cudaMemset(b->d_counter, 0, sizeof(unsigned)));
+  BA_ALLOC(b->d_scalars, 16); BA_ALLOC(b->d_counter, 4); BA_ALLOC(b->d_N, dmax * 7); BA_ALLOC(b->d_xAd, F2 * 8);
+  SDSO_CUDA(ctx, cudaMemset(b->d_counter, 0, 4 * sizeof(unsigned)));
   return SDSO_OK;
 }
 void ba_destroy(sdso_ctx* ctx) {
@@ -58,7 +58,7 @@ static BAView view(BAState* b) {
   v.tex0 = b->d_tex0; v.frameTH = b->d_frameTH; v.precalc = b->d_precalc;
   v.adHost = b->d_adHost; v.adTarget = b->d_adTarget; v.adHostF = b->d_adHostF; v.adTargetF = b->d_adTargetF;
   v.adHTdeltaF = b->d_adHTdeltaF; v.cDeltaF = b->d_cDeltaF; v.fprior = b->d_fprior;
-  v.p_host = b->d_p_host; v.p_u = b->d_p_u; v.p_v = b->d_p_v; v.p_idepth = b->d_p_idepth; v.p_idepth_zero = b->d_p_idepth_zero;
+  v.p_host = b->d_p_host; v.p_u = b->d_p_u; v.p_v = b->d_p_v; v.p_idepth = b->d_p_idepth; v.p_idepth_zero = b->d_p_idepth_zero; v.p_idepth_backup = b->d_p_idepth_backup;
   v.p_color = b->d_p_color; v.p_weights = b->d_p_weights; v.p_priorF = b->d_p_priorF; v.p_deltaF = b->d_p_deltaF;
   v.p_res_begin = b->d_p_res_begin; v.p_res_list = b->d_p_res_list; v.slot_of = b->d_slot_of; v.p_acc = b->d_p_acc; v.p_flag = b->d_p_flag;
   v.s_point = b->d_s_point; v.s_key = b->d_s_key; v.s_state = b->d_s_state; v.s_newstate = b->d_s_newstate; v.s_flags = b->d_s_flags; v.s_sel = b->d_s_sel;
@@ -420,6 +420,10 @@ int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_
   c.huberTH = ctx->S.huberTH; c.outlierTHSumComponent = ctx->S.outlierTHSumComponent;
   c.affineOptModeA = ctx->S.affineOptModeA; c.affineOptModeB = ctx->S.affineOptModeB;
   if (value_minus_value_zero) for (int i = 0; i < 4; i++) b->calib_delta[i] = value_minus_value_zero[i];
+  // CalibHessian: value = SCALE_*_INVERSE * value_scaled, value_zero = value - (value - value_zero)
+  b->calib_value[0] = (1.0f / SCALE_F) * (double)c.fxl; b->calib_value[1] = (1.0f / SCALE_F) * (double)c.fyl;
+  b->calib_value[2] = (1.0f / SCALE_C) * (double)c.cxl; b->calib_value[3] = (1.0f / SCALE_C) * (double)c.cyl;
+  for (int i = 0; i < 4; i++) b->calib_zero[i] = b->calib_value[i] - b->calib_delta[i];
   b->prepared = false;
   return SDSO_OK;
 }
@@ -476,7 +480,7 @@ int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, co
   if (P > b->capP) {
     const int cap = std::max(P, 1024);
     BA_ALLOC(b->d_p_host, cap); BA_ALLOC(b->d_p_u, cap); BA_ALLOC(b->d_p_v, cap); BA_ALLOC(b->d_p_idepth, cap); BA_ALLOC(b->d_p_idepth_zero, cap);
-    BA_ALLOC(b->d_p_color, 2 * (size_t)cap); BA_ALLOC(b->d_p_weights, 2 * (size_t)cap); BA_ALLOC(b->d_p_priorF, cap); BA_ALLOC(b->d_p_deltaF, cap);
+    BA_ALLOC(b->d_p_color, 2 * (size_t)cap); BA_ALLOC(b->d_p_weights, 2 * (size_t)cap); BA_ALLOC(b->d_p_priorF, cap); BA_ALLOC(b->d_p_deltaF, cap); BA_ALLOC(b->d_p_idepth_backup, cap);
     BA_ALLOC(b->d_p_res_begin, cap + 1); BA_ALLOC(b->d_slot_of, (size_t)cap * kMaxFrames); BA_ALLOC(b->d_p_acc, 16 * (size_t)cap);
     BA_ALLOC(b->d_p_flag, cap);
     const int pb = (cap + 127) / 128;
@@ -832,6 +836,153 @@ int sdso_ba_solve_assembled(sdso_ctx* ctx, int iteration, double* x, double* Hfi
   const int d = b->dim();
   if (x) SDSO_CUDA(ctx, cudaMemcpyAsync(x, sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   return download_sys(ctx, SYS_FINAL, Hfinal, bfinal);
+}
+
+// CalibHessian::setValue (HessianBlocks.h:316-331)
+static void set_calib_value(sdso_ctx* ctx, const double v[4]) {
+  BAState* b = ctx->ba;
+  BACalib& c = b->calib;
+  for (int i = 0; i < 4; i++) b->calib_value[i] = v[i];
+  const double vs[4] = {SCALE_F * v[0], SCALE_F * v[1], SCALE_C * v[2], SCALE_C * v[3]};
+  c.fxl = (float)vs[0]; c.fyl = (float)vs[1]; c.cxl = (float)vs[2]; c.cyl = (float)vs[3];
+  c.fxli = 1.0f / c.fxl; c.fyli = 1.0f / c.fyl; c.cxli = -c.cxl / c.fxl; c.cyli = -c.cyl / c.fyl;
+  for (int i = 0; i < 4; i++) b->calib_delta[i] = b->calib_value[i] - b->calib_zero[i];
+}
+
+static int launch_energy_th(sdso_ctx* ctx, float* th_host) {
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  const sdso_settings& S = ctx->S;
+  float* d_out = reinterpret_cast<float*>(b->d_scalars + 4);
+  ba_energy_th_kernel<<<1, 1024, 0, ctx->stream>>>(v, b->n - 1, S.frameEnergyTHN, S.frameEnergyTHFacMedian, S.frameEnergyTHConstWeight,
+                                                    S.overallEnergyTHWeight, b->d_frameTH, d_out);
+  SDSO_CHECK_LAUNCH(ctx);
+  float th = 0;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(&th, d_out, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  b->frames[b->n - 1].frameEnergyTH = th;  // host mirror (prepare re-uploads the thresholds)
+  if (th_host) *th_host = th;
+  return SDSO_OK;
+}
+
+int sdso_ba_new_frame_energy_th(sdso_ctx* ctx, float* th) {
+  BA_PREPARED(ctx)
+  return launch_energy_th(ctx, th);
+}
+
+int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idepth, double* calib) {
+  BA_CHECK(ctx)
+  for (int h = 0; h < b->n; h++) {
+    if (states) memcpy(states + 10 * h, b->frames[h].state, 10 * sizeof(double));
+    if (T_w2c) memcpy(T_w2c + 12 * h, b->frames[h].T_w2c, 12 * sizeof(double));
+  }
+  if (calib) { calib[0] = b->calib.fxl; calib[1] = b->calib.fyl; calib[2] = b->calib.cxl; calib[3] = b->calib.cyl; }
+  if (idepth && b->P > 0) {
+    SDSO_CUDA(ctx, cudaMemcpyAsync(idepth, b->d_p_idepth, b->P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SDSO_OK;
+}
+
+int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iterations_done) {
+  BA_PREPARED(ctx)
+  const int n = b->n, d = b->dim(), R = b->R, P = b->P;
+  if (rmse) *rmse = 0;
+  if (iterations_done) *iterations_done = 0;
+  if (n < 2) return SDSO_OK;
+  if (n < 3) mnumOptIts = 20;
+  if (n < 4) mnumOptIts = 15;
+  cudaStream_t st = ctx->stream;
+  const int rb = (R + 127) / 128, pb = (P + 127) / 128;
+  double* d_part = b->d_energy_part;  // reused: [pb][2] doubles (pb <= capacity of the energy partials: one per 128 slots... sized below)
+  int rc = SDSO_OK;
+  auto lin = [&](int fix) -> int {  // linearizeAll + setNewFrameEnergyTH (FullSystemOptimize.cpp:142-163)
+    if (R > 0) { BAView v = view(b); ba_linearize_kernel<<<rb, 128, 0, st>>>(v, fix); SDSO_CHECK_LAUNCH(ctx); }
+    return launch_energy_th(ctx, nullptr);
+  };
+  auto apply = [&]() -> int {
+    if (R > 0) { BAView v = view(b); ba_apply_res_kernel<<<rb, 128, 0, st>>>(v, 1); SDSO_CHECK_LAUNCH(ctx); }
+    return SDSO_OK;
+  };
+  if (R > 0) { BAView v = view(b); ba_reset_oob_kernel<<<rb, 128, 0, st>>>(v); SDSO_CHECK_LAUNCH(ctx); }
+  if ((rc = lin(0))) return rc;
+  if ((rc = apply())) return rc;
+  if (pb > b->step_part_cap) {
+    if (b->d_step_part) cudaFree(b->d_step_part);
+    b->d_step_part = nullptr;
+    SDSO_CUDA(ctx, cudaMalloc(&b->d_step_part, (size_t)(pb + 1) * 2 * sizeof(double)));
+    b->step_part_cap = pb;
+  }
+  (void)d_part;
+  std::vector<double> x(d);
+  int it = 0;
+  for (; it < mnumOptIts; it++) {
+    // backupState (:309-350)
+    for (int i = 0; i < 4; i++) b->calib_backup[i] = b->calib_value[i];
+    for (auto& f : b->frames) memcpy(f.state_backup, f.state, sizeof(f.state));
+    if (P > 0) { BAView v = view(b); ba_backup_points_kernel<<<pb, 128, 0, st>>>(v); SDSO_CHECK_LAUNCH(ctx); }
+    // solveSystem(iteration, lambda) (:1045-1053): accumulate, stitch, solve, back-substitute — all on the device
+    if ((rc = launch_solve(ctx, it, 1e-1))) return rc;
+    if ((rc = launch_resub(ctx, sysb(b, SYS_X)))) return rc;
+    SDSO_CUDA(ctx, cudaMemcpyAsync(x.data(), sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; i++) b->calib_step[i] = -x[i];
+    for (int h = 0; h < n; h++) { for (int i = 0; i < 8; i++) b->frames[h].step[i] = -x[kCPARS + 8 * h + i]; b->frames[h].step[8] = b->frames[h].step[9] = 0; }
+    // doStepFromBackup(1,1,1,1,1) (:207-305)
+    float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+    {
+      double v4[4];
+      for (int i = 0; i < 4; i++) v4[i] = b->calib_backup[i] + 1.0f * b->calib_step[i];
+      set_calib_value(ctx, v4);
+      for (auto& f : b->frames) {
+        double sn[10];
+        for (int i = 0; i < 10; i++) sn[i] = f.state_backup[i] + 1.0f * f.step[i];
+        frame_set_state(f, sn);
+        sumA += f.step[6] * f.step[6];
+        sumB += f.step[7] * f.step[7];
+        sumT += f.step[0] * f.step[0] + f.step[1] * f.step[1] + f.step[2] * f.step[2];
+        sumR += f.step[3] * f.step[3] + f.step[4] * f.step[4] + f.step[5] * f.step[5];
+      }
+    }
+    double sums[2] = {0, 0};
+    if (P > 0) {
+      BAView v = view(b);
+      ba_step_points_kernel<<<pb, 128, 0, st>>>(v, 1.0f, b->d_step_part); SDSO_CHECK_LAUNCH(ctx);
+      ba_sum_pairs_kernel<<<1, 32, 0, st>>>(b->d_step_part, pb, b->d_step_part + 2 * (size_t)pb); SDSO_CHECK_LAUNCH(ctx);
+      SDSO_CUDA(ctx, cudaMemcpyAsync(sums, b->d_step_part + 2 * (size_t)pb, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = prepare_window(ctx))) return rc;  // setPrecalcValues (+ setDeltaF); synchronises
+    sumA /= n; sumB /= n; sumR /= n; sumT /= n;
+    const float sumNID = P > 0 ? (float)(sums[1] / P) : 0.f;
+    const float th = ctx->S.thOptIterations;
+    const bool canbreak = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
+    if ((rc = lin(0))) return rc;
+    if ((rc = apply())) return rc;  // setting_forceAceptStep: every step is accepted (:965-978)
+    if (canbreak && it >= ctx->S.minOptIterations) { it++; break; }
+  }
+  if (iterations_done) *iterations_done = it;
+  // new evaluation point of the newest frame (:996-1005): setEvalPT(PRE_worldToCam, [0.., a, b, 0, 0])
+  {
+    HostBAFrame& nw = b->frames[n - 1];
+    const double nz[10] = {0, 0, 0, 0, 0, 0, nw.state[6], nw.state[7], 0, 0};
+    memcpy(nw.T_eval, nw.T_w2c, sizeof(nw.T_eval));
+    frame_set_state(nw, nz);
+    frame_set_state_zero(nw);
+  }
+  if ((rc = prepare_window(ctx))) return rc;  // setAdjointsF + setPrecalcValues
+  if ((rc = lin(1))) return rc;
+  double E = 0; unsigned resInA = 0;
+  if (R > 0) {
+    BAView v = view(b);
+    SDSO_CUDA(ctx, cudaMemsetAsync(b->d_counter + 1, 0, sizeof(unsigned), st));
+    ba_count_active_kernel<<<rb, 128, 0, st>>>(v, b->d_counter + 1); SDSO_CHECK_LAUNCH(ctx);
+    ba_drop_inactive_kernel<<<rb, 128, 0, st>>>(v); SDSO_CHECK_LAUNCH(ctx);
+    SDSO_CUDA(ctx, cudaMemcpyAsync(&E, b->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaMemcpyAsync(&resInA, b->d_counter + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  if (rmse) *rmse = sqrtf((float)(E / (8 * (double)(resInA > 0 ? resInA : 1))));
+  return SDSO_OK;
 }
 
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {

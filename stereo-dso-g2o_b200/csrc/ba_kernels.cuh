@@ -25,8 +25,8 @@ struct BAView {  // plain pointers handed to the kernels
   const float4* const* tex0; const float* frameTH; const PrecalcDev* precalc;
   const double* adHost; const double* adTarget; const float* adHostF; const float* adTargetF;
   const float* adHTdeltaF; const float* cDeltaF; const double* fprior;
-  const int* p_host; const float* p_u; const float* p_v; const float* p_idepth; const float* p_idepth_zero;
-  const float4* p_color; const float4* p_weights; const float* p_priorF; const float* p_deltaF;
+  const int* p_host; const float* p_u; const float* p_v; float* p_idepth; float* p_idepth_zero; float* p_idepth_backup;
+  const float4* p_color; const float4* p_weights; const float* p_priorF; float* p_deltaF;
   const int* p_res_begin; const int* p_res_list; const int* slot_of; float* p_acc; const unsigned char* p_flag;
   const int* s_point; const int* s_key;
   unsigned char* s_state; unsigned char* s_newstate; unsigned char* s_flags; unsigned char* s_sel;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void apply_res_slot(const BAView& B, int s, bool copy
 // ---- B1 ------------------------------------------------------------------------------------------
 __device__ double linearize_slot(const BAView& B, int s, bool fix) {
   const size_t cR = B.capR;
-  if (B.s_flags[s] & RF_LINEARIZED) return 0.0;  // activeResiduals = residuals that are not linearised (FullSystemOptimize.cpp:900-902)
+  if (B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED)) return 0.0;  // activeResiduals = residuals of the graph that are not linearised (FullSystemOptimize.cpp:900-902)
   B.s_energy[2 * cR + s] = -1;
   const float state_energy = B.s_energy[s];
   if (B.s_state[s] == RS_OOB) { B.s_newstate[s] = RS_OOB; return state_energy; }
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128) ba_linearize_kernel(BAView B, int fix) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0;
   if (s < B.R) {
-    const bool active_res = !(B.s_flags[s] & RF_LINEARIZED);
+    const bool active_res = !(B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED));
     e = linearize_slot(B, s, fix != 0);
     if (fix && active_res) apply_res_slot(B, s, true);
   }
@@ -237,9 +237,105 @@ __global__ void __launch_bounds__(128) ba_linearize_kernel(BAView B, int fix) {
   }
 }
 
-__global__ void ba_apply_res_kernel(BAView B, int copyJ) {
+__global__ void ba_apply_res_kernel(BAView B, int copyJ) {  // applyRes_Reductor over activeResiduals
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < B.R) apply_res_slot(B, s, copyJ != 0);
+  if (s < B.R && !(B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED))) apply_res_slot(B, s, copyJ != 0);
+}
+
+// ---- B12: pieces of FullSystem::optimize (FullSystemOptimize.cpp:870-1042) that touch per-point / per-residual state ------
+// resetOOB for the active residuals (:888-893, Residuals.h:107-115)
+__global__ void ba_reset_oob_kernel(BAView B) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.R || (B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED))) return;
+  B.s_state[s] = RS_IN; B.s_newstate[s] = RS_OUTLIER;
+  B.s_energy[s] = 0; B.s_energy[(size_t)B.capR + s] = 0;
+}
+// backupState (:309-350): idepth_backup = idepth
+__global__ void ba_backup_points_kernel(BAView B) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < B.P) B.p_idepth_backup[p] = B.p_idepth[p];
+}
+// doStepFromBackup (:268-279) / loadSateBackup (:355-362): idepth = idepth_zero = idepth_backup + stepfacD * step (points carry no FEJ
+// point), plus the sums the convergence test needs: out[0] += step^2, out[1] += |idepth_backup| (fixed-order double sums)
+__global__ void __launch_bounds__(128) ba_step_points_kernel(BAView B, float stepfacD, double* part /* [blocks][2] */) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double s2 = 0, sn = 0;
+  if (p < B.P) {
+    const float bak = B.p_idepth_backup[p], st = B.p_acc[14 * (size_t)B.capP + p];
+    const float nv = bak + stepfacD * st;
+    B.p_idepth[p] = nv; B.p_idepth_zero[p] = nv; B.p_deltaF[p] = nv - nv;
+    s2 = (double)(st * st); sn = (double)fabsf(bak);
+  }
+  const double a = block_sum_d(s2, red);
+  const double b = block_sum_d(sn, red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+__global__ void ba_sum_pairs_kernel(const double* part, int nblocks, double* out) {
+  if (threadIdx.x < 2) { double s = 0; for (int i = 0; i < nblocks; i++) s += part[2 * i + threadIdx.x]; out[threadIdx.x] = s; }
+}
+// number of residuals accumulateAF would count (ef->resInA): active, not linearised
+__global__ void ba_count_active_kernel(BAView B, unsigned int* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool a = s < B.R && (B.s_flags[s] & RF_ACTIVE) && !(B.s_flags[s] & RF_LINEARIZED);
+  const unsigned m = __ballot_sync(0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned)__popc(m));
+}
+// residuals that the final linearizeAll(true) found inactive leave the graph (toRemove, :170-200)
+__global__ void ba_drop_inactive_kernel(BAView B) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.R) return;
+  const unsigned char fl = B.s_flags[s];
+  if (!(fl & (RF_LINEARIZED | RF_DROPPED)) && !(fl & RF_ACTIVE)) B.s_flags[s] = fl | RF_DROPPED;
+}
+
+// setNewFrameEnergyTH (:98-139) on ONE CTA: exact selection of the floor(0.7 N)-th smallest state_NewEnergyWithOutlier among the
+// active residuals that target the newest frame — a 4-pass radix select on the (non-negative) float bit patterns, so the result
+// is the very element std::nth_element would deliver — then the threshold arithmetic in float as written.
+__global__ void __launch_bounds__(1024) ba_energy_th_kernel(BAView B, int newest, float thN, float facMedian, float constWeight, float overallW,
+                                                            float* frameTH, float* out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_mask, s_k, s_n;
+  const int tid = threadIdx.x, n = B.n;
+  const float* NE = B.s_energy + 2 * (size_t)B.capR;
+  if (tid == 0) { s_n = 0; s_prefix = 0; s_mask = 0; }
+  __syncthreads();
+  unsigned cnt = 0;
+  for (int s = tid; s < B.R; s += blockDim.x) {
+    const bool sel = !(B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED)) && (B.s_key[s] / n) == newest && NE[s] >= 0;
+    cnt += sel ? 1u : 0u;
+  }
+  atomicAdd(&s_n, cnt);
+  __syncthreads();
+  const unsigned N = s_n;
+  if (N == 0) { if (tid == 0) { const float th = 12 * 12 * 8; frameTH[newest] = th; out[0] = th; } return; }
+  if (tid == 0) s_k = (unsigned)(int)(thN * N);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, mask = s_mask;
+    for (int s = tid; s < B.R; s += blockDim.x) {
+      const bool sel = !(B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED)) && (B.s_key[s] / n) == newest && NE[s] >= 0;
+      if (!sel) continue;
+      const unsigned bits = __float_as_uint(NE[s] + 0.0f);  // +0.0f folds -0 into +0
+      if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned k = s_k, d = 0;
+      for (; d < 256; d++) { if (k < hist[d]) break; k -= hist[d]; }
+      s_k = k; s_prefix = prefix | (d << shift); s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float nthElement = sqrtf(__uint_as_float(s_prefix));
+    float th = nthElement * facMedian;
+    th = 26.0f * constWeight + th * (1 - constWeight);
+    th = th * th;
+    th *= overallW * overallW;
+    frameTH[newest] = th; out[0] = th;
+  }
 }
 
 // res_toZeroF = resF - J * delta  (EnergyFunctionalStructs.cpp:96-123); list == nullptr: every active residual

@@ -20,7 +20,7 @@ constexpr int kJ = 74;          // floats of RawResidualJacobian (OptimizationBa
 enum { J_RESF = 0, J_PDXI = 8, J_PDC = 20, J_PDD = 28, J_IDX = 30, J_AB = 46, J_IDX2 = 62, J_ABIDX = 66, J_AB2 = 70 };
 
 enum { RS_IN = 0, RS_OOB = 1, RS_OUTLIER = 2 };  // Residuals.h:49
-enum { RF_LINEARIZED = 1, RF_ACTIVE = 2 };       // EFResidual::isLinearized / isActiveAndIsGoodNEW
+enum { RF_LINEARIZED = 1, RF_ACTIVE = 2, RF_DROPPED = 4 };  // EFResidual::isLinearized / isActiveAndIsGoodNEW / removed from the graph (dropResidual)
 enum { PS_GOOD = 0, PS_MARGINALIZE = 1, PS_DROP = 2 };  // EnergyFunctionalStructs.h:97
 
 constexpr int kTopVals = 96;   // 55 (10x10 upper triangle) + 30 (10x3) + 6 (3x3 upper triangle), padded to 3x32
@@ -50,6 +50,7 @@ struct HostBAFrame {
   double T_w2c[12], T_c2w[12];             // PRE_worldToCam / PRE_camToWorld
   double ns_pose[36], ns_scale[6];         // nullspaces (HessianBlocks.cpp:78-123)
   double prior[8] = {0}, delta_prior[8] = {0}, delta[8] = {0};
+  double step[10] = {0}, state_backup[10] = {0};
 };
 
 struct Chunk { int key, begin, end, pad; };
@@ -60,6 +61,7 @@ struct BAState {
   BACalib calib;
   double calib_delta[4] = {0, 0, 0, 0};   // HCalib.value_minus_value_zero
   double cPrior[4] = {0, 0, 0, 0};
+  double calib_value[4] = {0, 0, 0, 0}, calib_zero[4] = {0, 0, 0, 0}, calib_step[4] = {0, 0, 0, 0}, calib_backup[4] = {0, 0, 0, 0};  // CalibHessian value / value_zero / step / value_backup
   std::vector<HostBAFrame> frames;
   // host copies of the graph
   std::vector<int> h_p_host, h_r_point, h_r_target, h_rid2slot, h_slot2rid, h_seg_begin;
@@ -79,7 +81,7 @@ struct BAState {
   int* d_p_host = nullptr; float* d_p_u = nullptr; float* d_p_v = nullptr;
   float* d_p_idepth = nullptr; float* d_p_idepth_zero = nullptr;
   float4* d_p_color = nullptr; float4* d_p_weights = nullptr;  // [P][2]
-  float* d_p_priorF = nullptr; float* d_p_deltaF = nullptr;
+  float* d_p_priorF = nullptr; float* d_p_deltaF = nullptr; float* d_p_idepth_backup = nullptr;
   int* d_p_res_begin = nullptr;           // CSR [P+1] into d_p_res_list (slots, residualsAll order)
   int* d_slot_of = nullptr;               // [P*n]: slot of the point's residual towards target t, or -1
   float* d_p_acc = nullptr;               // [16][capP]: Hdd_A, bd_A, Hcd_A[4], Hdd_L, bd_L, Hcd_L[4], HdiF, bdSumF, step, idepth_hessian
@@ -117,6 +119,7 @@ struct BAState {
   int nrank = 0;
   float* d_xAd = nullptr;                 // [n*n][8]
   int* d_list = nullptr;                  // scratch slot list
+  double* d_step_part = nullptr; int step_part_cap = 0;  // per-block partial sums of doStepFromBackup
   int shard_rank = 0, shard_n = 1;        // point-sharded window: priors and HM enter on rank 0 only
   bool have_M = false;                    // HM/bM (marginalisation prior) present in SYS_M
   std::vector<double> h_N, h_adH, h_adT;

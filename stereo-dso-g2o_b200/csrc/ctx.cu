@@ -120,6 +120,11 @@ void sdso_default_settings(sdso_settings* s) {
   s->initialCalibHessian = 5e9f;
   s->margWeightFac = 0.5f * 0.5f;
   s->solverModeDelta = 0.00001;
+  s->minOptIterations = 1;
+  s->thOptIterations = 1.2f;
+  s->frameEnergyTHConstWeight = 0.5f;
+  s->frameEnergyTHN = 0.7f;
+  s->frameEnergyTHFacMedian = 1.5f;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {

@@ -176,3 +176,31 @@ class OracleBA:
         N = np.zeros((d, 7))
         lib.orc_ba_nullspaces(self.h, _p(N, _dp))
         return N
+
+lib.orc_ba_optimize.restype = C.c_double
+lib.orc_ba_optimize.argtypes = [V, C.c_int, _ip]
+lib.orc_ba_new_frame_energy_th.restype = C.c_float
+lib.orc_ba_new_frame_energy_th.argtypes = [V]
+lib.orc_ba_get_state.argtypes = [V, _dp, _dp, _fp, _dp]
+
+
+def _optimize(self, iters=6):
+    done = C.c_int()
+    rmse = lib.orc_ba_optimize(self.h, iters, C.byref(done))
+    return rmse, done.value
+
+
+def _new_frame_energy_th(self):
+    return lib.orc_ba_new_frame_energy_th(self.h)
+
+
+def _get_state(self):
+    c = self.counts()
+    st, T, idp, cal = np.zeros((c["frames"], 10)), np.zeros((c["frames"], 3, 4)), np.zeros(c["points"], np.float32), np.zeros(4)
+    lib.orc_ba_get_state(self.h, _p(st, _dp), _p(T, _dp), _p(idp, _fp), _p(cal, _dp))
+    return dict(states=st, T_w2c=T, idepth=idp, calib=cal)
+
+
+OracleBA.optimize = _optimize
+OracleBA.new_frame_energy_th = _new_frame_energy_th
+OracleBA.get_state = _get_state

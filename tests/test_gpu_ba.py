@@ -241,3 +241,43 @@ def test_empty_and_degenerate_windows(pkg, scene):
     assert np.abs(po["step"]).max() > 0
     assert np.allclose(pg["step"], po["step"], rtol=1e-3, atol=1e-4 * np.abs(po["step"]).max())
     ctx.close()
+
+
+def test_new_frame_energy_threshold_is_exact(small):
+    """setNewFrameEnergyTH (FullSystemOptimize.cpp:98-139): the device radix select must return the very element nth_element picks."""
+    win, orc, ba, ctx, W = small
+    ba.linearize_all(False); W.linearize_all(False)
+    assert W.new_frame_energy_th() == ba.new_frame_energy_th()
+
+
+@pytest.mark.parametrize("shape", [(4, 300, 21), (7, 1400, 22)])
+def test_optimize_matches_oracle(pkg, scene, shape):
+    """B12: FullSystem::optimize (SSE body, forced accept): same iteration count, final frame states / idepths / energy close to the
+    oracle's. The first two iterations are not gauge-orthogonalised, so absolute states carry the gauge noise of the solve
+    (see test_solve_and_resubstitute); inverse depths and the final RMSE are gauge-free to first order."""
+    n, P, seed = shape
+    win = ba_synth.make_window(scene, n=n, P=P, seed=seed, spacing=0.5, w=640, h=192, K=(360.0, 360.0, 319.5, 95.5), idepth_noise=0.03,
+                               state_sigma=3e-3)
+    orc = O.Oracle(640, 192, (360.0, 360.0, 319.5, 95.5), synth.BASELINE)
+    ba, _, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)
+    ctx = pkg.Context(640, 192, (360.0, 360.0, 319.5, 95.5), synth.BASELINE)
+    W, _ = ba_synth.fill_device(win, ctx, pkg.Window, cw)
+    ro, io = ba.optimize(6)
+    rg, ig = W.optimize(6)
+    assert ig == io
+    so, sg = ba.get_state(), W.get_state()
+    assert np.isclose(rg, ro, rtol=2e-3)
+    true_id = np.array([1.0 / win["frames"][p["host"]]["depth"][int(p["v"]), int(p["u"])] for p in win["points"]])
+    # the optimisation must actually have improved the inverse depths, identically on both sides
+    assert np.median(np.abs(so["idepth"] - true_id) / true_id) < 0.015
+    # (a residual whose energy sits on the outlier threshold can flip IN/OUTLIER under float summation noise and move its
+    # point; such points are rare and bounded here instead of being hidden by a loose global tolerance)
+    rel = np.abs(sg["idepth"] - so["idepth"]) / np.abs(so["idepth"])
+    assert (rel < 5e-3).mean() > 0.995, float((rel < 5e-3).mean())
+    assert np.median(np.abs(sg["idepth"] - so["idepth"]) / np.abs(so["idepth"])) < 2e-4
+    assert np.abs(sg["T_w2c"] - so["T_w2c"]).max() < 2e-4
+    assert np.allclose(sg["calib"], so["calib"], rtol=1e-6)
+    ro_, rg_ = ba.get_res(1), W.get_res(1)
+    agree = (ro_["active"] == rg_["active"]).mean()
+    assert agree > 0.995, agree
+    ctx.close()
