@@ -247,6 +247,13 @@ int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iteration
 int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idepth, double* calib);
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM);   /* EnergyFunctional::HM, bM */
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM);
+/* EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736): points flagged PS_MARGINALIZE go into HM / bM and leave the graph */
+int sdso_ba_marginalize_points(sdso_ctx* ctx);
+/* EnergyFunctional::marginalizeFrame (:554-660): Schur-eliminates frame idx from HM / bM (now of dimension dim-8) and removes the
+ * frame from the window; points, residuals and states must be uploaded again afterwards (the reference calls makeIDX here) */
+int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx);
+/* EnergyFunctional::calcMEnergyF (:344-351) and calcLEnergyF_MT (:354-442); each output nullable */
+int sdso_ba_energies(sdso_ctx* ctx, double* menergy, double* lenergy);
 
 /* ---- point-sharded windowed BA over 2/4/8 GPUs ------------------------------------------------------
  * Every rank holds all keyframe pyramids and a contiguous block of the allPoints order with its residuals. Per LM

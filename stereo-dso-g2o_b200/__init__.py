@@ -642,3 +642,26 @@ def _w_get_state(self):
 Window.new_frame_energy_th = _w_new_frame_energy_th
 Window.optimize = _w_optimize
 Window.get_state = _w_get_state
+
+lib.sdso_ba_marginalize_points.argtypes = [C.c_void_p]
+lib.sdso_ba_marginalize_frame.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_ba_energies.argtypes = [C.c_void_p, _dp, _dp]
+
+
+def _w_marginalize_points(self):
+    self._ck(lib.sdso_ba_marginalize_points(self.h))
+
+
+def _w_marginalize_frame(self, idx):
+    self._ck(lib.sdso_ba_marginalize_frame(self.h, idx))
+
+
+def _w_energies(self):
+    m, l = C.c_double(), C.c_double()
+    self._ck(lib.sdso_ba_energies(self.h, C.byref(m), C.byref(l)))
+    return m.value, l.value
+
+
+Window.marginalize_points = _w_marginalize_points
+Window.marginalize_frame = _w_marginalize_frame
+Window.energies = _w_energies

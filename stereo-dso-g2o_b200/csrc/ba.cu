@@ -996,6 +996,85 @@ int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
   return SDSO_OK;
 }
 
+// EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736) for the points flagged PS_MARGINALIZE
+int sdso_ba_marginalize_points(sdso_ctx* ctx) {
+  BA_PREPARED(ctx)
+  const int d = b->dim(), P = b->P, R = b->R;
+  cudaStream_t st = ctx->stream;
+  if (P == 0) return SDSO_OK;
+  ba_marg_prior_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, b->d_p_flag, b->d_p_priorF, ctx->S.idepthFixPriorMargFac); SDSO_CHECK_LAUNCH(ctx);
+  int rc = launch_top(ctx, 2, SYS_A, false);   // accumulateTop<2> (:680-696)
+  if (!rc) rc = launch_sc(ctx, false, SYS_SC); // accumulateSC without the prior shift
+  if (rc) return rc;
+  const int cnt = d * d + d;
+  ba_marg_add_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(cnt, (double)ctx->S.margWeightFac, sysH(b, SYS_A), sysH(b, SYS_SC), sysH(b, SYS_M), b->have_M ? 0 : 1);
+  SDSO_CHECK_LAUNCH(ctx);
+  b->have_M = true;
+  BAView v = view(b);
+  if (R > 0) { ba_marg_remove_kernel<<<(R + 127) / 128, 128, 0, st>>>(v, b->d_p_flag); SDSO_CHECK_LAUNCH(ctx); }
+  ba_marg_flag_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, b->d_p_flag); SDSO_CHECK_LAUNCH(ctx);
+  return SDSO_OK;
+}
+
+// EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:554-660). The frame must own no points any more (as the reference
+// asserts). HM / bM shrink to dimension d-8 on the device; the host window loses the frame, so points / residuals / states have
+// to be uploaded again before the next operator call (the reference re-indexes with makeIDX at this point).
+int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx) {
+  BA_PREPARED(ctx)
+  if (idx < 0 || idx >= b->n) return SDSO_E_INVALID;
+  const int odim = b->dim(), ndim = odim - 8;
+  cudaStream_t st = ctx->stream;
+  if (!b->have_M) { SDSO_CUDA(ctx, cudaMemsetAsync(sysH(b, SYS_M), 0, ((size_t)odim * odim + odim) * sizeof(double), st)); b->have_M = true; }
+  const size_t smem = ((size_t)odim * odim + 2 * (size_t)odim + 64 + (size_t)ndim * 8) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(ba_marg_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  double* out = sysH(b, SYS_TMP);
+  ba_marg_frame_kernel<<<1, 256, smem, st>>>(odim, idx, sysH(b, SYS_M), sysb(b, SYS_M), b->d_fprior, out, out + (size_t)ndim * ndim);
+  SDSO_CHECK_LAUNCH(ctx);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(sysH(b, SYS_M), out, ((size_t)ndim * ndim + ndim) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  b->frames.erase(b->frames.begin() + idx);
+  b->n = (int)b->frames.size();
+  b->P = 0; b->R = 0; b->nchunks = 0;
+  b->prepared = false;
+  return SDSO_OK;
+}
+
+// EnergyFunctional::calcMEnergyF (:344-351) and calcLEnergyF_MT (:354-442)
+int sdso_ba_energies(sdso_ctx* ctx, double* menergy, double* lenergy) {
+  BA_PREPARED(ctx)
+  const int d = b->dim(), P = b->P;
+  cudaStream_t st = ctx->stream;
+  double M = 0, L = 0;
+  if (menergy && b->have_M) {
+    ba_menergy_kernel<<<1, 256, 0, st>>>(d, sysH(b, SYS_M), sysb(b, SYS_M), b->d_fprior, b->d_cDeltaF, b->d_scalars + 2); SDSO_CHECK_LAUNCH(ctx);
+    SDSO_CUDA(ctx, cudaMemcpyAsync(&M, b->d_scalars + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<double> part;
+  if (lenergy && P > 0) {
+    const int pb = (P + 127) / 128;
+    if (pb > b->step_part_cap) {
+      if (b->d_step_part) cudaFree(b->d_step_part);
+      b->d_step_part = nullptr;
+      SDSO_CUDA(ctx, cudaMalloc(&b->d_step_part, (size_t)(pb + 1) * 2 * sizeof(double)));
+      b->step_part_cap = pb;
+    }
+    BAView v = view(b);
+    ba_lenergy_kernel<<<pb, 128, 0, st>>>(v, b->d_step_part); SDSO_CHECK_LAUNCH(ctx);
+    part.resize(pb);
+    SDSO_CUDA(ctx, cudaMemcpyAsync(part.data(), b->d_step_part, pb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  if (lenergy) {
+    for (double v : part) L += v;
+    for (auto& f : b->frames) for (int i = 0; i < 8; i++) L += f.delta_prior[i] * f.prior[i] * f.delta_prior[i];   // :429-431
+    for (int i = 0; i < 4; i++) { const float cd = (float)b->calib_delta[i], cp = (float)b->cPrior[i]; L += cd * cp * cd; }
+    *lenergy = L;
+  }
+  if (menergy) *menergy = M;
+  return SDSO_OK;
+}
+
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM) {
   BA_CHECK(ctx)
   return download_sys(ctx, SYS_M, HM, bM);

@@ -956,6 +956,155 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   for (int i = tid; i < d; i += nt) S.x[i] = bs[i];
 }
 
+// ---- B11: marginalisation ------------------------------------------------------------------------------------------
+// marginalizePointsF (EnergyFunctional.cpp:663-736): priorF *= setting_idepthFixPriorMargFac for the flagged points
+__global__ void ba_marg_prior_kernel(int P, const unsigned char* flag, float* priorF, float fac) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P && flag[p] == PS_MARGINALIZE) priorF[p] *= fac;
+}
+// HM += w (M - Msc), bM += w (Mb - Mbsc)  (:712-718); src buffers are (H,b) pairs of (d*d + d) doubles
+__global__ void ba_marg_add_kernel(int count, double w, const double* M, const double* Msc, double* HM, int init) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < count) HM[e] = (init ? 0.0 : HM[e]) + w * (M[e] - Msc[e]);
+}
+// removePoint for the marginalised points (:720-735): the points and their residuals leave the graph
+__global__ void ba_marg_remove_kernel(BAView B, unsigned char* p_flag) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < B.R && p_flag[B.s_point[s]] == PS_MARGINALIZE) B.s_flags[s] = (B.s_flags[s] & ~RF_ACTIVE) | RF_DROPPED;
+}
+__global__ void ba_marg_flag_kernel(int P, unsigned char* p_flag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P && p_flag[p] == PS_MARGINALIZE) p_flag[p] = PS_DROP;
+}
+
+// marginalizeFrame (EnergyFunctional.cpp:554-660) on ONE CTA: move the frame's 8 rows/cols to the end, add its prior, scale by
+// (|diag|+10)^-1/2, invert the 8x8 corner, Schur complement, unscale, symmetrise. in: (HM,bM) of dimension odim; out: (H,b) of
+// dimension odim-8, b directly behind H.
+__global__ void __launch_bounds__(256) ba_marg_frame_kernel(int odim, int idx, const double* HMin, const double* bMin, const double* fprior,
+                                                            double* Hout, double* bout) {
+  extern __shared__ double sm[];
+  const int ndim = odim - 8, tid = threadIdx.x, nt = blockDim.x;
+  double* Hs = sm;                    // odim*odim, permuted + scaled
+  double* bs = Hs + odim * odim;      // odim
+  double* SV = bs + odim;             // odim
+  double* hpi = SV + odim;            // 64
+  double* bli = hpi + 64;             // ndim*8
+  __shared__ int perm[kCPARS + 8 * kMaxFrames];
+  for (int i = tid; i < odim; i += nt) {
+    const int io = kCPARS + idx * 8;
+    perm[i] = (i < io) ? i : (i < ndim ? i + 8 : io + (i - ndim));
+  }
+  __syncthreads();
+  for (int e = tid; e < odim * odim; e += nt) {
+    const int r = e / odim, c = e % odim;
+    double v = HMin[(size_t)perm[r] * odim + perm[c]];
+    if (r == c && r >= ndim) v += fprior[idx * 24 + (r - ndim)];
+    Hs[e] = v;
+  }
+  for (int i = tid; i < odim; i += nt) {
+    double v = bMin[perm[i]];
+    if (i >= ndim) v += fprior[idx * 24 + (i - ndim)] * fprior[idx * 24 + 8 + (i - ndim)];
+    bs[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < odim; i += nt) SV[i] = sqrt(fabs(Hs[i * odim + i]) + 10);
+  __syncthreads();
+  for (int e = tid; e < odim * odim; e += nt) Hs[e] = (1.0 / SV[e / odim]) * Hs[e] * (1.0 / SV[e % odim]);
+  for (int i = tid; i < odim; i += nt) bs[i] = (1.0 / SV[i]) * bs[i];
+  __syncthreads();
+  if (tid == 0) {  // 8x8 inverse: Gauss-Jordan with partial pivoting
+    double A[8][16];
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { const double h = Hs[(ndim + i) * odim + ndim + j]; A[i][j] = 0.5f * (h + h); A[i][8 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int k = 0; k < 8; k++) {
+      int p = k;
+      for (int i = k + 1; i < 8; i++) if (fabs(A[i][k]) > fabs(A[p][k])) p = i;
+      if (p != k) for (int j = 0; j < 16; j++) { const double t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
+      const double inv = 1.0 / A[k][k];
+      for (int j = 0; j < 16; j++) A[k][j] *= inv;
+      for (int i = 0; i < 8; i++) if (i != k) { const double f = A[i][k]; if (f != 0) for (int j = 0; j < 16; j++) A[i][j] -= f * A[k][j]; }
+    }
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { const double h = A[i][8 + j]; hpi[i * 8 + j] = 0.5f * (h + h); }
+  }
+  __syncthreads();
+  for (int e = tid; e < ndim * 8; e += nt) {
+    const int r = e / 8, c = e % 8;
+    double sacc = 0;
+    for (int k = 0; k < 8; k++) sacc += Hs[(ndim + k) * odim + r] * hpi[k * 8 + c];
+    bli[e] = sacc;
+  }
+  __syncthreads();
+  for (int e = tid; e < ndim * ndim; e += nt) {
+    const int r = e / ndim, c = e % ndim;
+    double sacc = 0;
+    for (int k = 0; k < 8; k++) sacc += bli[r * 8 + k] * Hs[(ndim + k) * odim + c];
+    Hs[r * odim + c] -= sacc;
+  }
+  for (int r = tid; r < ndim; r += nt) {
+    double sacc = 0;
+    for (int k = 0; k < 8; k++) sacc += bli[r * 8 + k] * bs[ndim + k];
+    bs[r] -= sacc;
+  }
+  __syncthreads();
+  for (int e = tid; e < ndim * ndim; e += nt) {
+    const int r = e / ndim, c = e % ndim;
+    const double a = SV[r] * Hs[r * odim + c] * SV[c], bb = SV[c] * Hs[c * odim + r] * SV[r];
+    Hout[e] = 0.5 * (a + bb);
+  }
+  for (int r = tid; r < ndim; r += nt) bout[r] = SV[r] * bs[r];
+}
+
+// calcMEnergyF (:344-351): delta^T (2 bM + HM delta) ; calcLEnergyF (:354-442): priors + linearised residuals + point priors
+__global__ void __launch_bounds__(256) ba_menergy_kernel(int d, const double* HM, const double* bM, const double* fprior, const float* cDeltaF, double* out) {
+  __shared__ double red[32];
+  double acc = 0;
+  for (int r = threadIdx.x; r < d; r += blockDim.x) {
+    const double dr = r < 4 ? (double)cDeltaF[r] : fprior[((r - 4) / 8) * 24 + 16 + (r - 4) % 8];
+    double sacc = 0;
+    for (int c = 0; c < d; c++) { const double dc = c < 4 ? (double)cDeltaF[c] : fprior[((c - 4) / 8) * 24 + 16 + (c - 4) % 8]; sacc += HM[(size_t)r * d + c] * dc; }
+    acc += dr * (2 * bM[r] + sacc);
+  }
+  const double t = block_sum_d(acc, red);
+  if (threadIdx.x == 0) out[0] = t;
+}
+__global__ void __launch_bounds__(128) ba_lenergy_kernel(BAView B, double* part) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0;
+  if (p < B.P && B.p_flag[p] != PS_DROP) {
+    const float dd = B.p_deltaF[p];
+    const float* cd = B.cDeltaF;
+    for (int i = B.p_res_begin[p]; i < B.p_res_begin[p + 1]; i++) {
+      const int s = B.p_res_list[i];
+      const unsigned char fl = B.s_flags[s];
+      if (!(fl & RF_LINEARIZED) || !(fl & RF_ACTIVE)) continue;
+      const int buf = B.s_sel[s];
+      const float* dp = B.adHTdeltaF + (size_t)B.s_key[s] * 8;
+      float jx[6], jy[6], cx[4], cy[4];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { jx[k] = *jplane(B, buf, J_PDXI + k, s); jy[k] = *jplane(B, buf, J_PDXI + 6 + k, s); }
+#pragma unroll
+      for (int k = 0; k < 4; k++) { cx[k] = *jplane(B, buf, J_PDC + k, s); cy[k] = *jplane(B, buf, J_PDC + 4 + k, s); }
+      const float Jpx = (jx[0] * dp[0] + jx[1] * dp[1] + jx[2] * dp[2] + jx[3] * dp[3] + jx[4] * dp[4] + jx[5] * dp[5]) +
+                        (cx[0] * cd[0] + cx[1] * cd[1] + cx[2] * cd[2] + cx[3] * cd[3]) + *jplane(B, buf, J_PDD, s) * dd;
+      const float Jpy = (jy[0] * dp[0] + jy[1] * dp[1] + jy[2] * dp[2] + jy[3] * dp[3] + jy[4] * dp[4] + jy[5] * dp[5]) +
+                        (cy[0] * cd[0] + cy[1] * cd[1] + cy[2] * cd[2] + cy[3] * cd[3]) + *jplane(B, buf, J_PDD + 1, s) * dd;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        float Jdelta = *jplane(B, buf, J_IDX + k, s) * Jpx;
+        Jdelta = Jdelta + *jplane(B, buf, J_IDX + 8 + k, s) * Jpy;
+        Jdelta = Jdelta + *jplane(B, buf, J_AB + k, s) * dp[6];
+        Jdelta = Jdelta + *jplane(B, buf, J_AB + 8 + k, s) * dp[7];
+        float r0 = B.s_rtz[(size_t)k * B.capR + s];
+        r0 = r0 + r0; r0 = r0 + Jdelta;
+        acc += Jdelta * r0;
+      }
+    }
+    acc += dd * dd * B.p_priorF[p];
+  }
+  const double t = block_sum_d((double)acc, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
 // ---- B9 -------------------------------------------------------------------------------------------------------
 // xAd[h*n + t] = x_h^T adHostF[h + t*n] + x_t^T adTargetF[h + t*n]   (EnergyFunctional.cpp:283-293)
 __global__ void ba_xad_kernel(BAView B, const double* x, float* xAd) {

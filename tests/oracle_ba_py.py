@@ -204,3 +204,13 @@ def _get_state(self):
 OracleBA.optimize = _optimize
 OracleBA.new_frame_energy_th = _new_frame_energy_th
 OracleBA.get_state = _get_state
+
+
+def _energies(self):
+    """(calcMEnergyF, calcLEnergyF)"""
+    l = C.c_double()
+    m = lib.orc_ba_energies(self.h, C.byref(l))
+    return m, l.value
+
+
+OracleBA.energies = _energies

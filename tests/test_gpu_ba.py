@@ -281,3 +281,52 @@ def test_optimize_matches_oracle(pkg, scene, shape):
     agree = (ro_["active"] == rg_["active"]).mean()
     assert agree > 0.995, agree
     ctx.close()
+
+
+def test_marginalisation_points_frame_and_energies(pkg, scene):
+    """B11: marginalizePointsF (HM += 0.25 (M - Msc), EnergyFunctional.cpp:663-736), calcMEnergyF / calcLEnergyF (:344-442),
+    marginalizeFrame (:554-660)."""
+    win, orc, ba, ctx, W = build(pkg, scene, 4, 240, 5)
+    n = win["n"]
+    ba.linearize_all(True); W.linearize_all(True)
+    r = ba.get_res(1)
+    flags = np.zeros(len(win["points"]), np.uint8)
+    fix = []
+    ridx = 0
+    for pi, p in enumerate(win["points"]):
+        if p["host"] == 0 or pi % 5 == 0:
+            flags[pi] = 1
+            fix += [ridx + k for k in range(len(p["targets"])) if r["active"][ridx + k]]
+        ridx += len(p["targets"])
+    for pi in np.nonzero(flags)[0]:
+        ba.set_point_flag(int(pi), 1)
+    W.set_point_flags(flags)
+    for k in fix:
+        ba.fix_linearization(int(k))
+    W.fix_linearization(fix)
+    # linearised energy of the fixed residuals before they leave the graph
+    mo = ba.energies(); mg = W.energies()
+    assert np.isclose(mg[1], mo[1], rtol=1e-4, atol=1e-6 * abs(mo[1]) + 1e-9)
+    d = 4 + 8 * n
+    ba.set_marg_prior(np.zeros((d, d)), np.zeros(d)); W.set_marg_prior(np.zeros((d, d)), np.zeros(d))
+    ba.marginalize_points(); W.marginalize_points()
+    HMo, bMo = ba.get_marg_prior(); HMg, bMg = W.get_marg_prior()
+    ok, why = blockwise_close(HMg, HMo, n)
+    assert ok, why
+    assert np.allclose(bMg, bMo, rtol=REL, atol=REL * np.abs(bMo).max())
+    assert np.abs(HMo).max() > 0
+    # the marginalised points are inert afterwards: the reduced system of the remaining window agrees
+    xo, Hfo, bfo = ba.solve(0); xg, Hfg, bfg = W.solve(0)
+    ok, why = blockwise_close(Hfg, Hfo, n)
+    assert ok, why
+    Mo, Lo = ba.energies(); Mg, Lg = W.energies()
+    assert np.isclose(Mg, Mo, rtol=1e-6, atol=1e-12)
+    ba.prepare()
+    ba.marginalize_frame(0); W.marginalize_frame(0)
+    H2o, b2o = ba.get_marg_prior(); H2g, b2g = W.get_marg_prior()
+    assert H2g.shape == (d - 8, d - 8)
+    ok, why = blockwise_close(H2g, H2o, n - 1)
+    assert ok, why
+    assert np.allclose(b2g, b2o, rtol=REL, atol=REL * np.abs(b2o).max())
+    assert np.allclose(H2g, H2g.T, rtol=1e-12, atol=1e-12 * np.abs(H2g).max())
+    ctx.close()
