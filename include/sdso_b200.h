@@ -255,6 +255,17 @@ int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx);
 /* EnergyFunctional::calcMEnergyF (:344-351) and calcLEnergyF_MT (:354-442); each output nullable */
 int sdso_ba_energies(sdso_ctx* ctx, double* menergy, double* lenergy);
 
+/* ---- E2: EdgeLBASE3PosePhotoIdepthCamDSO::computeError + linearizeOplus (dso_g2o_edge.cpp:5-128, 130-282) -----------------
+ * Every residual of the uploaded window is evaluated as one LBA edge with the given vertex estimates: VertexSE3PoseDSO T_wh
+ * [n][12] and VertexPhotometricDSO [n][2] of the HOST frames, VertexInverseDepthDSO idepth[R] (one per residual, as
+ * FullSystemOptimize.cpp:493-512 builds them), VertexCamDSO cam[4], and b0[n] (SetB). Targets use the window's PRE_worldToCam
+ * and aff_g2l. Outputs (caller's residual order): error[R][8]; the four Jacobian blocks J_xi[R][8][6], J_photo[R][8][2],
+ * J_idepth[R][8], J_C[R][8][4]; the side effects state_NewState / state_NewEnergy / state_NewEnergyWithOutlier,
+ * CenterProjectedTo, point->idepth_hessian, and the edge level (1 = setLevel(1) on an out-of-image pixel). */
+int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, const double* idepth, const double cam[4], const double* b0,
+                       double* error8, double* J_xi, double* J_photo, double* J_idepth, double* J_C, int* newState, double* newEnergy,
+                       double* newEnergyWithOutlier, float* center3, float* idepth_hessian, int* level);
+
 /* ---- point-sharded windowed BA over 2/4/8 GPUs ------------------------------------------------------
  * Every rank holds all keyframe pyramids and a contiguous block of the allPoints order with its residuals. Per LM
  * iteration: sdso_ba_linearize_all (local) -> sdso_ba_assemble (local partial damped system; priors and HM on rank 0)

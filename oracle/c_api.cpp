@@ -348,3 +348,20 @@ void orc_ba_get_state(void* p, double* states, double* T_w2c, float* idepth, dou
   if (calib) { calib[0] = c->ba.HCalib.fxl; calib[1] = c->ba.HCalib.fyl; calib[2] = c->ba.HCalib.cxl; calib[3] = c->ba.HCalib.cyl; }
 }
 }  // extern "C"
+
+// ---- E2 operator level: every residual of the window as one edge (oracle/lba_edge.cpp) ----------------------------------
+extern "C" void orc_lba_edge_eval(void* p, const double* T_wh /*[n][12]*/, const double* photo /*[n][2]*/, const double* idepth /*[R]*/,
+                                  const double cam[4], const double* b0 /*[n]*/, double* error8, double* Jxi, double* Jphoto, double* Jid,
+                                  double* JC, int* newState, double* newEnergy, double* newEnergyWO, float* center3, float* idepth_hessian,
+                                  int* level) {
+  Ctx* c = (Ctx*)p;
+  for (size_t i = 0; i < c->ba.res.size(); i++) {
+    const BARes& r = c->ba.res[i];
+    LBAEdgeOut o;
+    lbaEdgeEval(c->ba, r, SE3::fromMat34(T_wh + 12 * r.host), photo + 2 * r.host, idepth[i], cam, b0[r.host], o);
+    memcpy(error8 + 8 * i, o.error, sizeof(o.error)); memcpy(Jxi + 48 * i, o.J_xi, sizeof(o.J_xi)); memcpy(Jphoto + 16 * i, o.J_photo, sizeof(o.J_photo));
+    memcpy(Jid + 8 * i, o.J_idepth, sizeof(o.J_idepth)); memcpy(JC + 32 * i, o.J_C, sizeof(o.J_C));
+    newState[i] = o.newState; newEnergy[i] = o.newEnergy; newEnergyWO[i] = o.newEnergyWithOutlier;
+    memcpy(center3 + 3 * i, o.centerProjectedTo, sizeof(o.centerProjectedTo)); idepth_hessian[i] = o.idepth_hessian; level[i] = o.level;
+  }
+}

@@ -665,3 +665,22 @@ def _w_energies(self):
 Window.marginalize_points = _w_marginalize_points
 Window.marginalize_frame = _w_marginalize_frame
 Window.energies = _w_energies
+
+lib.sdso_lba_edge_eval.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _fp, _fp, _ip]
+
+
+def _w_lba_edge_eval(self, T_wh, photo, idepth, cam, b0):
+    c = self.counts()
+    n, R = c["frames"], c["res"]
+    T_wh, photo, idepth, cam, b0 = _f64(T_wh).reshape(n, 12), _f64(photo).reshape(n, 2), _f64(idepth).reshape(R), _f64(cam).reshape(4), _f64(b0).reshape(n)
+    o = dict(error=np.zeros((R, 8)), J_xi=np.zeros((R, 8, 6)), J_photo=np.zeros((R, 8, 2)), J_idepth=np.zeros((R, 8)), J_C=np.zeros((R, 8, 4)),
+             newState=np.zeros(R, np.int32), newEnergy=np.zeros(R), newEnergyWithOutlier=np.zeros(R), center=np.zeros((R, 3), np.float32),
+             idepth_hessian=np.zeros(R, np.float32), level=np.zeros(R, np.int32))
+    self._ck(lib.sdso_lba_edge_eval(self.h, _ptr(T_wh, _dp), _ptr(photo, _dp), _ptr(idepth, _dp), _ptr(cam, _dp), _ptr(b0, _dp),
+                                    _ptr(o["error"], _dp), _ptr(o["J_xi"], _dp), _ptr(o["J_photo"], _dp), _ptr(o["J_idepth"], _dp), _ptr(o["J_C"], _dp),
+                                    _ptr(o["newState"], _ip), _ptr(o["newEnergy"], _dp), _ptr(o["newEnergyWithOutlier"], _dp), _ptr(o["center"], _fp),
+                                    _ptr(o["idepth_hessian"], _fp), _ptr(o["level"], _ip)))
+    return o
+
+
+Window.lba_edge_eval = _w_lba_edge_eval

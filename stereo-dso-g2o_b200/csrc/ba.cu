@@ -996,6 +996,76 @@ int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
   return SDSO_OK;
 }
 
+// E2 at operator level: every residual of the uploaded window evaluated as one EdgeLBASE3PosePhotoIdepthCamDSO
+// (dso_g2o_edge.cpp:5-282) with the given vertex estimates. Outputs are in the caller's residual order.
+int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, const double* idepth, const double cam[4], const double* b0,
+                       double* error8, double* J_xi, double* J_photo, double* J_idepth, double* J_C, int* newState, double* newEnergy,
+                       double* newEnergyWithOutlier, float* center3, float* idepth_hessian, int* level) {
+  BA_PREPARED(ctx)
+  if (!T_wh || !photo || !idepth || !cam || !b0 || !error8 || !J_xi || !J_photo || !J_idepth || !J_C || !newState || !newEnergy ||
+      !newEnergyWithOutlier || !center3 || !idepth_hessian || !level) return SDSO_E_INVALID;
+  const int n = b->n, R = b->R;
+  if (R == 0) return SDSO_OK;
+  cudaStream_t st = ctx->stream;
+  // one scratch allocation: inputs then outputs
+  const size_t in_d = (size_t)n * 12 * 2 + (size_t)n * 2 + R + n + (size_t)n * 2;   // doubles
+  const size_t out_d = (size_t)R * (8 + 48 + 16 + 8 + 32 + 2);                      // doubles
+  const size_t bytes = (in_d + out_d) * sizeof(double) + (size_t)R * (3 + 1) * sizeof(float) + (size_t)R * 2 * sizeof(int) + (size_t)n * sizeof(float) + 64;
+  unsigned char* d = nullptr;
+  SDSO_CUDA(ctx, cudaMalloc(&d, bytes));
+  double* pd = reinterpret_cast<double*>(d);
+  LBAEdgeParams E;
+  std::vector<double> host_in(in_d);
+  double* hp = host_in.data();
+  double* h_Twh = hp; hp += n * 12;
+  double* h_Ttw = hp; hp += n * 12;
+  double* h_photo = hp; hp += n * 2;
+  double* h_id = hp; hp += R;
+  double* h_b0 = hp; hp += n;
+  double* h_taff = hp; hp += n * 2;
+  memcpy(h_Twh, T_wh, sizeof(double) * n * 12); memcpy(h_photo, photo, sizeof(double) * n * 2); memcpy(h_id, idepth, sizeof(double) * R); memcpy(h_b0, b0, sizeof(double) * n);
+  std::vector<float> h_exp(n);
+  for (int i = 0; i < n; i++) {
+    memcpy(h_Ttw + 12 * i, b->frames[i].T_w2c, sizeof(double) * 12);
+    h_taff[2 * i] = b->frames[i].state_scaled[6]; h_taff[2 * i + 1] = b->frames[i].state_scaled[7];
+    h_exp[i] = b->frames[i].ab_exposure;
+  }
+  SDSO_CUDA(ctx, cudaMemcpyAsync(pd, host_in.data(), in_d * sizeof(double), cudaMemcpyHostToDevice, st));
+  E.T_wh = pd; E.T_tw = pd + n * 12; E.photo = pd + n * 24; E.idepth = pd + n * 26; E.b0 = pd + n * 26 + R; E.target_aff = pd + n * 27 + R;
+  double* po = pd + in_d;
+  E.error8 = po; po += (size_t)R * 8; E.Jxi = po; po += (size_t)R * 48; E.Jphoto = po; po += (size_t)R * 16; E.Jid = po; po += (size_t)R * 8;
+  E.JC = po; po += (size_t)R * 32; E.newEnergy = po; po += R; E.newEnergyWO = po; po += R;
+  float* pf = reinterpret_cast<float*>(po);
+  E.center3 = pf; pf += (size_t)R * 3; E.idepth_hessian = pf; pf += R;
+  float* d_exp = pf; pf += n;
+  int* pi = reinterpret_cast<int*>(pf);
+  E.newState = pi; pi += R; E.level = pi;
+  E.exposure = d_exp;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_exp, h_exp.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < 4; i++) E.cam[i] = cam[i];
+  E.slot2rid = b->d_slot2rid;
+  BAView v = view(b);
+  ba_lba_edge_kernel<<<(R + 127) / 128, 128, 0, st>>>(v, E);
+  ctx->launches++;
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) { cudaFree(d); return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(le)); }
+  cudaMemcpyAsync(error8, E.error8, sizeof(double) * R * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(J_xi, E.Jxi, sizeof(double) * R * 48, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(J_photo, E.Jphoto, sizeof(double) * R * 16, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(J_idepth, E.Jid, sizeof(double) * R * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(J_C, E.JC, sizeof(double) * R * 32, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(newEnergy, E.newEnergy, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(newEnergyWithOutlier, E.newEnergyWO, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(center3, E.center3, sizeof(float) * R * 3, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(idepth_hessian, E.idepth_hessian, sizeof(float) * R, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(newState, E.newState, sizeof(int) * R, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(level, E.level, sizeof(int) * R, cudaMemcpyDeviceToHost, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (se != cudaSuccess) return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(se));
+  return SDSO_OK;
+}
+
 // EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736) for the points flagged PS_MARGINALIZE
 int sdso_ba_marginalize_points(sdso_ctx* ctx) {
   BA_PREPARED(ctx)

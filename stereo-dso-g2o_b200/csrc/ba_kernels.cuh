@@ -1105,6 +1105,125 @@ __global__ void __launch_bounds__(128) ba_lenergy_kernel(BAView B, double* part)
   if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
+// ---- E2: EdgeLBASE3PosePhotoIdepthCamDSO::computeError + linearizeOplus (dso_g2o_edge.cpp:5-282), one thread per residual ----
+struct LBAEdgeParams {
+  const double* T_wh;    // [n][12] vertex poses (per host frame)
+  const double* T_tw;    // [n][12] PRE_worldToCam of the frames (targets)
+  const double* photo;   // [n][2]
+  const double* idepth;  // [R] (caller order mapped through slot2rid)
+  const double* b0;      // [n]
+  const double* target_aff;  // [n][2] aff_g2l of the frames
+  const float* exposure;     // [n]
+  double cam[4];
+  const int* slot2rid;
+  double* error8; double* Jxi; double* Jphoto; double* Jid; double* JC;
+  int* newState; double* newEnergy; double* newEnergyWO; float* center3; float* idepth_hessian; int* level;
+};
+
+__global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParams E) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.R) return;
+  const int rid = E.slot2rid[s];
+  const int key = B.s_key[s], h = key % B.n, t = key / B.n, pidx = B.s_point[s];
+  double* err = E.error8 + 8 * (size_t)rid;
+  double* Jxi = E.Jxi + 48 * (size_t)rid; double* Jph = E.Jphoto + 16 * (size_t)rid; double* Jid = E.Jid + 8 * (size_t)rid; double* JC = E.JC + 32 * (size_t)rid;
+  for (int i = 0; i < 8; i++) { err[i] = 0; Jid[i] = 0; }
+  for (int i = 0; i < 48; i++) Jxi[i] = 0;
+  for (int i = 0; i < 16; i++) Jph[i] = 0;
+  for (int i = 0; i < 32; i++) JC[i] = 0;
+  E.newEnergy[rid] = -1; E.newEnergyWO[rid] = -1; E.level[rid] = 0; E.idepth_hessian[rid] = 0;
+  E.center3[3 * rid] = E.center3[3 * rid + 1] = E.center3[3 * rid + 2] = 0;
+  int newState = B.s_newstate[s];
+  const double fx = E.cam[0], fy = E.cam[1], cx = E.cam[2], cy = E.cam[3];
+  // Tth = Ttw * Twh in double, then cast to float (:23-29)
+  const double* A = E.T_tw + 12 * t; const double* Bm = E.T_wh + 12 * h;
+  float R[9], tt[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) R[r * 3 + c] = (float)(A[r * 4] * Bm[c] + A[r * 4 + 1] * Bm[4 + c] + A[r * 4 + 2] * Bm[8 + c]);
+    tt[r] = (float)(A[r * 4] * Bm[3] + A[r * 4 + 1] * Bm[7] + A[r * 4 + 2] * Bm[11] + A[r * 4 + 3]);
+  }
+  float eF = E.exposure[h], eT = E.exposure[t];
+  if (eF == 0 || eT == 0) { eT = eF = 1; }
+  const double aa = exp(E.target_aff[2 * t] - E.photo[2 * h]) * eT / eF;
+  const float ab0 = (float)aa, ab1 = (float)(E.target_aff[2 * t + 1] - aa * E.photo[2 * h + 1]);
+  const double idepth = E.idepth[rid], b0 = E.b0[h];
+  const float pu = B.p_u[pidx], pv = B.p_v[pidx];
+  const float4 col0 = B.p_color[2 * pidx], col1 = B.p_color[2 * pidx + 1], wt0 = B.p_weights[2 * pidx], wt1 = B.p_weights[2 * pidx + 1];
+  const float color[8] = {col0.x, col0.y, col0.z, col0.w, col1.x, col1.y, col1.z, col1.w};
+  const float weights[8] = {wt0.x, wt0.y, wt0.z, wt0.w, wt1.x, wt1.y, wt1.z, wt1.w};
+  const int wl = B.c.w0 - 3, hl = B.c.h0 - 3;
+  const float4* tex = B.tex0[t];
+  float energyLeft = 0, wJI2_sum = 0;
+  double drs[8], us[8], vs[8], nids[8]; float3 hits[8]; float K0s[8], K1s[8];
+  bool finite_all = true;
+  for (int idx = 0; idx < 8; idx++) {
+    const double u_host = pu + kPatternP[idx][0], v_host = pv + kPatternP[idx][1];
+    const float K0 = (float)((u_host - cx) / fx), K1 = (float)((v_host - cy) / fy);
+    const float idf = (float)idepth;
+    float ptp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) ptp[k] = (R[k * 3] * K0 + R[k * 3 + 1] * K1 + R[k * 3 + 2] * 1.0f) + tt[k] * idf;
+    const double drescale = 1.0f / ptp[2];
+    if (drescale <= 0) { E.newState[rid] = RS_OOB; for (int i = 0; i < 8; i++) err[i] = 0; return; }
+    const double new_idepth = idepth * drescale;
+    const double _u = ptp[0] * drescale, _v = ptp[1] * drescale;
+    const double _Ku = _u * fx + cx, _Kv = _v * fy + cy;
+    if ((_Ku - 2) < 0 || (_Ku + 3) > wl || (_Kv - 2) < 0 || (_Kv + 3) > hl) {
+      E.newState[rid] = RS_OOB; for (int i = 0; i < 8; i++) err[i] = 0; E.level[rid] = 1; return;
+    }
+    if (kPatternP[idx][0] == 0 && kPatternP[idx][1] == 0) { E.center3[3 * rid] = (float)_Ku; E.center3[3 * rid + 1] = (float)_Kv; E.center3[3 * rid + 2] = (float)new_idepth; }
+    const float3 hit = interp33(tex, (float)_Ku, (float)_Kv, B.c.w0);
+    drs[idx] = drescale; us[idx] = _u; vs[idx] = _v; nids[idx] = new_idepth; hits[idx] = hit; K0s[idx] = K0; K1s[idx] = K1;
+    if (!isfinite(hit.x)) { newState = RS_OOB; err[idx] = 0; finite_all = false; continue; }
+    const double e = hit.x - (ab0 * color[idx] + ab1);
+    err[idx] = e;
+    float w = sqrtf(B.c.outlierTHSumComponent / (B.c.outlierTHSumComponent + (hit.y * hit.y + hit.z * hit.z)));
+    w = 0.5f * (w + weights[idx]);
+    const float hw = fabsf((float)e) < B.c.huberTH ? 1 : B.c.huberTH / fabsf((float)e);
+    energyLeft += w * w * hw * e * e * (2 - hw);
+    wJI2_sum += hw * hw * (hit.y * hit.y + hit.z * hit.z);
+  }
+  E.newEnergyWO[rid] = energyLeft;
+  const float th = fmaxf(B.frameTH[h], B.frameTH[t]);
+  if (energyLeft > th || wJI2_sum < 2) { energyLeft = th; newState = RS_OUTLIER; }
+  else newState = RS_IN;
+  E.newEnergy[rid] = energyLeft;
+  if (!finite_all) { E.newState[rid] = RS_OOB; return; }  // linearizeOplus bails out at the first non-finite pixel (:205-208)
+  E.newState[rid] = newState;
+  float Hii = 0;
+  for (int idx = 0; idx < 8; idx++) {
+    const double drescale = drs[idx], _u = us[idx], _v = vs[idx], new_idepth = nids[idx];
+    const float3 hit = hits[idx];
+    const double fxi = 1 / fx, fyi = 1 / fy;
+    double dC[2][4];
+    dC[0][2] = drescale * (R[6] * _u - R[0]);
+    dC[0][3] = fx * fyi * drescale * (R[7] * _u - R[1]);
+    dC[0][0] = K0s[idx] * dC[0][2];
+    dC[0][1] = K1s[idx] * dC[0][3];
+    dC[1][2] = fy * fxi * drescale * (R[6] * _v - R[3]);
+    dC[1][3] = drescale * (R[7] * _v - R[4]);
+    dC[1][0] = K0s[idx] * dC[1][2];
+    dC[1][1] = K1s[idx] * dC[1][3];
+    for (int k = 0; k < 4; k++) JC[idx * 4 + k] = (double)hit.y * dC[0][k] + (double)hit.z * dC[1][k];
+    const double dx = hit.y * fx, dy = hit.z * fy;
+    Jxi[idx * 6 + 0] = new_idepth * dx;
+    Jxi[idx * 6 + 1] = new_idepth * dy;
+    Jxi[idx * 6 + 2] = -new_idepth * (_u * dx + _v * dy);
+    Jxi[idx * 6 + 3] = -(_u * _v * dx + (1 + _v * _v) * dy);
+    Jxi[idx * 6 + 4] = _u * _v * dy + (1 + _u * _u) * dx;
+    Jxi[idx * 6 + 5] = _u * dy - _v * dx;
+    Jph[idx * 2 + 0] = ab0 * (b0 - color[idx]);
+    Jph[idx * 2 + 1] = -1;
+    const double jd = dx * drescale * (tt[0] - tt[2] * _u) + dy * drescale * (tt[1] - tt[2] * _v);
+    Jid[idx] = jd;
+    Hii += jd * jd;
+  }
+  if (Hii < 1e-10) Hii = 1e-10;
+  E.idepth_hessian[rid] = Hii;
+}
+
 // ---- B9 -------------------------------------------------------------------------------------------------------
 // xAd[h*n + t] = x_h^T adHostF[h + t*n] + x_t^T adTargetF[h + t*n]   (EnergyFunctional.cpp:283-293)
 __global__ void ba_xad_kernel(BAView B, const double* x, float* xAd) {

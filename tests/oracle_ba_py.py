@@ -214,3 +214,21 @@ def _energies(self):
 
 
 OracleBA.energies = _energies
+
+lib.orc_lba_edge_eval.argtypes = [V, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _fp, _fp, _ip]
+
+
+def _lba_edge_eval(self, T_wh, photo, idepth, cam, b0):
+    c = self.counts()
+    n, R = c["frames"], c["res"]
+    T_wh, photo, idepth, cam, b0 = _f64(T_wh).reshape(n, 12), _f64(photo).reshape(n, 2), _f64(idepth).reshape(R), _f64(cam).reshape(4), _f64(b0).reshape(n)
+    o = dict(error=np.zeros((R, 8)), J_xi=np.zeros((R, 8, 6)), J_photo=np.zeros((R, 8, 2)), J_idepth=np.zeros((R, 8)), J_C=np.zeros((R, 8, 4)),
+             newState=np.zeros(R, np.int32), newEnergy=np.zeros(R), newEnergyWithOutlier=np.zeros(R), center=np.zeros((R, 3), np.float32),
+             idepth_hessian=np.zeros(R, np.float32), level=np.zeros(R, np.int32))
+    lib.orc_lba_edge_eval(self.h, _p(T_wh, _dp), _p(photo, _dp), _p(idepth, _dp), _p(cam, _dp), _p(b0, _dp), _p(o["error"], _dp), _p(o["J_xi"], _dp),
+                          _p(o["J_photo"], _dp), _p(o["J_idepth"], _dp), _p(o["J_C"], _dp), _p(o["newState"], _ip), _p(o["newEnergy"], _dp),
+                          _p(o["newEnergyWithOutlier"], _dp), _p(o["center"], _fp), _p(o["idepth_hessian"], _fp), _p(o["level"], _ip))
+    return o
+
+
+OracleBA.lba_edge_eval = _lba_edge_eval

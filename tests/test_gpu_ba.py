@@ -330,3 +330,24 @@ def test_marginalisation_points_frame_and_energies(pkg, scene):
     assert np.allclose(b2g, b2o, rtol=REL, atol=REL * np.abs(b2o).max())
     assert np.allclose(H2g, H2g.T, rtol=1e-12, atol=1e-12 * np.abs(H2g).max())
     ctx.close()
+
+
+def test_lba_edge_error_and_jacobians(window7):
+    """E2: EdgeLBASE3PosePhotoIdepthCamDSO computeError + linearizeOplus for every residual: states / levels exact, errors and
+    the four Jacobian blocks rel 1e-4 (device pose product in matrix form vs the oracle's quaternions: ~1e-16 before the float cast)."""
+    import lba_edge_inputs as LE
+    win, orc, ba, ctx, W = window7
+    T_wh, photo, idepth, b0 = LE.make(win, seed=3)
+    cam = LE.cam_vertex((360.0, 360.0, 319.5, 95.5))
+    o = ba.lba_edge_eval(T_wh, photo, idepth, cam, b0)
+    g = W.lba_edge_eval(T_wh, photo, idepth, cam, b0)
+    assert (g["newState"] == o["newState"]).mean() > 0.9995 and (g["level"] == o["level"]).mean() > 0.9995
+    same = (g["newState"] == o["newState"]) & (g["level"] == o["level"])
+    assert set(np.unique(o["newState"])) >= {0, 1} and (o["level"] == 1).any()
+    for key in ("error", "J_xi", "J_photo", "J_idepth", "J_C"):
+        a, b = g[key][same], o[key][same]
+        s = np.abs(b).max(axis=0, keepdims=True) + 1e-30
+        assert np.all(np.abs(a - b) <= REL * np.maximum(np.abs(b), 1e-2 * s)), key
+    for key in ("newEnergy", "newEnergyWithOutlier", "idepth_hessian"):
+        assert np.allclose(g[key][same], o[key][same], rtol=REL, atol=1e-6), key
+    assert np.allclose(g["center"][same], o["center"][same], rtol=1e-6, atol=1e-4)
