@@ -304,6 +304,14 @@ int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[
                   sdso_immature_point* pts, int* status /* nullable */);
 /* ImmaturePoint::traceStereo(frame, K, mode_right) (ImmaturePoint.cpp:94-451); baseline = the context's */
 int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, sdso_immature_point* pts, int* status /* nullable */);
+/* D4: FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:52-238) + ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:886-985)
+ * for n candidates, host[i] = index of the candidate's host frame in the window uploaded with sdso_ba_* (its FrameFramePrecalc
+ * and calibration are used). variant SDSO_VARIANT_SSE: the original body (Hdd/bd, 3 LM iterations, Hdd >= setting_minIdepthH_act);
+ * SDSO_VARIANT_G2O: the live code, whose activation edge projects once (the inverse depth stays 0.5 (idepth_min + idepth_max)).
+ * result[i]: 1 activated, 0 not well constrained (returns 0 in the reference), -1 outlier / invalid ((PointHessian*)-1);
+ * idepth[i]; states[i][nframes] = ResState per target (-1 for the host); energy[i] = lastEnergy. */
+int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immature_point* pts, int variant, int min_obs, int* result,
+                         float* idepth, int* states, float* energy);
 
 #ifdef __cplusplus
 }

@@ -365,3 +365,11 @@ extern "C" void orc_lba_edge_eval(void* p, const double* T_wh /*[n][12]*/, const
     memcpy(center3 + 3 * i, o.centerProjectedTo, sizeof(o.centerProjectedTo)); idepth_hessian[i] = o.idepth_hessian; level[i] = o.level;
   }
 }
+
+// ---- D4: activation of n candidates hosted in the window's frames (oracle/activate.cpp) ------------------------------------
+extern "C" void orc_activate_points(void* p, int n, const int* host, const ImmaturePoint* pts, int variant, int minObs, int* result, float* idepth,
+                                    int* states /*[n][nframes]*/, float* energy) {
+  Ctx* c = (Ctx*)p;
+  const int nf = c->ba.n();
+  for (int i = 0; i < n; i++) result[i] = activatePoint(c->ba, host[i], pts[i], variant, minObs, idepth + i, states + (size_t)i * nf, energy + i);
+}

@@ -60,6 +60,8 @@ struct Settings {
   double solverModeDelta = 0.00001;    // :52
   int maxOptIterations = 6, minOptIterations = 1;  // :67-68
   float thOptIterations = 1.2f;        // :69
+  float minIdepthH_act = 100;          // :56
+  int GNItsOnPointActivation = 3;      // :114
   float frameEnergyTHConstWeight = 0.5f, frameEnergyTHN = 0.7f, frameEnergyTHFacMedian = 1.5f;  // :98-100
 };
 

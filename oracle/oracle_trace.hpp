@@ -23,4 +23,8 @@ bool immatureInit(const GlobalCalib& G, const Settings& S, const Frame& host, fl
 int traceOn(const GlobalCalib& G, const Settings& S, ImmaturePoint& p, const Frame& frame, const float KRKi[9], const float Kt[3], const float aff[2]);
 int traceStereo(const GlobalCalib& G, const Settings& S, ImmaturePoint& p, const Frame& frame, const float K[9], bool mode_right);
 
+struct BAWindow;
+// D4 (oracle/activate.cpp)
+int activatePoint(const BAWindow& W, int host, const ImmaturePoint& p, int variant, int minObs, float* idepth_out, int* states, float* energy_out);
+
 }  // namespace orc

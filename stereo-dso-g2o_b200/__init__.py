@@ -684,3 +684,18 @@ def _w_lba_edge_eval(self, T_wh, photo, idepth, cam, b0):
 
 
 Window.lba_edge_eval = _w_lba_edge_eval
+
+lib.sdso_activate_points.argtypes = [C.c_void_p, C.c_int, _ip, C.c_void_p, C.c_int, C.c_int, _ip, _fp, _ip, _fp]
+
+
+def _w_activate_points(self, host, pts, variant=VARIANT_SSE, min_obs=1):
+    assert pts.dtype == IMMATURE_DTYPE and pts.flags["C_CONTIGUOUS"]
+    n, nf = pts.size, self.counts()["frames"]
+    host = np.ascontiguousarray(host, np.int32)
+    res, st = np.zeros(n, np.int32), np.zeros((n, nf), np.int32)
+    idp, en = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    self._ck(lib.sdso_activate_points(self.h, n, _ptr(host, _ip), pts.ctypes.data, variant, min_obs, _ptr(res, _ip), _ptr(idp, _fp), _ptr(st, _ip), _ptr(en, _fp)))
+    return dict(result=res, idepth=idp, states=st, energy=en)
+
+
+Window.activate_points = _w_activate_points

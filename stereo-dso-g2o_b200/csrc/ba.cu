@@ -996,6 +996,44 @@ int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
   return SDSO_OK;
 }
 
+// D4: FullSystem::optimizeImmaturePoint for n candidates hosted in frames of the uploaded window (variant: SDSO_VARIANT_SSE =
+// the original 3-iteration LM on the inverse depth, SDSO_VARIANT_G2O = the live frozen-projection semantics)
+int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immature_point* pts, int variant, int min_obs, int* result,
+                         float* idepth, int* states, float* energy) {
+  BA_PREPARED(ctx)
+  if (n < 0 || (n > 0 && (!host || !pts || !result || !idepth || !states || !energy))) return SDSO_E_INVALID;
+  if (variant != SDSO_VARIANT_SSE && variant != SDSO_VARIANT_G2O) return SDSO_E_INVALID;
+  if (n == 0) return SDSO_OK;
+  const int nf = b->n;
+  for (int i = 0; i < n; i++) if (host[i] < 0 || host[i] >= nf) return SDSO_E_INVALID;
+  cudaStream_t st = ctx->stream;
+  const size_t bytes = (size_t)n * (sizeof(sdso_immature_point) + sizeof(int) * 2 + sizeof(float) * 2 + sizeof(int) * nf);
+  unsigned char* d = nullptr;
+  SDSO_CUDA(ctx, cudaMalloc(&d, bytes + 64));
+  ActParams A;
+  sdso_immature_point* d_pts = reinterpret_cast<sdso_immature_point*>(d);
+  int* d_host = reinterpret_cast<int*>(d_pts + n);
+  int* d_res = d_host + n; int* d_states = d_res + n;
+  float* d_id = reinterpret_cast<float*>(d_states + (size_t)n * nf); float* d_en = d_id + n;
+  cudaMemcpyAsync(d_pts, pts, (size_t)n * sizeof(sdso_immature_point), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_host, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
+  A.pts = d_pts; A.host = d_host; A.n = n; A.variant = variant; A.minObs = min_obs; A.GNIts = 3; A.minIdepthH_act = 100;  // settings.cpp:114, :56
+  A.result = d_res; A.idepth = d_id; A.states = d_states; A.energy = d_en;
+  BAView v = view(b);
+  ba_activate_kernel<<<(n + 63) / 64, 64, 0, st>>>(v, A);
+  ctx->launches++;
+  cudaError_t le = cudaGetLastError();
+  cudaMemcpyAsync(result, d_res, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(states, d_states, (size_t)n * nf * sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(idepth, d_id, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(energy, d_en, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (le != cudaSuccess) return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(le));
+  if (se != cudaSuccess) return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(se));
+  return SDSO_OK;
+}
+
 // E2 at operator level: every residual of the uploaded window evaluated as one EdgeLBASE3PosePhotoIdepthCamDSO
 // (dso_g2o_edge.cpp:5-282) with the given vertex estimates. Outputs are in the caller's residual order.
 int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, const double* idepth, const double cam[4], const double* b0,

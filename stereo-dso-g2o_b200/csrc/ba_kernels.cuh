@@ -1224,6 +1224,127 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
   E.idepth_hessian[rid] = Hii;
 }
 
+// ---- D4: point activation (ImmaturePoint::linearizeResidual, ImmaturePoint.cpp:886-985; FullSystem::optimizeImmaturePoint,
+// FullSystemOptPoint.cpp:52-238). One thread per candidate: the sums over pixels and targets stay in the reference's order, so
+// the IN / OUTLIER states, the Hdd >= minIdepthH_act test and the accept / reject decisions are exact. ------------------------
+struct ActParams {
+  const sdso_immature_point* pts; const int* host; int n;
+  int variant, minObs, GNIts;
+  float minIdepthH_act;
+  int* result; float* idepth; int* states; float* energy;
+};
+
+struct ActRes { int state_state, state_NewState; float state_energy, state_NewEnergy; };
+
+template <bool G2O>
+__device__ __forceinline__ float act_lin_res(const BAView& B, const sdso_immature_point& p, int host, int target, float slack, ActRes& tr,
+                                             float& Hdd, float& bd, float idepth) {
+  if (tr.state_state == RS_OOB) { tr.state_NewState = RS_OOB; return tr.state_energy; }
+  const PrecalcDev& pc = B.precalc[host * B.n + target];
+  const float4* tex = B.tex0[target];
+  const BACalib& c = B.c;
+  float Ku[8], Kv[8], uu[8], vv[8], dr[8];
+  bool inside[8];
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) {
+    const float K0 = (p.u + kPatternP[idx][0] - c.cxl) * c.fxli, K1 = (p.v + kPatternP[idx][1] - c.cyl) * c.fyli;
+    float ptp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) ptp[k] = (pc.PRE_RTll[k * 3] * K0 + pc.PRE_RTll[k * 3 + 1] * K1 + pc.PRE_RTll[k * 3 + 2] * 1.0f) + pc.PRE_tTll[k] * idepth;
+    const float drescale = 1.0f / ptp[2];
+    dr[idx] = drescale;
+    bool ok = drescale > 0;
+    uu[idx] = vv[idx] = Ku[idx] = Kv[idx] = 0;
+    if (ok) {
+      uu[idx] = ptp[0] * drescale; vv[idx] = ptp[1] * drescale;
+      Ku[idx] = uu[idx] * c.fxl + c.cxl; Kv[idx] = vv[idx] * c.fyl + c.cyl;
+      if (G2O) ok = !(((double)Ku[idx] - 2) < 0 || ((double)Ku[idx] + 3) > c.w0 - 3 || ((double)Kv[idx] - 2) < 0 || ((double)Kv[idx] + 3) > c.h0 - 3);
+      else ok = Ku[idx] > 1.1f && Kv[idx] > 1.1f && Ku[idx] < c.wM3G && Kv[idx] < c.hM3G;
+    }
+    inside[idx] = ok;
+  }
+  float3 hit[8];
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) hit[idx] = inside[idx] ? interp33(tex, Ku[idx], Kv[idx], c.w0) : make_float3(0.f, 0.f, 0.f);
+  float energyLeft = 0;
+#pragma unroll
+  for (int idx = 0; idx < 8; idx++) {
+    float residual = 0;
+    if (G2O) {
+      if (inside[idx] && isfinite(hit[idx].x)) residual = (float)((double)hit[idx].x - ((double)pc.PRE_aff_mode[0] * (double)p.color[idx] + (double)pc.PRE_aff_mode[1]));  // _measurement is a double
+    } else {
+      // the reference returns at the FIRST failing pixel, after the pixels before it have already been added to Hdd / bd
+      if (!inside[idx] || !isfinite(hit[idx].x)) { tr.state_NewState = RS_OOB; return tr.state_energy; }
+      residual = hit[idx].x - (pc.PRE_aff_mode[0] * p.color[idx] + pc.PRE_aff_mode[1]);
+    }
+    float hw = fabsf(residual) < c.huberTH ? 1 : c.huberTH / fabsf(residual);
+    energyLeft += p.weights[idx] * p.weights[idx] * hw * residual * residual * (2 - hw);
+    if (!G2O) {
+      const float dxInterp = hit[idx].y * c.fxl, dyInterp = hit[idx].z * c.fyl;
+      const float d_idepth = (dxInterp * dr[idx] * (pc.PRE_tTll[0] - pc.PRE_tTll[2] * uu[idx]) + dyInterp * dr[idx] * (pc.PRE_tTll[1] - pc.PRE_tTll[2] * vv[idx])) * SCALE_IDEPTH;
+      hw *= p.weights[idx] * p.weights[idx];
+      Hdd += (hw * d_idepth) * d_idepth;
+      bd += (hw * residual) * d_idepth;
+    }
+  }
+  if (energyLeft > p.energyTH * slack) { energyLeft = p.energyTH * slack; tr.state_NewState = RS_OUTLIER; }
+  else tr.state_NewState = RS_IN;
+  tr.state_NewEnergy = energyLeft;
+  return energyLeft;
+}
+
+__global__ void __launch_bounds__(64) ba_activate_kernel(BAView B, ActParams A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const sdso_immature_point p = A.pts[i];
+  const int host = A.host[i], nf = B.n;
+  ActRes res[kMaxFrames];
+  for (int f = 0; f < nf; f++) { res[f].state_state = RS_IN; res[f].state_NewState = RS_OUTLIER; res[f].state_energy = 0; res[f].state_NewEnergy = 0; A.states[(size_t)i * nf + f] = -1; }
+  float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+  float currentIdepth = (p.idepth_max + p.idepth_min) * 0.5f;
+  int result = 1;
+  bool done = false;
+  if (A.variant == 1) {
+    for (int f = 0; f < nf; f++) {
+      if (f == host) continue;
+      lastEnergy += act_lin_res<true>(B, p, host, f, 1000, res[f], lastHdd, lastbd, (float)(double)currentIdepth);
+      res[f].state_state = res[f].state_NewState; res[f].state_energy = res[f].state_NewEnergy;
+    }
+  } else {
+    for (int f = 0; f < nf; f++) {
+      if (f == host) continue;
+      lastEnergy += act_lin_res<false>(B, p, host, f, 1000, res[f], lastHdd, lastbd, currentIdepth);
+      res[f].state_state = res[f].state_NewState; res[f].state_energy = res[f].state_NewEnergy;
+    }
+    if (!isfinite(lastEnergy) || lastHdd < A.minIdepthH_act) { result = 0; done = true; }
+    float lambda = 0.1f;
+    for (int it = 0; it < A.GNIts && !done; it++) {
+      float Hh = lastHdd;
+      Hh *= 1 + lambda;
+      const float step = (float)((1.0 / Hh) * lastbd);
+      const float newIdepth = currentIdepth - step;
+      float newHdd = 0, newbd = 0, newEnergy = 0;
+      for (int f = 0; f < nf; f++) { if (f == host) continue; newEnergy += act_lin_res<false>(B, p, host, f, 1, res[f], newHdd, newbd, newIdepth); }
+      if (!isfinite(lastEnergy) || newHdd < A.minIdepthH_act) { result = 0; done = true; break; }
+      if (newEnergy < lastEnergy) {
+        currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        for (int f = 0; f < nf; f++) { res[f].state_state = res[f].state_NewState; res[f].state_energy = res[f].state_NewEnergy; }
+        lambda *= 0.5f;
+      } else lambda *= 5;
+      if (fabsf(step) < 0.0001 * currentIdepth) break;
+    }
+  }
+  A.idepth[i] = currentIdepth; A.energy[i] = lastEnergy;
+  if (!done) {
+    int numGood = 0;
+    for (int f = 0; f < nf; f++) { if (f == host) continue; A.states[(size_t)i * nf + f] = res[f].state_state; if (res[f].state_state == RS_IN) numGood++; }
+    if (!isfinite(currentIdepth)) result = -1;
+    else if (numGood < A.minObs) result = -1;
+    else if (!isfinite(p.energyTH)) result = -1;
+  }
+  A.result[i] = result;
+}
+
 // ---- B9 -------------------------------------------------------------------------------------------------------
 // xAd[h*n + t] = x_h^T adHostF[h + t*n] + x_t^T adTargetF[h + t*n]   (EnergyFunctional.cpp:283-293)
 __global__ void ba_xad_kernel(BAView B, const double* x, float* xAd) {

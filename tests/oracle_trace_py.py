@@ -43,3 +43,16 @@ def trace_stereo(orc, fid, K, mode_right, pts):
     st = np.zeros(pts.size, np.int32)
     lib.orc_trace_stereo(orc._h, fid, K_.ctypes.data_as(_fp), int(mode_right), pts.size, pts.ctypes.data, st.ctypes.data_as(_ip))
     return st
+
+lib.orc_activate_points.argtypes = [C.c_void_p, C.c_int, _ip, C.c_void_p, C.c_int, C.c_int, _ip, _fp, _ip, _fp]
+
+
+def activate_points(orc, nframes, host, pts, variant=0, min_obs=1):
+    """D4 on the window currently held by the oracle context (oracle_ba_py.OracleBA of the same Oracle)."""
+    n = pts.size
+    host = np.ascontiguousarray(host, np.int32)
+    res, st = np.zeros(n, np.int32), np.zeros((n, nframes), np.int32)
+    idp, en = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    lib.orc_activate_points(orc._h, n, host.ctypes.data_as(_ip), pts.ctypes.data, variant, min_obs, res.ctypes.data_as(_ip), idp.ctypes.data_as(_fp),
+                            st.ctypes.data_as(_ip), en.ctypes.data_as(_fp))
+    return dict(result=res, idepth=idp, states=st, energy=en)
