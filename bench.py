@@ -35,9 +35,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BYTES_PER_EVAL = 64  # tracking eval = 16 B point record + 4 texels x 12 B
 N_POINTS = 2000
-SEQS = 296           # independent sequences tracked per GPU per step: one CTA each, two resident CTAs per SM -> 2 x 148 SMs
+SEQS = 592           # independent sequences per GPU per step: persistent grid of 2 x 148 CTAs (two per SM) pulls them from a work counter
 PATH = 37            # distinct positions along the rendered path; sequence s starts at position s % PATH
-POSES = 6            # new frames per sequence (cycled)
+POSES = int(os.environ.get("SDSO_BENCH_POSES", "6"))   # new frames per sequence (cycled)
 SETS = 2             # frame-slot sets (double buffering: upload of step i+1 overlaps the kernels of step i)
 
 
@@ -189,7 +189,7 @@ def main():
     host_cores = os.cpu_count() or 1
     config = dict(workload=f"CoarseTracker pose tracking, 1232x368 (1241x376 cropped), 5-level pyramid, 2000 template points per keyframe, variant={args.variant}; "
                            f"step = one new frame for each of {S} independent sequences sharing the GPU: makeImages (8-bit source, batched) + "
-                           "trackNewestCoarse against each sequence's own reference keyframe (one CTA per sequence, two resident CTAs per SM, one launch)",
+                           "trackNewestCoarse against each sequence's own reference keyframe (one CTA per sequence, persistent grid of two CTAs per SM pulling sequences from a work counter, one launch)",
                   points=N_POINTS, levels=5, variant=args.variant, sequences_per_gpu=S,
                   cache=f"inputs larger than L2: {S} new pyramids per step x {SETS} rotating slot sets (~{S * SETS * 12} MB of pyramids + sources), {S} templates",
                   parallelism=(f"{S} independent sequences per GPU; GPUs are replicas (no collective)" if args.gpus > 1 else f"{S} independent sequences on one GPU"))

@@ -80,6 +80,9 @@ struct TrackParams {
   int g2o_stop_persists;
   int timing;
   TrackProblem* problems;
+  int nb;                  // problems in this launch
+  int dynamic;             // 1: CTAs pull problems from work_counter (cluster size 1 only)
+  unsigned int* work_counter;
   // g2o variant scratch: per level edge flags/errors for each problem
   unsigned char* edge_flag[kPyrLevels];  // [problem][n_l]
   double* edge_err[kPyrLevels];          // [problem][n_l]
@@ -786,23 +789,37 @@ __global__ void __launch_bounds__(256, (kU == 1 ? 2 : 1)) track_kernel(TrackPara
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks(), rank = cluster.block_rank();
-  const int prob_id = blockIdx.x / C;
-  TrackProblem& prob = P.problems[prob_id];
   const int tid = threadIdx.x;
   const int gtid = rank * blockDim.x + tid, gthreads = C * blockDim.x;
   LMState& lm = sm->lm;
   float acc[kAccPad];
-  unsigned evals = 0;
   Exchange ex;
-
+  __shared__ int s_prob;
   if (tid == 0) {
-    for (int i = 0; i < 9; i++) lm.R[i] = prob.T[(i / 3) * 4 + (i % 3)];
-    for (int i = 0; i < 3; i++) lm.t[i] = prob.T[i * 4 + 3];
-    lm.aff[0] = prob.aff[0]; lm.aff[1] = prob.aff[1];
     mbar_init(&sm->bar[0], 1); mbar_init(&sm->bar[1], 1);
     mbar_fence_init();
   }
   cluster.sync();  // barriers initialised and every CTA of the cluster resident before any DSMEM push
+
+  // Problems of this CTA: its own one (static), or — throughput configuration, cluster size 1 — pulled from a work counter
+  // until the batch is empty, so a sequence whose LM needs many iterations does not leave the other SMs idle.
+  for (;;) {
+  int prob_id = blockIdx.x / C;
+  if (P.dynamic) {
+    __syncthreads();
+    if (tid == 0) s_prob = (int)atomicAdd(P.work_counter, 1u);
+    __syncthreads();
+    prob_id = s_prob;
+    if (prob_id >= P.nb) break;
+  }
+  TrackProblem& prob = P.problems[prob_id];
+  unsigned evals = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 9; i++) lm.R[i] = prob.T[(i / 3) * 4 + (i % 3)];
+    for (int i = 0; i < 3; i++) lm.t[i] = prob.T[i * 4 + 3];
+    lm.aff[0] = prob.aff[0]; lm.aff[1] = prob.aff[1];
+  }
+  __syncthreads();
 
   // phase timers accumulate in SHARED memory (a global read-modify-write per tick would cost more than the phases)
   __shared__ long long s_cyc[16];
@@ -939,6 +956,8 @@ __global__ void __launch_bounds__(256, (kU == 1 ? 2 : 1)) track_kernel(TrackPara
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((tid & 31) == 0) atomicAdd(&prob.evals, (unsigned long long)e);
   }
+  if (!P.dynamic) break;
+  }  // problems
   cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -962,6 +981,7 @@ int tracker_create(sdso_ctx* ctx) {
   SDSO_CUDA(ctx, cudaMalloc(&t->d_counts, 64 * sizeof(int)));
   SDSO_CUDA(ctx, cudaMalloc(&t->d_problems, t->max_problems * sizeof(TrackProblem)));
   SDSO_CUDA(ctx, cudaMallocHost(&t->h_problems, t->max_problems * sizeof(TrackProblem)));
+  SDSO_CUDA(ctx, cudaMalloc(&t->d_work_counter, 4 * sizeof(unsigned)));
   return SDSO_OK;
 }
 
@@ -979,6 +999,7 @@ void tracker_destroy(sdso_ctx* ctx) {
   if (t->d_problems) cudaFree(t->d_problems);
   if (t->h_problems) cudaFreeHost(t->h_problems);
   if (t->d_dump) cudaFree(t->d_dump);
+  if (t->d_work_counter) cudaFree(t->d_work_counter);
   for (size_t k = 0; k < t->saved.size(); k++)
     if ((int)k != t->cur_slot) for (int l = 0; l < kPyrLevels; l++) if (t->saved[k].pc[l]) cudaFree(t->saved[k].pc[l]);
   for (int l = 0; l < kPyrLevels; l++) { if (t->edge_flag[l]) cudaFree(t->edge_flag[l]); if (t->edge_err[l]) cudaFree(t->edge_err[l]); }
@@ -1058,8 +1079,19 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
+  // Throughput configuration (cluster size 1, SSE path): a persistent grid of at most two CTAs per SM pulls the problems from a
+  // counter (dynamic load balance across sequences); otherwise one cluster per problem.
+  const bool dynamic = (!g2o && C == 1 && P.mode == 0);
+  int grid = C * nb;
+  TrackParams Pl = P;
+  Pl.nb = nb; Pl.dynamic = dynamic ? 1 : 0; Pl.work_counter = ctx->tracker->d_work_counter;
+  if (dynamic) {
+    const int cap = 2 * ctx->num_sms;
+    if (grid > cap) grid = cap;
+    SDSO_CUDA(ctx, cudaMemsetAsync(ctx->tracker->d_work_counter, 0, sizeof(unsigned), ctx->stream));
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(C * nb);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(BT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
@@ -1067,12 +1099,12 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (g2o) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_g2o_kernel, P));
+  if (g2o) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_g2o_kernel, Pl));
   else {
     const int U = ctx->S.gather_batch > 0 ? ctx->S.gather_batch : 2;
-    if (U == 1) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<1>, P));
-    else if (U == 2) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<2>, P));
-    else if (U == 4) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<4>, P));
+    if (U == 1) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<1>, Pl));
+    else if (U == 2) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<2>, Pl));
+    else if (U == 4) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<4>, Pl));
     else return fail(ctx, SDSO_E_INVALID, "gather_batch must be 1, 2 or 4");
   }
   ctx->launches++;

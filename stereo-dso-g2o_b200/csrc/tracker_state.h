@@ -26,7 +26,8 @@ struct TrackerState {
   bool have_ref = false;
   TrackProblem* d_problems = nullptr;
   TrackProblem* h_problems = nullptr;  // pinned
-  int max_problems = 320;
+  int max_problems = 2048;
+  unsigned int* d_work_counter = nullptr;  // dynamic problem scheduling of the throughput configuration
   std::vector<RefSlot> saved;  // parked reference slots (independent sequences tracked by one launch); saved[cur_slot] is stale
   int cur_slot = 0;
   float* d_dump = nullptr;

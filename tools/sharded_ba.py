@@ -1,5 +1,5 @@
 """Point-sharded windowed BA over N GPUs, run under torchrun:
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/sharded_ba.py [--n 7 --points 2000]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/sharded_ba.py [--frames 7 --points 2000]
 Checks the sharded solve against the single-GPU solve of the same window (rank 0) and times one LM iteration
 (linearizeAll + accumulate + stitch + allreduce + solve + resubstitute) sharded vs unsharded with CUDA events (max over ranks)."""
 import argparse, json, os, sys, time
@@ -39,7 +39,7 @@ def build(pkg, ctx, win, fids, rank, world, shard):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=7); ap.add_argument("--points", type=int, default=2002)
+    ap.add_argument("--frames", dest="n", type=int, default=7); ap.add_argument("--points", type=int, default=2002)
     ap.add_argument("--w", type=int, default=synth.W); ap.add_argument("--h", type=int, default=synth.H)
     ap.add_argument("--iters", type=int, default=50)
     a = ap.parse_args()
