@@ -266,6 +266,16 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
                        double* error8, double* J_xi, double* J_photo, double* J_idepth, double* J_C, int* newState, double* newEnergy,
                        double* newEnergyWithOutlier, float* center3, float* idepth_hessian, int* level);
 
+/* FullSystem::optimize, g2o body (FullSystemOptimize.cpp:404-868): LM over the graph of E2 edges of the uploaded window's active
+ * residuals with one marginalised inverse-depth vertex PER RESIDUAL (:493-512), the restated g2o Levenberg-Marquardt (lambda_init
+ * 0.1, additive damping, gain-ratio accept / reject, <= 10 trials, gain-threshold terminate action) and the Schur complement
+ * over the idepth vertices. In: cam[4] (VertexCamDSO), T_wh[n][12] (host PRE_camToWorld), photo[n][2] (host aff_g2l), idepth[R].
+ * Out: the same arrays hold the optimised estimates (the write-back of :676-727 is the caller's: a point takes the idepth of its
+ * LAST active residual); used_host[n]; final robust chi2; per residual state_NewState / CenterProjectedTo / idepth_hessian.
+ * mnumOptIts is overridden as the reference does (10 / 7 / 3 for 2 / 3 / >= 4 frames). */
+int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, double* photo, double* idepth, int* used_host, double* chi2_out,
+                 int* newState, float* center3, float* idepth_hessian, int* iterations_out, int* trials_out);
+
 /* ---- point-sharded windowed BA over 2/4/8 GPUs ------------------------------------------------------
  * Every rank holds all keyframe pyramids and a contiguous block of the allPoints order with its residuals. Per LM
  * iteration: sdso_ba_linearize_all (local) -> sdso_ba_assemble (local partial damped system; priors and HM on rank 0)

@@ -373,3 +373,9 @@ extern "C" void orc_activate_points(void* p, int n, const int* host, const Immat
   const int nf = c->ba.n();
   for (int i = 0; i < n; i++) result[i] = activatePoint(c->ba, host[i], pts[i], variant, minObs, idepth + i, states + (size_t)i * nf, energy + i);
 }
+
+extern "C" int orc_lba_g2o(void* p, int iters, double cam[4], double* T_wh, double* photo, double* idepth, int* used_host, double* chi2, int* newState,
+                           float* center3, float* idepth_hessian, int* trials) {
+  Ctx* c = (Ctx*)p;
+  return lbaG2O(c->ba, iters, cam, T_wh, photo, idepth, used_host, chi2, newState, center3, idepth_hessian, trials);
+}

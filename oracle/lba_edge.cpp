@@ -40,7 +40,7 @@ void lbaEdgeEval(const BAWindow& W, const BARes& r, const SE3& T_wh, const doubl
     const double _u = ptp[0] * drescale, _v = ptp[1] * drescale;
     const double _Ku = _u * fx + cx, _Kv = _v * fy + cy;
     if (CheckBoundaryD(_Ku, _Kv, wl, hl)) { o.newState = RS_OOB; for (int i = 0; i < 8; i++) o.error[i] = 0; o.level = 1; return; }
-    if (patternP[idx][0] == 0 && patternP[idx][1] == 0) { o.centerProjectedTo[0] = (float)_Ku; o.centerProjectedTo[1] = (float)_Kv; o.centerProjectedTo[2] = (float)new_idepth; }
+    if (patternP[idx][0] == 0 && patternP[idx][1] == 0) { o.centerProjectedTo[0] = (float)_Ku; o.centerProjectedTo[1] = (float)_Kv; o.centerProjectedTo[2] = (float)new_idepth; o.center_set = 1; }
     float hit[3];
     getInterpolatedElement33(dIl, (float)_Ku, (float)_Kv, w0, hit);
     drescale_[idx] = drescale; u_[idx] = _u; v_[idx] = _v; nid_[idx] = new_idepth;

@@ -136,9 +136,13 @@ struct BAWindow {
 struct LBAEdgeOut {
   double error[8];
   double J_xi[8][6], J_photo[8][2], J_idepth[8], J_C[8][4];
-  int newState; double newEnergy, newEnergyWithOutlier; float centerProjectedTo[3]; float idepth_hessian; int level;
+  int newState; double newEnergy, newEnergyWithOutlier; float centerProjectedTo[3]; float idepth_hessian; int level; int center_set;
 };
 void lbaEdgeEval(const BAWindow& W, const BARes& r, const SE3& T_wh /*vertex pose*/, const double photo[2], double idepth,
                  const double cam[4], double b0, LBAEdgeOut& out);
+
+// FullSystem::optimize, g2o body (FullSystemOptimize.cpp:404-868) with the restated g2o LM (oracle/lba_g2o.cpp)
+int lbaG2O(BAWindow& W, int mnumOptIts, double cam[4], double* T_wh, double* photo, double* idepth_io, int* used_host, double* chi2_out,
+           int* newState_out, float* center_out, float* idepth_hessian_out, int* trials_out);
 
 }  // namespace orc

@@ -699,3 +699,22 @@ def _w_activate_points(self, host, pts, variant=VARIANT_SSE, min_obs=1):
 
 
 Window.activate_points = _w_activate_points
+
+lib.sdso_lba_g2o.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip, _dp, _ip, _fp, _fp, _ip, _ip]
+
+
+def _w_lba_g2o(self, cam, T_wh, photo, idepth, iters=3):
+    c = self.counts()
+    n, R = c["frames"], c["res"]
+    cam, T_wh, photo, idepth = _f64(cam).copy(), _f64(T_wh).reshape(n, 12).copy(), _f64(photo).reshape(n, 2).copy(), _f64(idepth).reshape(R).copy()
+    used, ns = np.zeros(n, np.int32), np.zeros(R, np.int32)
+    chi2 = C.c_double()
+    its, trials = C.c_int(), C.c_int()
+    ce, ih = np.zeros((R, 3), np.float32), np.zeros(R, np.float32)
+    self._ck(lib.sdso_lba_g2o(self.h, iters, _ptr(cam, _dp), _ptr(T_wh, _dp), _ptr(photo, _dp), _ptr(idepth, _dp), _ptr(used, _ip), C.byref(chi2),
+                              _ptr(ns, _ip), _ptr(ce, _fp), _ptr(ih, _fp), C.byref(its), C.byref(trials)))
+    return dict(iterations=its.value, trials=trials.value, cam=cam, T_wh=T_wh.reshape(n, 3, 4), photo=photo, idepth=idepth, used_host=used,
+                chi2=chi2.value, newState=ns, center=ce, idepth_hessian=ih)
+
+
+Window.lba_g2o = _w_lba_g2o

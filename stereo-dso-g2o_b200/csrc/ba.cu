@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 namespace sdso {
 
@@ -1081,7 +1082,7 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
   E.exposure = d_exp;
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_exp, h_exp.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
   for (int i = 0; i < 4; i++) E.cam[i] = cam[i];
-  E.slot2rid = b->d_slot2rid;
+  E.slot2rid = b->d_slot2rid; E.driver = 0; E.active = nullptr; E.linearize = 1;
   BAView v = view(b);
   ba_lba_edge_kernel<<<(R + 127) / 128, 128, 0, st>>>(v, E);
   ctx->launches++;
@@ -1102,6 +1103,220 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
   cudaFree(d);
   if (se != cudaSuccess) return fail(ctx, SDSO_E_CUDA, cudaGetErrorString(se));
   return SDSO_OK;
+}
+
+// FullSystem::optimize, g2o body (FullSystemOptimize.cpp:404-868): the graph of E2 edges over {cam, pose+photo per host frame, one
+// marginalised idepth vertex per residual}, Huber(9) per edge, driven by the restated g2o Levenberg-Marquardt with Schur complement
+// (g2o is not in the reference tree, so the driver is unpinned). All per-edge work runs on the device; the
+// host loop moves the (4+8n)-vector increment and the n host poses per trial.
+int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, double* photo, double* idepth, int* used_host, double* chi2_out,
+                 int* newState, float* center3, float* idepth_hessian, int* iterations_out, int* trials_out) {
+  BA_PREPARED(ctx)
+  if (!cam || !T_wh || !photo || !idepth || !used_host) return SDSO_E_INVALID;
+  const int n = b->n, R = b->R, d = b->dim();
+  if (iterations_out) *iterations_out = 0;
+  if (trials_out) *trials_out = 0;
+  if (n < 2 || R == 0) return SDSO_OK;
+  if (n < 3) mnumOptIts = 10; else if (n < 4) mnumOptIts = 7; else mnumOptIts = 3;
+  cudaStream_t st = ctx->stream;
+  const int rb = (R + 127) / 128;
+  // ---- one scratch allocation for the graph
+  const size_t nd = (size_t)R * (1 + 1 + 8 + 48 + 16 + 8 + 32 + 1 + 1 + 12 + 2)   // idepth, bak, err, J blocks, hll, bl, hpl, energies
+                    + (size_t)n * (12 + 12 + 2 + 1 + 2)                            // T_wh, T_tw, photo, b0, target aff
+                    + (size_t)(b->nchunks + 1) * 96 * 2 + (size_t)n * 96 * 2 + rb + 64;
+  const size_t bytes = nd * sizeof(double) + (size_t)R * (4 * sizeof(float) + 2 * sizeof(int) + 2) + (size_t)n * (sizeof(float) + sizeof(int)) + 256;
+  unsigned char* raw = nullptr;
+  SDSO_CUDA(ctx, cudaMalloc(&raw, bytes));
+  SDSO_CUDA(ctx, cudaMemsetAsync(raw, 0, bytes, st));
+  double* pd = reinterpret_cast<double*>(raw);
+  auto takeD = [&](size_t k) { double* q = pd; pd += k; return q; };
+  double* d_idepth = takeD(R); double* d_idbak = takeD(R); double* d_err = takeD((size_t)R * 8);
+  double* d_Jxi = takeD((size_t)R * 48); double* d_Jph = takeD((size_t)R * 16); double* d_Jid = takeD((size_t)R * 8); double* d_JC = takeD((size_t)R * 32);
+  double* d_hll = takeD(R); double* d_bl = takeD(R); double* d_hpl = takeD((size_t)R * 12); double* d_ne = takeD(R); double* d_newo = takeD(R);
+  double* d_est = takeD((size_t)n * 29);
+  double* d_partA = takeD((size_t)(b->nchunks + 1) * 96); double* d_partS = takeD((size_t)(b->nchunks + 1) * 96);
+  double* d_hostA = takeD((size_t)n * 96); double* d_hostS = takeD((size_t)n * 96);
+  double* d_bpart = takeD(rb); double* d_sc = takeD(64);
+  float* pf = reinterpret_cast<float*>(pd);
+  float* d_center = pf; pf += (size_t)R * 3; float* d_ih = pf; pf += R; float* d_exp = pf; pf += n;
+  int* pi = reinterpret_cast<int*>(pf);
+  int* d_ns = pi; pi += R; int* d_level = pi; pi += R; int* d_used = pi; pi += n;
+  unsigned char* d_active = reinterpret_cast<unsigned char*>(pi); unsigned char* d_ingraph = d_active + R;
+  auto cleanup = [&](int rc) { cudaStreamSynchronize(st); cudaFree(raw); return rc; };
+
+  // ---- graph build on the host side: active residuals (not linearised, not dropped), used hosts, b0 (:438-542)
+  std::vector<unsigned char> flags(R);
+  SDSO_CUDA(ctx, cudaMemcpyAsync(flags.data(), b->d_s_flags, R, cudaMemcpyDeviceToHost, st));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  std::vector<unsigned char> ingraph(R, 0);
+  std::vector<double> id_slot(R);
+  std::vector<int> ns_init(R, RS_OUTLIER);
+  for (int h = 0; h < n; h++) used_host[h] = 0;
+  std::vector<double> b0(n, 0.0);
+  for (int rid = 0; rid < R; rid++) {
+    const int sl = b->h_rid2slot[rid];
+    id_slot[sl] = idepth[rid];
+    if (flags[sl] & (RF_LINEARIZED | RF_DROPPED)) continue;
+    ingraph[sl] = 1;
+    const int host = b->h_p_host[b->h_r_point[rid]];
+    if (!used_host[host]) { used_host[host] = 1; b0[host] = photo[2 * host + 1]; }
+  }
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_ingraph, ingraph.data(), R, cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_idepth, id_slot.data(), R * sizeof(double), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_ns, ns_init.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_used, used_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  std::vector<float> h_exp(n);
+  std::vector<double> est((size_t)n * 29);
+  auto upload_est = [&]() -> int {
+    double* e = est.data();
+    memcpy(e, T_wh, sizeof(double) * n * 12);
+    for (int i = 0; i < n; i++) memcpy(e + n * 12 + 12 * i, b->frames[i].T_w2c, sizeof(double) * 12);
+    memcpy(e + n * 24, photo, sizeof(double) * n * 2);
+    memcpy(e + n * 26, b0.data(), sizeof(double) * n);
+    for (int i = 0; i < n; i++) { e[n * 27 + 2 * i] = b->frames[i].state_scaled[6]; e[n * 27 + 2 * i + 1] = b->frames[i].state_scaled[7]; }
+    SDSO_CUDA(ctx, cudaMemcpyAsync(d_est, e, est.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    return SDSO_OK;
+  };
+  for (int i = 0; i < n; i++) h_exp[i] = b->frames[i].ab_exposure;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(d_exp, h_exp.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
+
+  BAView v = view(b);
+  LBAEdgeParams E;
+  E.T_wh = d_est; E.T_tw = d_est + n * 12; E.photo = d_est + n * 24; E.b0 = d_est + n * 26; E.target_aff = d_est + n * 27; E.exposure = d_exp;
+  E.idepth = d_idepth; E.slot2rid = nullptr; E.driver = 1;
+  E.error8 = d_err; E.Jxi = d_Jxi; E.Jphoto = d_Jph; E.Jid = d_Jid; E.JC = d_JC;
+  E.newState = d_ns; E.newEnergy = d_ne; E.newEnergyWO = d_newo; E.center3 = d_center; E.idepth_hessian = d_ih; E.level = d_level;
+  LBAGraph G;
+  G.R = R; G.active = d_active; G.idepth = d_idepth; G.idepth_bak = d_idbak; G.err = d_err; G.Jxi = d_Jxi; G.Jph = d_Jph; G.Jid = d_Jid; G.JC = d_JC;
+  G.hll = d_hll; G.bl = d_bl; G.hpl = d_hpl; G.delta = ctx->S.huberTH;
+  auto eval = [&](const unsigned char* active, int linearize) -> int {
+    for (int i = 0; i < 4; i++) E.cam[i] = cam[i];
+    E.active = active; E.linearize = linearize;
+    ba_lba_edge_kernel<<<rb, 128, 0, st>>>(v, E); SDSO_CHECK_LAUNCH(ctx);
+    return SDSO_OK;
+  };
+  auto chi2 = [&](double* out) -> int {
+    lba_chi2_kernel<<<rb, 128, 0, st>>>(G, d_bpart); SDSO_CHECK_LAUNCH(ctx);
+    lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc); SDSO_CHECK_LAUNCH(ctx);
+    SDSO_CUDA(ctx, cudaMemcpyAsync(out, d_sc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+    return SDSO_OK;
+  };
+  int rc = upload_est();
+  if (rc) return cleanup(rc);
+  // first computeError of every edge while the graph is built (:538), then initializeOptimization(): level-0 edges are active
+  if ((rc = eval(d_ingraph, 0))) return cleanup(rc);
+  lba_activate_kernel<<<rb, 128, 0, st>>>(R, d_ingraph, d_level, d_active); ctx->launches++;
+
+  SolveParams S;
+  fill_solve_params(ctx, S, 0);
+  S.plain = 1; S.N = nullptr; S.have_M = 0;
+  const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
+  cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  std::vector<double> x(d), bp(d);
+  double lambda = 0, ni = 2, lastChi = 0;
+  int it = 0, trials = 0;
+  bool stop = false;
+  for (; it < mnumOptIts && !stop; it++) {
+    double currentChi = 0;
+    if ((rc = eval(d_active, 0))) return cleanup(rc);           // computeActiveErrors
+    if ((rc = chi2(&currentChi))) return cleanup(rc);
+    if ((rc = eval(d_active, 1))) return cleanup(rc);           // buildSystem: linearizeOplus ...
+    if (b->nchunks > 0) { lba_build_kernel<<<b->nchunks, kChunk, 0, st>>>(v, G, 0, 0.0, d_partA); SDSO_CHECK_LAUNCH(ctx); }
+    lba_host_sum_kernel<<<n, 96, 0, st>>>(v, d_partA, d_hostA); SDSO_CHECK_LAUNCH(ctx);
+    if (it == 0) { lambda = 0.1; ni = 2; }                       // setUserLambdaInit(0.1) (:425)
+    double rho = 0;
+    int qmax = 0;
+    bool have_bp = false;
+    do {
+      // push()
+      lba_copy_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, d_idepth, d_idbak); SDSO_CHECK_LAUNCH(ctx);
+      std::vector<double> T_b(T_wh, T_wh + 12 * n), ph_b(photo, photo + 2 * n);
+      double cam_b[4] = {cam[0], cam[1], cam[2], cam[3]};
+      if (b->nchunks > 0) { lba_build_kernel<<<b->nchunks, kChunk, 0, st>>>(v, G, 1, lambda, d_partS); SDSO_CHECK_LAUNCH(ctx); }
+      lba_host_sum_kernel<<<n, 96, 0, st>>>(v, d_partS, d_hostS); SDSO_CHECK_LAUNCH(ctx);
+      lba_assemble_kernel<<<(d * d + d + 127) / 128, 128, 0, st>>>(n, d_hostA, d_hostS, d_used, lambda, S.HF, S.bF); SDSO_CHECK_LAUNCH(ctx);
+      ba_solve_kernel<<<1, 256, smem, st>>>(S); SDSO_CHECK_LAUNCH(ctx);
+      SDSO_CUDA(ctx, cudaMemcpyAsync(x.data(), S.x, d * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (!have_bp) {  // the un-reduced b of the non-marginalised block, for computeScale: bp = A's b part per host / cam
+        std::vector<double> hA((size_t)n * 96);
+        SDSO_CUDA(ctx, cudaMemcpyAsync(hA.data(), d_hostA, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+        std::fill(bp.begin(), bp.end(), 0.0);
+        for (int h = 0; h < n; h++) if (used_host[h]) {
+          for (int l = 0; l < 8; l++) bp[kCPARS + 8 * h + l] = hA[(size_t)h * 96 + 78 + l];
+          for (int c = 0; c < 4; c++) bp[c] += hA[(size_t)h * 96 + 78 + 8 + c];
+        }
+        have_bp = true;
+      } else {
+        SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+      }
+      bool ok = true;
+      for (int k = 0; k < d; k++) ok = ok && std::isfinite(x[k]);
+      double tempChi = std::numeric_limits<double>::max(), scale = 0;
+      if (ok) {
+        for (int k = 0; k < 4; k++) cam[k] += x[k];
+        for (int h = 0; h < n; h++) if (used_host[h]) {
+          double Ex[12], Tn[12];
+          se3_exp(&x[kCPARS + 8 * h], Ex);
+          se3_mul(Ex, T_wh + 12 * h, Tn);
+          memcpy(T_wh + 12 * h, Tn, sizeof(Tn));
+          photo[2 * h] += x[kCPARS + 8 * h + 6]; photo[2 * h + 1] += x[kCPARS + 8 * h + 7];
+        }
+        for (int k = 0; k < d; k++) scale += x[k] * (lambda * x[k] + bp[k]);
+        lba_update_kernel<<<rb, 128, 0, st>>>(v, G, S.x, lambda, d_bpart); SDSO_CHECK_LAUNCH(ctx);
+        lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc + 1); SDSO_CHECK_LAUNCH(ctx);
+        double sl = 0;
+        SDSO_CUDA(ctx, cudaMemcpyAsync(&sl, d_sc + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        if ((rc = upload_est())) return cleanup(rc);
+        if ((rc = eval(d_active, 0))) return cleanup(rc);
+        if ((rc = chi2(&tempChi))) return cleanup(rc);
+        scale += sl;
+      }
+      rho = (currentChi - tempChi) / (scale + 1e-3);
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        lambda *= std::max(1. / 3., alpha);
+        ni = 2; currentChi = tempChi;
+      } else {
+        lambda *= ni; ni *= 2;
+        lba_copy_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, d_idbak, d_idepth); SDSO_CHECK_LAUNCH(ctx);   // pop()
+        memcpy(T_wh, T_b.data(), sizeof(double) * 12 * n); memcpy(photo, ph_b.data(), sizeof(double) * 2 * n);
+        for (int k = 0; k < 4; k++) cam[k] = cam_b[k];
+        if ((rc = upload_est())) return cleanup(rc);
+        if (!std::isfinite(lambda)) break;
+      }
+      qmax++; trials++;
+    } while (rho < 0 && qmax < 10);
+    const bool terminate_lm = (qmax == 10 || rho == 0 || !std::isfinite(lambda));
+    double chi = 0;
+    if ((rc = eval(d_active, 0))) return cleanup(rc);           // SparseOptimizerTerminateAction: computeActiveErrors + chi2
+    if ((rc = chi2(&chi))) return cleanup(rc);
+    if (it == 0) lastChi = chi;
+    else { const double gain = (lastChi - chi) / chi; lastChi = chi; if (gain >= 0 && gain < 1e-3) stop = true; }
+    if (terminate_lm) { it++; break; }
+  }
+  // ---- results in the caller's residual order
+  std::vector<double> id_out(R);
+  std::vector<int> ns_out(R);
+  std::vector<float> ce_out((size_t)R * 3), ih_out(R);
+  cudaMemcpyAsync(id_out.data(), d_idepth, R * sizeof(double), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(ns_out.data(), d_ns, R * sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(ce_out.data(), d_center, (size_t)R * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(ih_out.data(), d_ih, R * sizeof(float), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  for (int rid = 0; rid < R; rid++) {
+    const int sl = b->h_rid2slot[rid];
+    idepth[rid] = id_out[sl];
+    if (newState) newState[rid] = ns_out[sl];
+    if (center3) for (int k = 0; k < 3; k++) center3[3 * rid + k] = ce_out[(size_t)sl * 3 + k];
+    if (idepth_hessian) idepth_hessian[rid] = ih_out[sl];
+  }
+  if (chi2_out) *chi2_out = lastChi;
+  if (iterations_out) *iterations_out = it;
+  if (trials_out) *trials_out = trials;
+  return cleanup(SDSO_OK);
 }
 
 // EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736) for the points flagged PS_MARGINALIZE

@@ -809,6 +809,7 @@ struct SolveParams {
   const double* fprior; const float* cDeltaF;
   const double* N;   // d x 7 (row-major): orthonormal basis of the gauge nullspace in the first nrank columns, or null
   int nrank;
+  int plain;         // 1: solve HF x = bF as is (g2o LinearSolver semantics): no (diag+10)^-1/2 scaling, no orthogonalisation
   double* HF; double* bF; double* x;
 };
 
@@ -879,7 +880,7 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   __shared__ double pivval;
   const int lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 tiling of the trailing update
-  for (int i = tid; i < d; i += nt) { bs[i] = S.bF[i]; sv[i] = 1.0 / sqrt(S.HF[(size_t)i * d + i] + 10); perm[i] = i; }
+  for (int i = tid; i < d; i += nt) { bs[i] = S.bF[i]; sv[i] = S.plain ? 1.0 : 1.0 / sqrt(S.HF[(size_t)i * d + i] + 10); perm[i] = i; }
   __syncthreads();
   for (int r = ty; r < d; r += 16)
     for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
@@ -952,7 +953,7 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   __syncthreads();
   for (int i = tid; i < d; i += nt) bs[i] *= sv[i];
   __syncthreads();
-  if (S.iteration >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
+  if (!S.plain && S.iteration >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
   for (int i = tid; i < d; i += nt) S.x[i] = bs[i];
 }
 
@@ -1115,7 +1116,11 @@ struct LBAEdgeParams {
   const double* target_aff;  // [n][2] aff_g2l of the frames
   const float* exposure;     // [n]
   double cam[4];
-  const int* slot2rid;
+  const int* slot2rid;   // operator mode: outputs in the caller's residual order; null (driver mode): slot order
+  int driver;            // 1: g2o driver semantics — skip inactive edges, keep stale Jacobians / energies where the edge returns early,
+                         //    sticky level, idepth / outputs indexed by slot
+  const unsigned char* active;   // driver mode: level-0 edges of initializeOptimization() (null while the graph is being built)
+  int linearize;         // driver mode: 0 = computeError only, 1 = computeError + linearizeOplus
   double* error8; double* Jxi; double* Jphoto; double* Jid; double* JC;
   int* newState; double* newEnergy; double* newEnergyWO; float* center3; float* idepth_hessian; int* level;
 };
@@ -1123,17 +1128,20 @@ struct LBAEdgeParams {
 __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParams E) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B.R) return;
-  const int rid = E.slot2rid[s];
+  const int rid = E.slot2rid ? E.slot2rid[s] : s;
+  if (E.driver && E.active && !E.active[s]) return;
   const int key = B.s_key[s], h = key % B.n, t = key / B.n, pidx = B.s_point[s];
   double* err = E.error8 + 8 * (size_t)rid;
   double* Jxi = E.Jxi + 48 * (size_t)rid; double* Jph = E.Jphoto + 16 * (size_t)rid; double* Jid = E.Jid + 8 * (size_t)rid; double* JC = E.JC + 32 * (size_t)rid;
-  for (int i = 0; i < 8; i++) { err[i] = 0; Jid[i] = 0; }
-  for (int i = 0; i < 48; i++) Jxi[i] = 0;
-  for (int i = 0; i < 16; i++) Jph[i] = 0;
-  for (int i = 0; i < 32; i++) JC[i] = 0;
-  E.newEnergy[rid] = -1; E.newEnergyWO[rid] = -1; E.level[rid] = 0; E.idepth_hessian[rid] = 0;
-  E.center3[3 * rid] = E.center3[3 * rid + 1] = E.center3[3 * rid + 2] = 0;
-  int newState = B.s_newstate[s];
+  if (!E.driver) {
+    for (int i = 0; i < 8; i++) { err[i] = 0; Jid[i] = 0; }
+    for (int i = 0; i < 48; i++) Jxi[i] = 0;
+    for (int i = 0; i < 16; i++) Jph[i] = 0;
+    for (int i = 0; i < 32; i++) JC[i] = 0;
+    E.newEnergy[rid] = -1; E.newEnergyWO[rid] = -1; E.level[rid] = 0; E.idepth_hessian[rid] = 0;
+    E.center3[3 * rid] = E.center3[3 * rid + 1] = E.center3[3 * rid + 2] = 0;
+  }
+  int newState = E.driver ? E.newState[rid] : B.s_newstate[s];
   const double fx = E.cam[0], fy = E.cam[1], cx = E.cam[2], cy = E.cam[3];
   // Tth = Ttw * Twh in double, then cast to float (:23-29)
   const double* A = E.T_tw + 12 * t; const double* Bm = E.T_wh + 12 * h;
@@ -1192,6 +1200,7 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
   E.newEnergy[rid] = energyLeft;
   if (!finite_all) { E.newState[rid] = RS_OOB; return; }  // linearizeOplus bails out at the first non-finite pixel (:205-208)
   E.newState[rid] = newState;
+  if (E.driver && (!E.linearize || E.level[rid] == 1)) return;  // computeError only / `if(level() == 1) return;` (:131)
   float Hii = 0;
   for (int idx = 0; idx < 8; idx++) {
     const double drescale = drs[idx], _u = us[idx], _v = vs[idx], new_idepth = nids[idx];
@@ -1343,6 +1352,181 @@ __global__ void __launch_bounds__(64) ba_activate_kernel(BAView B, ActParams A) 
     else if (!isfinite(p.energyTH)) result = -1;
   }
   A.result[i] = result;
+}
+
+// ---- g2o LBA driver (FullSystem::optimize, g2o body, FullSystemOptimize.cpp:404-868; restated g2o LM + Schur) ----
+struct LBAGraph {   // per-edge arrays in SLOT order
+  int R;
+  const unsigned char* active;
+  double* idepth; double* idepth_bak;
+  const double* err;      // [R][8]
+  const double* Jxi; const double* Jph; const double* Jid; const double* JC;   // [R][48], [R][16], [R][8], [R][32]
+  double* hll; double* bl; double* hpl;   // [R], [R], [R][12]
+  double delta;
+};
+
+__device__ __forceinline__ double huber_rho_d(double e2, double delta, double& rho1) {
+  if (e2 <= delta * delta) { rho1 = 1.0; return e2; }
+  const double sq = sqrt(e2);
+  rho1 = delta / sq;
+  return 2 * sq * delta - delta * delta;
+}
+// column a (0..11 = pose 6 | photo 2 | cam 4, 12 = idepth) of the 8x13 edge Jacobian, row k
+__device__ __forceinline__ double lba_J(const LBAGraph& G, int s, int k, int a) {
+  if (a < 6) return G.Jxi[(size_t)s * 48 + k * 6 + a];
+  if (a < 8) return G.Jph[(size_t)s * 16 + k * 2 + (a - 6)];
+  if (a < 12) return G.JC[(size_t)s * 32 + k * 4 + (a - 8)];
+  return G.Jid[(size_t)s * 8 + k];
+}
+
+// activeRobustChi2: sum over the active edges of Huber(e^T e); fixed-order block partials
+__global__ void __launch_bounds__(128) lba_chi2_kernel(LBAGraph G, double* part) {
+  __shared__ double red[32];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0;
+  if (s < G.R && G.active[s]) {
+    double e2 = 0, r1;
+    for (int k = 0; k < 8; k++) { const double e = G.err[(size_t)s * 8 + k]; e2 += e * e; }
+    v = huber_rho_d(e2, G.delta, r1);
+  }
+  const double t = block_sum_d(v, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void lba_sum_kernel(const double* part, int n, int stride, int nvals, double* out) {
+  const int v = threadIdx.x;
+  if (v < nvals) { double s = 0; for (int i = 0; i < n; i++) s += part[(size_t)i * stride + v]; out[v] = s; }
+}
+
+// One CTA per chunk (<= 256 edges of one (host,target) pair). what == 0: buildSystem — J^T rho' J (12x12 upper triangle, 78 values)
+// and -J^T rho' e (12) of every active edge summed over the chunk, and the edge's own idepth terms hll, bl, hpl stored per edge.
+// what == 1: the Schur complement terms hpl hpl^T / (hll + lambda) (78) and hpl bl / (hll + lambda) (12) for the current lambda.
+// Sums in double, fixed order, through shared memory (64-bit shuffles are slow on this part).
+__global__ void __launch_bounds__(kChunk) lba_build_kernel(BAView B, LBAGraph G, int what, double lambda, double* part /* [nchunks][96] */) {
+  __shared__ double wbuf[kChunk / 32][32][14];   // per warp: 32 lanes x up to 13 values (+1 pad)
+  __shared__ double wtot[kChunk / 32][14];
+  const Chunk ch = B.chunks[blockIdx.x];
+  const int s = ch.begin + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool use = s < ch.end && G.active[s];
+  double rho1 = 0, inv = 0, blv = 0;
+  double hp[12];
+#pragma unroll
+  for (int a = 0; a < 12; a++) hp[a] = 0;
+  if (use) {
+    if (what == 0) {
+      double e2 = 0;
+      for (int k = 0; k < 8; k++) { const double e = G.err[(size_t)s * 8 + k]; e2 += e * e; }
+      huber_rho_d(e2, G.delta, rho1);
+      double hll = 0, bl = 0;
+      for (int k = 0; k < 8; k++) { const double jd = G.Jid[(size_t)s * 8 + k]; hll += jd * rho1 * jd; bl -= jd * rho1 * G.err[(size_t)s * 8 + k]; }
+      G.hll[s] = hll; G.bl[s] = bl;
+    } else {
+      inv = 1.0 / (G.hll[s] + lambda); blv = G.bl[s];
+#pragma unroll
+      for (int a = 0; a < 12; a++) hp[a] = G.hpl[(size_t)s * 12 + a];
+    }
+  }
+  int out = 0;  // running index into the 90 values: row a -> (12 - a) matrix entries, then all 12 b entries
+  for (int a = 0; a < 13; a++) {
+    const int nv = (a < 12) ? 12 - a : 12;
+    double v[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) v[q] = 0;
+    if (use) {
+      if (what == 0) {
+        if (a < 12) {
+          double ja[8];
+          for (int k = 0; k < 8; k++) ja[k] = lba_J(G, s, k, a) * rho1;
+          for (int q = 0; q < nv; q++) { double t = 0; for (int k = 0; k < 8; k++) t += ja[k] * lba_J(G, s, k, a + q); v[q] = t; }
+          double t = 0;
+          for (int k = 0; k < 8; k++) t += ja[k] * G.Jid[(size_t)s * 8 + k];
+          G.hpl[(size_t)s * 12 + a] = t;
+        } else {
+          for (int q = 0; q < 12; q++) { double t = 0; for (int k = 0; k < 8; k++) t += lba_J(G, s, k, q) * rho1 * G.err[(size_t)s * 8 + k]; v[q] = -t; }
+        }
+      } else {
+        if (a < 12) { for (int q = 0; q < nv; q++) v[q] = hp[a] * inv * hp[a + q]; }
+        else { for (int q = 0; q < 12; q++) v[q] = hp[q] * inv * blv; }
+      }
+    }
+    for (int q = 0; q < nv; q++) wbuf[warp][lane][q] = v[q];
+    __syncwarp();
+    if (lane < nv) { double t = 0; for (int l = 0; l < 32; l++) t += wbuf[warp][l][lane]; wtot[warp][lane] = t; }
+    __syncthreads();
+    if (threadIdx.x < nv) { double t = 0; for (int w = 0; w < kChunk / 32; w++) t += wtot[w][threadIdx.x]; part[(size_t)blockIdx.x * 96 + out + threadIdx.x] = t; }
+    __syncthreads();
+    out += nv;
+  }
+}
+
+// per host: fixed-order sum of the chunk partials whose key has that host. grid = n hosts, 96 threads
+__global__ void lba_host_sum_kernel(BAView B, const double* part, double* hostsum /* [n][96] */) {
+  const int h = blockIdx.x, v = threadIdx.x, n = B.n;
+  double s = 0;
+  for (int t = 0; t < n; t++) {
+    const int key = h + t * n;
+    for (int c = B.key_chunk_begin[key]; c < B.key_chunk_begin[key + 1]; c++) s += part[(size_t)c * 96 + v];
+  }
+  hostsum[(size_t)h * 96 + v] = s;
+}
+
+// (Hpp + lambda I - Schur(lambda)) and (bp - schur_b) as a dense (4+8n) system in the layout [cam 4 | host h: pose 6, photo 2]
+__device__ __forceinline__ int lba_tri(int a, int c) { if (a > c) { const int q = a; a = c; c = q; } return a * 12 - (a * (a - 1)) / 2 + (c - a); }
+__global__ void lba_assemble_kernel(int n, const double* A /* [n][96] */, const double* Sc /* [n][96] */, const int* used, double lambda, double* H, double* bvec) {
+  const int d = kCPARS + 8 * n;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d * d + d) return;
+  if (e >= d * d) {
+    const int r = e - d * d;
+    double s = 0;
+    if (r < 4) { for (int h = 0; h < n; h++) if (used[h]) s += A[(size_t)h * 96 + 78 + 8 + r] - Sc[(size_t)h * 96 + 78 + 8 + r]; }
+    else { const int h = (r - 4) / 8, l = (r - 4) % 8; s = used[h] ? A[(size_t)h * 96 + 78 + l] - Sc[(size_t)h * 96 + 78 + l] : 0.0; }
+    bvec[r] = s;
+    return;
+  }
+  const int r = e / d, c = e % d;
+  double s = 0;
+  if (r < 4 && c < 4) {
+    for (int h = 0; h < n; h++) if (used[h]) { const int i = lba_tri(8 + r, 8 + c); s += A[(size_t)h * 96 + i] - Sc[(size_t)h * 96 + i]; }
+    if (r == c) s += lambda;
+  } else if (r < 4 || c < 4) {
+    const int cam = r < 4 ? r : c, o = r < 4 ? c : r;
+    const int h = (o - 4) / 8, l = (o - 4) % 8;
+    if (used[h]) { const int i = lba_tri(l, 8 + cam); s = A[(size_t)h * 96 + i] - Sc[(size_t)h * 96 + i]; }
+  } else {
+    const int h1 = (r - 4) / 8, l1 = (r - 4) % 8, h2 = (c - 4) / 8, l2 = (c - 4) % 8;
+    if (h1 == h2) {
+      if (used[h1]) { const int i = lba_tri(l1, l2); s = A[(size_t)h1 * 96 + i] - Sc[(size_t)h1 * 96 + i]; if (r == c) s += lambda; }
+      else s = (r == c) ? 1.0 : 0.0;
+    }
+  }
+  H[e] = s;
+}
+
+// idepth_r += (bl - hpl^T dx) / (hll + lambda); partial sums of dl (lambda dl + bl) for computeScale
+__global__ void __launch_bounds__(128) lba_update_kernel(BAView B, LBAGraph G, const double* x, double lambda, double* part) {
+  __shared__ double red[32];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0;
+  if (s < G.R && G.active[s]) {
+    const int hb = kCPARS + 8 * (B.s_key[s] % B.n);
+    double t = G.bl[s];
+    for (int a = 0; a < 12; a++) t -= G.hpl[(size_t)s * 12 + a] * x[a < 8 ? hb + a : a - 8];
+    const double dl = t / (G.hll[s] + lambda);
+    G.idepth[s] += dl;
+    v = dl * (lambda * dl + G.bl[s]);
+  }
+  const double t = block_sum_d(v, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void lba_copy_kernel(int n, const double* src, double* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+// initializeOptimization(): the level-0 edges among the graph's edges
+__global__ void lba_activate_kernel(int R, const unsigned char* in_graph, const int* level, unsigned char* active) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < R) active[s] = (in_graph[s] && level[s] == 0) ? 1 : 0;
 }
 
 // ---- B9 -------------------------------------------------------------------------------------------------------

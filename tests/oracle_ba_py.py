@@ -232,3 +232,23 @@ def _lba_edge_eval(self, T_wh, photo, idepth, cam, b0):
 
 
 OracleBA.lba_edge_eval = _lba_edge_eval
+
+lib.orc_lba_g2o.restype = C.c_int
+lib.orc_lba_g2o.argtypes = [V, C.c_int, _dp, _dp, _dp, _dp, _ip, _dp, _ip, _fp, _fp, _ip]
+
+
+def _lba_g2o(self, cam, T_wh, photo, idepth, iters=3):
+    """FullSystem::optimize g2o body with the restated g2o LM. Returns the final vertex estimates and bookkeeping."""
+    c = self.counts()
+    n, R = c["frames"], c["res"]
+    cam, T_wh, photo, idepth = _f64(cam).copy(), _f64(T_wh).reshape(n, 12).copy(), _f64(photo).reshape(n, 2).copy(), _f64(idepth).reshape(R).copy()
+    used, ns = np.zeros(n, np.int32), np.zeros(R, np.int32)
+    chi2, trials = C.c_double(), C.c_int()
+    ce, ih = np.zeros((R, 3), np.float32), np.zeros(R, np.float32)
+    its = lib.orc_lba_g2o(self.h, iters, _p(cam, _dp), _p(T_wh, _dp), _p(photo, _dp), _p(idepth, _dp), _p(used, _ip), C.byref(chi2), _p(ns, _ip),
+                          _p(ce, _fp), _p(ih, _fp), C.byref(trials))
+    return dict(iterations=its, trials=trials.value, cam=cam, T_wh=T_wh.reshape(n, 3, 4), photo=photo, idepth=idepth, used_host=used, chi2=chi2.value,
+                newState=ns, center=ce, idepth_hessian=ih)
+
+
+OracleBA.lba_g2o = _lba_g2o

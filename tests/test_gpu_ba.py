@@ -351,3 +351,43 @@ def test_lba_edge_error_and_jacobians(window7):
     for key in ("newEnergy", "newEnergyWithOutlier", "idepth_hessian"):
         assert np.allclose(g[key][same], o[key][same], rtol=REL, atol=1e-6), key
     assert np.allclose(g["center"][same], o["center"][same], rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(5, 500, 3), (7, 1400, 22)])
+def test_lba_g2o_driver_matches_restated_g2o(pkg, scene, shape):
+    """FullSystem::optimize, g2o body: E2 graph + restated g2o LM with Schur over the per-residual idepth vertices. Iteration-level
+    parity is against the RESTATED driver (oracle/lba_g2o.cpp; g2o is not in the reference tree — unpinned)."""
+    n, P, seed = shape
+    w, h, K = 640, 192, (360.0, 360.0, 319.5, 95.5)
+    win = ba_synth.make_window(scene, n=n, P=P, seed=seed, spacing=0.5, w=w, h=h, K=K, idepth_noise=0.03, state_sigma=0)
+    orc = O.Oracle(w, h, K, synth.BASELINE)
+    ba, _, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)
+    ctx = pkg.Context(w, h, K, synth.BASELINE)
+    W, _ = ba_synth.fill_device(win, ctx, pkg.Window, cw)
+    st = ba.get_state()
+    T_wh = np.stack([np.hstack([T[:, :3].T, (-T[:, :3].T @ T[:, 3])[:, None]]) for T in st["T_w2c"]])
+    rng = np.random.default_rng(0)
+    Tp = np.stack([synth.perturb_T(T, rng, 3e-3, 3e-4) for T in T_wh])
+    idepth = np.array([float(p["idepth"]) for p in win["points"] for _ in p["targets"]])
+    photo = np.zeros((n, 2))
+    o = ba.lba_g2o(np.array(K, float), Tp, photo, idepth, 3)
+    g = W.lba_g2o(np.array(K, float), Tp, photo, idepth, 3)
+    assert g["iterations"] == o["iterations"] and g["trials"] == o["trials"]
+    assert np.array_equal(g["used_host"], o["used_host"])
+    assert np.isclose(g["chi2"], o["chi2"], rtol=1e-6)
+    assert (g["newState"] == o["newState"]).mean() > 0.999
+    assert np.allclose(g["cam"], o["cam"], rtol=1e-7, atol=1e-6)
+    assert np.abs(g["T_wh"] - o["T_wh"]).max() < 1e-6
+    assert np.allclose(g["photo"], o["photo"], rtol=1e-4, atol=1e-5)
+    rel = np.abs(g["idepth"] - o["idepth"]) / np.abs(o["idepth"])
+    assert (rel < 1e-4).mean() > 0.999
+    # the LM must have reduced the robust cost it minimises
+    assert o["chi2"] < 0.98 * ba_initial_chi2(ba, Tp, photo, idepth, K, n)
+    ctx.close()
+
+
+def ba_initial_chi2(ba, T_wh, photo, idepth, K, n):
+    o0 = ba.lba_edge_eval(T_wh, photo, idepth, np.array(K, float), np.zeros(n))
+    e2 = (o0["error"] ** 2).sum(1)
+    rho = np.where(e2 <= 81, e2, 2 * 9 * np.sqrt(e2) - 81)
+    return rho[o0["level"] == 0].sum()
