@@ -199,8 +199,8 @@ def main():
         if rank != 0:
             return 0
         wl = build_workload(seqs=min(S, host_cores))
-        per_thread = max(1, (K_ * 2 + host_cores - 1) // host_cores)   # bounded sample: ~2 frames per requested step, spread over the cores
-        ev, fr, sec = cpu_track_loop(wl, variant, 0.0, per_thread, host_cores, warm_frames=max(W_, 3))
+        per_thread = max(4 * POSES, 5 * K_)   # bounded sample: 5 tracked frames per requested step on EVERY host thread (seconds of CPU work)
+        ev, fr, sec = cpu_track_loop(wl, variant, 1e9, per_thread, host_cores, warm_frames=max(W_, 3))
         val = ev / sec
         line = dict(metric="photometric residual+Jacobian evals/s", value=val, unit="evals/s", n_gpus=args.gpus, steps=K_, warmup=W_,
                     ms_per_step=1e3 * sec / max(K_, 1), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
