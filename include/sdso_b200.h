@@ -22,6 +22,7 @@
 #ifndef SDSO_B200_H_
 #define SDSO_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -82,6 +83,10 @@ typedef struct sdso_settings {
   float frameEnergyTHConstWeight;   /* :98 */
   float frameEnergyTHN;             /* :99 */
   float frameEnergyTHFacMedian;     /* :100 */
+  float minGradHistCut;             /* :105  pixel selector */
+  float minGradHistAdd;             /* :106 */
+  float gradDownweightPerLevel;     /* :107 */
+  float desiredImmatureDensity;     /* :59 */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);
@@ -322,6 +327,32 @@ int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right
  * idepth[i]; states[i][nframes] = ResState per target (-1 for the host); energy[i] = lastEnergy. */
 int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immature_point* pts, int variant, int min_obs, int* result,
                          float* idepth, int* states, float* energy);
+
+/* ---- candidate pixel selection (FullSystem/PixelSelector2.{h,cpp}) ----------------------------------------------------
+ * One PixelSelector per context (FullSystem holds one, FullSystem.cpp:168). State as in the reference: currentPotential
+ * (starts at 3), the frame the block thresholds were last made for (gradHistFrame), and randomPattern — glibc's
+ * srand(3141592); rand() & 0xFF sequence (PixelSelector2.cpp:42-44), generated by the library without touching the
+ * process-wide rand() state. Every result is integer / index work and bit-exact. */
+/* new PixelSelector(w, h): currentPotential = 3, gradHistFrame = 0 */
+int sdso_selector_reset(sdso_ctx* ctx);
+/* The generator behind randomPattern: out[i] = i-th value of srand(seed); rand() & 0xFF. Host only, needs no context. */
+void sdso_selector_pattern_host(unsigned seed, unsigned char* out, size_t n);
+/* randomPattern[0..w*h) (for checks against the platform's rand()) */
+int sdso_selector_random_pattern(sdso_ctx* ctx, unsigned char* out);
+/* currentPotential; set > 0 overwrites it first */
+int sdso_selector_potential(sdso_ctx* ctx, int set, int* potential);
+/* PixelSelector::makeHists(fh) (PixelSelector2.cpp:84-178): 32x32-block gradient histograms -> ths, thsSmoothed ((w/32)*(h/32) floats each) */
+int sdso_selector_make_hists(sdso_ctx* ctx, int frame, float* ths /* nullable */, float* ths_smoothed /* nullable */);
+/* PixelSelector::select(fh, map_out, pot, thFactor) (PixelSelector2.cpp:340-536); thresholds = those of the last makeHists.
+ * map_out: w*h floats in {0,1,2,4} (nullable: the map stays on the device); n = {n2, n3, n4}. */
+int sdso_selector_select(sdso_ctx* ctx, int frame, int pot, float thFactor, float* map_out, int n[3]);
+/* PixelSelector::makeMaps(fh, map_out, density, recursionsLeft, plot=false, thFactor) (PixelSelector2.cpp:192-327): select at
+ * currentPotential, re-select once per recursion when the count is off by > 25 % / < 1/4, random sub-sampling to the wanted
+ * density, currentPotential update. Returns numHaveSub in *num_selected. */
+int sdso_make_maps(sdso_ctx* ctx, int frame, float density, int recursionsLeft, float thFactor, float* map_out /* nullable */, int* num_selected);
+/* The selected pixels of the last select / makeMaps in raster order, as FullSystem::makeNewTraces walks selectionMap
+ * (FullSystem.cpp:1609-1621): uv[2i] = x, uv[2i+1] = y, type[i] = map value (1, 2 or 4). *n = count (<= max_n else SDSO_E_INVALID). */
+int sdso_selector_points(sdso_ctx* ctx, int max_n, float* uv, float* type, int* n);
 
 #ifdef __cplusplus
 }

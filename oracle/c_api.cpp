@@ -3,6 +3,7 @@
 #include "oracle_core.hpp"
 #include "oracle_ba.hpp"
 #include "oracle_trace.hpp"
+#include "oracle_select.hpp"
 #include <memory>
 
 using namespace orc;
@@ -378,4 +379,28 @@ extern "C" int orc_lba_g2o(void* p, int iters, double cam[4], double* T_wh, doub
                            float* center3, float* idepth_hessian, int* trials) {
   Ctx* c = (Ctx*)p;
   return lbaG2O(c->ba, iters, cam, T_wh, photo, idepth, used_host, chi2, newState, center3, idepth_hessian, trials);
+}
+
+// ---- pixel selector (PixelSelector2.cpp) ----
+extern "C" {
+void* orc_sel_create(int w, int h) { auto* s = new orc::PixelSelector(); s->init(w, h); return s; }
+void orc_sel_destroy(void* s) { delete (orc::PixelSelector*)s; }
+void orc_sel_random_pattern(void* s, unsigned char* out) { auto* p = (orc::PixelSelector*)s; memcpy(out, p->randomPattern.data(), p->randomPattern.size()); }
+int orc_sel_potential(void* s, int set) { auto* p = (orc::PixelSelector*)s; if (set > 0) p->currentPotential = set; return p->currentPotential; }
+void orc_sel_forget_hist(void* s) { ((orc::PixelSelector*)s)->gradHistFrame = nullptr; }
+void orc_sel_ths(void* s, float* ths, float* smoothed) {
+  auto* p = (orc::PixelSelector*)s; int k = (p->w / 32) * (p->h / 32);
+  memcpy(ths, p->ths.data(), k * sizeof(float)); memcpy(smoothed, p->thsSmoothed.data(), k * sizeof(float));
+}
+void orc_sel_make_hists(void* s, void* ctx, int fid) { ((orc::PixelSelector*)s)->makeHists(*((Ctx*)ctx)->frames[fid]); }
+void orc_sel_select(void* s, void* ctx, int fid, float* map_out, int pot, float thFactor, int n[3]) {
+  Ctx* c = (Ctx*)ctx;
+  if (c->G.levels < 3) { n[0] = n[1] = n[2] = -1; return; }  // select reads absSquaredGrad[0..2]
+  ((orc::PixelSelector*)s)->select(*c->frames[fid], c->G, map_out, pot, thFactor, n);
+}
+int orc_sel_make_maps(void* s, void* ctx, int fid, float* map_out, float density, int recursionsLeft, float thFactor) {
+  Ctx* c = (Ctx*)ctx;
+  if (c->G.levels < 3) return -1;
+  return ((orc::PixelSelector*)s)->makeMaps(*c->frames[fid], c->G, map_out, density, recursionsLeft, thFactor);
+}
 }

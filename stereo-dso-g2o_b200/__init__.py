@@ -37,6 +37,8 @@ class Settings(C.Structure):
         ("initialCalibHessian", C.c_float), ("margWeightFac", C.c_float), ("solverModeDelta", C.c_double),
         ("minOptIterations", C.c_int32), ("thOptIterations", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
         ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float),
+        ("minGradHistCut", C.c_float), ("minGradHistAdd", C.c_float), ("gradDownweightPerLevel", C.c_float),
+        ("desiredImmatureDensity", C.c_float),
     ]
 
 
@@ -718,3 +720,85 @@ def _w_lba_g2o(self, cam, T_wh, photo, idepth, iters=3):
 
 
 Window.lba_g2o = _w_lba_g2o
+
+
+# ---------------------------------------------------------------------------------------------------
+# candidate pixel selection (PixelSelector2.cpp)
+_ubp = C.POINTER(C.c_ubyte)
+lib.sdso_selector_pattern_host.argtypes = [C.c_uint, _ubp, C.c_size_t]
+lib.sdso_selector_pattern_host.restype = None
+lib.sdso_selector_reset.argtypes = [C.c_void_p]
+lib.sdso_selector_random_pattern.argtypes = [C.c_void_p, _ubp]
+lib.sdso_selector_potential.argtypes = [C.c_void_p, C.c_int, _ip]
+lib.sdso_selector_make_hists.argtypes = [C.c_void_p, C.c_int, _fp, _fp]
+lib.sdso_selector_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, _fp, _ip]
+lib.sdso_make_maps.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, _fp, _ip]
+lib.sdso_selector_points.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _ip]
+
+
+def selector_pattern_host(n, seed=3141592):
+    out = np.zeros(n, np.uint8)
+    lib.sdso_selector_pattern_host(seed, _ptr(out, _ubp), n)
+    return out
+
+
+def _selector_reset(self):
+    self._ck(lib.sdso_selector_reset(self._h))
+
+
+def _selector_random_pattern(self):
+    w, h = self.level_size(0)
+    out = np.zeros(w * h, np.uint8)
+    self._ck(lib.sdso_selector_random_pattern(self._h, _ptr(out, _ubp)))
+    return out
+
+
+def _selector_potential(self, set=0):
+    p = C.c_int(0)
+    self._ck(lib.sdso_selector_potential(self._h, int(set), C.byref(p)))
+    return p.value
+
+
+def _selector_make_hists(self, fid):
+    w, h = self.level_size(0)
+    ths = np.zeros((h // 32, w // 32), np.float32)
+    sm = np.zeros_like(ths)
+    self._ck(lib.sdso_selector_make_hists(self._h, fid, _ptr(ths, _fp), _ptr(sm, _fp)))
+    return ths, sm
+
+
+def _selector_select(self, fid, pot, th_factor=1.0, want_map=True):
+    w, h = self.level_size(0)
+    m = np.zeros((h, w), np.float32) if want_map else None
+    n = np.zeros(3, np.int32)
+    self._ck(lib.sdso_selector_select(self._h, fid, int(pot), float(th_factor), _ptr(m, _fp) if want_map else None, _ptr(n, _ip)))
+    return m, n
+
+
+def _make_maps(self, fid, density=None, recursions_left=1, th_factor=1.0, want_map=True):
+    """PixelSelector::makeMaps; density defaults to setting_desiredImmatureDensity (FullSystem.cpp:1605)."""
+    w, h = self.level_size(0)
+    if density is None:
+        density = default_settings().desiredImmatureDensity
+    m = np.zeros((h, w), np.float32) if want_map else None
+    n = C.c_int(0)
+    self._ck(lib.sdso_make_maps(self._h, fid, float(density), int(recursions_left), float(th_factor), _ptr(m, _fp) if want_map else None, C.byref(n)))
+    return m, n.value
+
+
+def _selector_points(self):
+    w, h = self.level_size(0)
+    uv = np.zeros((w * h, 2), np.float32)
+    ty = np.zeros(w * h, np.float32)
+    n = C.c_int(0)
+    self._ck(lib.sdso_selector_points(self._h, w * h, _ptr(uv, _fp), _ptr(ty, _fp), C.byref(n)))
+    return uv[:n.value].copy(), ty[:n.value].copy()
+
+
+Context.selector_reset = _selector_reset
+Context.selector_random_pattern = _selector_random_pattern
+Context.selector_potential = _selector_potential
+Context.selector_make_hists = _selector_make_hists
+Context.selector_select = _selector_select
+Context.make_maps = _make_maps
+Context.selector_points = _selector_points

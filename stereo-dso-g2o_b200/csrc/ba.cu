@@ -328,7 +328,7 @@ static int download_sys(sdso_ctx* ctx, int which, double* H, double* bv) {
 
 static void fill_solve_params(sdso_ctx* ctx, SolveParams& S, int iteration) {
   BAState* b = ctx->ba;
-  S.n = b->n; S.d = b->dim(); S.iteration = iteration;
+  S.n = b->n; S.d = b->dim(); S.iteration = iteration; S.plain = 0;
   S.have_M = (b->have_M && b->shard_rank == 0) ? 1 : 0;  // HM / bM enter once (rank 0 of a sharded window)
   S.lambda = 1e-5;  // SOLVER_FIX_LAMBDA (EnergyFunctional.cpp:844-846): setting_solverMode fixes lambda regardless of the argument
   S.solverModeDelta = ctx->S.solverModeDelta;
@@ -347,7 +347,7 @@ static int launch_assemble(sdso_ctx* ctx) {
   if (!rc) rc = launch_top(ctx, 1, SYS_L, b->shard_rank == 0);  // priors enter once
   if (!rc) rc = launch_sc(ctx, true, SYS_SC);
   if (rc) return rc;
-  SolveParams S;
+  SolveParams S{};
   fill_solve_params(ctx, S, 0);
   ba_assemble_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(S);
   SDSO_CHECK_LAUNCH(ctx);
@@ -357,7 +357,7 @@ static int launch_assemble(sdso_ctx* ctx) {
 static int launch_factor_solve(sdso_ctx* ctx, int iteration) {
   BAState* b = ctx->ba;
   const int d = b->dim();
-  SolveParams S;
+  SolveParams S{};
   fill_solve_params(ctx, S, iteration);
   const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
   static bool attr_set = false;
@@ -1011,7 +1011,7 @@ int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immat
   const size_t bytes = (size_t)n * (sizeof(sdso_immature_point) + sizeof(int) * 2 + sizeof(float) * 2 + sizeof(int) * nf);
   unsigned char* d = nullptr;
   SDSO_CUDA(ctx, cudaMalloc(&d, bytes + 64));
-  ActParams A;
+  ActParams A{};
   sdso_immature_point* d_pts = reinterpret_cast<sdso_immature_point*>(d);
   int* d_host = reinterpret_cast<int*>(d_pts + n);
   int* d_res = d_host + n; int* d_states = d_res + n;
@@ -1053,7 +1053,7 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
   unsigned char* d = nullptr;
   SDSO_CUDA(ctx, cudaMalloc(&d, bytes));
   double* pd = reinterpret_cast<double*>(d);
-  LBAEdgeParams E;
+  LBAEdgeParams E{};
   std::vector<double> host_in(in_d);
   double* hp = host_in.data();
   double* h_Twh = hp; hp += n * 12;
@@ -1181,7 +1181,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_exp, h_exp.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
 
   BAView v = view(b);
-  LBAEdgeParams E;
+  LBAEdgeParams E{};
   E.T_wh = d_est; E.T_tw = d_est + n * 12; E.photo = d_est + n * 24; E.b0 = d_est + n * 26; E.target_aff = d_est + n * 27; E.exposure = d_exp;
   E.idepth = d_idepth; E.slot2rid = nullptr; E.driver = 1;
   E.error8 = d_err; E.Jxi = d_Jxi; E.Jphoto = d_Jph; E.Jid = d_Jid; E.JC = d_JC;
@@ -1208,7 +1208,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   if ((rc = eval(d_ingraph, 0))) return cleanup(rc);
   lba_activate_kernel<<<rb, 128, 0, st>>>(R, d_ingraph, d_level, d_active); ctx->launches++;
 
-  SolveParams S;
+  SolveParams S{};
   fill_solve_params(ctx, S, 0);
   S.plain = 1; S.N = nullptr; S.have_M = 0;
   const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);

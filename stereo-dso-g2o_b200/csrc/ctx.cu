@@ -125,6 +125,10 @@ void sdso_default_settings(sdso_settings* s) {
   s->frameEnergyTHConstWeight = 0.5f;
   s->frameEnergyTHN = 0.7f;
   s->frameEnergyTHFacMedian = 1.5f;
+  s->minGradHistCut = 0.5f;
+  s->minGradHistAdd = 7;
+  s->gradDownweightPerLevel = 0.75f;
+  s->desiredImmatureDensity = 3000;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {
@@ -151,6 +155,7 @@ int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], 
   if (rc == SDSO_OK) rc = tracker_create(c);
   if (rc == SDSO_OK) rc = ba_create(c);
   if (rc == SDSO_OK) rc = trace_create(c);
+  if (rc == SDSO_OK) rc = selector_create(c);
   if (rc != SDSO_OK) { sdso_ctx_destroy(c); return rc; }
   *out = c;
   return SDSO_OK;
@@ -162,6 +167,7 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   cudaDeviceSynchronize();
   collective_destroy(ctx);
   trace_destroy(ctx);
+  selector_destroy(ctx);
   ba_destroy(ctx);
   tracker_destroy(ctx);
   for (auto& f : ctx->frames) {
@@ -246,7 +252,7 @@ int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float
   f.ab_exposure = ab_exposure;
   int rc = make_images_launch(ctx, f, f.image, use_hcalib != 0);
   if (rc) return rc;
-  f.valid = true;
+  f.valid = true; f.gen++;
   return SDSO_OK;
 }
 
@@ -258,7 +264,7 @@ int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_ima
   f.ab_exposure = ab_exposure;
   int rc = make_images_launch(ctx, f, device_image, use_hcalib != 0);
   if (rc) return rc;
-  f.valid = true;
+  f.valid = true; f.gen++;
   return SDSO_OK;
 }
 
@@ -334,7 +340,7 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
     rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
-  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }
   return SDSO_OK;
 }
 
@@ -351,7 +357,7 @@ int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, c
     rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, device_images + o, src_u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
-  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->pending_u8 = -1; }
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }
   return SDSO_OK;
 }
 

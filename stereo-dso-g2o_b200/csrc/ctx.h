@@ -17,6 +17,7 @@ struct Frame {
   float* image = nullptr;               // level-0 intensity plane (the uploaded image)
   float ab_exposure = 1.0f;
   bool valid = false;
+  unsigned gen = 0;                     // bumped by every makeImages on this slot (the selector keys its histograms on it)
   unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (a slice of a batch arena)
   bool src8_owned = false;
   cudaEvent_t uploaded = nullptr;       // recorded on the copy stream after the asynchronous upload of this frame's source
@@ -34,6 +35,7 @@ struct HostCalib {  // per level, float, as util/globalCalib.cpp:48-108 computes
 struct TrackerState;  // tracker.cu
 struct BAState;       // ba.cu
 struct TraceState;    // trace.cu
+struct SelectorState; // pixel_select.cu
 
 }  // namespace sdso
 
@@ -51,6 +53,7 @@ struct sdso_ctx {
   sdso::TrackerState* tracker = nullptr;
   sdso::BAState* ba = nullptr;
   sdso::TraceState* trace = nullptr;
+  sdso::SelectorState* selector = nullptr;
   uint64_t launches = 0;
   // optional CUDA-event profiling of the two hot launches (bench.py roofline); see sdso_profile_*
   bool profile = false;
@@ -110,5 +113,7 @@ void ba_destroy(sdso_ctx* ctx);
 void collective_destroy(sdso_ctx* ctx);
 int trace_create(sdso_ctx* ctx);
 void trace_destroy(sdso_ctx* ctx);
+int selector_create(sdso_ctx* ctx);
+void selector_destroy(sdso_ctx* ctx);
 
 }  // namespace sdso

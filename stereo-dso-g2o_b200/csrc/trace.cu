@@ -376,7 +376,7 @@ int sdso_immature_init(sdso_ctx* ctx, int host_frame, int n, const float* uv, sd
 
 int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[3], const float aff[2], int n, sdso_immature_point* pts, int* status) {
   if (!ctx || !KRKi || !Kt || !aff) return SDSO_E_INVALID;
-  TraceParams T;
+  TraceParams T{};
   fill_settings(ctx, T);
   for (int i = 0; i < 9; i++) T.KRKi[i] = KRKi[i];
   for (int i = 0; i < 3; i++) T.Kt[i] = Kt[i];
@@ -387,7 +387,7 @@ int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[
 
 int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, sdso_immature_point* pts, int* status) {
   if (!ctx || !K) return SDSO_E_INVALID;
-  TraceParams T;
+  TraceParams T{};
   fill_settings(ctx, T);
   const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int i = 0; i < 9; i++) T.KRKi[i] = I3[i];

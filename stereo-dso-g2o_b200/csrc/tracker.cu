@@ -1190,7 +1190,7 @@ int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNe
   if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
   int rc = check_frame(ctx, new_frame);
   if (rc) return rc;
-  TrackParams P;
+  TrackParams P{};
   fill_params(ctx, P);
   P.mode = 1; P.eval_lvl = lvl; P.eval_cutoff = cutoffTH; P.variant = SDSO_VARIANT_SSE;
   const int n = t->pc_n[lvl];
@@ -1248,7 +1248,7 @@ int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[
   if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
   int rc = check_frame(ctx, new_frame);
   if (rc) return rc;
-  TrackParams P;
+  TrackParams P{};
   fill_params(ctx, P);
   P.mode = 2; P.eval_lvl = lvl; P.eval_cutoff = 1e30f; P.variant = SDSO_VARIANT_G2O;
   rc = ensure_edge_scratch(ctx, P, 1);
@@ -1322,7 +1322,7 @@ int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const 
   if (nb > t->max_problems) return fail(ctx, SDSO_E_INVALID, "too many problems in one batch");
   if (coarsest_lvl < 0 || coarsest_lvl >= ctx->G.levels || coarsest_lvl >= 5) return fail(ctx, SDSO_E_INVALID, "coarsest_lvl out of range");
   if (variant != SDSO_VARIANT_SSE && variant != SDSO_VARIANT_G2O) return SDSO_E_INVALID;
-  TrackParams P;
+  TrackParams P{};
   fill_params(ctx, P);
   P.mode = 0; P.coarsest = coarsest_lvl; P.variant = variant;
   if (variant == SDSO_VARIANT_G2O) { int rc = ensure_edge_scratch(ctx, P, nb); if (rc) return rc; }
