@@ -87,6 +87,7 @@ typedef struct sdso_settings {
   float minGradHistAdd;             /* :106 */
   float gradDownweightPerLevel;     /* :107 */
   float desiredImmatureDensity;     /* :59 */
+  float minTraceQuality;            /* :112 activation candidate filter */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);
@@ -353,6 +354,23 @@ int sdso_make_maps(sdso_ctx* ctx, int frame, float density, int recursionsLeft, 
 /* The selected pixels of the last select / makeMaps in raster order, as FullSystem::makeNewTraces walks selectionMap
  * (FullSystem.cpp:1609-1621): uv[2i] = x, uv[2i+1] = y, type[i] = map value (1, 2 or 4). *n = count (<= max_n else SDSO_E_INVALID). */
 int sdso_selector_points(sdso_ctx* ctx, int max_n, float* uv, float* type, int* n);
+
+/* ---- coarse distance map and the activation candidate filter --------------------------------------------------------
+ * CoarseDistanceMap (FullSystem/CoarseTracker.cpp:1186-1420) lives on the level-1 grid (w >> 1, h >> 1). Hosts are the
+ * keyframes other than the newest one, in frameHessians order; per host the caller passes
+ * KRKi = K[1] * R(newest <- host) * Ki[0] and Kt = K[1] * t (floats, CoarseTracker.cpp:1233-1235 / FullSystem.cpp:845-847). */
+/* makeDistanceMap(frameHessians, newest) (:1216-1253) + growDistBFS (:1258-1355): pt_uvid[i] = {u, v, idepth_scaled} of the
+ * active points grouped by host (pt_host[i] = host index). map_out: (w >> 1) * (h >> 1) floats (0..39, 1000), nullable. */
+int sdso_distmap_make(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float* Kt, int n_pts, const int* pt_host, const float* pt_uvid, float* map_out);
+/* addIntoDistFinal(u, v) (:1358-1366) for n cells; the field of the interior cells does not depend on the insertion order. */
+int sdso_distmap_add(sdso_ctx* ctx, int n, const int* uv, float* map_out);
+/* FullSystem::activatePointsMT STEP2 (FullSystem.cpp:838-901) over the candidates in the reference's order (host by host,
+ * immaturePoints order): cand_host[i], pts[i], my_type[i] (1, 2 or 4), host_flagged[h] = flaggedForMarginalization.
+ * verdict[i]: 0 stays immature, 1 goes to toOptimize (and was inserted into the distance field), 2 deleted.
+ * Needs the field of sdso_distmap_make; leaves the field with the accepted candidates inserted. *rounds (nullable) =
+ * dependency rounds the device needed. */
+int sdso_activation_filter(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float* Kt, const unsigned char* host_flagged, int n, const int* cand_host,
+                           const sdso_immature_point* pts, const float* my_type, float currentMinActDist, int* verdict, int* rounds, float* map_out);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 #include "oracle_ba.hpp"
 #include "oracle_trace.hpp"
 #include "oracle_select.hpp"
+#include "oracle_distmap.hpp"
 #include <memory>
 
 using namespace orc;
@@ -402,5 +403,27 @@ int orc_sel_make_maps(void* s, void* ctx, int fid, float* map_out, float density
   Ctx* c = (Ctx*)ctx;
   if (c->G.levels < 3) return -1;
   return ((orc::PixelSelector*)s)->makeMaps(*c->frames[fid], c->G, map_out, density, recursionsLeft, thFactor);
+}
+}
+
+// ---- coarse distance map + activation candidate filter ----
+extern "C" {
+void* orc_dm_create(void* ctx) { Ctx* c = (Ctx*)ctx; auto* m = new orc::CoarseDistanceMap(); m->init(c->G.w[1], c->G.h[1]); return m; }
+void orc_dm_destroy(void* m) { delete (orc::CoarseDistanceMap*)m; }
+// makeDistanceMap: hosts in frameHessians order (the newest frame is simply not listed), points grouped by host
+void orc_dm_make(void* mp, int n_hosts, const float* KRKi, const float* Kt, const int* host_count, const float* uvid) {
+  auto* m = (orc::CoarseDistanceMap*)mp;
+  std::fill(m->fwdWarpedIDDistFinal.begin(), m->fwdWarpedIDDistFinal.end(), 1000.f);
+  int numItems = 0, off = 0;
+  for (int h = 0; h < n_hosts; h++) { numItems = m->seed(KRKi + 9 * h, Kt + 3 * h, host_count[h], uvid + 3 * off, numItems); off += host_count[h]; }
+  m->growDistBFS(numItems);
+}
+void orc_dm_add(void* mp, int n, const int* uv) { auto* m = (orc::CoarseDistanceMap*)mp; for (int i = 0; i < n; i++) m->addIntoDistFinal(uv[2 * i], uv[2 * i + 1]); }
+void orc_dm_get(void* mp, float* out) { auto* m = (orc::CoarseDistanceMap*)mp; memcpy(out, m->fwdWarpedIDDistFinal.data(), m->fwdWarpedIDDistFinal.size() * sizeof(float)); }
+void orc_dm_filter(void* mp, void* ctx, int n_hosts, const float* KRKi, const float* Kt, const unsigned char* flagged, int n, const int* cand_host,
+                   const void* pts, const float* my_type, float currentMinActDist, int* verdict) {
+  Ctx* c = (Ctx*)ctx;
+  orc::activationFilter(*(orc::CoarseDistanceMap*)mp, n_hosts, KRKi, Kt, flagged, n, cand_host, (const orc::ImmaturePoint*)pts, my_type, currentMinActDist,
+                        c->S.minTraceQuality, verdict);
 }
 }

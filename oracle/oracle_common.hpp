@@ -63,6 +63,7 @@ struct Settings {
   float thOptIterations = 1.2f;        // :69
   float minIdepthH_act = 100;          // :56
   int GNItsOnPointActivation = 3;      // :114
+  float minTraceQuality = 3;           // :112
   float frameEnergyTHConstWeight = 0.5f, frameEnergyTHN = 0.7f, frameEnergyTHFacMedian = 1.5f;  // :98-100
 };
 

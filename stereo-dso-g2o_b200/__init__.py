@@ -38,7 +38,7 @@ class Settings(C.Structure):
         ("minOptIterations", C.c_int32), ("thOptIterations", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
         ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float),
         ("minGradHistCut", C.c_float), ("minGradHistAdd", C.c_float), ("gradDownweightPerLevel", C.c_float),
-        ("desiredImmatureDensity", C.c_float),
+        ("desiredImmatureDensity", C.c_float), ("minTraceQuality", C.c_float),
     ]
 
 
@@ -802,3 +802,50 @@ Context.selector_make_hists = _selector_make_hists
 Context.selector_select = _selector_select
 Context.make_maps = _make_maps
 Context.selector_points = _selector_points
+
+
+# ---------------------------------------------------------------------------------------------------
+# coarse distance map + activation candidate filter (CoarseTracker.cpp:1216-1366, FullSystem.cpp:838-901)
+lib.sdso_distmap_make.argtypes = [C.c_void_p, C.c_int, _fp, _fp, C.c_int, _ip, _fp, _fp]
+lib.sdso_distmap_add.argtypes = [C.c_void_p, C.c_int, _ip, _fp]
+lib.sdso_activation_filter.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _ubp, C.c_int, _ip, C.c_void_p, _fp, C.c_float, _ip, _ip, _fp]
+
+
+def _distmap_make(self, KRKi, Kt, pt_host, pt_uvid, want_map=True):
+    w1, h1 = self.level_size(1)
+    K_, t_ = _f32(KRKi).reshape(-1, 9), _f32(Kt).reshape(-1, 3)
+    ph = np.ascontiguousarray(pt_host, dtype=np.int32)
+    pv = _f32(pt_uvid).reshape(-1, 3)
+    m = np.zeros((h1, w1), np.float32) if want_map else None
+    self._ck(lib.sdso_distmap_make(self._h, K_.shape[0], _ptr(K_, _fp), _ptr(t_, _fp), ph.size, _ptr(ph, _ip), _ptr(pv, _fp),
+                                   _ptr(m, _fp) if want_map else None))
+    return m
+
+
+def _distmap_add(self, uv):
+    w1, h1 = self.level_size(1)
+    uv = np.ascontiguousarray(uv, dtype=np.int32).reshape(-1, 2)
+    m = np.zeros((h1, w1), np.float32)
+    self._ck(lib.sdso_distmap_add(self._h, uv.shape[0], _ptr(uv, _ip), _ptr(m, _fp)))
+    return m
+
+
+def _activation_filter(self, KRKi, Kt, host_flagged, cand_host, pts, my_type, current_min_act_dist, want_map=True):
+    w1, h1 = self.level_size(1)
+    K_, t_ = _f32(KRKi).reshape(-1, 9), _f32(Kt).reshape(-1, 3)
+    fl = np.ascontiguousarray(host_flagged, dtype=np.uint8)
+    ch = np.ascontiguousarray(cand_host, dtype=np.int32)
+    ty = _f32(my_type)
+    pts = np.ascontiguousarray(pts)
+    verdict = np.zeros(ch.size, np.int32)
+    rounds = C.c_int(0)
+    m = np.zeros((h1, w1), np.float32) if want_map else None
+    self._ck(lib.sdso_activation_filter(self._h, K_.shape[0], _ptr(K_, _fp), _ptr(t_, _fp), _ptr(fl, _ubp), ch.size, _ptr(ch, _ip), pts.ctypes.data,
+                                        _ptr(ty, _fp), float(current_min_act_dist), _ptr(verdict, _ip), C.byref(rounds),
+                                        _ptr(m, _fp) if want_map else None))
+    return verdict, m, rounds.value
+
+
+Context.distmap_make = _distmap_make
+Context.distmap_add = _distmap_add
+Context.activation_filter = _activation_filter

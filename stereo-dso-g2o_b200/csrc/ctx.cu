@@ -129,6 +129,7 @@ void sdso_default_settings(sdso_settings* s) {
   s->minGradHistAdd = 7;
   s->gradDownweightPerLevel = 0.75f;
   s->desiredImmatureDensity = 3000;
+  s->minTraceQuality = 3;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {
@@ -156,6 +157,7 @@ int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], 
   if (rc == SDSO_OK) rc = ba_create(c);
   if (rc == SDSO_OK) rc = trace_create(c);
   if (rc == SDSO_OK) rc = selector_create(c);
+  if (rc == SDSO_OK) rc = distmap_create(c);
   if (rc != SDSO_OK) { sdso_ctx_destroy(c); return rc; }
   *out = c;
   return SDSO_OK;
@@ -168,6 +170,7 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   collective_destroy(ctx);
   trace_destroy(ctx);
   selector_destroy(ctx);
+  distmap_destroy(ctx);
   ba_destroy(ctx);
   tracker_destroy(ctx);
   for (auto& f : ctx->frames) {

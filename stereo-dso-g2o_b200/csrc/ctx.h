@@ -36,6 +36,7 @@ struct TrackerState;  // tracker.cu
 struct BAState;       // ba.cu
 struct TraceState;    // trace.cu
 struct SelectorState; // pixel_select.cu
+struct DistMapState;  // distmap.cu
 
 }  // namespace sdso
 
@@ -54,6 +55,7 @@ struct sdso_ctx {
   sdso::BAState* ba = nullptr;
   sdso::TraceState* trace = nullptr;
   sdso::SelectorState* selector = nullptr;
+  sdso::DistMapState* distmap = nullptr;
   uint64_t launches = 0;
   // optional CUDA-event profiling of the two hot launches (bench.py roofline); see sdso_profile_*
   bool profile = false;
@@ -115,5 +117,7 @@ int trace_create(sdso_ctx* ctx);
 void trace_destroy(sdso_ctx* ctx);
 int selector_create(sdso_ctx* ctx);
 void selector_destroy(sdso_ctx* ctx);
+int distmap_create(sdso_ctx* ctx);
+void distmap_destroy(sdso_ctx* ctx);
 
 }  // namespace sdso
