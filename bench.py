@@ -379,7 +379,7 @@ def main():
             traffic = json.load(open(tp)).get(f"track_{args.variant}_batch{S}_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    img_bytes = 32 * (npx * 1 + 4 * 603911 + 16 * 603911)  # per launch of 32 images: u8 read + intensity planes + texels written
+    img_bytes = npx * 1 + 4 * 603911 + 16 * 603911  # per image: u8 read + intensity planes + texels written
     # CPU baseline (rank 0, bounded sample of the same workload on all host cores)
     cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
     line = dict(
@@ -399,7 +399,7 @@ def main():
                       kernel="track_kernel" if variant == 0 else "track_g2o_kernel", peak_source=peak_src,
                       algorithmic_bytes_per_launch=evals_per_launch * BYTES_PER_EVAL, avg_launch_ms=track_ms_per_launch,
                       share_of_step=prof["track_ms"] / ms_dev,
-                      make_images=dict(achieved=img_bytes * prof["images_launches"] / max(prof["images_ms"], 1e-9) / 1e6,
+                      make_images=dict(achieved=img_bytes * S * K_ / max(prof["images_ms"], 1e-9) / 1e6,
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
                                        algorithmic_bytes=img_bytes)),
         cpu_baseline=dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",

@@ -339,8 +339,8 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
     f.ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f;
   }
   SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[frame_ids[nb - 1]].uploaded, 0));
-  for (int o = 0; o < nb; o += 32) {  // 32 frames per launch pair (kernel-parameter space)
-    rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
+  for (int o = 0; o < nb; o += 128) {  // 128 frames per launch pair (kernel-parameter space)
+    rc = make_images_batch_launch(ctx, nb - o < 128 ? nb - o : 128, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
   for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }
@@ -356,8 +356,8 @@ int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, c
   if (!device_images) return SDSO_E_INVALID;
   std::vector<Frame*> fr(nb);
   for (int i = 0; i < nb; i++) { fr[i] = &ctx->frames[frame_ids[i]]; fr[i]->ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f; }
-  for (int o = 0; o < nb; o += 32) {
-    rc = make_images_batch_launch(ctx, nb - o < 32 ? nb - o : 32, fr.data() + o, device_images + o, src_u8 != 0, use_hcalib != 0);
+  for (int o = 0; o < nb; o += 128) {
+    rc = make_images_batch_launch(ctx, nb - o < 128 ? nb - o : 128, fr.data() + o, device_images + o, src_u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
   for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }

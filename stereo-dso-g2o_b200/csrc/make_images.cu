@@ -1,6 +1,6 @@
 // A1 — FrameHessian::makeImages (FullSystem/HessianBlocks.cpp:141-203) on the device.
 //
-// One streaming (HBM-bound) pass per batch of up to 32 images:
+// One streaming (HBM-bound) pass per batch of up to 128 images:
 //   pyr_fused_kernel : one CTA per 64x64 level-0 tile (+ halo): source (float or 8-bit) -> shared memory -> all pyramid
 //                      levels of the tile in shared memory (2x2 box mean in the reference's order 0.25f*(((a+b)+c)+d),
 //                      :172-178) -> central differences, non-finite -> 0, absSquaredGrad (+ gamma factor, :196-200) ->
@@ -11,7 +11,7 @@
 
 namespace sdso {
 
-constexpr int kMaxBatch = 32;  // images per launch (blockIdx.z)
+constexpr int kMaxBatch = 128;  // images per launch (blockIdx.z); 3 pointers per image in the 4 KB kernel-parameter space
 
 struct PyrGeom {  // identical for every frame of a context
   int levels;
@@ -50,38 +50,129 @@ __device__ __forceinline__ float4 make_texel(float c, float dx, float dy, int us
 // texels and the intensity planes of ALL levels from there. The source is read once (the halo re-reads hit L2), nothing is
 // read back from HBM. Image columns 0 and w-1, whose horizontal difference wraps to the neighbouring row in the reference
 // (flat idx +- 1, HessianBlocks.cpp:182-184), are finished by pyr_wrap_kernel.
+// The level count is a template parameter: every region size, divisor and trip count is a constant, and the write phase
+// maps threads to (column, row-stride) so a warp stores 32 consecutive texels (512 B) per instruction with no index
+// division — the first version of this kernel spent 170 instructions per pixel and was issue-bound at 48 % of HBM.
+template <int L, int l, bool FINITE, bool GAMMA>
+__device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* __restrict__ src, float* __restrict__ base, float4* __restrict__ tbase,
+                                                int tid, const float* __restrict__ s_dB) {
+  constexpr int H0 = 1 << (L - 1), R0 = kTile + 2 * H0;
+  constexpr int Rs = R0 >> l, T = kTile >> l, Hl = H0 >> l;
+  constexpr int TX = T < 32 ? T : (T > 64 ? 64 : T);   // threads along x
+  constexpr int NB = 256 / TX;                           // row bands
+  constexpr int BR = (T + NB - 1) / NB;                  // consecutive rows per band (0 threads idle when NB > T)
+  const int wl = P.w[l], hl = P.h[l];
+  const int tx0 = (blockIdx.x * kTile) >> l, ty0 = (blockIdx.y * kTile) >> l;
+  const int lx = tid % TX, ly0 = (tid / TX) * BR;
+  const int x = tx0 + lx;
+  if (x >= wl || ly0 >= T) return;
+  const int ylast = min(min(T, ly0 + BR), hl - ty0);     // end of this band inside the image
+  const size_t o0 = (size_t)P.px_offset[l] + x + (size_t)(ty0 + ly0) * wl;
+  float* __restrict__ Il = base + o0;
+  float4* __restrict__ Tl = tbase + o0;
+  const float* q = src + (Hl + ly0) * Rs + (lx + Hl);
+  // a thread walks down its column: the centre values of the rows above / below stay in registers
+  float cu = q[-Rs], c = q[0];
+#pragma unroll 4
+  for (int ly = ly0; ly < ylast; ly++, q += Rs, Il += wl, Tl += wl) {
+    const int y = ty0 + ly;
+    const float cd = q[Rs];
+    // the halo holds the neighbours of every tile pixel, so the differences are formed unconditionally and dropped for the
+    // first / last image row (flat idx outside [w, w(h-1)), :182); columns 0 and w-1 are redone by pyr_wrap_kernel
+    float dx = 0.5f * (q[1] - q[-1]);
+    float dy = 0.5f * (cd - cu);
+    if (!FINITE) { if (!isfinite(dx)) dx = 0.f; if (!isfinite(dy)) dy = 0.f; }
+    float ag = dx * dx + dy * dy;
+    if (GAMMA) {
+      int ci = (int)(c + 0.5f);  // CalibHessian::getBGradOnly (HessianBlocks.h:356-362)
+      ci = min(max(ci, 5), 250);
+      const float gw = s_dB[ci];
+      ag *= gw * gw;
+    }
+    const bool inner = (y >= 1 && y < hl - 1);
+    *Il = c;
+    *Tl = make_float4(c, inner ? dx : 0.f, inner ? dy : 0.f, inner ? ag : 0.f);
+    cu = c; c = cd;
+  }
+}
+
+template <int L, int l, bool FINITE, bool GAMMA>
+struct PyrWriteLevels {
+  static __device__ __forceinline__ void run(const PyrGeom& P, const float* src, float* base, float4* tbase, int tid, const float* s_dB) {
+    constexpr int H0 = 1 << (L - 1), R0 = kTile + 2 * H0, Rs = R0 >> l;
+    pyr_write_level<L, l, FINITE, GAMMA>(P, src, base, tbase, tid, s_dB);
+    PyrWriteLevels<L, l + 1, FINITE, GAMMA>::run(P, src + Rs * Rs, base, tbase, tid, s_dB);
+  }
+};
+template <int L, bool FINITE, bool GAMMA>
+struct PyrWriteLevels<L, L, FINITE, GAMMA> {
+  static __device__ __forceinline__ void run(const PyrGeom&, const float*, float*, float4*, int, const float*) {}
+};
+
+template <int L>
 __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
-  const int L = P.levels;
-  const int H0 = 1 << (L - 1);              // level-0 halo
-  const int R0 = kTile + 2 * H0;            // level-0 region side
+  constexpr int H0 = 1 << (L - 1);          // level-0 halo
+  constexpr int R0 = kTile + 2 * H0;        // level-0 region side
   const int ox = blockIdx.x * kTile - H0, oy = blockIdx.y * kTile - H0;  // level-0 origin of the region
   const int w0 = P.w[0], h0 = P.h[0];
   float* __restrict__ base = B.img[blockIdx.z];
   float4* __restrict__ tbase = B.tex[blockIdx.z];
   // ---- level 0 region into shared memory (0 outside the image)
   float* s0 = sm;
-  if (P.src_u8) {
+  __shared__ float s_dB[256];   // B[ci + 1] - B[ci], the factor getBGradOnly returns
+  if (P.use_gamma) s_dB[tid] = tid < 255 ? g_Bgamma[tid + 1] - g_Bgamma[tid] : 0.f;
+  if (P.src_u8 && (w0 & 15) == 0) {
+    // 16 pixels per load: ox and w0 are multiples of 16, so a group lies inside or outside the image as a whole
     const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
-    if ((w0 & 3) == 0) {
-      const int R4 = R0 >> 2;
-      for (int k = tid; k < R0 * R4; k += 256) {
-        const int ly = k / R4, lx = (k - ly * R4) * 4;
-        const int x = ox + lx, y = oy + ly;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < h0 && x >= 0 && x + 3 < w0) {
-          const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(S8 + x + (size_t)y * w0));
-          v = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
-        }
-        *reinterpret_cast<float4*>(s0 + ly * R0 + lx) = v;
+    constexpr int R16 = R0 >> 4, NG = R0 * R16, NIT = (NG + 255) / 256;
+    uint4 qv[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {   // every load of the thread is in flight before the first conversion
+      const int k = tid + it * 256;
+      const int ly = k / R16, lx = (k - ly * R16) * 16;
+      const int x = ox + lx, y = oy + ly;
+      qv[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (k < NG && y >= 0 && y < h0 && x >= 0 && x < w0) qv[it] = __ldg(reinterpret_cast<const uint4*>(S8 + x + y * w0));
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int k = tid + it * 256;
+      if (k >= NG) break;
+      const int ly = k / R16, lx = (k - ly * R16) * 16;
+      const uint4 q = qv[it];
+      float4* d = reinterpret_cast<float4*>(s0 + ly * R0 + lx);
+      // lanes are 64 B apart: rotating the order in which a lane stores its four float4 spreads every 8-lane wavefront over
+      // all 32 banks (in lane order the 128-bit stores are 4-way conflicted)
+      const int rot = (tid >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int jj = (j + rot) & 3;
+        const unsigned wv = jj == 0 ? q.x : (jj == 1 ? q.y : (jj == 2 ? q.z : q.w));
+        d[jj] = make_float4((float)(wv & 0xffu), (float)((wv >> 8) & 0xffu), (float)((wv >> 16) & 0xffu), (float)(wv >> 24));
       }
-    } else {
-      for (int k = tid; k < R0 * R0; k += 256) {
-        const int ly = k / R0, lx = k - ly * R0;
-        const int x = ox + lx, y = oy + ly;
-        s0[k] = (y >= 0 && y < h0 && x >= 0 && x < w0) ? (float)__ldg(S8 + x + (size_t)y * w0) : 0.f;
+    }
+  } else if (P.src_u8 && (w0 & 3) == 0) {
+    const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
+    constexpr int R4 = R0 >> 2;
+#pragma unroll 3
+    for (int k = tid; k < R0 * R4; k += 256) {
+      const int ly = k / R4, lx = (k - ly * R4) * 4;
+      const int x = ox + lx, y = oy + ly;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= 0 && y < h0 && x >= 0 && x < w0) {   // x and w0 are multiples of 4: the group is inside or outside as a whole
+        const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(S8 + x + y * w0));
+        v = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
       }
+      *reinterpret_cast<float4*>(s0 + ly * R0 + lx) = v;
+    }
+  } else if (P.src_u8) {
+    const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
+    for (int k = tid; k < R0 * R0; k += 256) {
+      const int ly = k / R0, lx = k - ly * R0;
+      const int x = ox + lx, y = oy + ly;
+      s0[k] = (y >= 0 && y < h0 && x >= 0 && x < w0) ? (float)__ldg(S8 + x + (size_t)y * w0) : 0.f;
     }
   } else {
     const float* __restrict__ SF = (const float*)B.src[blockIdx.z];
@@ -96,43 +187,36 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
   {
     float* src = s0; int Rs = R0;
     float* dst = s0 + R0 * R0;
+#pragma unroll
     for (int l = 1; l < L; l++) {
       const int Rd = Rs >> 1;
-      for (int k = tid; k < Rd * Rd; k += 256) {
-        const int ly = k / Rd, lx = k - ly * Rd;
-        const float* q = src + (2 * ly) * Rs + 2 * lx;
-        dst[k] = 0.25f * (((q[0] + q[1]) + q[Rs]) + q[Rs + 1]);
+      if (Rd % 2 == 0) {      // two outputs per thread from two 16-byte rows
+        const int Rh = Rd >> 1;
+        for (int k = tid; k < Rd * Rh; k += 256) {
+          const int ly = k / Rh, lx = (k - ly * Rh) * 2;
+          const float4 a = *reinterpret_cast<const float4*>(src + (2 * ly) * Rs + 2 * lx);
+          const float4 b = *reinterpret_cast<const float4*>(src + (2 * ly + 1) * Rs + 2 * lx);
+          *reinterpret_cast<float2*>(dst + ly * Rd + lx) = make_float2(0.25f * (((a.x + a.y) + b.x) + b.y), 0.25f * (((a.z + a.w) + b.z) + b.w));
+        }
+      } else {
+        for (int k = tid; k < Rd * Rd; k += 256) {
+          const int ly = k / Rd, lx = k - ly * Rd;
+          const float2 a = *reinterpret_cast<const float2*>(src + (2 * ly) * Rs + 2 * lx);
+          const float2 b = *reinterpret_cast<const float2*>(src + (2 * ly + 1) * Rs + 2 * lx);
+          dst[k] = 0.25f * (((a.x + a.y) + b.x) + b.y);
+        }
       }
       __syncthreads();
       src = dst; Rs = Rd; dst = dst + Rd * Rd;
     }
   }
   // ---- texels + intensity planes of every level from shared memory
-  {
-    const float* src = s0; int Rs = R0;
-    for (int l = 0; l < L; l++) {
-      const int wl = P.w[l], hl = P.h[l];
-      const int T = kTile >> l, Hl = H0 >> l;           // tile side and halo at this level
-      const int tx0 = (blockIdx.x * kTile) >> l, ty0 = (blockIdx.y * kTile) >> l;
-      float* __restrict__ Il = base + P.px_offset[l];
-      float4* __restrict__ Tl = tbase + P.px_offset[l];
-      for (int k = tid; k < T * T; k += 256) {
-        const int ly = k / T, lx = k - ly * T;
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (x >= wl || y >= hl) continue;
-        const float* q = src + (ly + Hl) * Rs + (lx + Hl);
-        const float c = q[0];
-        float dx = 0.f, dy = 0.f;
-        const bool inner = (y >= 1 && y < hl - 1);        // flat idx in [w, w(h-1))
-        if (inner) {
-          dx = 0.5f * (q[1] - q[-1]);                   // columns 0 and w-1 are redone by pyr_wrap_kernel
-          dy = 0.5f * (q[Rs] - q[-Rs]);
-        }
-        Il[x + (size_t)y * wl] = c;
-        Tl[x + (size_t)y * wl] = inner ? make_texel(c, dx, dy, P.use_gamma) : make_float4(c, 0.f, 0.f, 0.f);
-      }
-      src += Rs * Rs; Rs >>= 1;
-    }
+  if (P.src_u8) {   // 8-bit sources cannot produce non-finite differences
+    if (P.use_gamma) PyrWriteLevels<L, 0, true, true>::run(P, s0, base, tbase, tid, s_dB);
+    else PyrWriteLevels<L, 0, true, false>::run(P, s0, base, tbase, tid, s_dB);
+  } else {
+    if (P.use_gamma) PyrWriteLevels<L, 0, false, true>::run(P, s0, base, tbase, tid, s_dB);
+    else PyrWriteLevels<L, 0, false, false>::run(P, s0, base, tbase, tid, s_dB);
   }
 }
 
@@ -163,7 +247,7 @@ __global__ void __launch_bounds__(128) pyr_wrap_kernel(PyrGeom P, PyrBatch B) {
 // nb frames, one launch pair. srcs[i]: device pointer to the level-0 source of frames[i] (float, or uint8 when src_u8).
 int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const void* const* srcs, bool src_u8, bool use_hcalib) {
   if (nb <= 0) return SDSO_OK;
-  if (nb > kMaxBatch) return fail(ctx, SDSO_E_INVALID, "make_images batch larger than 32");
+  if (nb > kMaxBatch) return fail(ctx, SDSO_E_INVALID, "make_images batch larger than 128");
   PyrGeom P;
   P.levels = ctx->G.levels;
   int off = 0;
@@ -184,10 +268,22 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
     const int H0 = 1 << (P.levels - 1);
     size_t smem = 0;
     for (int l = 0, R = kTile + 2 * H0; l < P.levels; l++, R >>= 1) smem += (size_t)R * R * sizeof(float);
-    static size_t smem_set = 0;
-    if (smem > smem_set) { SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
     dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile, nb);
-    pyr_fused_kernel<<<grid, 256, smem, ctx->stream>>>(P, B);
+    static bool attr_set = false;
+    if (!attr_set) {   // the 6-level region needs 87 KB of dynamic shared memory
+      SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    switch (P.levels) {
+      case 1: pyr_fused_kernel<1><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      case 2: pyr_fused_kernel<2><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      case 3: pyr_fused_kernel<3><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      case 4: pyr_fused_kernel<4><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      case 5: pyr_fused_kernel<5><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      case 6: pyr_fused_kernel<6><<<grid, 256, smem, ctx->stream>>>(P, B); break;
+      default: return fail(ctx, SDSO_E_INVALID, "make_images: unsupported pyramid depth");
+    }
     SDSO_CHECK_LAUNCH(ctx);
     int rows = 0;
     for (int l = 0; l < P.levels; l++) rows += 2 * (P.h[l] - 2);
