@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=SEQS)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--gather", type=int, default=1, help="points in flight per thread (1: 128-register kernel, 2 with --threads 192: 168-register kernel)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     variant = 0 if args.variant == "sse" else 1
@@ -231,7 +232,7 @@ def main():
     st = pkg.default_settings()
     st.cluster_size = args.cluster if args.cluster > 0 else 1   # throughput configuration: one CTA per sequence ...
     st.block_threads = args.threads
-    st.gather_batch = 1                                          # ... compiled for two resident CTAs per SM
+    st.gather_batch = args.gather                                # ... compiled for two resident CTAs per SM
     ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE, device=dev, settings=st)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -261,17 +262,28 @@ def main():
     coarsest = ctx.levels - 1
     ref_slots = list(range(S))
 
+    dev_ptrs = [[dev8[j][s_].data_ptr() for s_ in range(S)] for j in range(POSES)]
+
+    def images_device(i):
+        ctx.make_images_batch_device(slots[i % SETS], dev_ptrs[i % POSES], u8=True)
+
+    def track_device(i):
+        ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, variant)
+
     def enqueue_device(i):
-        j, fs = i % POSES, slots[i % SETS]
-        ctx.make_images_batch_device(fs, [dev8[j][s_].data_ptr() for s_ in range(S)], u8=True)
-        ctx.track_enqueue_multi(ref_slots, fs, T_init[j], aff0, coarsest, mr, variant)
+        images_device(i); track_device(i)
 
     def upload(i):
         ctx.upload_images_async(slots[i % SETS], [host8[i % POSES][s_].data_ptr() for s_ in range(S)], u8=True)
 
-    def enqueue_host(i):
+    def images_host(i):
         ctx.make_images_uploaded(slots[i % SETS])
+
+    def track_host(i):
         ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, variant)
+
+    def enqueue_host(i):
+        images_host(i); track_host(i)
 
     def barrier():
         if dist is not None:
@@ -298,9 +310,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evals = 0
     e0.record(stream)
+    images_device(W_)
     for i in range(K_):
-        enqueue_device(W_ + i)
-        evals += ctx.track_collect(S)["evals"]   # the LM results of step i gate step i+1 of every sequence
+        track_device(W_ + i)
+        if i + 1 < K_:
+            images_device(W_ + i + 1)            # the next frames' pyramids do not depend on this step's poses: queued behind the tracker
+        evals += ctx.track_collect(S)["evals"]   # the LM results of step i gate the tracking of step i+1 of every sequence
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
@@ -316,11 +331,16 @@ def main():
     evals_e2e = 0
     t0.record(stream)
     upload(W_)
+    images_host(W_)
+    if K_ > 1:
+        upload(W_ + 1)
     for i in range(K_):
-        enqueue_host(W_ + i)
+        track_host(W_ + i)
         if i + 1 < K_:
-            upload(W_ + i + 1)
-        evals_e2e += ctx.track_collect(S)["evals"]   # D2H of every sequence's result (pose, aff, residuals) + stream sync
+            images_host(W_ + i + 1)                  # waits for upload i+1 (copy stream), runs behind the tracker of step i
+        evals_e2e += ctx.track_collect(S)["evals"]   # D2H of every sequence's result (pose, aff, residuals)
+        if i + 2 < K_:
+            upload(W_ + i + 2)                       # into the slot set step i just released
     t1.record(stream)
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -379,6 +399,17 @@ def main():
             traffic = json.load(open(tp)).get(f"track_{args.variant}_batch{S}_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # what HBM delivers for this access pattern with no arithmetic at all (tools/gather_microbench.cu), measured on this GPU now
+    pattern = None
+    gm = os.path.join(ROOT, "tools", "gather_microbench")
+    if rank == 0 and os.path.exists(gm):
+        try:
+            import subprocess
+            pattern = json.loads(subprocess.run([gm, "--json"], capture_output=True, text=True, timeout=60,
+                                                env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev))).stdout.strip().splitlines()[-1])
+            pattern["frac_of_pattern_ceiling"] = achieved / pattern["gather_gbs"]
+        except Exception:
+            pattern = None
     img_bytes = npx * 1 + 4 * 603911 + 16 * 603911  # per image: u8 read + intensity planes + texels written
     # CPU baseline (rank 0, bounded sample of the same workload on all host cores)
     cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
@@ -398,7 +429,7 @@ def main():
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                       kernel="track_kernel" if variant == 0 else "track_g2o_kernel", peak_source=peak_src,
                       algorithmic_bytes_per_launch=evals_per_launch * BYTES_PER_EVAL, avg_launch_ms=track_ms_per_launch,
-                      share_of_step=prof["track_ms"] / ms_dev,
+                      share_of_step=prof["track_ms"] / ms_dev, scattered_gather_ceiling=pattern,
                       make_images=dict(achieved=img_bytes * S * K_ / max(prof["images_ms"], 1e-9) / 1e6,
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
                                        algorithmic_bytes=img_bytes)),

@@ -419,6 +419,37 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
   for (int k = 0; k < 3; k++) tt[k] = ec.t[k];
   const float affLL0 = ec.affLL[0], affLL1 = ec.affLL[1], cutoff = ec.cutoff, maxEnergy = ec.maxEnergy, ea = ec.a, eb0 = ec.b0;
 
+  // flow indicators (:662-693) of every 32nd point, level 0 only. A separate dense pass: inside the main loop exactly one
+  // lane of each warp would take this branch and the warp would pay its ~150 instructions for every point
+  if (lvl == 0) {
+    for (int i = 32 * gtid; i < n; i += 32 * gthreads) {
+      const float4 pp = __ldg(pc + i);
+      const float x = pp.x, y = pp.y, id = pp.z;
+      float pt[3], ptT[3], ptT2[3], pt3[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
+        const float rp = RKi[r * 3 + 0] * x + RKi[r * 3 + 1] * y + RKi[r * 3 + 2];
+        ptT[r] = kp + tt[r] * id;
+        ptT2[r] = kp - tt[r] * id;
+        pt[r] = rp + tt[r] * id;
+        pt3[r] = rp - tt[r] * id;
+      }
+      const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+      const float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+      const float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
+      const float KuT = fxl * uT + cxl, KvT = fyl * vT + cyl;
+      const float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
+      const float KuT2 = fxl * uT2 + cxl, KvT2 = fyl * vT2 + cyl;
+      const float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
+      const float Ku3 = fxl * u3 + cxl, Kv3 = fyl * v3 + cyl;
+      acc[A_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      acc[A_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      acc[A_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      acc[A_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      acc[A_SN] += 2.f;
+    }
+  }
   for (int base = gtid; base < n; base += gthreads * U) {
     float4 p[U];
 #pragma unroll
@@ -442,27 +473,6 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       uu[q] = u; vv[q] = v; Kuu[q] = Ku; Kvv[q] = Kv; nid[q] = new_idepth;
       if (i < n) {
         evals++;
-        if (lvl == 0 && (i % 32) == 0) {  // flow indicators :662-693
-          float ptT[3], ptT2[3], pt3[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
-            ptT[r] = kp + tt[r] * id;
-            ptT2[r] = kp - tt[r] * id;
-            pt3[r] = (RKi[r * 3 + 0] * x + RKi[r * 3 + 1] * y + RKi[r * 3 + 2]) - tt[r] * id;
-          }
-          float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
-          float KuT = fxl * uT + cxl, KvT = fyl * vT + cyl;
-          float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
-          float KuT2 = fxl * uT2 + cxl, KvT2 = fyl * vT2 + cyl;
-          float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
-          float Ku3 = fxl * u3 + cxl, Kv3 = fyl * v3 + cyl;
-          acc[A_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-          acc[A_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-          acc[A_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-          acc[A_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-          acc[A_SN] += 2.f;
-        }
       }
       inb[q] = (i < n) && (Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0);  // :696
       if (inb[q]) {
@@ -783,8 +793,8 @@ enum { ST_LEVEL_INIT = 0, ST_CUTOFF_REPEAT = 1, ST_ITER = 2 };
 // kU = gather batch per thread. kU == 1 is compiled for two resident CTAs per SM (<= 128 registers): the throughput
 // configuration (many independent sequences, one small cluster each); kU >= 2 keeps all 255 registers for one CTA per SM,
 // the latency configuration (one sequence spread over an 8-CTA cluster).
-template <int kU>
-__global__ void __launch_bounds__(256, (kU == 1 ? 2 : 1)) track_kernel(TrackParams P) {
+template <int kU, int kBT = 256, int kMB = (kU == 1 ? 2 : 1)>
+__global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -1000,6 +1010,7 @@ void tracker_destroy(sdso_ctx* ctx) {
   if (t->h_problems) cudaFreeHost(t->h_problems);
   if (t->d_dump) cudaFree(t->d_dump);
   if (t->d_work_counter) cudaFree(t->d_work_counter);
+  if (t->results_ready) cudaEventDestroy(t->results_ready);
   for (size_t k = 0; k < t->saved.size(); k++)
     if ((int)k != t->cur_slot) for (int l = 0; l < kPyrLevels; l++) if (t->saved[k].pc[l]) cudaFree(t->saved[k].pc[l]);
   for (int l = 0; l < kPyrLevels; l++) { if (t->edge_flag[l]) cudaFree(t->edge_flag[l]); if (t->edge_err[l]) cudaFree(t->edge_err[l]); }
@@ -1076,6 +1087,7 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute((track_kernel<2, 192, 2>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_g2o_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
@@ -1103,6 +1115,7 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   else {
     const int U = ctx->S.gather_batch > 0 ? ctx->S.gather_batch : 2;
     if (U == 1) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<1>, Pl));
+    else if (U == 2 && BT <= 192 && C == 1) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, (track_kernel<2, 192, 2>), Pl));   // 170 registers, 2 CTAs / SM
     else if (U == 2) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<2>, Pl));
     else if (U == 4) SDSO_CUDA(ctx, cudaLaunchKernelEx(&cfg, track_kernel<4>, Pl));
     else return fail(ctx, SDSO_E_INVALID, "gather_batch must be 1, 2 or 4");
@@ -1346,6 +1359,8 @@ int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const 
   if (rc) return rc;
   prof_end(ctx, 0);
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->h_problems, t->d_problems, nb * sizeof(TrackProblem), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!t->results_ready) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&t->results_ready, cudaEventDisableTiming));
+  SDSO_CUDA(ctx, cudaEventRecord(t->results_ready, ctx->stream));
   t->last_nb = nb;
   return SDSO_OK;
 }
@@ -1355,7 +1370,9 @@ int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, do
   if (!ctx) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (nb != t->last_nb) return fail(ctx, SDSO_E_STATE, "collect does not match the last enqueue");
-  SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // wait for this enqueue's results only: work queued behind it (the next frames' makeImages) keeps running
+  if (t->results_ready) SDSO_CUDA(ctx, cudaEventSynchronize(t->results_ready));
+  else SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   uint64_t ev = 0;
   for (int k = 0; k < nb; k++) {
     const TrackProblem& hp = t->h_problems[k];

@@ -27,6 +27,7 @@ struct TrackerState {
   TrackProblem* d_problems = nullptr;
   TrackProblem* h_problems = nullptr;  // pinned
   int max_problems = 2048;
+  cudaEvent_t results_ready = nullptr;     // recorded behind the D2H copy of the results: collect waits for it, not for the whole stream
   unsigned int* d_work_counter = nullptr;  // dynamic problem scheduling of the throughput configuration
   std::vector<RefSlot> saved;  // parked reference slots (independent sequences tracked by one launch); saved[cur_slot] is stale
   int cur_slot = 0;
