@@ -372,6 +372,20 @@ int sdso_distmap_add(sdso_ctx* ctx, int n, const int* uv, float* map_out);
 int sdso_activation_filter(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float* Kt, const unsigned char* host_flagged, int n, const int* cand_host,
                            const sdso_immature_point* pts, const float* my_type, float currentMinActDist, int* verdict, int* rounds, float* map_out);
 
+/* ---- input preparation and trajectory rows (the wire formats either side of the path) ---------------------------------
+ * Undistort::undistort<unsigned char> (util/Undistort.cpp:398-489) = PhotometricUndistorter::processFrame (:222-260) + the
+ * bilinear remap, with the benchmark noise switched off as in the reference's defaults. The remap tables (w*h floats in
+ * raw-image pixels, negative x = outside) and the photometric calibration (G: 256 floats or NULL = no response calibration;
+ * vignetteMapInv: wOrg*hOrg floats or NULL) come from the caller's Undistort object, which computes them once per run. */
+int sdso_undistort_setup(sdso_ctx* ctx, int wOrg, int hOrg, const float* remapX, const float* remapY, const float* G, const float* vignetteMapInv,
+                         int photometricCalibration /* setting_photometricCalibration 0..2 */, int useExposure /* setting_useExposure */);
+/* raw: wOrg*hOrg bytes (host). out_image: w*h floats (nullable). frame >= 0: FrameHessian::makeImages runs on the rectified
+ * image without leaving the device (ab_exposure = the returned exposure). *exposure_out = ImageAndExposure::exposure_time. */
+int sdso_undistort(sdso_ctx* ctx, const unsigned char* raw, float exposure, float factor, float* out_image, int frame, int use_hcalib, float* exposure_out);
+/* One row of FullSystem::printResult (FullSystem.cpp:236-285): camToWorld as "R00 R01 R02 t0 R10 ... t2\n" with 15 significant
+ * digits. Host only. Returns the length written (without the terminator) or SDSO_E_INVALID if buf is too small. */
+int sdso_trajectory_row(const double camToWorld[12], char* buf, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 #include "oracle_trace.hpp"
 #include "oracle_select.hpp"
 #include "oracle_distmap.hpp"
+#include "oracle_undistort.hpp"
 #include <memory>
 
 using namespace orc;
@@ -425,5 +426,25 @@ void orc_dm_filter(void* mp, void* ctx, int n_hosts, const float* KRKi, const fl
   Ctx* c = (Ctx*)ctx;
   orc::activationFilter(*(orc::CoarseDistanceMap*)mp, n_hosts, KRKi, Kt, flagged, n, cand_host, (const orc::ImmaturePoint*)pts, my_type, currentMinActDist,
                         c->S.minTraceQuality, verdict);
+}
+}
+
+// ---- undistortion + trajectory rows ----
+extern "C" {
+float orc_undistort(int wOrg, int hOrg, int w, int h, const float* remapX, const float* remapY, const float* G, const float* vignetteInv, int photoCalib,
+                    int useExposure, const unsigned char* raw, float exposure, float factor, float* out) {
+  orc::Undistorter u;
+  u.wOrg = wOrg; u.hOrg = hOrg; u.w = w; u.h = h;
+  u.remapX.assign(remapX, remapX + (size_t)w * h); u.remapY.assign(remapY, remapY + (size_t)w * h);
+  if (G) u.G.assign(G, G + 256);
+  if (vignetteInv) u.vignetteMapInv.assign(vignetteInv, vignetteInv + (size_t)wOrg * hOrg);
+  u.photometricCalibration = photoCalib; u.useExposure = useExposure != 0;
+  return u.undistort(raw, exposure, factor, out);
+}
+int orc_trajectory_row(const double T[12], char* buf, int n) {
+  const std::string s = orc::trajectoryRow(T);
+  if ((int)s.size() + 1 > n) return -1;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
 }
 }

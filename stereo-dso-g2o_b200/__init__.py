@@ -849,3 +849,41 @@ def _activation_filter(self, KRKi, Kt, host_flagged, cand_host, pts, my_type, cu
 Context.distmap_make = _distmap_make
 Context.distmap_add = _distmap_add
 Context.activation_filter = _activation_filter
+
+
+# ---------------------------------------------------------------------------------------------------
+# input preparation + trajectory rows (Undistort.cpp:222-260, 398-489; FullSystem.cpp:236-285)
+lib.sdso_undistort_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int]
+lib.sdso_undistort.argtypes = [C.c_void_p, _ubp, C.c_float, C.c_float, _fp, C.c_int, C.c_int, _fp]
+lib.sdso_trajectory_row.argtypes = [_dp, C.c_char_p, C.c_int]
+
+
+def _undistort_setup(self, w_org, h_org, remap_x, remap_y, G=None, vignette_inv=None, photometric_calibration=2, use_exposure=True):
+    rx, ry = _f32(remap_x), _f32(remap_y)
+    g = _f32(G) if G is not None else None
+    v = _f32(vignette_inv) if vignette_inv is not None else None
+    self._ck(lib.sdso_undistort_setup(self._h, w_org, h_org, _ptr(rx, _fp), _ptr(ry, _fp), _ptr(g, _fp) if g is not None else None,
+                                      _ptr(v, _fp) if v is not None else None, int(photometric_calibration), int(use_exposure)))
+
+
+def _undistort(self, raw, exposure=1.0, factor=1.0, frame=-1, use_hcalib=True, want_image=True):
+    w, h = self.level_size(0)
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.zeros((h, w), np.float32) if want_image else None
+    e = C.c_float(0)
+    self._ck(lib.sdso_undistort(self._h, _ptr(raw, _ubp), float(exposure), float(factor), _ptr(out, _fp) if want_image else None, int(frame),
+                                int(use_hcalib), C.byref(e)))
+    return out, e.value
+
+
+def trajectory_row(T):
+    T = _f64(T).reshape(12)
+    buf = C.create_string_buffer(512)
+    n = lib.sdso_trajectory_row(_ptr(T, _dp), buf, 512)
+    if n < 0:
+        raise RuntimeError("sdso_trajectory_row failed")
+    return buf.value.decode()
+
+
+Context.undistort_setup = _undistort_setup
+Context.undistort = _undistort

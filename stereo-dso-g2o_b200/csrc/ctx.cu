@@ -158,6 +158,7 @@ int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], 
   if (rc == SDSO_OK) rc = trace_create(c);
   if (rc == SDSO_OK) rc = selector_create(c);
   if (rc == SDSO_OK) rc = distmap_create(c);
+  if (rc == SDSO_OK) rc = undistort_create(c);
   if (rc != SDSO_OK) { sdso_ctx_destroy(c); return rc; }
   *out = c;
   return SDSO_OK;
@@ -171,6 +172,7 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   trace_destroy(ctx);
   selector_destroy(ctx);
   distmap_destroy(ctx);
+  undistort_destroy(ctx);
   ba_destroy(ctx);
   tracker_destroy(ctx);
   for (auto& f : ctx->frames) {

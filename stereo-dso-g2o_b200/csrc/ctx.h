@@ -37,6 +37,7 @@ struct BAState;       // ba.cu
 struct TraceState;    // trace.cu
 struct SelectorState; // pixel_select.cu
 struct DistMapState;  // distmap.cu
+struct UndistortState; // undistort.cu
 
 }  // namespace sdso
 
@@ -56,6 +57,7 @@ struct sdso_ctx {
   sdso::TraceState* trace = nullptr;
   sdso::SelectorState* selector = nullptr;
   sdso::DistMapState* distmap = nullptr;
+  sdso::UndistortState* undistort = nullptr;
   uint64_t launches = 0;
   // optional CUDA-event profiling of the two hot launches (bench.py roofline); see sdso_profile_*
   bool profile = false;
@@ -119,5 +121,7 @@ int selector_create(sdso_ctx* ctx);
 void selector_destroy(sdso_ctx* ctx);
 int distmap_create(sdso_ctx* ctx);
 void distmap_destroy(sdso_ctx* ctx);
+int undistort_create(sdso_ctx* ctx);
+void undistort_destroy(sdso_ctx* ctx);
 
 }  // namespace sdso
