@@ -1,0 +1,200 @@
+"""One key-frame insertion, chained end to end (the mapping half of FullSystem::makeKeyFrame, FullSystem.cpp:1290-1480):
+immature points of every window frame are traced into the newest key frame (traceOn) -> the distance map of the active points
+and the candidate loop pick the ones to activate -> optimizeImmaturePoint -> the activated points join the window -> the
+windowed optimisation runs -> the oldest key frame's points and the frame itself are marginalised. Every stage consumes what
+the SAME backend produced in the stage before (nothing is re-synchronised between the oracle and the device), so this is the
+operator chain a drop-in user runs; integer results must agree exactly, floats within the north_star tolerance."""
+import numpy as np
+import pytest
+import oracle_py as O
+import oracle_ba_py as OB
+import oracle_trace_py as OT
+import oracle_distmap_py as OD
+import ba_synth
+import synth
+import trace_synth as TS
+
+W_, H_, K_ = 640, 192, (360.0, 360.0, 319.5, 95.5)
+N_KF, N_ACTIVE, PER_HOST, MIN_ACT_DIST = 5, 400, 260, 1.0
+
+
+class Backend:
+    """the same operator names for the oracle (test infrastructure) and the device library"""
+
+    def __init__(self, pkg=None):
+        self.dev = pkg is not None
+        self.pkg = pkg
+        self.api = pkg.Context(W_, H_, K_, synth.BASELINE) if self.dev else O.Oracle(W_, H_, K_, synth.BASELINE)
+        self.dm = None if self.dev else OD.DistMap(self.api)
+
+    def frames(self, win):
+        self.fids = []
+        for f in win["frames"]:
+            fid = self.api.frame_create() if self.dev else self.api.frame_new()
+            self.api.make_images(fid, f["image"])
+            self.fids.append(fid)
+
+    def immature_init(self, h, uv):
+        return self.api.immature_init(self.fids[h], uv) if self.dev else OT.immature_init(self.api, self.fids[h], uv)
+
+    def trace_on(self, t, KRKi, Kt, pts):
+        return self.api.trace_on(self.fids[t], KRKi, Kt, (1.0, 0.0), pts) if self.dev else OT.trace_on(self.api, self.fids[t], KRKi, Kt, (1.0, 0.0), pts)
+
+    def window(self, win):
+        """(re)build the backend window from the neutral description; colour / weights come from this backend's D1 operator"""
+        pts = win["points"]
+        cw = {}
+        for h in range(win["n"]):
+            idx = [i for i, p in enumerate(pts) if p["host"] == h]
+            if idx:
+                rec, _ = self.immature_init(h, np.array([[pts[i]["u"], pts[i]["v"]] for i in idx], np.float32))
+                for i, r in zip(idx, rec):
+                    cw[i] = (r["color"].copy(), r["weights"].copy())
+        Wn = self.pkg.Window(self.api) if self.dev else OB.OracleBA(self.api)
+        for k, f in enumerate(win["frames"]):
+            i = Wn.add_frame(self.fids[k], f["T_w2c"], f["a"], f["b"], f["frameID"])
+            Wn.set_state(i, f["state"]); Wn.set_energy_th(i, f["energyTH"])
+        if self.dev:
+            Wn.set_points([p["host"] for p in pts], [p["u"] for p in pts], [p["v"] for p in pts], [p["idepth"] for p in pts],
+                          [p["idepth_zero"] for p in pts], np.stack([cw[i][0] for i in range(len(pts))]), np.stack([cw[i][1] for i in range(len(pts))]),
+                          [p["has_prior"] for p in pts])
+            rp, rt = [], []
+            for pi, p in enumerate(pts):
+                for t in p["targets"]:
+                    rp.append(pi); rt.append(t)
+            Wn.set_residuals(rp, rt)
+        else:
+            for pi, p in enumerate(pts):
+                q = Wn.add_point(p["host"], p["u"], p["v"], p["idepth"], p["idepth_zero"], cw[pi][0], cw[pi][1], p["has_prior"])
+                for t in p["targets"]:
+                    Wn.add_residual(q, t)
+        Wn.prepare()
+        self.W = Wn
+        return Wn
+
+    def distmap_make(self, KRKi, Kt, pt_host, pt_uvid):
+        return self.api.distmap_make(KRKi, Kt, pt_host, pt_uvid) if self.dev else self.dm.make(KRKi, Kt, pt_host, pt_uvid)
+
+    def activation_filter(self, KRKi, Kt, flagged, cand_host, pts, my_type, mad):
+        if self.dev:
+            v, m, _ = self.api.activation_filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
+            return v, m
+        return self.dm.filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
+
+    def activate(self, n, host, pts):
+        return self.W.activate_points(host, pts, variant=0) if self.dev else OT.activate_points(self.api, n, host, pts, variant=0)
+
+    def set_point_flags(self, flags):
+        if self.dev:
+            self.W.set_point_flags(flags)
+        else:
+            for i, f in enumerate(flags):
+                if f:
+                    self.W.set_point_flag(i, int(f))
+
+
+def host_to_newest(win, h, level1=True):
+    """K[1] * R * Ki[0], K[1] * t of host h into the newest key frame (CoarseTracker.cpp:1233-1235), float"""
+    newest = win["n"] - 1
+    T = synth.T_rel(win["poses"][h], win["poses"][newest])
+    K0 = TS.K33(K_).astype(np.float32)
+    K1 = K0.copy(); K1[0, 0] *= 0.5; K1[1, 1] *= 0.5; K1[0, 2] = (K0[0, 2] + 0.5) / 2 - 0.5; K1[1, 2] = (K0[1, 2] + 0.5) / 2 - 0.5
+    Kt = K1 if level1 else K0
+    R, t = T[:, :3].astype(np.float32), T[:, 3].astype(np.float32)
+    return ((Kt @ R) @ np.linalg.inv(K0).astype(np.float32)).astype(np.float32).reshape(9), (Kt @ t).astype(np.float32)
+
+
+def mapping_step(B, scene):
+    out = {}
+    win = ba_synth.make_window(scene, n=N_KF, P=N_ACTIVE, seed=3, spacing=0.5, w=W_, h=H_, K=K_)
+    n, newest = win["n"], win["n"] - 1
+    B.frames(win)
+    # 1. immature candidates of the older key frames, traced into the newest one
+    rng = np.random.default_rng(12)
+    cand, cand_host = [], []
+    for h in range(newest):
+        uv = TS.candidate_pixels(win["frames"][h]["image"], PER_HOST, rng, margin=16, min_grad=6.0)
+        pts, ok = B.immature_init(h, uv)
+        pts = pts[ok]
+        tid = 1.0 / win["frames"][h]["depth"][pts["v"].astype(int), pts["u"].astype(int)]
+        pts["idepth_min"] = (tid * 0.6).astype(np.float32); pts["idepth_max"] = (tid * 1.5).astype(np.float32)   # the prior interval
+        KRKi, Kt = TS.krki_kt(win["poses"][h], win["poses"][newest], K_)
+        st = B.trace_on(newest, KRKi, Kt, pts)
+        out[f"trace_status_{h}"] = st
+        cand.append(pts); cand_host.append(np.full(pts.size, h, np.int32))
+    cand, cand_host = np.concatenate(cand), np.concatenate(cand_host)
+    out["trace_pts"] = cand.copy()
+    # 2. distance map of the active points in the newest frame + the candidate loop
+    hosts = list(range(newest))
+    KK = [host_to_newest(win, h) for h in hosts]
+    KRKi1, Kt1 = np.stack([k[0] for k in KK]), np.stack([k[1] for k in KK])
+    act = [p for p in win["points"] if p["host"] != newest]
+    pt_host = np.array([p["host"] for p in act], np.int32)
+    order = np.argsort(pt_host, kind="stable")
+    pt_uvid = np.array([[p["u"], p["v"], p["idepth"]] for p in act], np.float32)[order]
+    out["distmap"] = B.distmap_make(KRKi1, Kt1, pt_host[order], pt_uvid)
+    my_type = np.where(np.arange(cand.size) % 7 == 0, 2.0, 1.0).astype(np.float32)
+    verdict, after = B.activation_filter(KRKi1, Kt1, np.zeros(len(hosts), np.uint8), cand_host, cand, my_type, MIN_ACT_DIST)
+    out["verdict"] = verdict; out["distmap_after"] = after
+    # 3. optimizeImmaturePoint for the accepted candidates, against the current window
+    B.window(win)
+    sel = np.nonzero(verdict == 1)[0]
+    a = B.activate(n, cand_host[sel], np.ascontiguousarray(cand[sel]))
+    out["act_result"] = a["result"]; out["act_states"] = a["states"]; out["act_idepth"] = a["idepth"]
+    # 4. the activated points join the window (residuals towards the frames where they were IN), then the windowed optimisation
+    for k in np.nonzero(a["result"] == 1)[0]:
+        c = cand[sel[k]]
+        targets = [t for t in range(n) if a["states"][k, t] == 0]
+        win["points"].append(dict(host=int(cand_host[sel[k]]), u=float(c["u"]), v=float(c["v"]), idepth=np.float32(a["idepth"][k]),
+                                  idepth_zero=np.float32(a["idepth"][k]), has_prior=False, targets=targets))
+    out["n_points"] = len(win["points"])
+    Wn = B.window(win)
+    out["rmse"], out["iterations"] = Wn.optimize(4)
+    s = Wn.get_state()
+    out["T_w2c"] = s["T_w2c"]; out["idepth"] = s["idepth"]; out["states"] = s["states"]
+    # 5. marginalise the oldest key frame: its points first, then the frame
+    flags = [1 if p["host"] == 0 else 0 for p in win["points"]]
+    B.set_point_flags(flags)
+    Wn.marginalize_points()
+    Wn.marginalize_frame(0)
+    HM, bM = Wn.get_marg_prior()
+    out["HM"], out["bM"] = HM, bM
+    out["energyTH"] = Wn.new_frame_energy_th()
+    return out
+
+
+def test_oracle_mapping_step_is_sane(scene):
+    o = mapping_step(Backend(), scene)
+    assert (o["verdict"] == 1).sum() > 50 and (o["verdict"] == 0).sum() > 50
+    assert (o["act_result"] == 1).mean() > 0.5
+    assert o["n_points"] > N_ACTIVE // N_KF * N_KF + 30
+    assert np.isfinite(o["rmse"]) and o["iterations"] >= 1
+    assert np.isfinite(o["HM"]).all() and np.abs(o["HM"]).max() > 0
+
+
+@pytest.mark.gpu
+def test_device_mapping_step_matches_oracle(pkg, scene):
+    o = mapping_step(Backend(), scene)
+    g = mapping_step(Backend(pkg), scene)
+    for h in range(N_KF - 1):
+        assert np.array_equal(g[f"trace_status_{h}"], o[f"trace_status_{h}"]), h
+    for f in ("idepth_min", "idepth_max", "lastTraceUV", "lastTracePixelInterval", "quality"):
+        assert np.allclose(g["trace_pts"][f], o["trace_pts"][f], rtol=1e-4, atol=1e-6, equal_nan=True), f
+    assert np.array_equal(g["distmap"], o["distmap"])
+    # a candidate whose traced interval differs in the last bits may land in a neighbouring cell; none does here
+    assert np.array_equal(g["verdict"], o["verdict"])
+    assert np.array_equal(g["distmap_after"][1:-1, 1:-1], o["distmap_after"][1:-1, 1:-1])
+    assert np.array_equal(g["act_result"], o["act_result"]) and np.array_equal(g["act_states"], o["act_states"])
+    assert np.allclose(g["act_idepth"], o["act_idepth"], rtol=1e-4, atol=1e-7)
+    assert g["n_points"] == o["n_points"] and g["iterations"] == o["iterations"]
+    assert np.isclose(g["rmse"], o["rmse"], rtol=2e-3)
+    for k in range(N_KF):
+        assert np.abs(g["T_w2c"][k][:, 3] - o["T_w2c"][k][:, 3]).max() < 1e-4, k
+        Rg, Ro = g["T_w2c"][k][:, :3], o["T_w2c"][k][:, :3]
+        assert np.arccos(np.clip((np.trace(Rg.T @ Ro) - 1) / 2, -1, 1)) < 1e-5, k
+    rel = np.abs(g["idepth"] - o["idepth"]) / np.abs(o["idepth"])
+    assert (rel < 5e-3).mean() > 0.995 and np.median(rel) < 2e-4
+    sc = np.abs(o["HM"]).max()
+    assert np.abs(g["HM"] - o["HM"]).max() < 2e-3 * sc, float(np.abs(g["HM"] - o["HM"]).max() / sc)
+    assert np.abs(g["bM"] - o["bM"]).max() < 2e-3 * np.abs(o["bM"]).max()
+    assert np.isclose(g["energyTH"], o["energyTH"], rtol=1e-3)
