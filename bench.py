@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--seqs", type=int, default=SEQS)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cache", action="store_true", help="disable the tracker's shared-memory texel / point cache")
+    ap.add_argument("--probe", action="store_true", help="also time the tracker alone on resident pyramids (no makeImages in between)")
     ap.add_argument("--gather", type=int, default=1, help="points in flight per thread (1: 128-register kernel, 2 with --threads 192: 168-register kernel)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -230,8 +232,9 @@ def main():
     torch.cuda.set_device(dev)
     pkg = load_pkg()
     st = pkg.default_settings()
-    st.cluster_size = args.cluster if args.cluster > 0 else 1   # throughput configuration: one CTA per sequence ...
+    st.cluster_size = args.cluster if args.cluster > 0 else 2   # throughput configuration: a 2-CTA cluster per sequence (148 sequences in flight keep their texel working set in L2) ...
     st.block_threads = args.threads
+    st.track_cache = 0 if args.no_cache else 1
     st.gather_batch = args.gather                                # ... compiled for two resident CTAs per SM
     ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE, device=dev, settings=st)
     stream = torch.cuda.current_stream()
@@ -322,6 +325,15 @@ def main():
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     launches = ctx.launch_count() - launches0
+
+    probe = None
+    if args.probe:   # the tracker on pyramids that stay resident: separates the kernel from whatever the alternating writes cost it
+        ctx.profile_enable(True)
+        for i in range(K_):
+            track_device(W_ + K_ - 1)
+            ctx.track_collect(S)
+        pp = ctx.profile_read(); ctx.profile_enable(False)
+        probe = dict(track_only_ms_per_launch=pp["track_ms"] / max(pp["track_launches"], 1), launches=pp["track_launches"])
 
     # ---- end-to-end timing: pinned host sources; the upload of step i+1 runs on the copy stream under the kernels of step i
     for i in range(3):
@@ -433,6 +445,7 @@ def main():
                       make_images=dict(achieved=img_bytes * S * K_ / max(prof["images_ms"], 1e-9) / 1e6,
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
                                        algorithmic_bytes=img_bytes)),
+        probe=probe,
         cpu_baseline=dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",
                           sample=f"{cfr} tracked frames in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
                                  "trackNewestCoarse is single-threaded per sequence in the reference)",

@@ -88,6 +88,7 @@ typedef struct sdso_settings {
   float gradDownweightPerLevel;     /* :107 */
   float desiredImmatureDensity;     /* :59 */
   float minTraceQuality;            /* :112 activation candidate filter */
+  int32_t track_cache;              /* device tuning: 1 = per-CTA shared-memory cache of texel patches / point records across LM iterations (default) */
 } sdso_settings;
 
 void sdso_default_settings(sdso_settings* s);

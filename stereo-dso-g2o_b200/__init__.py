@@ -38,7 +38,7 @@ class Settings(C.Structure):
         ("minOptIterations", C.c_int32), ("thOptIterations", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
         ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float),
         ("minGradHistCut", C.c_float), ("minGradHistAdd", C.c_float), ("gradDownweightPerLevel", C.c_float),
-        ("desiredImmatureDensity", C.c_float), ("minTraceQuality", C.c_float),
+        ("desiredImmatureDensity", C.c_float), ("minTraceQuality", C.c_float), ("track_cache", C.c_int32),
     ]
 
 

@@ -130,6 +130,7 @@ void sdso_default_settings(sdso_settings* s) {
   s->gradDownweightPerLevel = 0.75f;
   s->desiredImmatureDensity = 3000;
   s->minTraceQuality = 3;
+  s->track_cache = 1;
 }
 
 int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], float baseline, const sdso_settings* settings) {

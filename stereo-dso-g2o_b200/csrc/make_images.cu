@@ -90,8 +90,9 @@ __device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* _
       ag *= gw * gw;
     }
     const bool inner = (y >= 1 && y < hl - 1);
-    *Il = c;
-    *Tl = make_float4(c, inner ? dx : 0.f, inner ? dy : 0.f, inner ? ag : 0.f);
+    // streaming stores: 12.5 MB per image pass through L2 once and must not evict what the tracker keeps there (templates)
+    __stcs(Il, c);
+    __stcs(Tl, make_float4(c, inner ? dx : 0.f, inner ? dy : 0.f, inner ? ag : 0.f));
     cu = c; c = cd;
   }
 }

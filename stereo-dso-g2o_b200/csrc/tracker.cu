@@ -82,6 +82,7 @@ struct TrackParams {
   TrackProblem* problems;
   int nb;                  // problems in this launch
   int dynamic;             // 1: CTAs pull problems from work_counter (cluster size 1 only)
+  int use_cache;           // 1: kCacheBytes of dynamic shared memory follow TrackSmem (texel / point cache of the SSE evaluation)
   unsigned int* work_counter;
   // g2o variant scratch: per level edge flags/errors for each problem
   unsigned char* edge_flag[kPyrLevels];  // [problem][n_l]
@@ -234,6 +235,21 @@ struct __align__(16) TrackSmem {
   double total_d;
   unsigned long long bar[2];                 // mbarriers of the two exchange buffers
 };
+
+// Per-CTA cache of what the LM iterations of one level keep re-reading (dynamic shared memory behind TrackSmem): the point
+// records of the level and, per point, the 2x2 texel patch {I, dx, dy} of the last evaluation with its integer position as tag.
+// Between two iterations of a level the pose moves by a fraction of a pixel, so most patches are the same texels again; without
+// the cache every one of those re-reads is four scattered 32-byte sectors that, with ~300 sequences in flight, no longer fit L2.
+// Slot (m, tid) belongs to thread tid alone (its m-th point), so no synchronisation is involved.
+constexpr int kCacheRounds = 4;                  // points per thread that are cached (the rest gathers from global memory)
+constexpr int kCacheSlots = kCacheRounds * 256;
+struct TexCache {
+  float* tex;      // [12][kCacheSlots]: t00.xyz, t10.xyz, t01.xyz, t11.xyz, component-major (conflict-free per warp)
+  int* tag;        // [kCacheSlots]: (lvl << 28) | (iy << 14) | ix, -1 = empty
+  float4* pc;      // [kCacheSlots] point records of level *pc_lvl
+  int* pc_lvl;     // level whose point records are cached (-1 = none); set by thread 0 behind the evaluation's barrier
+};
+constexpr size_t kCacheBytes = (size_t)kCacheSlots * (12 * sizeof(float) + sizeof(int) + sizeof(float4)) + 16;
 
 struct PhaseTimer {  // phase breakdown of the persistent kernel, enabled by TrackParams::timing
   long long last = 0;
@@ -406,9 +422,11 @@ __device__ __forceinline__ void warp_solve8(double (&row)[9], int lane, double (
 template <int U>
 __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex,
                                 const EvalConst& ec, float (&acc)[kAccPad], unsigned& evals, int gtid, int gthreads,
-                                float* dump, const float4* __restrict__ pc, const int n) {
+                                float* dump, const float4* __restrict__ pc, const int n, const TexCache tc) {
 #pragma unroll
   for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
+  const bool use_cache = tc.tex != nullptr;
+  const bool pc_cached = use_cache && *tc.pc_lvl == lvl;
   const float fxl = L.fx, fyl = L.fy, cxl = L.cx, cyl = L.cy;
   const int wl = L.w, hl = L.h;
   const float huberTH = P.huberTH;
@@ -450,12 +468,16 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       acc[A_SN] += 2.f;
     }
   }
-  for (int base = gtid; base < n; base += gthreads * U) {
+  for (int base = gtid, m0 = 0; base < n; base += gthreads * U, m0 += U) {
     float4 p[U];
 #pragma unroll
     for (int q = 0; q < U; q++) {
       const int i = base + q * gthreads;
-      p[q] = (i < n) ? __ldg(pc + i) : make_float4(0.f, 0.f, 1.f, 0.f);
+      const int m = m0 + q;                                      // this thread's m-th point
+      const int slot = (use_cache && m < kCacheRounds) ? m * 256 + (int)threadIdx.x : -1;
+      if (i >= n) p[q] = make_float4(0.f, 0.f, 1.f, 0.f);
+      else if (slot >= 0 && pc_cached) p[q] = tc.pc[slot];
+      else { p[q] = __ldg(pc + i); if (slot >= 0) tc.pc[slot] = p[q]; }
     }
     float uu[U], vv[U], Kuu[U], Kvv[U], nid[U];
     bool inb[U];
@@ -476,8 +498,28 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       }
       inb[q] = (i < n) && (Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0);  // :696
       if (inb[q]) {
-        const float4* bp = tex + (int)Ku + (int)Kv * wl;
-        t00[q] = __ldg(bp); t10[q] = __ldg(bp + 1); t01[q] = __ldg(bp + wl); t11[q] = __ldg(bp + 1 + wl);
+        const int ix = (int)Ku, iy = (int)Kv;
+        const int m = m0 + q;
+        const int slot = (use_cache && m < kCacheRounds) ? m * 256 + (int)threadIdx.x : -1;
+        const int tag = (lvl << 28) | (iy << 14) | ix;
+        if (slot >= 0 && tc.tag[slot] == tag) {   // same texels as in the last evaluation of this point
+          const float* c = tc.tex + slot;
+          t00[q] = make_float4(c[0 * kCacheSlots], c[1 * kCacheSlots], c[2 * kCacheSlots], 0.f);
+          t10[q] = make_float4(c[3 * kCacheSlots], c[4 * kCacheSlots], c[5 * kCacheSlots], 0.f);
+          t01[q] = make_float4(c[6 * kCacheSlots], c[7 * kCacheSlots], c[8 * kCacheSlots], 0.f);
+          t11[q] = make_float4(c[9 * kCacheSlots], c[10 * kCacheSlots], c[11 * kCacheSlots], 0.f);
+        } else {
+          const float4* bp = tex + ix + iy * wl;
+          t00[q] = __ldg(bp); t10[q] = __ldg(bp + 1); t01[q] = __ldg(bp + wl); t11[q] = __ldg(bp + 1 + wl);
+          if (slot >= 0) {
+            float* c = tc.tex + slot;
+            c[0 * kCacheSlots] = t00[q].x; c[1 * kCacheSlots] = t00[q].y; c[2 * kCacheSlots] = t00[q].z;
+            c[3 * kCacheSlots] = t10[q].x; c[4 * kCacheSlots] = t10[q].y; c[5 * kCacheSlots] = t10[q].z;
+            c[6 * kCacheSlots] = t01[q].x; c[7 * kCacheSlots] = t01[q].y; c[8 * kCacheSlots] = t01[q].z;
+            c[9 * kCacheSlots] = t11[q].x; c[10 * kCacheSlots] = t11[q].y; c[11 * kCacheSlots] = t11[q].z;
+            tc.tag[slot] = tag;
+          }
+        }
       }
     }
 #pragma unroll
@@ -805,6 +847,14 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   float acc[kAccPad];
   Exchange ex;
   __shared__ int s_prob;
+  __shared__ int s_pc_lvl;
+  TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl};
+  if (P.use_cache) {
+    unsigned char* cb = smem_raw + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
+    tc.pc = reinterpret_cast<float4*>(cb);
+    tc.tex = reinterpret_cast<float*>(cb + (size_t)kCacheSlots * sizeof(float4));
+    tc.tag = reinterpret_cast<int*>(tc.tex + 12 * kCacheSlots);
+  }
   if (tid == 0) {
     mbar_init(&sm->bar[0], 1); mbar_init(&sm->bar[1], 1);
     mbar_fence_init();
@@ -824,7 +874,9 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   }
   TrackProblem& prob = P.problems[prob_id];
   unsigned evals = 0;
+  if (tc.tex) for (int k = tid; k < kCacheSlots; k += blockDim.x) tc.tag[k] = -1;   // a new frame: nothing cached
   if (tid == 0) {
+    s_pc_lvl = -1;
     for (int i = 0; i < 9; i++) lm.R[i] = prob.T[(i / 3) * 4 + (i % 3)];
     for (int i = 0; i < 3; i++) lm.t[i] = prob.T[i * 4 + 3];
     lm.aff[0] = prob.aff[0]; lm.aff[1] = prob.aff[1];
@@ -864,9 +916,12 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
     __syncthreads();
     tm.tick(0);
     // ---- the evaluation + the exchange: the only instance of this code in the kernel ----
-    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl], tc);
     tm.tick(1);
     const int pb = reduce_exchange<false>(acc, sm, ex, C, rank, 0.0, &tm);
+    // behind the block barriers of the reduction: every thread has read the flag for this evaluation and stored its point
+    // records of this level; the next evaluation reads the flag behind the prologue's barrier
+    if (tid == 0) s_pc_lvl = lvl;
     const float sumE = gather_sumf(sm, pb, C, A_E), sumNE = gather_sumf(sm, pb, C, A_NE);
 
     // ---- epilogue ----
@@ -1082,8 +1137,15 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   if (BT > 256 || BT < 128 || (BT & 31)) return fail(ctx, SDSO_E_INVALID, "block_threads must be a multiple of 32 in [128,256]");
   if (C < 1 || C > 16) return fail(ctx, SDSO_E_INVALID, "cluster_size must be in [1,16]");
   size_t smem = sizeof(TrackSmem);
+  const bool use_cache = !g2o && ctx->S.track_cache != 0;
+  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + kCacheBytes;
   static bool attr_set = false;
   if (!attr_set) {
+    const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + kCacheBytes);
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    SDSO_CUDA(ctx, cudaFuncSetAttribute((track_kernel<2, 192, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1097,6 +1159,7 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   int grid = C * nb;
   TrackParams Pl = P;
   Pl.nb = nb; Pl.dynamic = dynamic ? 1 : 0; Pl.work_counter = ctx->tracker->d_work_counter;
+  Pl.use_cache = use_cache ? 1 : 0;
   if (dynamic) {
     const int cap = 2 * ctx->num_sms;
     if (grid > cap) grid = cap;

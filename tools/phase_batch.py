@@ -7,7 +7,7 @@ import bench, synth
 pkg = bench.load_pkg()
 SMAX = 37
 wl = bench.build_workload(seqs=SMAX)
-for C_, BT, U, S in ((1, 256, 1, 296), (1, 256, 1, 148), (1, 256, 2, 148), (8, 256, 2, 1)):
+for C_, BT, U, S in ((2, 256, 1, 592), (1, 256, 1, 592), (8, 256, 2, 1)):
     s = pkg.default_settings(); s.cluster_size = C_; s.block_threads = BT; s.gather_batch = U
     ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE, settings=s)
     fn = []
