@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BYTES_PER_EVAL = 64  # tracking eval = 16 B point record + 4 texels x 12 B
 N_POINTS = 2000
-SEQS = 592           # independent sequences per GPU per step: persistent grid of 2 x 148 CTAs (two per SM) pulls them from a work counter
+SEQS = 592           # independent sequences per GPU per step (4 x 148: whole waves of 2-CTA clusters at two CTAs per SM)
 PATH = 37            # distinct positions along the rendered path; sequence s starts at position s % PATH
 POSES = int(os.environ.get("SDSO_BENCH_POSES", "6"))   # new frames per sequence (cycled)
 SETS = 2             # frame-slot sets (double buffering: upload of step i+1 overlaps the kernels of step i)
@@ -192,7 +192,9 @@ def main():
     host_cores = os.cpu_count() or 1
     config = dict(workload=f"CoarseTracker pose tracking, 1232x368 (1241x376 cropped), 5-level pyramid, 2000 template points per keyframe, variant={args.variant}; "
                            f"step = one new frame for each of {S} independent sequences sharing the GPU: makeImages (8-bit source, batched) + "
-                           "trackNewestCoarse against each sequence's own reference keyframe (one CTA per sequence, persistent grid of two CTAs per SM pulling sequences from a work counter, one launch)",
+                           "trackNewestCoarse against each sequence's own reference keyframe ("
+                           + ("one CTA per sequence, persistent grid of two CTAs per SM pulling sequences from a work counter" if args.cluster == 1 else
+                              f"one {args.cluster if args.cluster > 0 else 2}-CTA cluster per sequence, two CTAs per SM") + ", one launch)",
                   points=N_POINTS, levels=5, variant=args.variant, sequences_per_gpu=S,
                   cache=f"inputs larger than L2: {S} new pyramids per step x {SETS} rotating slot sets (~{S * SETS * 12} MB of pyramids + sources), {S} templates",
                   parallelism=(f"{S} independent sequences per GPU; GPUs are replicas (no collective)" if args.gpus > 1 else f"{S} independent sequences on one GPU"))

@@ -152,7 +152,6 @@ def mapping_step(B, scene):
     out["rmse"], out["iterations"] = Wn.optimize(4)
     s = Wn.get_state()
     out["T_w2c"] = s["T_w2c"]; out["idepth"] = s["idepth"]; out["states"] = s["states"]
-    out["energyTH"] = Wn.new_frame_energy_th()
     # 5. marginalise the oldest key frame: its points first, then the frame (the device window has to be rebuilt afterwards,
     #    as the reference rebuilds its index structures in makeIDX)
     flags = [1 if p["host"] == 0 else 0 for p in win["points"]]
@@ -200,4 +199,3 @@ def test_device_mapping_step_matches_oracle(pkg, scene):
     # bM is the gradient at the optimised state: small numbers made of cancelling terms, so the chained 1e-4 state differences
     # show up more strongly than in HM (the operator alone, on identical inputs, is held to 1e-4 in tests/test_gpu_ba.py)
     assert np.abs(g["bM"] - o["bM"]).max() <= 3e-2 * np.abs(o["bM"]).max() + 1e-12
-    assert np.isclose(g["energyTH"], o["energyTH"], rtol=1e-3)
