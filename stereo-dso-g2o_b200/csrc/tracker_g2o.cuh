@@ -40,6 +40,37 @@ __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int l
   chi = 0.0;
   const int wl = L.w, hl = L.h;
   const double delta = P.huberTH;
+  // flow indicators (:662-693) of every 32nd point, level 0, edge construction only — a separate dense pass: inside the main
+  // loop exactly one lane of each warp would take the branch
+  if (MODE == 0 && lvl == 0) {
+    for (int i = 32 * gtid; i < npc; i += 32 * gthreads) {
+      const float4 p = __ldg(pc + i);
+      const float x = p.x, y = p.y, id = p.z;
+      float pt[3], ptT[3], ptT2[3], pt3[3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
+        const float rp = gc.RKi[r * 3 + 0] * x + gc.RKi[r * 3 + 1] * y + gc.RKi[r * 3 + 2];
+        ptT[r] = kp + gc.t[r] * id;
+        ptT2[r] = kp - gc.t[r] * id;
+        pt[r] = rp + gc.t[r] * id;
+        pt3[r] = rp - gc.t[r] * id;
+      }
+      const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+      const float Ku = L.fx * u + L.cx, Kv = L.fy * v + L.cy;
+      const float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
+      const float KuT = L.fx * uT + L.cx, KvT = L.fy * vT + L.cy;
+      const float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
+      const float KuT2 = L.fx * uT2 + L.cx, KvT2 = L.fy * vT2 + L.cy;
+      const float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
+      const float Ku3 = L.fx * u3 + L.cx, Kv3 = L.fy * v3 + L.cy;
+      acc[G_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      acc[G_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      acc[G_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      acc[G_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      acc[G_SN] += 2.f;
+    }
+  }
   for (int i = gtid; i < npc; i += gthreads) {
     const float4 p = __ldg(pc + i);
     const float x = p.x, y = p.y, id = p.z;
@@ -51,27 +82,6 @@ __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int l
       const float u = pt[0] / pt[2], v = pt[1] / pt[2];
       const float Ku = L.fx * u + L.cx, Kv = L.fy * v + L.cy;
       const float new_idepth = id / pt[2];
-      if (lvl == 0 && (i % 32) == 0) {
-        float ptT[3], ptT2[3], pt3[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-          float kp = L.Ki[r * 3 + 0] * x + L.Ki[r * 3 + 1] * y + L.Ki[r * 3 + 2];
-          ptT[r] = kp + gc.t[r] * id;
-          ptT2[r] = kp - gc.t[r] * id;
-          pt3[r] = (gc.RKi[r * 3 + 0] * x + gc.RKi[r * 3 + 1] * y + gc.RKi[r * 3 + 2]) - gc.t[r] * id;
-        }
-        float uT = ptT[0] / ptT[2], vT = ptT[1] / ptT[2];
-        float KuT = L.fx * uT + L.cx, KvT = L.fy * vT + L.cy;
-        float uT2 = ptT2[0] / ptT2[2], vT2 = ptT2[1] / ptT2[2];
-        float KuT2 = L.fx * uT2 + L.cx, KvT2 = L.fy * vT2 + L.cy;
-        float u3 = pt3[0] / pt3[2], v3 = pt3[1] / pt3[2];
-        float Ku3 = L.fx * u3 + L.cx, Kv3 = L.fy * v3 + L.cy;
-        acc[G_ST] += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
-        acc[G_ST] += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
-        acc[G_SRT] += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
-        acc[G_SRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
-        acc[G_SN] += 2.f;
-      }
       if (!(Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0)) {
         flag[i] = 0;
         if (dump) dump[i] = 0.0;
@@ -208,7 +218,7 @@ struct G2OState {  // shared memory, thread-0 owned, read by all after barriers
   unsigned long long totalEdges;
 };
 
-__global__ void __launch_bounds__(256, 1) track_g2o_kernel(TrackParams P) {
+__global__ void __launch_bounds__(256, 2) track_g2o_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackSmem* sm = reinterpret_cast<TrackSmem*>(smem_raw);
   __shared__ G2OConst gc;
