@@ -433,7 +433,7 @@ def main():
             pattern["frac_of_pattern_ceiling"] = achieved / pattern["gather_gbs"]
         except Exception:
             pattern = None
-    img_bytes = npx * 1 + 4 * 603911 + 16 * 603911  # per image: u8 read + intensity planes + texels written
+    img_bytes = npx * 1 + 16 * 603911  # per image: u8 read + texels written
     # CPU baseline (rank 0, bounded sample of the same workload on all host cores)
     cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
     line = dict(

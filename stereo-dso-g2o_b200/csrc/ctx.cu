@@ -258,7 +258,7 @@ int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float
   f.ab_exposure = ab_exposure;
   int rc = make_images_launch(ctx, f, f.image, use_hcalib != 0);
   if (rc) return rc;
-  f.valid = true; f.gen++;
+  f.valid = true; f.gen++; f.plane_valid = true;
   return SDSO_OK;
 }
 
@@ -270,7 +270,7 @@ int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_ima
   f.ab_exposure = ab_exposure;
   int rc = make_images_launch(ctx, f, device_image, use_hcalib != 0);
   if (rc) return rc;
-  f.valid = true; f.gen++;
+  f.valid = true; f.gen++; f.plane_valid = (device_image == f.image);
   return SDSO_OK;
 }
 
@@ -346,7 +346,7 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
     rc = make_images_batch_launch(ctx, nb - o < 128 ? nb - o : 128, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
-  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; fr[i]->plane_valid = (!u8); }  // float uploads land in the plane
   return SDSO_OK;
 }
 
@@ -363,7 +363,7 @@ int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, c
     rc = make_images_batch_launch(ctx, nb - o < 128 ? nb - o : 128, fr.data() + o, device_images + o, src_u8 != 0, use_hcalib != 0);
     if (rc) return rc;
   }
-  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; }
+  for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; fr[i]->plane_valid = false; }
   return SDSO_OK;
 }
 

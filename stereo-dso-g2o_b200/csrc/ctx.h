@@ -17,6 +17,7 @@ struct Frame {
   float* image = nullptr;               // level-0 intensity plane (the uploaded image)
   float ab_exposure = 1.0f;
   bool valid = false;
+  bool plane_valid = false;             // `image` holds the level-0 intensities (true when the source was uploaded into it; else extracted on demand)
   unsigned gen = 0;                     // bumped by every makeImages on this slot (the selector keys its histograms on it)
   unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (a slice of a batch arena)
   bool src8_owned = false;
@@ -108,6 +109,7 @@ void prof_end(sdso_ctx* ctx, int which);
 // make_images.cu
 int make_images_launch(sdso_ctx* ctx, Frame& f, const float* dev_image, bool use_hcalib);
 int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const void* const* srcs, bool src_u8, bool use_hcalib);
+int ensure_intensity_plane(sdso_ctx* ctx, Frame& f);  // level-0 intensity plane for the kernels that read 4-byte pixels (epipolar search)
 // tracker.cu
 int tracker_create(sdso_ctx* ctx);
 void tracker_destroy(sdso_ctx* ctx);

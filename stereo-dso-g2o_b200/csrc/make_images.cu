@@ -68,13 +68,12 @@ __device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* _
   if (x >= wl || ly0 >= T) return;
   const int ylast = min(min(T, ly0 + BR), hl - ty0);     // end of this band inside the image
   const size_t o0 = (size_t)P.px_offset[l] + x + (size_t)(ty0 + ly0) * wl;
-  float* __restrict__ Il = base + o0;
   float4* __restrict__ Tl = tbase + o0;
   const float* q = src + (Hl + ly0) * Rs + (lx + Hl);
   // a thread walks down its column: the centre values of the rows above / below stay in registers
   float cu = q[-Rs], c = q[0];
 #pragma unroll 4
-  for (int ly = ly0; ly < ylast; ly++, q += Rs, Il += wl, Tl += wl) {
+  for (int ly = ly0; ly < ylast; ly++, q += Rs, Tl += wl) {
     const int y = ty0 + ly;
     const float cd = q[Rs];
     // the halo holds the neighbours of every tile pixel, so the differences are formed unconditionally and dropped for the
@@ -90,8 +89,8 @@ __device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* _
       ag *= gw * gw;
     }
     const bool inner = (y >= 1 && y < hl - 1);
-    // streaming stores: 12.5 MB per image pass through L2 once and must not evict what the tracker keeps there (templates)
-    __stcs(Il, c);
+    // streaming store: the texels of an image pass through L2 once and must not evict what the tracker keeps there.
+    // (No separate intensity plane is written: the epipolar search extracts its level-0 plane on first use, trace.cu.)
     __stcs(Tl, make_float4(c, inner ? dx : 0.f, inner ? dy : 0.f, inner ? ag : 0.f));
     cu = c; c = cd;
   }
@@ -222,22 +221,22 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
 }
 
 // The reference differentiates on the flat index, so at x = 0 the left neighbour is (w-1, y-1) and at x = w-1 the right
-// neighbour is (0, y+1) (HessianBlocks.cpp:182-184). One thread per (level, row, side); reads the planes written above.
+// neighbour is (0, y+1) (HessianBlocks.cpp:182-184). One thread per (level, row, side); reads the intensities (.x) of the texels
+// written above (a neighbour may be rewritten concurrently by another thread of this kernel, with the same .x).
 __global__ void __launch_bounds__(128) pyr_wrap_kernel(PyrGeom P, PyrBatch B) {
-  const float* __restrict__ base = B.img[blockIdx.z];
-  float4* __restrict__ tbase = B.tex[blockIdx.z];
+  float4* tbase = B.tex[blockIdx.z];
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   for (int l = 0; l < P.levels; l++) {
     const int wl = P.w[l], hl = P.h[l];
     const int cnt = 2 * (hl - 2);
     if (k < cnt) {
       const int y = 1 + (k >> 1), side = k & 1;
-      const float* __restrict__ I = base + P.px_offset[l];
+      const float4* I = tbase + P.px_offset[l];
       const int x = side ? wl - 1 : 0;
       const int idx = x + y * wl;
-      const float c = I[idx];
-      const float dx = 0.5f * (I[idx + 1] - I[idx - 1]);
-      const float dy = 0.5f * (I[idx + wl] - I[idx - wl]);
+      const float c = I[idx].x;
+      const float dx = 0.5f * (I[idx + 1].x - I[idx - 1].x);
+      const float dy = 0.5f * (I[idx + wl].x - I[idx - wl].x);
       tbase[P.px_offset[l] + idx] = make_texel(c, dx, dy, P.use_gamma);
       return;
     }
@@ -292,6 +291,22 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
     SDSO_CHECK_LAUNCH(ctx);
   }
   prof_end(ctx, 1);
+  return SDSO_OK;
+}
+
+__global__ void plane_extract_kernel(const float4* __restrict__ tex0, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tex0[i].x;
+}
+
+// The epipolar search reads 4-byte pixels; makeImages does not write a separate plane (19 % of its traffic), so the plane is
+// extracted from the level-0 texels the first time a frame is searched.
+int ensure_intensity_plane(sdso_ctx* ctx, Frame& f) {
+  if (f.plane_valid) return SDSO_OK;
+  const int n = ctx->G.w[0] * ctx->G.h[0];
+  plane_extract_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f.tex[0], n, f.image);
+  SDSO_CHECK_LAUNCH(ctx);
+  f.plane_valid = true;
   return SDSO_OK;
 }
 

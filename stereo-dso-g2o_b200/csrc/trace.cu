@@ -329,6 +329,8 @@ static int run_trace(sdso_ctx* ctx, int frame, TraceParams& T, bool stereo, int 
   int rc = ensure_pts(ctx, n);
   if (rc) return rc;
   TraceState* t = ctx->trace;
+  rc = ensure_intensity_plane(ctx, ctx->frames[frame]);
+  if (rc) return rc;
   T.tex = ctx->frames[frame].tex[0]; T.img = ctx->frames[frame].image;
   SDSO_CUDA(ctx, cudaMemcpyAsync(t->d_pts, pts, (size_t)n * sizeof(sdso_immature_point), cudaMemcpyHostToDevice, ctx->stream));
   if (stereo) trace_kernel<true><<<n, 128, 0, ctx->stream>>>(T, t->d_pts, n);

@@ -26,5 +26,5 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
 levels = ctx.levels
 px = sum((w >> l) * (h >> l) for l in range(levels))
-bytes_img = w * h + 20 * px
+bytes_img = w * h + 16 * px
 print(json.dumps({"frames": N, "ms_per_pass": ms, "us_per_32": ms / (N / 32) * 1e3, "GBps": bytes_img * N / ms / 1e6, "bytes_per_image": bytes_img}))
