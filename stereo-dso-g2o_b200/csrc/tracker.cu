@@ -82,7 +82,7 @@ struct TrackParams {
   TrackProblem* problems;
   int nb;                  // problems in this launch
   int dynamic;             // 1: CTAs pull problems from work_counter (cluster size 1 only)
-  int use_cache;           // 1: kCacheBytes of dynamic shared memory follow TrackSmem (texel / point cache of the SSE evaluation)
+  int use_cache;           // 1: cache_bytes(blockDim.x) of dynamic shared memory follow TrackSmem (texel / point cache of the SSE evaluation)
   unsigned int* work_counter;
   // g2o variant scratch: per level edge flags/errors for each problem
   unsigned char* edge_flag[kPyrLevels];  // [problem][n_l]
@@ -242,14 +242,16 @@ struct __align__(16) TrackSmem {
 // the cache every one of those re-reads is four scattered 32-byte sectors that, with ~300 sequences in flight, no longer fit L2.
 // Slot (m, tid) belongs to thread tid alone (its m-th point), so no synchronisation is involved.
 constexpr int kCacheRounds = 4;                  // points per thread that are cached (the rest gathers from global memory)
-constexpr int kCacheSlots = kCacheRounds * 256;
 struct TexCache {
-  float* tex;      // [12][kCacheSlots]: t00.xyz, t10.xyz, t01.xyz, t11.xyz, component-major (conflict-free per warp)
-  int* tag;        // [kCacheSlots]: (lvl << 28) | (iy << 14) | ix, -1 = empty
-  float4* pc;      // [kCacheSlots] point records of level *pc_lvl
+  float* tex;      // [12][slots]: t00.xyz, t10.xyz, t01.xyz, t11.xyz, component-major (conflict-free per warp)
+  int* tag;        // [slots]: (lvl << 28) | (iy << 14) | ix, -1 = empty
+  float4* pc;      // [slots] point records of level *pc_lvl
   int* pc_lvl;     // level whose point records are cached (-1 = none); set by thread 0 behind the evaluation's barrier
+  int slots;       // kCacheRounds * blockDim.x
 };
-constexpr size_t kCacheBytes = (size_t)kCacheSlots * (12 * sizeof(float) + sizeof(int) + sizeof(float4)) + 16;
+__host__ __device__ constexpr size_t cache_bytes(int block_threads) {
+  return (size_t)kCacheRounds * block_threads * (12 * sizeof(float) + sizeof(int) + sizeof(float4)) + 16;
+}
 
 struct PhaseTimer {  // phase breakdown of the persistent kernel, enabled by TrackParams::timing
   long long last = 0;
@@ -474,7 +476,7 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
     for (int q = 0; q < U; q++) {
       const int i = base + q * gthreads;
       const int m = m0 + q;                                      // this thread's m-th point
-      const int slot = (use_cache && m < kCacheRounds) ? m * 256 + (int)threadIdx.x : -1;
+      const int slot = (use_cache && m < kCacheRounds) ? m * (int)blockDim.x + (int)threadIdx.x : -1;
       if (i >= n) p[q] = make_float4(0.f, 0.f, 1.f, 0.f);
       else if (slot >= 0 && pc_cached) p[q] = tc.pc[slot];
       else { p[q] = __ldg(pc + i); if (slot >= 0) tc.pc[slot] = p[q]; }
@@ -500,23 +502,25 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       if (inb[q]) {
         const int ix = (int)Ku, iy = (int)Kv;
         const int m = m0 + q;
-        const int slot = (use_cache && m < kCacheRounds) ? m * 256 + (int)threadIdx.x : -1;
+        const int slot = (use_cache && m < kCacheRounds) ? m * (int)blockDim.x + (int)threadIdx.x : -1;
         const int tag = (lvl << 28) | (iy << 14) | ix;
         if (slot >= 0 && tc.tag[slot] == tag) {   // same texels as in the last evaluation of this point
           const float* c = tc.tex + slot;
-          t00[q] = make_float4(c[0 * kCacheSlots], c[1 * kCacheSlots], c[2 * kCacheSlots], 0.f);
-          t10[q] = make_float4(c[3 * kCacheSlots], c[4 * kCacheSlots], c[5 * kCacheSlots], 0.f);
-          t01[q] = make_float4(c[6 * kCacheSlots], c[7 * kCacheSlots], c[8 * kCacheSlots], 0.f);
-          t11[q] = make_float4(c[9 * kCacheSlots], c[10 * kCacheSlots], c[11 * kCacheSlots], 0.f);
+          const int cs = tc.slots;
+          t00[q] = make_float4(c[0 * cs], c[1 * cs], c[2 * cs], 0.f);
+          t10[q] = make_float4(c[3 * cs], c[4 * cs], c[5 * cs], 0.f);
+          t01[q] = make_float4(c[6 * cs], c[7 * cs], c[8 * cs], 0.f);
+          t11[q] = make_float4(c[9 * cs], c[10 * cs], c[11 * cs], 0.f);
         } else {
           const float4* bp = tex + ix + iy * wl;
           t00[q] = __ldg(bp); t10[q] = __ldg(bp + 1); t01[q] = __ldg(bp + wl); t11[q] = __ldg(bp + 1 + wl);
           if (slot >= 0) {
             float* c = tc.tex + slot;
-            c[0 * kCacheSlots] = t00[q].x; c[1 * kCacheSlots] = t00[q].y; c[2 * kCacheSlots] = t00[q].z;
-            c[3 * kCacheSlots] = t10[q].x; c[4 * kCacheSlots] = t10[q].y; c[5 * kCacheSlots] = t10[q].z;
-            c[6 * kCacheSlots] = t01[q].x; c[7 * kCacheSlots] = t01[q].y; c[8 * kCacheSlots] = t01[q].z;
-            c[9 * kCacheSlots] = t11[q].x; c[10 * kCacheSlots] = t11[q].y; c[11 * kCacheSlots] = t11[q].z;
+            const int cs = tc.slots;
+            c[0 * cs] = t00[q].x; c[1 * cs] = t00[q].y; c[2 * cs] = t00[q].z;
+            c[3 * cs] = t10[q].x; c[4 * cs] = t10[q].y; c[5 * cs] = t10[q].z;
+            c[6 * cs] = t01[q].x; c[7 * cs] = t01[q].y; c[8 * cs] = t01[q].z;
+            c[9 * cs] = t11[q].x; c[10 * cs] = t11[q].y; c[11 * cs] = t11[q].z;
             tc.tag[slot] = tag;
           }
         }
@@ -848,12 +852,12 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   Exchange ex;
   __shared__ int s_prob;
   __shared__ int s_pc_lvl;
-  TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl};
+  TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl, kCacheRounds * (int)blockDim.x};
   if (P.use_cache) {
     unsigned char* cb = smem_raw + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     tc.pc = reinterpret_cast<float4*>(cb);
-    tc.tex = reinterpret_cast<float*>(cb + (size_t)kCacheSlots * sizeof(float4));
-    tc.tag = reinterpret_cast<int*>(tc.tex + 12 * kCacheSlots);
+    tc.tex = reinterpret_cast<float*>(cb + (size_t)tc.slots * sizeof(float4));
+    tc.tag = reinterpret_cast<int*>(tc.tex + 12 * tc.slots);
   }
   if (tid == 0) {
     mbar_init(&sm->bar[0], 1); mbar_init(&sm->bar[1], 1);
@@ -874,7 +878,7 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   }
   TrackProblem& prob = P.problems[prob_id];
   unsigned evals = 0;
-  if (tc.tex) for (int k = tid; k < kCacheSlots; k += blockDim.x) tc.tag[k] = -1;   // a new frame: nothing cached
+  if (tc.tex) for (int k = tid; k < tc.slots; k += blockDim.x) tc.tag[k] = -1;   // a new frame: nothing cached
   if (tid == 0) {
     s_pc_lvl = -1;
     for (int i = 0; i < 9; i++) lm.R[i] = prob.T[(i / 3) * 4 + (i % 3)];
@@ -1138,10 +1142,10 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   if (C < 1 || C > 16) return fail(ctx, SDSO_E_INVALID, "cluster_size must be in [1,16]");
   size_t smem = sizeof(TrackSmem);
   const bool use_cache = !g2o && ctx->S.track_cache != 0;
-  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + kCacheBytes;
+  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(BT);
   static bool attr_set = false;
   if (!attr_set) {
-    const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + kCacheBytes);
+    const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(256));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
