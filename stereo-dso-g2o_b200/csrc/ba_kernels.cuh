@@ -886,23 +886,26 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
     for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
   for (int i = tid; i < d; i += nt) bs[i] = sv[i] * bs[i];
   __syncthreads();
-  // diagonal-pivoted LDLT (the strategy of Eigen::LDLT, which EnergyFunctional.cpp:976 calls)
-  for (int k = 0; k < d; k++) {
-    if (warp == 0) {  // arg max |M_ii|, i >= k, lowest index on ties
-      double best = -1.0; int p = k;
-      for (int i = k + lane; i < d; i += 32) { const double v = fabs(M[i * ld + i]); if (v > best) { best = v; p = i; } }
+  // diagonal-pivoted LDLT (the strategy of Eigen::LDLT, which EnergyFunctional.cpp:976 calls). Two block barriers per pivot:
+  // after the swap + scale of column k, warp 0 updates the DIAGONAL of the trailing matrix and picks the next pivot from it
+  // while warps 1..7 update the strict lower triangle — the pivot search is off the critical path.
+  auto pick_pivot = [&](int k0) {  // warp 0: arg max |M_ii|, i >= k0, lowest index on ties; publishes piv / pivval and swaps perm
+    double best = -1.0; int p = k0;
+    for (int i = k0 + lane; i < d; i += 32) { const double v = fabs(M[i * ld + i]); if (v > best) { best = v; p = i; } }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int op = __shfl_xor_sync(0xffffffffu, p, o);
-        if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
-      }
-      if (lane == 0) {
-        piv = p; pivval = M[p * ld + p];
-        if (p != k) { const int q = perm[k]; perm[k] = perm[p]; perm[p] = q; }
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, p, o);
+      if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
     }
-    __syncthreads();
+    if (lane == 0) {
+      piv = p; pivval = M[p * ld + p];
+      if (p != k0) { const int q = perm[k0]; perm[k0] = perm[p]; perm[p] = q; }
+    }
+  };
+  if (warp == 0 && d > 0) pick_pivot(0);
+  __syncthreads();
+  for (int k = 0; k < d; k++) {
     const int p = piv;
     // Symmetric swap of k and p fused with the scaling of column k, one phase: thread j owns (k,j),(p,j),(j,k),(j,p); the thread
     // with j == p owns the 2x2 corner. Only the lower triangle (and the diagonal) is kept current from here on.
@@ -926,10 +929,17 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
       if (j > k) { const double l = singular ? 0.0 : M[j * ld + k] / dk; M[j * ld + k] = l; lcol[j] = l; }
     }
     if (tid == 0) dg[k] = dk;
-    __syncthreads();
-    if (!singular) {
-      for (int i = k + 1 + ty; i < d; i += 16)
-        for (int j = k + 1 + tx; j <= i; j += 16) M[i * ld + j] -= lcol[i] * dk * lcol[j];
+    __syncthreads();   // piv / pivval of step k are consumed, column k is final
+    if (warp == 0) {
+      if (!singular) {
+        for (int j = k + 1 + lane; j < d; j += 32) M[j * ld + j] -= lcol[j] * dk * lcol[j];
+      }
+      __syncwarp();
+      if (k + 1 < d) pick_pivot(k + 1);
+    } else if (!singular) {
+      const int t2 = tid - 32, tx2 = t2 & 15, ty2 = t2 >> 4;   // 16 x 14 tiling over the 224 threads of warps 1..7
+      for (int i = k + 2 + ty2; i < d; i += 14)
+        for (int j = k + 1 + tx2; j < i; j += 16) M[i * ld + j] -= lcol[i] * dk * lcol[j];
     }
     __syncthreads();
   }
