@@ -435,7 +435,8 @@ def main():
             pattern = None
     img_bytes = npx * 1 + 16 * 603911  # per image: u8 read + texels written
     # CPU baseline (rank 0, bounded sample of the same workload on all host cores)
-    cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
+    if world == 1:
+        cev, cfr, csec = cpu_track_loop(wl, variant, args.cpu_seconds, 100000, host_cores)
     line = dict(
         metric="photometric residual+Jacobian evals/s", value=value, unit="evals/s", n_gpus=args.gpus, steps=K_, warmup=W_,
         ms_per_step=ms_dev / K_, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -446,7 +447,7 @@ def main():
                  ms_per_step=ms_e2e / K_, tracked_frames_per_s=world * S * K_ / (ms_e2e * 1e-3),
                  h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=S * npx / (ms_e2e / K_ * 1e-3) / 1e9),
         single_sequence=dict(ms_per_frame=ms_single, tracked_frames_per_s=1e3 / ms_single,
-                             note="latency of one sequence alone on the GPU in this (throughput) configuration: one CTA; the latency configuration (8-CTA cluster, gather batch 2) tracks a frame in ~0.2 ms, profiles/r1_bench_sse_first.json"),
+                             note="latency of one sequence alone on the GPU in this (throughput) configuration; the latency configuration (8-CTA cluster, gather batch 2) tracks a frame in ~0.2 ms, profiles/r1_bench_sse_first.json"),
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
@@ -457,10 +458,10 @@ def main():
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
                                        algorithmic_bytes=img_bytes)),
         probe=probe,
-        cpu_baseline=dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",
-                          sample=f"{cfr} tracked frames in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
-                                 "trackNewestCoarse is single-threaded per sequence in the reference)",
-                          tracked_frames_per_s=cfr / csec),
+        cpu_baseline=(dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",
+                           sample=f"{cfr} tracked frames in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
+                                  "trackNewestCoarse is single-threaded per sequence in the reference)",
+                           tracked_frames_per_s=cfr / csec) if world == 1 else None),
     )
     print(json.dumps(line))
     if dist is not None:
