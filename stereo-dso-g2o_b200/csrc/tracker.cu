@@ -247,7 +247,7 @@ struct TexCache {
   int* tag;        // [slots]: (lvl << 28) | (iy << 14) | ix, -1 = empty
   float4* pc;      // [slots] point records of level *pc_lvl
   int* pc_lvl;     // level whose point records are cached (-1 = none); set by thread 0 behind the evaluation's barrier
-  int slots;       // kCacheRounds * blockDim.x
+  int slots;       // kCacheRounds * kBT: the capacity the kernel instance was compiled for (>= kCacheRounds * blockDim.x)
 };
 __host__ __device__ constexpr size_t cache_bytes(int block_threads) {
   return (size_t)kCacheRounds * block_threads * (12 * sizeof(float) + sizeof(int) + sizeof(float4)) + 16;
@@ -421,7 +421,7 @@ __device__ __forceinline__ void warp_solve8(double (&row)[9], int lane, double (
 // ---- SSE-path evaluation: calcRes (:645-773) + calcGSSSE (:537-596) fused over this CTA's points ----
 // Points are processed in batches of U per thread: all point records first, then all 4xU texel gathers,
 // then the arithmetic, so up to 4U independent 16-byte loads are in flight per thread.
-template <int U>
+template <int U, int CS /* slots of the texel cache = component stride: a constant, so the 12 offsets are immediates */>
 __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex,
                                 const EvalConst& ec, float (&acc)[kAccPad], unsigned& evals, int gtid, int gthreads,
                                 float* dump, const float4* __restrict__ pc, const int n, const TexCache tc) {
@@ -476,7 +476,7 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
     for (int q = 0; q < U; q++) {
       const int i = base + q * gthreads;
       const int m = m0 + q;                                      // this thread's m-th point
-      const int slot = (use_cache && m < kCacheRounds) ? m * (int)blockDim.x + (int)threadIdx.x : -1;
+      const int slot = (use_cache && m < kCacheRounds) ? m * (CS / kCacheRounds) + (int)threadIdx.x : -1;
       if (i >= n) p[q] = make_float4(0.f, 0.f, 1.f, 0.f);
       else if (slot >= 0 && pc_cached) p[q] = tc.pc[slot];
       else { p[q] = __ldg(pc + i); if (slot >= 0) tc.pc[slot] = p[q]; }
@@ -502,11 +502,11 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       if (inb[q]) {
         const int ix = (int)Ku, iy = (int)Kv;
         const int m = m0 + q;
-        const int slot = (use_cache && m < kCacheRounds) ? m * (int)blockDim.x + (int)threadIdx.x : -1;
+        const int slot = (use_cache && m < kCacheRounds) ? m * (CS / kCacheRounds) + (int)threadIdx.x : -1;
         const int tag = (lvl << 28) | (iy << 14) | ix;
         if (slot >= 0 && tc.tag[slot] == tag) {   // same texels as in the last evaluation of this point
           const float* c = tc.tex + slot;
-          const int cs = tc.slots;
+          constexpr int cs = CS;
           t00[q] = make_float4(c[0 * cs], c[1 * cs], c[2 * cs], 0.f);
           t10[q] = make_float4(c[3 * cs], c[4 * cs], c[5 * cs], 0.f);
           t01[q] = make_float4(c[6 * cs], c[7 * cs], c[8 * cs], 0.f);
@@ -516,7 +516,7 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
           t00[q] = __ldg(bp); t10[q] = __ldg(bp + 1); t01[q] = __ldg(bp + wl); t11[q] = __ldg(bp + 1 + wl);
           if (slot >= 0) {
             float* c = tc.tex + slot;
-            const int cs = tc.slots;
+            constexpr int cs = CS;
             c[0 * cs] = t00[q].x; c[1 * cs] = t00[q].y; c[2 * cs] = t00[q].z;
             c[3 * cs] = t10[q].x; c[4 * cs] = t10[q].y; c[5 * cs] = t10[q].z;
             c[6 * cs] = t01[q].x; c[7 * cs] = t01[q].y; c[8 * cs] = t01[q].z;
@@ -560,12 +560,14 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
         const float u = uu[q], v = vv[q], id = nid[q];
         const float dx = hity * fxl, dy = hitz * fyl;
         float J[9];
+        // (the Jacobian only enters the accumulated H / b, which are held to 1e-4, not the bit-exact buffers: fused multiply-adds)
+        const float uv = u * v;
         J[0] = id * dx;
         J[1] = id * dy;
-        J[2] = 0.f - id * (u * dx + v * dy);
-        J[3] = 0.f - ((u * v) * dx + dy * (1.f + v * v));
-        J[4] = (u * v) * dy + dx * (1.f + u * u);
-        J[5] = u * dy - v * dx;
+        J[2] = -(id * __fmaf_rn(u, dx, v * dy));
+        J[3] = -__fmaf_rn(uv, dx, dy * __fmaf_rn(v, v, 1.f));
+        J[4] = __fmaf_rn(uv, dy, dx * __fmaf_rn(u, u, 1.f));
+        J[5] = __fmaf_rn(u, dy, -(v * dx));
         J[6] = ea * (eb0 - refColor);
         J[7] = -1.f;
         J[8] = residual;
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   Exchange ex;
   __shared__ int s_prob;
   __shared__ int s_pc_lvl;
-  TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl, kCacheRounds * (int)blockDim.x};
+  TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl, kCacheRounds * kBT};
   if (P.use_cache) {
     unsigned char* cb = smem_raw + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
     tc.pc = reinterpret_cast<float4*>(cb);
@@ -920,7 +922,7 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
     __syncthreads();
     tm.tick(0);
     // ---- the evaluation + the exchange: the only instance of this code in the kernel ----
-    eval_points_sse<kU>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl], tc);
+    eval_points_sse<kU, kCacheRounds * kBT>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl], tc);
     tm.tick(1);
     const int pb = reduce_exchange<false>(acc, sm, ex, C, rank, 0.0, &tm);
     // behind the block barriers of the reduction: every thread has read the flag for this evaluation and stored its point
@@ -1142,7 +1144,8 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   if (C < 1 || C > 16) return fail(ctx, SDSO_E_INVALID, "cluster_size must be in [1,16]");
   size_t smem = sizeof(TrackSmem);
   const bool use_cache = !g2o && ctx->S.track_cache != 0;
-  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(BT);
+  // (the cache is sized for the thread count the kernel instance was compiled for: 256, or 192 for the 168-register build)
+  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes((ctx->S.gather_batch == 2 && BT <= 192 && C == 1) ? 192 : 256);
   static bool attr_set = false;
   if (!attr_set) {
     const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(256));
