@@ -37,9 +37,21 @@ for name, n, P, w, h, K in cfgs:
     for _ in range(reps):
         ba.linearize_all(True); x, _, _ = ba.solve(2); ba.resubstitute(x)
     ms_cpu = 1e3 * (time.perf_counter() - t0) / reps
+    # the fork's live LBA: FullSystem::optimize g2o body (E2 graph + restated g2o LM), wall time of 3 LM iterations, before the SSE
+    # driver below moves the window's state
+    st0 = ba.get_state()
+    T_wh = np.stack([np.hstack([T[:, :3].T, (-T[:, :3].T @ T[:, 3])[:, None]]) for T in st0["T_w2c"]])
+    rng = np.random.default_rng(0)
+    Tp = np.stack([synth.perturb_T(T, rng, 3e-3, 3e-4) for T in T_wh])
+    idp = np.array([float(p["idepth"]) for p in win["points"] for _ in p["targets"]])
+    W.lba_g2o(np.array(K, float), Tp, np.zeros((n, 2)), idp, 3)
+    t0 = time.perf_counter(); gg = W.lba_g2o(np.array(K, float), Tp, np.zeros((n, 2)), idp, 3); t_g2o_dev = time.perf_counter() - t0
+    t0 = time.perf_counter(); go = ba.lba_g2o(np.array(K, float), Tp, np.zeros((n, 2)), idp, 3); t_g2o_cpu = time.perf_counter() - t0
     t0 = time.perf_counter(); ro, io = ba.optimize(6); t_opt_cpu = time.perf_counter() - t0
     t0 = time.perf_counter(); rg, ig = W.optimize(6); t_opt_dev = time.perf_counter() - t0
     print(json.dumps(dict(config=name, frames=n, points=len(win["points"]), residuals=R, size=[w, h], ms_per_lm_iteration_device=ms_dev,
                           ms_per_lm_iteration_cpu_port_1thread=ms_cpu, speedup=ms_cpu / ms_dev, ba_evals_per_s_device=8 * R / (ms_dev * 1e-3),
-                          optimize6_wall_ms_device=1e3 * t_opt_dev, optimize6_wall_ms_cpu_port=1e3 * t_opt_cpu, rmse_device=rg, rmse_cpu=ro, iterations=[ig, io])), flush=True)
+                          optimize6_wall_ms_device=1e3 * t_opt_dev, optimize6_wall_ms_cpu_port=1e3 * t_opt_cpu, rmse_device=rg, rmse_cpu=ro, iterations=[ig, io],
+                          lba_g2o_3its_wall_ms_device=1e3 * t_g2o_dev, lba_g2o_3its_wall_ms_cpu_port=1e3 * t_g2o_cpu,
+                          lba_g2o_iterations=[gg["iterations"], go["iterations"]], lba_g2o_chi2=[gg["chi2"], go["chi2"]])), flush=True)
     ctx.close()
