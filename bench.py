@@ -190,7 +190,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     host_cores = os.cpu_count() or 1
-    config = dict(workload=f"CoarseTracker pose tracking, 1232x368 (1241x376 cropped), 5-level pyramid, 2000 template points per keyframe, variant={args.variant}; "
+    config = dict(workload=f"CoarseTracker pose tracking, 1232x368 (1241x376 cropped), 5-level pyramid, 2000 active points splatted per keyframe (makeCoarseDepthL0 dilates them to ~9.9 k template points at level 0), variant={args.variant}; "
                            f"step = one new frame for each of {S} independent sequences sharing the GPU: makeImages (8-bit source, batched) + "
                            "trackNewestCoarse against each sequence's own reference keyframe ("
                            + ("one CTA per sequence, persistent grid of two CTAs per SM pulling sequences from a work counter" if args.cluster == 1 else
