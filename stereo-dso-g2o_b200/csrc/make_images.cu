@@ -53,8 +53,8 @@ __device__ __forceinline__ float4 make_texel(float c, float dx, float dy, int us
 // The level count is a template parameter: every region size, divisor and trip count is a constant, and the write phase
 // maps threads to (column, row-stride) so a warp stores 32 consecutive texels (512 B) per instruction with no index
 // division — the first version of this kernel spent 170 instructions per pixel and was issue-bound at 48 % of HBM.
-template <int L, int l, bool FINITE, bool GAMMA>
-__device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* __restrict__ src, float* __restrict__ base, float4* __restrict__ tbase,
+template <int L, int l, bool FINITE, bool GAMMA, typename TS = float>
+__device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const TS* __restrict__ src, float* __restrict__ base, float4* __restrict__ tbase,
                                                 int tid, const float* __restrict__ s_dB) {
   constexpr int H0 = 1 << (L - 1), R0 = kTile + 2 * H0;
   constexpr int Rs = R0 >> l, T = kTile >> l, Hl = H0 >> l;
@@ -69,16 +69,16 @@ __device__ __forceinline__ void pyr_write_level(const PyrGeom& P, const float* _
   const int ylast = min(min(T, ly0 + BR), hl - ty0);     // end of this band inside the image
   const size_t o0 = (size_t)P.px_offset[l] + x + (size_t)(ty0 + ly0) * wl;
   float4* __restrict__ Tl = tbase + o0;
-  const float* q = src + (Hl + ly0) * Rs + (lx + Hl);
+  const TS* q = src + (Hl + ly0) * Rs + (lx + Hl);
   // a thread walks down its column: the centre values of the rows above / below stay in registers
-  float cu = q[-Rs], c = q[0];
+  float cu = (float)q[-Rs], c = (float)q[0];
 #pragma unroll 4
   for (int ly = ly0; ly < ylast; ly++, q += Rs, Tl += wl) {
     const int y = ty0 + ly;
-    const float cd = q[Rs];
+    const float cd = (float)q[Rs];
     // the halo holds the neighbours of every tile pixel, so the differences are formed unconditionally and dropped for the
     // first / last image row (flat idx outside [w, w(h-1)), :182); columns 0 and w-1 are redone by pyr_wrap_kernel
-    float dx = 0.5f * (q[1] - q[-1]);
+    float dx = 0.5f * ((float)q[1] - (float)q[-1]);
     float dy = 0.5f * (cd - cu);
     if (!FINITE) { if (!isfinite(dx)) dx = 0.f; if (!isfinite(dy)) dy = 0.f; }
     float ag = dx * dx + dy * dy;
@@ -220,6 +220,90 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
   }
 }
 
+// 8-bit sources whose width is a multiple of 16 and pyramids of >= 4 levels (region side a multiple of 16): the level-0 region is
+// staged as BYTES (9 KB instead of 37 KB for 5 levels, 21 KB per CTA in all), so six CTAs are resident per SM instead of four, the
+// load phase is one 16-byte shared store per 16 pixels, and the widening happens where the values are consumed. Same arithmetic
+// on the same values as pyr_fused_kernel (every 8-bit value is exact in float).
+template <int L>
+__global__ void __launch_bounds__(256) pyr_fused_u8_kernel(PyrGeom P, PyrBatch B) {
+  extern __shared__ __align__(16) unsigned char smb[];
+  const int tid = threadIdx.x;
+  constexpr int H0 = 1 << (L - 1), R0 = kTile + 2 * H0;
+  static_assert(R0 % 16 == 0, "region side must be a multiple of 16");
+  const int ox = blockIdx.x * kTile - H0, oy = blockIdx.y * kTile - H0;
+  const int w0 = P.w[0], h0 = P.h[0];
+  float* __restrict__ base = B.img[blockIdx.z];
+  float4* __restrict__ tbase = B.tex[blockIdx.z];
+  unsigned char* s0 = smb;
+  float* s1 = reinterpret_cast<float*>(smb + R0 * R0);   // R0 * R0 is a multiple of 16
+  __shared__ float s_dB[256];
+  if (P.use_gamma) s_dB[tid] = tid < 255 ? g_Bgamma[tid + 1] - g_Bgamma[tid] : 0.f;
+  {
+    const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
+    constexpr int R16 = R0 >> 4, NG = R0 * R16, NIT = (NG + 255) / 256;
+    uint4 qv[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {   // every load of the thread is in flight before the first store
+      const int k = tid + it * 256;
+      const int ly = k / R16, lx = (k - ly * R16) * 16;
+      const int x = ox + lx, y = oy + ly;
+      qv[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (k < NG && y >= 0 && y < h0 && x >= 0 && x < w0) qv[it] = __ldg(reinterpret_cast<const uint4*>(S8 + x + y * w0));
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int k = tid + it * 256;
+      if (k >= NG) break;
+      const int ly = k / R16, lx = (k - ly * R16) * 16;
+      *reinterpret_cast<uint4*>(s0 + ly * R0 + lx) = qv[it];
+    }
+  }
+  __syncthreads();
+  // level 1 from the bytes: 2x2 mean in the reference's order 0.25f*(((a+b)+c)+d) (:172-178), two outputs per thread
+  {
+    constexpr int Rd = R0 >> 1, Rh = Rd >> 1;
+    for (int k = tid; k < Rd * Rh; k += 256) {
+      const int ly = k / Rh, lx = (k - ly * Rh) * 2;
+      const uchar4 a = *reinterpret_cast<const uchar4*>(s0 + (2 * ly) * R0 + 2 * lx);
+      const uchar4 b = *reinterpret_cast<const uchar4*>(s0 + (2 * ly + 1) * R0 + 2 * lx);
+      *reinterpret_cast<float2*>(s1 + ly * Rd + lx) =
+          make_float2(0.25f * ((((float)a.x + (float)a.y) + (float)b.x) + (float)b.y), 0.25f * ((((float)a.z + (float)a.w) + (float)b.z) + (float)b.w));
+    }
+    __syncthreads();
+    float* src = s1; int Rs = Rd;
+    float* dst = s1 + Rd * Rd;
+#pragma unroll
+    for (int l = 2; l < L; l++) {
+      const int Rn = Rs >> 1;
+      if (Rn % 2 == 0) {
+        const int Rq = Rn >> 1;
+        for (int k = tid; k < Rn * Rq; k += 256) {
+          const int ly = k / Rq, lx = (k - ly * Rq) * 2;
+          const float4 a = *reinterpret_cast<const float4*>(src + (2 * ly) * Rs + 2 * lx);
+          const float4 b = *reinterpret_cast<const float4*>(src + (2 * ly + 1) * Rs + 2 * lx);
+          *reinterpret_cast<float2*>(dst + ly * Rn + lx) = make_float2(0.25f * (((a.x + a.y) + b.x) + b.y), 0.25f * (((a.z + a.w) + b.z) + b.w));
+        }
+      } else {
+        for (int k = tid; k < Rn * Rn; k += 256) {
+          const int ly = k / Rn, lx = k - ly * Rn;
+          const float2 a = *reinterpret_cast<const float2*>(src + (2 * ly) * Rs + 2 * lx);
+          const float2 b = *reinterpret_cast<const float2*>(src + (2 * ly + 1) * Rs + 2 * lx);
+          dst[k] = 0.25f * (((a.x + a.y) + b.x) + b.y);
+        }
+      }
+      __syncthreads();
+      src = dst; Rs = Rn; dst = dst + Rn * Rn;
+    }
+  }
+  if (P.use_gamma) {
+    pyr_write_level<L, 0, true, true, unsigned char>(P, s0, base, tbase, tid, s_dB);
+    PyrWriteLevels<L, 1, true, true>::run(P, s1, base, tbase, tid, s_dB);
+  } else {
+    pyr_write_level<L, 0, true, false, unsigned char>(P, s0, base, tbase, tid, s_dB);
+    PyrWriteLevels<L, 1, true, false>::run(P, s1, base, tbase, tid, s_dB);
+  }
+}
+
 // The reference differentiates on the flat index, so at x = 0 the left neighbour is (w-1, y-1) and at x = w-1 the right
 // neighbour is (0, y+1) (HessianBlocks.cpp:182-184). One thread per (level, row, side); reads the intensities (.x) of the texels
 // written above (a neighbour may be rewritten concurrently by another thread of this kernel, with the same .x).
@@ -275,6 +359,17 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
       SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       attr_set = true;
     }
+    const bool fast8 = src_u8 && (P.w[0] & 15) == 0 && P.levels >= 4;
+    if (fast8) {
+      const int R0 = kTile + 2 * H0;
+      size_t smem8 = (size_t)R0 * R0;
+      for (int l = 1, R = R0 >> 1; l < P.levels; l++, R >>= 1) smem8 += (size_t)R * R * sizeof(float);
+      switch (P.levels) {
+        case 4: pyr_fused_u8_kernel<4><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
+        case 5: pyr_fused_u8_kernel<5><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
+        default: pyr_fused_u8_kernel<6><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
+      }
+    } else
     switch (P.levels) {
       case 1: pyr_fused_kernel<1><<<grid, 256, smem, ctx->stream>>>(P, B); break;
       case 2: pyr_fused_kernel<2><<<grid, 256, smem, ctx->stream>>>(P, B); break;
