@@ -4,9 +4,11 @@
 //   pyr_fused_kernel : one CTA per 64x64 level-0 tile (+ halo): source (float or 8-bit) -> shared memory -> all pyramid
 //                      levels of the tile in shared memory (2x2 box mean in the reference's order 0.25f*(((a+b)+c)+d),
 //                      :172-178) -> central differences, non-finite -> 0, absSquaredGrad (+ gamma factor, :196-200) ->
-//                      one coalesced 16-byte store {I,dx,dy,absSquaredGrad} per pixel of every level + the intensity planes.
+//                      one coalesced 16-byte streaming store {I,dx,dy,absSquaredGrad} per pixel of every level.
+//   pyr_fused_u8_kernel : the same for 8-bit sources (width a multiple of 16, >= 4 levels) with the level-0 tile staged as bytes.
 //   pyr_wrap_kernel  : the two image columns whose flat-index difference wraps to the neighbouring row (:182-184).
-// Algorithmic bytes per image: read W*H (8-bit) or 4*W*H + write 16*sum_l(w_l*h_l) texels + 4*sum_l planes.
+// Algorithmic bytes per image: read W*H (8-bit) or 4*W*H + write 16*sum_l(w_l*h_l) texels. No separate intensity
+// plane is written; the epipolar search extracts its level-0 plane on first use (ensure_intensity_plane).
 #include "ctx.h"
 
 namespace sdso {
