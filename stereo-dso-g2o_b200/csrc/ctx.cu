@@ -180,10 +180,13 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
     if (f.tex[0]) cudaFree(f.tex[0]);
     if (f.image) cudaFree(f.image);
     if (f.src8 && f.src8_owned) cudaFree(f.src8);
-    if (f.uploaded) cudaEventDestroy(f.uploaded);
   }
   for (void* a : ctx->arenas) cudaFree(a);
   if (ctx->staging) cudaFreeHost(ctx->staging);
+  for (int i = 0; i < sdso_ctx::kEventRing; i++) {
+    if (ctx->upload_events[i]) cudaEventDestroy(ctx->upload_events[i]);
+    if (ctx->consume_events[i]) cudaEventDestroy(ctx->consume_events[i]);
+  }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->ev_track) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : ctx->ev_images) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -303,6 +306,19 @@ int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const 
     }
   }
   const size_t bytes = src_u8 ? n : n * sizeof(float);
+  // a makeImages still queued on the compute stream may be reading these staging buffers: the copies wait for it
+  {
+    cudaEvent_t seen[8]; int ns = 0;
+    for (int i = 0; i < nb; i++) {
+      cudaEvent_t e = ctx->frames[frame_ids[i]].consumed;
+      if (!e) continue;
+      bool dup = false;
+      for (int k = 0; k < ns; k++) dup |= (seen[k] == e);
+      if (dup) continue;
+      SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, e, 0));
+      if (ns < 8) seen[ns++] = e;
+    }
+  }
   for (int i = 0; i < nb;) {
     Frame& f = ctx->frames[frame_ids[i]];
     unsigned char* dst = src_u8 ? f.src8 : (unsigned char*)f.image;
@@ -317,14 +333,18 @@ int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const 
     SDSO_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)run * bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     i += run;
   }
+  if (nb == 0) return SDSO_OK;
+  // one event for the whole batch (copies on one stream complete in order); EVERY frame of the batch points at it, so any subset
+  // or reordering of the batch handed to sdso_make_images_uploaded waits for its copies
+  cudaEvent_t& ev = ctx->upload_events[ctx->upload_seq++ % sdso_ctx::kEventRing];
+  if (!ev) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  SDSO_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
   for (int i = 0; i < nb; i++) {
     Frame& f = ctx->frames[frame_ids[i]];
-    if (!f.uploaded) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+    f.uploaded = ev;
     f.pending_u8 = src_u8 ? 1 : 0;
     f.valid = false;
   }
-  // one event for the whole batch is enough: copies on one stream complete in order
-  if (nb > 0) SDSO_CUDA(ctx, cudaEventRecord(ctx->frames[frame_ids[nb - 1]].uploaded, ctx->copy_stream));
   return SDSO_OK;
 }
 
@@ -341,10 +361,25 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
     fr[i] = &f; src[i] = u8 ? (const void*)f.src8 : (const void*)f.image;
     f.ab_exposure = ab_exposure ? ab_exposure[i] : 1.0f;
   }
-  SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->frames[frame_ids[nb - 1]].uploaded, 0));
+  {  // wait for every distinct upload batch these frames came from
+    cudaEvent_t last = nullptr;
+    for (int i = 0; i < nb; i++) {
+      cudaEvent_t e = fr[i]->uploaded;
+      if (!e) return fail(ctx, SDSO_E_STATE, "make_images_uploaded: frame has no upload event");
+      if (e == last) continue;
+      SDSO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+      last = e;
+    }
+  }
   for (int o = 0; o < nb; o += 128) {  // 128 frames per launch pair (kernel-parameter space)
     rc = make_images_batch_launch(ctx, nb - o < 128 ? nb - o : 128, fr.data() + o, src.data() + o, u8 != 0, use_hcalib != 0);
     if (rc) return rc;
+  }
+  {  // the next upload into these slots must not overwrite the staging while these launches read it
+    cudaEvent_t& ev = ctx->consume_events[ctx->consume_seq++ % sdso_ctx::kEventRing];
+    if (!ev) SDSO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SDSO_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+    for (int i = 0; i < nb; i++) fr[i]->consumed = ev;
   }
   for (int i = 0; i < nb; i++) { fr[i]->valid = true; fr[i]->gen++; fr[i]->pending_u8 = -1; fr[i]->plane_valid = (!u8); }  // float uploads land in the plane
   return SDSO_OK;

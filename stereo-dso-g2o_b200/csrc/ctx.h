@@ -21,7 +21,8 @@ struct Frame {
   unsigned gen = 0;                     // bumped by every makeImages on this slot (the selector keys its histograms on it)
   unsigned char* src8 = nullptr;        // device staging of an 8-bit source image (a slice of a batch arena)
   bool src8_owned = false;
-  cudaEvent_t uploaded = nullptr;       // recorded on the copy stream after the asynchronous upload of this frame's source
+  cudaEvent_t uploaded = nullptr;       // NOT owned: the event (ctx->upload_events ring) recorded on the copy stream after the upload batch this frame's source was in
+  cudaEvent_t consumed = nullptr;       // NOT owned: the event (ctx->consume_events ring) recorded on the compute stream after the last makeImages that read src8 / image
   int pending_u8 = -1;                  // source format of the pending upload: -1 none, 0 float (in `image`), 1 uint8 (in `src8`)
 };
 
@@ -53,6 +54,11 @@ struct sdso_ctx {
   float* staging = nullptr;  // pinned host staging for image upload
   std::vector<void*> arenas;           // batch allocations of 8-bit staging
   cudaStream_t copy_stream = nullptr;  // H2D uploads that overlap the kernels of the previous step (sdso_upload_images_async)
+  // one event per upload batch / per makeImages batch, shared by every frame of the batch. Rings: a slot that is re-recorded while an
+  // old frame still points at it only makes that frame's wait more conservative (both streams complete in order).
+  static constexpr int kEventRing = 64;
+  cudaEvent_t upload_events[kEventRing] = {nullptr}, consume_events[kEventRing] = {nullptr};
+  unsigned upload_seq = 0, consume_seq = 0;
   sdso::TrackerState* tracker = nullptr;
   sdso::BAState* ba = nullptr;
   sdso::TraceState* trace = nullptr;

@@ -5,7 +5,7 @@
 //                      levels of the tile in shared memory (2x2 box mean in the reference's order 0.25f*(((a+b)+c)+d),
 //                      :172-178) -> central differences, non-finite -> 0, absSquaredGrad (+ gamma factor, :196-200) ->
 //                      one coalesced 16-byte streaming store {I,dx,dy,absSquaredGrad} per pixel of every level.
-//   pyr_fused_u8_kernel : the same for 8-bit sources (width a multiple of 16, >= 4 levels) with the level-0 tile staged as bytes.
+//   pyr_fused_u8_kernel : the same for 8-bit sources (width and pointer multiples of 16, >= 5 levels) with the level-0 tile staged as bytes.
 //   pyr_wrap_kernel  : the two image columns whose flat-index difference wraps to the neighbouring row (:182-184).
 // Algorithmic bytes per image: read W*H (8-bit) or 4*W*H + write 16*sum_l(w_l*h_l) texels. No separate intensity
 // plane is written; the epipolar search extracts its level-0 plane on first use (ensure_intensity_plane).
@@ -20,7 +20,8 @@ struct PyrGeom {  // identical for every frame of a context
   int w[kPyrLevels], h[kPyrLevels];
   int px_offset[kPyrLevels + 1];  // prefix sum of w_l*h_l: level l of a frame lives at base + px_offset[l]
   int use_gamma;
-  int src_u8;                     // source images are 8-bit (PhotometricUndistorter::processFrame in mode 1 = plain widening, Undistort.cpp:222-260)
+  int src_u8;                     // 0: float sources; else 8-bit sources (PhotometricUndistorter::processFrame in mode 1 = plain widening,
+                                  // Undistort.cpp:222-260) and the widest load every row start / region origin / pointer allows: 1, 4 or 16 bytes
 };
 struct PyrBatch {
   const void* src[kMaxBatch];     // level-0 source (float or uint8), device memory
@@ -125,8 +126,9 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
   float* s0 = sm;
   __shared__ float s_dB[256];   // B[ci + 1] - B[ci], the factor getBGradOnly returns
   if (P.use_gamma) s_dB[tid] = tid < 255 ? g_Bgamma[tid + 1] - g_Bgamma[tid] : 0.f;
-  if (P.src_u8 && (w0 & 15) == 0) {
-    // 16 pixels per load: ox and w0 are multiples of 16, so a group lies inside or outside the image as a whole
+  if (P.src_u8 == 16 && H0 % 16 == 0) {
+    // 16 pixels per load: ox (= 64 bx - H0, L >= 5), w0 and the source pointer are multiples of 16 (checked by the host, src_u8 == 16),
+    // so a group is aligned and lies inside or outside the image as a whole
     const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
     constexpr int R16 = R0 >> 4, NG = R0 * R16, NIT = (NG + 255) / 256;
     uint4 qv[NIT];
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
         d[jj] = make_float4((float)(wv & 0xffu), (float)((wv >> 8) & 0xffu), (float)((wv >> 16) & 0xffu), (float)(wv >> 24));
       }
     }
-  } else if (P.src_u8 && (w0 & 3) == 0) {
+  } else if (P.src_u8 >= 4 && H0 % 4 == 0) {   // L >= 3; w0 and the pointer are multiples of 4 (host check)
     const unsigned char* __restrict__ S8 = (const unsigned char*)B.src[blockIdx.z];
     constexpr int R4 = R0 >> 2;
 #pragma unroll 3
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(PyrGeom P, PyrBatch B) {
   }
 }
 
-// 8-bit sources whose width is a multiple of 16 and pyramids of >= 4 levels (region side a multiple of 16): the level-0 region is
+// 8-bit sources whose width and pointer are multiples of 16 and pyramids of >= 5 levels (region side and origin multiples of 16): the level-0 region is
 // staged as BYTES (9 KB instead of 37 KB for 5 levels, 21 KB per CTA in all), so six CTAs are resident per SM instead of four, the
 // load phase is one 16-byte shared store per 16 pixels, and the widening happens where the values are consumed. Same arithmetic
 // on the same values as pyr_fused_kernel (every 8-bit value is exact in float).
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(256) pyr_fused_u8_kernel(PyrGeom P, PyrBatch B
   extern __shared__ __align__(16) unsigned char smb[];
   const int tid = threadIdx.x;
   constexpr int H0 = 1 << (L - 1), R0 = kTile + 2 * H0;
-  static_assert(R0 % 16 == 0, "region side must be a multiple of 16");
+  static_assert(R0 % 16 == 0 && H0 % 16 == 0, "region side and origin must be multiples of 16");
   const int ox = blockIdx.x * kTile - H0, oy = blockIdx.y * kTile - H0;
   const int w0 = P.w[0], h0 = P.h[0];
   float* __restrict__ base = B.img[blockIdx.z];
@@ -345,7 +347,12 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
   P.px_offset[kPyrLevels] = off;
   for (int l = P.levels; l <= kPyrLevels; l++) P.px_offset[l] = off;
   P.use_gamma = (use_hcalib && ctx->S.gammaWeightsPixelSelect == 1) ? 1 : 0;
-  P.src_u8 = src_u8 ? 1 : 0;
+  P.src_u8 = 0;
+  if (src_u8) {   // widest aligned load: every row start (w0), every source pointer; the region origin is checked per kernel (H0)
+    uintptr_t bits = (uintptr_t)P.w[0];
+    for (int i = 0; i < nb; i++) bits |= (uintptr_t)srcs[i];
+    P.src_u8 = (bits & 15) == 0 ? 16 : ((bits & 3) == 0 ? 4 : 1);
+  }
   PyrBatch B;
   for (int i = 0; i < kMaxBatch; i++) { B.src[i] = nullptr; B.img[i] = nullptr; B.tex[i] = nullptr; }
   for (int i = 0; i < nb; i++) { B.src[i] = srcs[i]; B.img[i] = frames[i]->image; B.tex[i] = frames[i]->tex[0]; }
@@ -361,13 +368,13 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
       SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       attr_set = true;
     }
-    const bool fast8 = src_u8 && (P.w[0] & 15) == 0 && P.levels >= 4;
+    // byte-staged kernel: 16-byte loads at x = 64 bx - H0 + 16 j need H0 = 2^(L-1) to be a multiple of 16, i.e. L >= 5
+    const bool fast8 = P.src_u8 == 16 && P.levels >= 5;
     if (fast8) {
       const int R0 = kTile + 2 * H0;
       size_t smem8 = (size_t)R0 * R0;
       for (int l = 1, R = R0 >> 1; l < P.levels; l++, R >>= 1) smem8 += (size_t)R * R * sizeof(float);
       switch (P.levels) {
-        case 4: pyr_fused_u8_kernel<4><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
         case 5: pyr_fused_u8_kernel<5><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
         default: pyr_fused_u8_kernel<6><<<grid, 256, smem8, ctx->stream>>>(P, B); break;
       }

@@ -1091,7 +1091,7 @@ static void fill_params(sdso_ctx* ctx, TrackParams& P) {
     for (int i = 0; i < 9; i++) L.Ki[i] = t->K.Ki[l][i];
     L.gfx = ctx->G.K[l][0]; L.gfy = ctx->G.K[l][4]; L.gcx = ctx->G.K[l][2]; L.gcy = ctx->G.K[l][5];
   }
-  P.ref_exposure = ctx->frames[t->ref_frame].ab_exposure;
+  P.ref_exposure = t->ref_exposure;  // (the kernels read the per-problem copy; the current slot may be empty in a multi-reference batch)
   P.ref_aff[0] = t->ref_aff[0]; P.ref_aff[1] = t->ref_aff[1];
   P.huberTH = ctx->S.huberTH; P.coarseCutoffTH = ctx->S.coarseCutoffTH;
   P.affineOptModeA = ctx->S.affineOptModeA; P.affineOptModeB = ctx->S.affineOptModeB;
@@ -1122,7 +1122,7 @@ static RefSlot slot_view(const TrackerState* t, int slot) {
   if (slot == t->cur_slot || slot < 0) {
     RefSlot r;
     for (int l = 0; l < kPyrLevels; l++) { r.pc[l] = t->pc[l]; r.pc_n[l] = t->pc_n[l]; r.pc_cap[l] = t->pc_cap[l]; }
-    r.ref_frame = t->ref_frame; r.ref_aff[0] = t->ref_aff[0]; r.ref_aff[1] = t->ref_aff[1]; r.have_ref = t->have_ref;
+    r.ref_frame = t->ref_frame; r.ref_exposure = t->ref_exposure; r.ref_aff[0] = t->ref_aff[0]; r.ref_aff[1] = t->ref_aff[1]; r.have_ref = t->have_ref;
     return r;
   }
   if (slot >= (int)t->saved.size()) return RefSlot();
@@ -1132,7 +1132,7 @@ static int fill_problem_ref(sdso_ctx* ctx, TrackProblem& hp, int slot) {
   const RefSlot r = slot_view(ctx->tracker, slot);
   if (!r.have_ref) return fail(ctx, SDSO_E_STATE, "trackNewestCoarse before setCoarseTrackingRef (reference slot is empty)");
   for (int l = 0; l < ctx->G.levels; l++) { hp.pc[l] = r.pc[l]; hp.pc_n[l] = r.pc_n[l]; }
-  hp.ref_exposure = ctx->frames[r.ref_frame].ab_exposure;
+  hp.ref_exposure = r.ref_exposure;
   hp.ref_aff[0] = r.ref_aff[0]; hp.ref_aff[1] = r.ref_aff[1];
   return SDSO_OK;
 }
@@ -1195,10 +1195,16 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
 }
 
 // per-problem, per-level edge flags / errors of the g2o path
-static int ensure_edge_scratch(sdso_ctx* ctx, TrackParams& P, int nb) {
+// (the stride is the largest template of the batch: each problem of a multi-reference batch has its own pc_n)
+static int ensure_edge_scratch(sdso_ctx* ctx, TrackParams& P, int nb, const int* ref_slots = nullptr) {
   TrackerState* t = ctx->tracker;
   for (int l = 0; l < ctx->G.levels; l++) {
-    int stride = (t->pc_n[l] + 63) & ~63;
+    int nmax = t->pc_n[l];
+    if (ref_slots) {
+      nmax = 0;
+      for (int k = 0; k < nb; k++) { const int n = slot_view(t, ref_slots[k]).pc_n[l]; if (n > nmax) nmax = n; }
+    }
+    int stride = (nmax + 63) & ~63;
     if (stride < 64) stride = 64;
     size_t need = (size_t)stride * nb;
     if (need > t->edge_cap[l]) {
@@ -1239,6 +1245,7 @@ int sdso_tracker_set_pc(sdso_ctx* ctx, int ref_frame, int lvl, int n, const floa
   SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   t->pc_n[lvl] = n;
   t->ref_frame = ref_frame;
+  t->ref_exposure = ctx->frames[ref_frame].ab_exposure;
   t->ref_aff[0] = ref_aff[0]; t->ref_aff[1] = ref_aff[1];
   t->have_ref = true;
   return SDSO_OK;
@@ -1392,7 +1399,7 @@ int sdso_tracker_select_ref(sdso_ctx* ctx, int slot) {
     }
   }
   for (int l = 0; l < kPyrLevels; l++) { t->pc[l] = r.pc[l]; t->pc_n[l] = r.pc_n[l]; t->pc_cap[l] = r.pc_cap[l]; }
-  t->ref_frame = r.ref_frame; t->ref_aff[0] = r.ref_aff[0]; t->ref_aff[1] = r.ref_aff[1]; t->have_ref = r.have_ref;
+  t->ref_frame = r.ref_frame; t->ref_exposure = r.ref_exposure; t->ref_aff[0] = r.ref_aff[0]; t->ref_aff[1] = r.ref_aff[1]; t->have_ref = r.have_ref;
   t->cur_slot = slot;
   return SDSO_OK;
 }
@@ -1408,7 +1415,7 @@ int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const 
   TrackParams P{};
   fill_params(ctx, P);
   P.mode = 0; P.coarsest = coarsest_lvl; P.variant = variant;
-  if (variant == SDSO_VARIANT_G2O) { int rc = ensure_edge_scratch(ctx, P, nb); if (rc) return rc; }
+  if (variant == SDSO_VARIANT_G2O) { int rc = ensure_edge_scratch(ctx, P, nb, ref_slots); if (rc) return rc; }
   for (int k = 0; k < nb; k++) {
     int rc = check_frame(ctx, new_frames[k]);
     if (rc) return rc;

@@ -14,16 +14,37 @@
 
 namespace sdso {
 
-__global__ void splat_kernel(const float4* __restrict__ pts, int n, float* idepth0, float* wsum0, int w0, int h0) {
+__device__ __forceinline__ int splat_pixel(const float4 p, int w0, int h0) {
+  const int u = (int)(p.x + 0.5f), v = (int)(p.y + 0.5f);
+  if (u < 0 || v < 0 || u >= w0 || v >= h0) return -1;  // the reference would write out of bounds
+  return u + w0 * v;
+}
+// Splats that share a pixel must add in POINT order as the reference's loop does (:350-354); float atomics would add in arrival
+// order. Pass 1 finds, per pixel, the lowest point index (owner) and the number of splats; pass 2: a pixel with one splat is
+// written directly, a shared pixel is summed by its owner in index order (collisions are rare: a scan of the later points).
+__global__ void splat_owner_kernel(const float4* __restrict__ pts, int n, int* owner, int* count, int w0, int h0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float4 p = pts[i];
-  int u = (int)(p.x + 0.5f), v = (int)(p.y + 0.5f);
-  if (u < 0 || v < 0 || u >= w0 || v >= h0) return;  // the reference would write out of bounds
-  // NOTE: two splats on the same pixel add in arrival order (float atomics); the reference adds in
-  // point order. Identical whenever splat pixels are distinct, as for points chosen by the selector.
-  atomicAdd(&idepth0[u + w0 * v], p.z * p.w);
-  atomicAdd(&wsum0[u + w0 * v], p.w);
+  const int pix = splat_pixel(pts[i], w0, h0);
+  if (pix < 0) return;
+  atomicMin(&owner[pix], i);
+  atomicAdd(&count[pix], 1);
+}
+__global__ void splat_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ owner, const int* __restrict__ count,
+                             float* idepth0, float* wsum0, int w0, int h0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const int pix = splat_pixel(p, w0, h0);
+  if (pix < 0 || owner[pix] != i) return;
+  float id = p.z * p.w, ws = p.w;   // 0 + x == x
+  int left = count[pix] - 1;
+  for (int j = i + 1; j < n && left > 0; j++) {
+    const float4 q = pts[j];
+    if (splat_pixel(q, w0, h0) == pix) { id += q.z * q.w; ws += q.w; left--; }
+  }
+  idepth0[pix] = id;
+  wsum0[pix] = ws;
 }
 
 __global__ void pool_kernel(const float* __restrict__ id_lm, const float* __restrict__ ws_lm, float* id_l, float* ws_l, int wl, int hl, int wlm1) {
@@ -119,7 +140,13 @@ extern "C" int sdso_tracker_set_ref(sdso_ctx* ctx, int ref_frame, const float* u
   if (n > 0) {
     SDSO_CUDA(ctx, cudaMallocAsync(&dpts, (size_t)n * sizeof(float4), st));
     SDSO_CUDA(ctx, cudaMemcpyAsync(dpts, uvidw, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
-    splat_kernel<<<(n + 255) / 256, 256, 0, st>>>(dpts, n, t->idepth[0], t->wsum[0], w0, h0);
+    int* owner = t->scan_tmp;                              // free until the row counts below
+    int* count = reinterpret_cast<int*>(t->wsum_bak[0]);   // free until the dilation backup below
+    SDSO_CUDA(ctx, cudaMemsetAsync(owner, 0x7f, (size_t)w0 * h0 * sizeof(int), st));
+    SDSO_CUDA(ctx, cudaMemsetAsync(count, 0, (size_t)w0 * h0 * sizeof(int), st));
+    splat_owner_kernel<<<(n + 255) / 256, 256, 0, st>>>(dpts, n, owner, count, w0, h0);
+    SDSO_CHECK_LAUNCH(ctx);
+    splat_kernel<<<(n + 255) / 256, 256, 0, st>>>(dpts, n, owner, count, t->idepth[0], t->wsum[0], w0, h0);
     SDSO_CHECK_LAUNCH(ctx);
   }
   for (int l = 1; l < L; l++) {
@@ -156,6 +183,7 @@ extern "C" int sdso_tracker_set_ref(sdso_ctx* ctx, int ref_frame, const float* u
   SDSO_CUDA(ctx, cudaStreamSynchronize(st));
   for (int l = 0; l < L; l++) t->pc_n[l] = counts[l];
   t->ref_frame = ref_frame;
+  t->ref_exposure = ctx->frames[ref_frame].ab_exposure;
   t->ref_aff[0] = ref_aff[0]; t->ref_aff[1] = ref_aff[1];
   t->have_ref = true;
   return SDSO_OK;

@@ -12,6 +12,7 @@ struct RefSlot {
   int pc_n[kPyrLevels] = {0};
   int pc_cap[kPyrLevels] = {0};
   int ref_frame = -1;
+  float ref_exposure = 1.0f;  // snapshot at setCoarseTrackingRef time: the frame slot may be released / reused afterwards
   double ref_aff[2] = {0, 0};
   bool have_ref = false;
 };
@@ -22,6 +23,7 @@ struct TrackerState {
   int pc_n[kPyrLevels] = {0};
   int pc_cap[kPyrLevels] = {0};
   int ref_frame = -1;
+  float ref_exposure = 1.0f;
   double ref_aff[2] = {0, 0};
   bool have_ref = false;
   TrackProblem* d_problems = nullptr;

@@ -102,3 +102,64 @@ def test_tracker_configurations_are_bitwise_identical(pkg, frames, cluster, thre
             on = r
         else:
             assert np.array_equal(r["T"], on["T"]) and np.array_equal(r["lastResiduals"], on["lastResiduals"]), "cache on/off must be bitwise equal"
+
+
+@pytest.mark.parametrize("shape", [(640, 480), (640, 192), (1920, 1088), (96, 64), (100, 60), (1241, 376), (136, 104)])
+def test_make_images_u8_equals_float_at_every_depth(pkg, shape):
+    """8-bit sources take wider loads where the region origin (64 bx - 2^(L-1)), the row pitch and the pointer allow it: 16-byte
+    (L >= 5), 4-byte (L >= 3), scalar otherwise. Every combination must equal the float path bit for bit — including 4-level
+    pyramids (640x480, 640x192), 1-3 level sizes, odd widths, and device pointers that are not 16-byte aligned."""
+    import torch
+    w, h = shape
+    rng = np.random.default_rng(w * 13 + h)
+    img8 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    K = (500.0, 500.0, w / 2 - 0.5, h / 2 - 0.5)
+    ctx = pkg.Context(w, h, K)
+    ff = ctx.frame_create()
+    ctx.make_images(ff, img8.astype(np.float32))
+    slab = torch.zeros(w * h + 64, dtype=torch.uint8, device="cuda")
+    for shift in (0, 4, 1):   # 16-byte aligned, 4-byte aligned, unaligned device pointer
+        view = slab[shift:shift + w * h]
+        view.copy_(torch.from_numpy(img8.reshape(-1)).cuda())
+        fu = ctx.frame_create()
+        ctx.make_images_batch_device([fu], [view.data_ptr()], u8=True)
+        ctx.synchronize()
+        for lvl in range(ctx.levels):
+            a, ag = ctx.frame_download(ff, lvl)
+            b, bg = ctx.frame_download(fu, lvl)
+            assert np.array_equal(a, b) and np.array_equal(ag, bg), (shape, shift, lvl)
+        ctx.frame_release(fu)
+    ctx.close()
+
+
+def test_multi_reference_g2o_batch_equals_separate_tracking(pkg, frames):
+    """g2o variant with per-problem templates of DIFFERENT sizes in one launch: the per-problem edge flag / error scratch must be
+    strided by the largest template of the batch (a later, smaller current slot used to size it)."""
+    ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE)
+    fid = {k: ctx.frame_create() for k in (0, 1, 2)}
+    for k in (0, 1, 2):
+        ctx.make_images(fid[k], frames[k][0])
+    rng = np.random.default_rng(2)
+    seqs = [(0, 1), (1, 2), (0, 2), (1, 0)]
+    npts = [2400, 1500, 900, 300]   # the current slot after the loop is the smallest
+    singles, T0s = [], []
+    for s, (r, nw) in enumerate(seqs):
+        ctx.tracker_select_ref(s)
+        ctx.tracker_set_ref(fid[r], synth.pick_points(rng, frames[r][1], npts[s]), (0.0, 0.0))
+        Ttrue = synth.T_rel(synth.camera_pose(r), synth.camera_pose(nw))
+        T0 = synth.perturb_T(Ttrue, rng, 0.02, np.deg2rad(0.2))
+        T0s.append(T0)
+        singles.append(ctx.track(fid[nw], T0, (0.0, 0.0), ctx.levels - 1, [np.nan] * 5, pkg.VARIANT_G2O))
+    for rep in range(2):
+        ctx.track_enqueue_multi(list(range(4)), [fid[nw] for _, nw in seqs], np.stack(T0s), np.zeros((4, 2)), ctx.levels - 1,
+                                np.full((4, 5), np.nan), pkg.VARIANT_G2O)
+        b = ctx.track_collect(4)
+        for s in range(4):
+            assert np.array_equal(b["T"][s], singles[s]["T"]), (rep, s)
+            assert np.array_equal(b["lastResiduals"][s], singles[s]["lastResiduals"], equal_nan=True), (rep, s)
+            assert b["ok"][s] == singles[s]["ok"]
+    # an empty current slot must not break a multi-reference enqueue (fill_params used to index frames[-1])
+    ctx.tracker_select_ref(7)
+    ctx.track_enqueue_multi([0, 1], [fid[1], fid[2]], np.stack(T0s[:2]), np.zeros((2, 2)), ctx.levels - 1, np.full((2, 5), np.nan), 0)
+    ctx.track_collect(2)
+    ctx.close()
