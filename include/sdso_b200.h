@@ -197,7 +197,7 @@ int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const doubl
 int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, double* lastResiduals,
                        double* flowIndicators, int* iterations, int* ok, uint64_t* evals /* nullable, total */);
 
-/* ---- B1-B12: windowed bundle adjustment, SSE path (Residuals.cpp, OptimizationBackend/*) ----------------
+/* ---- B1-B12: windowed bundle adjustment, SSE path (Residuals.cpp, OptimizationBackend/) ----------------
  * The window is uploaded once as SoA arenas (frames, points, residuals); every operator below runs on the
  * device. Indices: frames 0..n-1 in insertion order (= EFFrame::idx), points 0..P-1 in the reference's
  * allPoints order (EnergyFunctional.cpp:1003-1016), residuals 0..R-1 in the order given to
@@ -282,6 +282,26 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
  * mnumOptIts is overridden as the reference does (10 / 7 / 3 for 2 / 3 / >= 4 frames). */
 int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, double* photo, double* idepth, int* used_host, double* chi2_out,
                  int* newState, float* center3, float* idepth_hessian, int* iterations_out, int* trials_out);
+
+/* ---- V1-V5, E3: the g2o vertices and the trace edge as operators over SoA batches (FullSystem/dso_g2o_vertex.cpp, dso_g2o_edge.cpp) ----
+ * oplusImpl of n vertices of one kind in one launch; estimate is updated in place (caller-owned host arrays):
+ *   SDSO_VERTEX_SE3_POSE      VertexSE3PoseDSO::oplusImpl      (:15-18)    estimate[n][12] row-major 3x4, update[n][6] = [upsilon; omega]: exp(update) * T
+ *   SDSO_VERTEX_PHOTOMETRIC   VertexPhotometricDSO::oplusImpl  (:30-40)    estimate[n][2] = {a, b} += update[n][2]
+ *   SDSO_VERTEX_INVERSE_DEPTH VertexInverseDepthDSO::oplusImpl (:56-58)    estimate[n] += update[n]
+ *   SDSO_VERTEX_UV            VertexUVDSO::oplusImpl           (:73-88)    estimate[n][2] += clamp(update[n], +-0.5; non-finite -> 0) * aux[n][2] (SetDxDy)
+ *   SDSO_VERTEX_CAM           VertexCamDSO::oplusImpl          (:100-106)  estimate[n][4] = {fx, fy, cx, cy} += update[n][4] */
+#define SDSO_VERTEX_SE3_POSE 1
+#define SDSO_VERTEX_PHOTOMETRIC 2
+#define SDSO_VERTEX_INVERSE_DEPTH 3
+#define SDSO_VERTEX_UV 4
+#define SDSO_VERTEX_CAM 5
+int sdso_vertex_oplus(sdso_ctx* ctx, int kind, int n, double* estimate, const double* update, const double* aux /* VertexUVDSO only */);
+/* EdgeTracePointUVDSO::computeError + linearizeOplus (dso_g2o_edge.cpp:571-619) for n edges on level 0 of `frame`: VertexUVDSO
+ * estimates uv[n][2], rotatePattern[n][2], _measurement[n], affLL[2], (dx_, dy_)[n][2]. error[n] / J[n] are read AND written: an edge
+ * whose uv fails util::CheckBoundary gets error 0 and keeps its Jacobian, a non-finite intensity keeps both (g2o leaves the members
+ * untouched). flag[n] (nullable): 1 evaluated, 0 outside, 2 non-finite. */
+int sdso_edge_trace_uv_eval(sdso_ctx* ctx, int frame, int n, const double* uv, const float* rotatePattern, const double* measurement,
+                            const float affLL[2], const double* dxdy, double* error, double* J, int* flag);
 
 /* ---- point-sharded windowed BA over 2/4/8 GPUs ------------------------------------------------------
  * Every rank holds all keyframe pyramids and a contiguous block of the allPoints order with its residuals. Per LM

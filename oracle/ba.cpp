@@ -450,10 +450,14 @@ void addABt(std::vector<double>& H, int d, int r0, int c0, const double* A, cons
 // stitchDoubleInternal with tid=-1 (:265-337) and the symmetrisation of stitchDoubleMT (.h:134-147)
 void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<double>& b, bool usePrior) {
   const int nf = n(), d = dim();
-  std::vector<AccumulatorApprox> acc((size_t)nf * nf);
+  const int NT = reduce_threads > 1 ? reduce_threads : 1;   // per-worker accumulator sets (acc[tid][aidx], AccumulatedTopHessian.h:60-75)
+  const size_t nf2s = (size_t)nf * nf;
+  std::vector<AccumulatorApprox> acc(nf2s * NT);
   for (auto& a : acc) a.initialize();
   int resInA_tmp = 0;
-  for (auto& p : points) {
+  for (size_t pi_ = 0; pi_ < points.size(); pi_++) {
+    auto& p = points[pi_];
+    const size_t tbase = nf2s * (size_t)reduce_tid((int)pi_);
     if (mode == 2 && p.stateFlag != 1) continue;  // marginalizePointsF feeds only PS_MARGINALIZE points (:680-696)
     const float* dc = cDeltaF;
     float dd = p.deltaF;
@@ -491,7 +495,7 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
         Jab_r[1] += resApprox[i] * rJ.JabF[1][i];
         rr += resApprox[i] * resApprox[i];
       }
-      AccumulatorApprox& a = acc[htIDX];
+      AccumulatorApprox& a = acc[tbase + htIDX];
       if (mode == 0) resInA_tmp++;
       a.update(rJ.Jpdc[0], rJ.Jpdxi[0], rJ.Jpdc[1], rJ.Jpdxi[1], rJ.JIdx2[0], rJ.JIdx2[1], rJ.JIdx2[3]);
       a.updateBotRight(rJ.Jab2[0], rJ.Jab2[1], Jab_r[0], rJ.Jab2[3], Jab_r[1], rr);
@@ -512,11 +516,18 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
   for (int k = 0; k < nf * nf; k++) {
     int h = k % nf, t = k / nf;
     int hIdx = CPARS + h * 8, tIdx = CPARS + t * 8;
-    acc[k].finish();
-    for (int i = 0; i < 169; i++) lastTopBlocks[(size_t)k * 169 + i] = acc[k].H[i];
-    if (acc[k].num == 0) continue;
     double accH[169];
-    for (int i = 0; i < 169; i++) accH[i] = acc[k].H[i];
+    for (int i = 0; i < 169; i++) accH[i] = 0;
+    size_t num_all = 0;
+    for (int tid2 = 0; tid2 < NT; tid2++) {   // :299-308
+      AccumulatorApprox& a = acc[nf2s * tid2 + k];
+      a.finish();
+      if (a.num == 0) continue;
+      num_all += a.num;
+      for (int i = 0; i < 169; i++) accH[i] += (double)a.H[i];
+    }
+    for (int i = 0; i < 169; i++) lastTopBlocks[(size_t)k * 169 + i] = (float)accH[i];   // (exact for one worker)
+    if (num_all == 0) continue;
     double A88[64], A8C[32], ACC[16], b8[8], bC[4];
     for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) A88[i * 8 + j] = accH[(CPARS + i) * 13 + CPARS + j];
     for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) A8C[i * 4 + j] = accH[(CPARS + i) * 13 + j];
@@ -562,15 +573,23 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
 // AccumulatedSCHessianSSE::addPoint (AccumulatedSCHessian.cpp:34-103) + stitchDoubleInternal tid=-1 (:106-195)
 void BAWindow::accumulateSC(bool shiftPriorToZero, std::vector<double>& H, std::vector<double>& b) {
   const int nf = n(), d = dim(), nf2 = nf * nf;
-  std::vector<AccumulatorXX<8, 4>> accE(nf2);
-  std::vector<AccumulatorX<8>> accEB(nf2);
-  std::vector<AccumulatorXX<8, 8>> accD((size_t)nf2 * nf);
-  AccumulatorXX<4, 4> accHcc; AccumulatorX<4> accbc;
-  for (auto& a : accE) a.initialize();
-  for (auto& a : accEB) a.initialize();
-  for (auto& a : accD) a.initialize();
-  accHcc.initialize(); accbc.initialize();
-  for (auto& p : points) {
+  const int NT = reduce_threads > 1 ? reduce_threads : 1;   // per-worker accumulator sets (AccumulatedSCHessian.h:52-72)
+  std::vector<AccumulatorXX<8, 4>> accE_all((size_t)nf2 * NT);
+  std::vector<AccumulatorX<8>> accEB_all((size_t)nf2 * NT);
+  std::vector<AccumulatorXX<8, 8>> accD_all((size_t)nf2 * nf * NT);
+  std::vector<AccumulatorXX<4, 4>> accHcc_all(NT); std::vector<AccumulatorX<4>> accbc_all(NT);
+  for (auto& a : accE_all) a.initialize();
+  for (auto& a : accEB_all) a.initialize();
+  for (auto& a : accD_all) a.initialize();
+  for (auto& a : accHcc_all) a.initialize();
+  for (auto& a : accbc_all) a.initialize();
+  for (size_t pi_ = 0; pi_ < points.size(); pi_++) {
+    auto& p = points[pi_];
+    const int tid = reduce_tid((int)pi_);
+    AccumulatorXX<8, 4>* accE = &accE_all[(size_t)nf2 * tid];
+    AccumulatorX<8>* accEB = &accEB_all[(size_t)nf2 * tid];
+    AccumulatorXX<8, 8>* accD = &accD_all[(size_t)nf2 * nf * tid];
+    AccumulatorXX<4, 4>& accHcc = accHcc_all[tid]; AccumulatorX<4>& accbc = accbc_all[tid];
     if (!shiftPriorToZero && p.stateFlag != 1) continue;  // marginalizePointsF path: only PS_MARGINALIZE points
     int ngoodres = 0;
     for (int ri : p.residuals) if (res[ri].isActive()) ngoodres++;
@@ -602,10 +621,15 @@ void BAWindow::accumulateSC(bool shiftPriorToZero, std::vector<double>& H, std::
   for (int k = 0; k < nf2; k++) {
     int i = k % nf, j = k / nf;
     int iIdx = CPARS + i * 8, jIdx = CPARS + j * 8, ijIdx = i + nf * j;
-    accE[ijIdx].finish(); accEB[ijIdx].finish();
     double Hpc[32], bp[8];
-    for (int q = 0; q < 32; q++) Hpc[q] = accE[ijIdx].A1m[q];
-    for (int q = 0; q < 8; q++) bp[q] = accEB[ijIdx].A1m[q];
+    for (int q = 0; q < 32; q++) Hpc[q] = 0;
+    for (int q = 0; q < 8; q++) bp[q] = 0;
+    for (int tid2 = 0; tid2 < NT; tid2++) {   // sum of all workers (:140-146)
+      auto& aE = accE_all[(size_t)nf2 * tid2 + ijIdx]; auto& aEB = accEB_all[(size_t)nf2 * tid2 + ijIdx];
+      aE.finish(); aEB.finish();
+      for (int q = 0; q < 32; q++) Hpc[q] += (double)aE.A1m[q];
+      for (int q = 0; q < 8; q++) bp[q] += (double)aEB.A1m[q];
+    }
     const double* AH = &adHost[(size_t)ijIdx * 64]; const double* AT = &adTarget[(size_t)ijIdx * 64];
     for (int r = 0; r < 8; r++) {
       for (int c = 0; c < 4; c++) {
@@ -619,10 +643,17 @@ void BAWindow::accumulateSC(bool shiftPriorToZero, std::vector<double>& H, std::
     }
     for (int kk = 0; kk < nf; kk++) {
       int kIdx = CPARS + kk * 8, ijkIdx = ijIdx + kk * nf2, ikIdx = i + nf * kk;
-      accD[ijkIdx].finish();
-      if (accD[ijkIdx].num == 0) continue;
       double Dm[64];
-      for (int q = 0; q < 64; q++) Dm[q] = accD[ijkIdx].A1m[q];
+      for (int q = 0; q < 64; q++) Dm[q] = 0;
+      size_t numD = 0;
+      for (int tid2 = 0; tid2 < NT; tid2++) {   // (:163-168)
+        auto& aD = accD_all[(size_t)nf2 * nf * tid2 + ijkIdx];
+        aD.finish();
+        if (aD.num == 0) continue;
+        numD += aD.num;
+        for (int q = 0; q < 64; q++) Dm[q] += (double)aD.A1m[q];
+      }
+      if (numD == 0) continue;
       const double* AHik = &adHost[(size_t)ikIdx * 64]; const double* ATik = &adTarget[(size_t)ikIdx * 64];
       addABt(H, d, iIdx, iIdx, AH, Dm, AHik);
       addABt(H, d, jIdx, kIdx, AT, Dm, ATik);
@@ -630,8 +661,10 @@ void BAWindow::accumulateSC(bool shiftPriorToZero, std::vector<double>& H, std::
       addABt(H, d, iIdx, kIdx, AH, Dm, ATik);
     }
   }
-  accHcc.finish(); accbc.finish();
-  for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) M(H, d, i, j) += accHcc.A1m[i * 4 + j]; b[i] += accbc.A1m[i]; }
+  for (int tid2 = 0; tid2 < NT; tid2++) {   // (:183-190)
+    accHcc_all[tid2].finish(); accbc_all[tid2].finish();
+    for (int i = 0; i < 4; i++) { for (int j = 0; j < 4; j++) M(H, d, i, j) += accHcc_all[tid2].A1m[i * 4 + j]; b[i] += accbc_all[tid2].A1m[i]; }
+  }
   for (int h = 0; h < nf; h++) {  // .h:130-134
     int hIdx = CPARS + h * 8;
     for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) M(H, d, i, hIdx + j) = M(H, d, hIdx + j, i);

@@ -142,6 +142,43 @@ void orc_se3_exp(const double a[6], double T[12]) { SE3::exp(a).toMat34(T); }
 void orc_se3_log(const double T[12], double a[6]) { SE3::fromMat34(T).log(a); }
 void orc_se3_adj(const double T[12], double A[36]) { SE3::fromMat34(T).Adj(A); }
 void orc_se3_mul(const double A[12], const double B[12], double C[12]) { (SE3::fromMat34(A) * SE3::fromMat34(B)).toMat34(C); }
+// V1-V5 oplusImpl (dso_g2o_vertex.cpp:15-18, 30-40, 56-58, 73-88, 100-106); kinds numbered as in include/sdso_b200.h
+void orc_vertex_oplus(int kind, int n, double* est, const double* upd, const double* aux) {
+  for (int i = 0; i < n; i++) {
+    switch (kind) {
+      case 1: { SE3 T = SE3::exp(upd + 6 * i) * SE3::fromMat34(est + 12 * i); T.toMat34(est + 12 * i); break; }
+      case 2: est[2 * i] += upd[2 * i]; est[2 * i + 1] += upd[2 * i + 1]; break;
+      case 3: est[i] += upd[i]; break;
+      case 4: {
+        double update = upd[i];
+        if (update < -0.5) update = -0.5;
+        else if (update > 0.5) update = 0.5;
+        else if (!std::isfinite(update)) update = 0;
+        est[2 * i] += update * aux[2 * i]; est[2 * i + 1] += update * aux[2 * i + 1];
+        break;
+      }
+      case 5: for (int k = 0; k < 4; k++) est[4 * i + k] += upd[4 * i + k]; break;
+    }
+  }
+}
+// E3: EdgeTracePointUVDSO::computeError + linearizeOplus (dso_g2o_edge.cpp:571-619); error / J keep their previous contents where
+// the edge leaves its members untouched
+void orc_edge_trace_uv(void* p, int fid, int n, const double* uv, const float* rot, const double* meas, const float aff[2], const double* dxdy,
+                       double* err, double* J, int* flag) {
+  Ctx* c = (Ctx*)p;
+  const Frame& f = *c->frames[fid];
+  const int wl = c->G.w[0] - 3, hl = c->G.h[0] - 3;
+  for (int i = 0; i < n; i++) {
+    const double U = uv[2 * i], V = uv[2 * i + 1];
+    if ((U - 2) < 0 || (U + 3) > wl || (V - 2) < 0 || (V + 3) > hl) { err[i] = 0.0; if (flag) flag[i] = 0; continue; }
+    float hit[3];
+    getInterpolatedElement33(f.dIp[0].data(), (float)(U + rot[2 * i]), (float)(V + rot[2 * i + 1]), c->G.w[0], hit);
+    if (!std::isfinite(hit[0])) { if (flag) flag[i] = 2; continue; }
+    err[i] = hit[0] - (aff[0] * meas[i] + aff[1]);
+    J[i] = dxdy[2 * i] * hit[1] + dxdy[2 * i + 1] * hit[2];
+    if (flag) flag[i] = 1;
+  }
+}
 void orc_se3_inv(const double A[12], double B[12]) { SE3::fromMat34(A).inverse().toMat34(B); }
 void orc_ldlt_solve(int n, const double* A, const double* b, double* x) { ldlt_solve(n, A, b, x); }
 
@@ -338,6 +375,8 @@ void orc_trace_stereo(void* p, int fid, const float K[9], int mode_right, int n,
 }  // extern "C"
 
 extern "C" {
+// worker partition of the accumulators (oracle_ba.hpp: reduce_threads / reduce_seed); 1, 0 = the single-threaded path
+void orc_ba_set_reduce(void* p, int threads, unsigned seed) { Ctx* c = (Ctx*)p; c->ba.reduce_threads = threads; c->ba.reduce_seed = seed; }
 double orc_ba_optimize(void* p, int iters, int* done) { return ((Ctx*)p)->ba.optimize(iters, done); }
 float orc_ba_new_frame_energy_th(void* p) { return ((Ctx*)p)->ba.newFrameEnergyTH(); }
 // frame states [n][10], world-to-camera [n][12], point idepths [P], calibration value_scaled [4]

@@ -97,6 +97,22 @@ struct BAWindow {
   float cPriorF[4], cDeltaF[4];
   std::vector<double> HM, bM;              // (4+8n)^2, 4+8n
   std::vector<std::vector<double>> lastNullspaces_pose, lastNullspaces_scale;
+  // Model of the reference's multi-threaded accumulation (IndexThreadReduce.h:69-123 driven by EnergyFunctional.cpp:214-257:
+  // chunks of 50 points of allPoints go to whichever of the NUM_THREADS=6 workers asks next, each worker owns a float accumulator set,
+  // the stitch sums the sets in double, AccumulatedTopHessian.cpp:299-308 / AccumulatedSCHessian.cpp:140-146). reduce_threads = 1 is
+  // the reference's single-threaded path (tid = -1); reduce_seed picks the chunk -> worker assignment (0: round robin) — the
+  // reference's own assignment is a race, so ANY seed is a result the reference can produce. Used by the tests that measure the
+  // oracle's own run-to-run spread (tests/test_oracle_spread.py).
+  int reduce_threads = 1;
+  unsigned reduce_seed = 0;
+  int reduce_tid(int point_index) const {
+    if (reduce_threads <= 1) return 0;
+    unsigned c = (unsigned)(point_index / 50);
+    if (reduce_seed == 0) return (int)(c % (unsigned)reduce_threads);
+    unsigned x = c * 2654435761u ^ (reduce_seed * 0x9E3779B9u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return (int)(x % (unsigned)reduce_threads);
+  }
   int n() const { return (int)frames.size(); }
   int dim() const { return CPARS + 8 * n(); }
 

@@ -498,6 +498,42 @@ Context.trace_stereo = _trace_stereo
 
 
 # ---------------------------------------------------------------------------------------------------
+# V1-V5, E3: g2o vertices / trace edge as operators over SoA batches
+VERTEX_SE3_POSE, VERTEX_PHOTOMETRIC, VERTEX_INVERSE_DEPTH, VERTEX_UV, VERTEX_CAM = 1, 2, 3, 4, 5
+lib.sdso_vertex_oplus.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
+lib.sdso_edge_trace_uv_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _fp, _dp, _fp, _dp, _dp, _dp, _ip]
+
+
+def _vertex_oplus(self, kind, estimate, update, aux=None):
+    """oplusImpl of a batch of vertices of one kind; returns the updated estimates (same shape as `estimate`)."""
+    est = np.array(estimate, np.float64, order="C")
+    shape = est.shape
+    width = {VERTEX_SE3_POSE: 12, VERTEX_PHOTOMETRIC: 2, VERTEX_INVERSE_DEPTH: 1, VERTEX_UV: 2, VERTEX_CAM: 4}[kind]
+    n = est.size // width
+    upd = _f64(update)
+    a = _f64(aux) if aux is not None else None
+    self._ck(lib.sdso_vertex_oplus(self._h, kind, n, _ptr(est, _dp), _ptr(upd, _dp), _ptr(a, _dp) if a is not None else None))
+    return est.reshape(shape)
+
+
+def _edge_trace_uv_eval(self, fid, uv, rot, meas, aff, dxdy, error=None, J=None):
+    """EdgeTracePointUVDSO computeError + linearizeOplus for n edges; error / J (optional) carry the members' previous contents."""
+    uv_, rot_, me_, dx_ = _f64(uv).reshape(-1, 2), _f32(rot).reshape(-1, 2), _f64(meas).reshape(-1), _f64(dxdy).reshape(-1, 2)
+    n = uv_.shape[0]
+    a_ = _f32(aff).reshape(2)
+    err = np.zeros(n) if error is None else np.array(error, np.float64)
+    Jo = np.zeros(n) if J is None else np.array(J, np.float64)
+    flag = np.zeros(n, np.int32)
+    self._ck(lib.sdso_edge_trace_uv_eval(self._h, fid, n, _ptr(uv_, _dp), _ptr(rot_, _fp), _ptr(me_, _dp), _ptr(a_, _fp), _ptr(dx_, _dp),
+                                         _ptr(err, _dp), _ptr(Jo, _dp), _ptr(flag, _ip)))
+    return err, Jo, flag
+
+
+Context.vertex_oplus = _vertex_oplus
+Context.edge_trace_uv_eval = _edge_trace_uv_eval
+
+
+# ---------------------------------------------------------------------------------------------------
 # point-sharded windowed BA (SURVEY.md 8e)
 lib.sdso_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip]
 lib.sdso_ba_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]

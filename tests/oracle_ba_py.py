@@ -37,6 +37,7 @@ lib.orc_ba_orthogonalize.argtypes = [V, _dp, _dp]
 lib.orc_ba_energies.restype = C.c_double
 lib.orc_ba_energies.argtypes = [V, _dp]
 lib.orc_ba_nullspaces.argtypes = [V, _dp]
+lib.orc_ba_set_reduce.argtypes = [V, C.c_int, C.c_uint]
 
 _p = O._p
 _f32, _f64 = O._f32, O._f64
@@ -135,6 +136,11 @@ class OracleBA:
         H, b = np.zeros((d, d)), np.zeros(d)
         lib.orc_ba_accumulate_sc(self.h, int(shift), _p(H, _dp), _p(b, _dp))
         return H, b
+
+    def set_reduce(self, threads=1, seed=0):
+        """Worker partition of the float accumulators (the reference's NUM_THREADS=6 IndexThreadReduce; any seed is an assignment the
+        reference's dynamic chunk queue can produce). (1, 0) = the single-threaded path."""
+        lib.orc_ba_set_reduce(self.h, threads, seed)
 
     def solve(self, iteration, lam=1e-5):
         d = self.counts()["dim"]

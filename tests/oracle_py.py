@@ -74,6 +74,32 @@ lib.orc_se3_mul.argtypes = [_dp, _dp, _dp]
 lib.orc_ldlt_solve.argtypes = [C.c_int, _dp, _dp, _dp]
 
 
+lib.orc_vertex_oplus.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
+lib.orc_edge_trace_uv.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _fp, _dp, _fp, _dp, _dp, _dp, _ip]
+
+
+def vertex_oplus(kind, estimate, update, aux=None):
+    """V1-V5 oplusImpl (dso_g2o_vertex.cpp); kind 1 pose, 2 photometric, 3 inverse depth, 4 uv, 5 camera."""
+    est = np.array(estimate, np.float64, order="C")
+    width = {1: 12, 2: 2, 3: 1, 4: 2, 5: 4}[kind]
+    upd = _f64(update)
+    a = _f64(aux) if aux is not None else None
+    lib.orc_vertex_oplus(kind, est.size // width, _p(est, _dp), _p(upd, _dp), _p(a, _dp) if a is not None else None)
+    return est
+
+
+def edge_trace_uv(orc, fid, uv, rot, meas, aff, dxdy, error=None, J=None):
+    """E3 computeError + linearizeOplus (dso_g2o_edge.cpp:571-619)."""
+    uv_, rot_, me_, dx_ = _f64(uv).reshape(-1, 2), _f32(rot).reshape(-1, 2), _f64(meas).reshape(-1), _f64(dxdy).reshape(-1, 2)
+    n = uv_.shape[0]
+    a_ = _f32(aff).reshape(2)
+    err = np.zeros(n) if error is None else np.array(error, np.float64)
+    Jo = np.zeros(n) if J is None else np.array(J, np.float64)
+    flag = np.zeros(n, np.int32)
+    lib.orc_edge_trace_uv(orc._h, fid, n, _p(uv_, _dp), _p(rot_, _fp), _p(me_, _dp), _p(a_, _fp), _p(dx_, _dp), _p(err, _dp), _p(Jo, _dp), _p(flag, _ip))
+    return err, Jo, flag
+
+
 def se3_exp(a):
     a = _f64(a)
     T = np.zeros(12)

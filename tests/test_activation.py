@@ -8,7 +8,8 @@ import ba_synth
 import synth
 import trace_synth as TS
 
-W_, H_, K_ = 640, 192, (360.0, 360.0, 319.5, 95.5)
+SHAPES = {"640x192-n4": (640, 192, (360.0, 360.0, 319.5, 95.5), 4, 80, 150),
+          "1232x368-n7": (synth.W, synth.H, synth.K4, 7, 140, 220)}   # config-3 window (7 key frames at the KITTI working resolution)
 
 
 def candidates(win, orc, fids, rng, per_host=150, noise=0.15):
@@ -25,12 +26,14 @@ def candidates(win, orc, fids, rng, per_host=150, noise=0.15):
     return np.concatenate(pts_all), np.concatenate(host_all), np.concatenate(true_all)
 
 
-@pytest.fixture(scope="module")
-def window(scene):
-    win = ba_synth.make_window(scene, n=4, P=80, seed=8, spacing=0.5, w=W_, h=H_, K=K_)
+@pytest.fixture(scope="module", params=list(SHAPES))
+def window(scene, request):
+    W_, H_, K_, n, P, per_host = SHAPES[request.param]
+    win = ba_synth.make_window(scene, n=n, P=P, seed=8, spacing=0.5, w=W_, h=H_, K=K_)
+    win["shape"] = (W_, H_, K_)
     orc = O.Oracle(W_, H_, K_, synth.BASELINE)
     ba, fids, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)
-    pts, host, tid = candidates(win, orc, fids, np.random.default_rng(5))
+    pts, host, tid = candidates(win, orc, fids, np.random.default_rng(5), per_host=per_host)
     return win, orc, ba, cw, pts, host, tid
 
 
@@ -56,6 +59,7 @@ def test_oracle_g2o_activation_keeps_the_initial_inverse_depth(window):
 @pytest.mark.parametrize("variant", [0, 1])
 def test_gpu_activation_matches_oracle(pkg, window, variant):
     win, orc, ba, cw, pts, host, tid = window
+    W_, H_, K_ = win["shape"]
     ctx = pkg.Context(W_, H_, K_, synth.BASELINE)
     Wd, _ = ba_synth.fill_device(win, ctx, pkg.Window, cw)
     rng = np.random.default_rng(1)

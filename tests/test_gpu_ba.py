@@ -2,7 +2,17 @@
 
 Tolerances (north_star): ResState / active flags / integer outputs bit-exact; residuals, Jacobians, Hessians,
 solved increments relative 1e-4. Matrices whose entries span many decades (priors 1e10-1e14 next to photometric
-terms) are compared block-wise against the block's own magnitude."""
+terms) are compared block-wise against the block's own magnitude.
+
+Where a quantity is ill-conditioned with respect to the float summation order of the accumulators (the solve along the
+gauge directions, everything downstream of it), the reference itself does not reproduce it: its accumulation runs on six
+workers fed from a dynamic chunk queue (IndexThreadReduce.h:69-123, EnergyFunctional.cpp:214-257), so the partition of the
+float sums is a race. Those assertions are "device within the ORACLE'S OWN spread": the oracle is re-run with the 6-worker
+partition under several chunk->worker assignments (OracleBA.set_reduce) and the tolerance is max(1e-4, 3 x that spread),
+measured in the test, never a constant above north_star. tests/test_oracle_spread.py shows the spread on the CPU.
+
+Configurations: `small` (4 key frames, 640x192), `window7` = SURVEY config 3 as written (7 key frames, 2002 points, ~12k residuals,
+1232x368), `dense10` = config 4 (10 key frames, 20 000 points, 180 000 residuals, 1920x1088, SSE semantics)."""
 import numpy as np
 import pytest
 import oracle_py as O
@@ -32,10 +42,44 @@ def small(pkg, scene):
 
 @pytest.fixture(scope="module")
 def window7(pkg, scene):
-    """SURVEY config 3 shape at reduced resolution: 7 keyframes, 2000 points, ~12k residuals."""
-    out = build(pkg, scene, 7, 2002, 11, spacing=0.35)
+    """SURVEY config 3 as written: 7 keyframes, 2002 points, ~12k residuals, 1232x368."""
+    out = build(pkg, scene, 7, 2002, 11, w=synth.W, h=synth.H, K=synth.K4, spacing=0.35)
     yield out
     out[3].close()
+
+
+DENSE_K = (1100.0, 1100.0, 959.5, 543.5)
+
+
+@pytest.fixture(scope="module")
+def dense10(pkg, scene):
+    """SURVEY config 4: 1920x1088 (6 levels), 10 keyframes, 20 000 points, 180 000 residuals."""
+    out = build(pkg, scene, 10, 20000, 12, w=1920, h=1088, K=DENSE_K, spacing=0.3)
+    yield out
+    out[3].close()
+
+
+SPREAD_SEEDS = (0, 1, 2, 3)
+
+
+def gauge_projector(ba, n):
+    """Orthogonal projector off the 7 gauge directions + the global brightness gauge (a common shift of every frame's a, resp. b;
+    affine priors are 0 for frameID != 0), which the reference's orthogonalisation does not remove either."""
+    N = ba.nullspaces()
+    d = N.shape[0]
+    A2 = np.zeros((d, 2)); A2[10::8, 0] = 1; A2[11::8, 1] = 1
+    Qa, _ = np.linalg.qr(np.hstack([N / np.linalg.norm(N, axis=0), A2]))
+    return lambda v: v - Qa @ (Qa.T @ v)
+
+
+def block_err(a, b, n):
+    """max over the (calib | frame) blocks of |a - b| / max(|b| of the block, 1e-2 of the vector's scale)"""
+    glob = np.abs(b).max()
+    worst = 0.0
+    for lo, hi in [(0, 4)] + [(4 + 8 * i, 12 + 8 * i) for i in range(n)]:
+        s = max(np.abs(b[lo:hi]).max(), 1e-2 * glob)
+        worst = max(worst, float(np.abs(a[lo:hi] - b[lo:hi]).max() / s))
+    return worst
 
 
 def blockwise_close(A, B, n, rel=REL):
@@ -67,9 +111,10 @@ def test_precalc_adjoints_nullspaces(small):
     assert np.allclose(W.nullspaces(), ba.nullspaces(), rtol=1e-6, atol=1e-9)
 
 
-def test_linearize_states_energies_jacobians(small):
+@pytest.mark.parametrize("fixture_name", ["small", "window7", "dense10"])
+def test_linearize_states_energies_jacobians(fixture_name, request):
     """B1: ResState / energies bit-exact given identical precalcs; all 74 floats of RawResidualJacobian rel 1e-4."""
-    win, orc, ba, ctx, W = small
+    win, orc, ba, ctx, W = request.getfixturevalue(fixture_name)
     Eo = ba.linearize_all(False)
     Eg = W.linearize_all(False)
     ro, rg = ba.get_res(0), W.get_res(0)
@@ -85,9 +130,10 @@ def test_linearize_states_energies_jacobians(small):
     assert np.allclose(rg["center"][ok], ro["center"][ok], rtol=1e-6)
 
 
-def test_apply_res_takes_jacobians(small):
+@pytest.mark.parametrize("fixture_name", ["small", "window7"])
+def test_apply_res_takes_jacobians(fixture_name, request):
     """B3: applyRes(true) swaps J into the EF mirror and forms JpJdF."""
-    win, orc, ba, ctx, W = small
+    win, orc, ba, ctx, W = request.getfixturevalue(fixture_name)
     ba.linearize_all(False); W.linearize_all(False)
     ba.apply_res(True); W.apply_res(True)
     ro, rg = ba.get_res(1), W.get_res(1)
@@ -99,7 +145,7 @@ def test_apply_res_takes_jacobians(small):
     assert np.all(np.abs(rg["JpJdF"][act] - ro["JpJdF"][act]) <= REL * np.maximum(np.abs(ro["JpJdF"][act]), 1e-3 * s))
 
 
-@pytest.mark.parametrize("fixture_name", ["small", "window7"])
+@pytest.mark.parametrize("fixture_name", ["small", "window7", "dense10"])
 def test_top_and_schur_accumulators(fixture_name, request):
     """B4-B7: per-(h,t) 13x13 blocks, stitched H_top/b_top (active), H_sc/b_sc, per-point Hdd/bd/Hcd/HdiF."""
     win, orc, ba, ctx, W = request.getfixturevalue(fixture_name)
@@ -157,41 +203,56 @@ def test_linearized_mode_uses_res_to_zero(small):
 
 
 @pytest.mark.parametrize("iteration", [0, 2])
-@pytest.mark.parametrize("fixture_name", ["small", "window7"])
+@pytest.mark.parametrize("fixture_name", ["small", "window7", "dense10"])
 def test_solve_and_resubstitute(fixture_name, iteration, request):
-    """B8/B9: HFinal, bFinal, x (orthogonalised from iteration 2), frame / calib / point steps."""
+    """B8/B9: HFinal, bFinal, x (orthogonalised from iteration 2), frame / calib / point steps.
+
+    H and b agree block-wise to 1e-4. x is compared (a) as solved, (b) with the gauge directions projected out of both sides;
+    each against max(1e-4, 3 x the oracle's own spread of the same quantity under the reference's 6-worker accumulation). Before
+    iteration 2 the reduced system is held along the 7 gauge directions only by the 1e-5 damping, so the oracle's own x moves by
+    1e-3..1e-2 relative there from one worker assignment to the next — (a) shows the device is inside that, (b) that the
+    well-conditioned part is right."""
     win, orc, ba, ctx, W = request.getfixturevalue(fixture_name)
     n = win["n"]
+    ba.set_reduce(1, 0)
     ba.linearize_all(True); W.linearize_all(True)
     xo, Hfo, bfo = ba.solve(iteration)
     xg, Hfg, bfg = W.solve(iteration)
     ok, why = blockwise_close(Hfg, Hfo, n)
     assert ok, why
     assert np.allclose(bfg, bfo, rtol=REL, atol=REL * np.abs(bfo).max())
-    # The un-orthogonalised solve (iteration < 2) is free along the 7 gauge directions (the reduced system is only held
-    # there by the 1e-5 damping), so float accumulation noise of H moves x along them by ~1e-2 relative — in the oracle
-    # itself as much as on the device (tools/diag_ba.py). Parity is therefore asserted on the gauge-free part; from
-    # iteration 2 on the reference orthogonalises x and the comparison is direct.
-    N = ba.nullspaces()
-    Q, _ = np.linalg.qr(N / np.linalg.norm(N, axis=0))
-    # the global brightness gauge (a common shift of every frame's a, resp. b; affine priors are 0 for frameID != 0) is
-    # not removed by the reference's orthogonalisation either, so it is projected out of BOTH solutions here
-    d = xo.size
-    A2 = np.zeros((d, 2)); A2[10::8, 0] = 1; A2[11::8, 1] = 1
-    Qa, _ = np.linalg.qr(np.hstack([N / np.linalg.norm(N, axis=0), A2]))
-    po_, pg_ = xo - Qa @ (Qa.T @ xo), xg - Qa @ (Qa.T @ xg)
-    glob = np.abs(po_).max()
-    for lo, hi in [(0, 4)] + [(4 + 8 * i, 12 + 8 * i) for i in range(n)]:
-        s = max(np.abs(po_[lo:hi]).max(), 1e-2 * glob)
-        assert np.abs(pg_[lo:hi] - po_[lo:hi]).max() <= 3e-4 * s, (lo, float(np.abs(pg_[lo:hi] - po_[lo:hi]).max()), float(s))
-    if iteration >= 2:
-        assert np.abs(Q.T @ xg).max() <= 1e-9 * np.abs(xg).max() + 1e-15, "x must be orthogonal to the gauge nullspace"
-    # back-substitution with the ORACLE's x isolates B9 from the conditioning of the solve
+    proj = gauge_projector(ba, n)
+    # B9 with the ORACLE's x isolates the back-substitution from the conditioning of the solve: same float operations in the same
+    # order on both sides
     fso, cso = ba.resubstitute(xo)
     fsg, csg = W.resubstitute(xo)
     assert np.allclose(fsg, fso, rtol=1e-12) and np.allclose(csg, cso, rtol=1e-12)
-    so, sg = ba.get_points()["step"], W.get_points()["step"]
-    assert np.allclose(sg, so, rtol=1e-3, atol=1e-4 * np.abs(so).max())
+    so, sg = ba.get_points()["step"].copy(), W.get_points()["step"].copy()
+    assert np.allclose(sg, so, rtol=1e-6, atol=1e-7 * np.abs(so).max())
+    # the device's own solve + back-substitution
+    W.solve(iteration); W.resubstitute(None)
+    sg_own = W.get_points()["step"].copy()
+    # the oracle's own spread
+    sp_raw = sp_proj = sp_step = 0.0
+    for seed in SPREAD_SEEDS:
+        ba.set_reduce(6, seed)
+        x2, _, _ = ba.solve(iteration)
+        ba.resubstitute(x2)
+        s2 = ba.get_points()["step"]
+        sp_raw = max(sp_raw, block_err(x2, xo, n)); sp_proj = max(sp_proj, block_err(proj(x2), proj(xo), n))
+        sp_step = max(sp_step, float(np.abs(s2 - so).max() / np.abs(so).max()))
+    ba.set_reduce(1, 0)
+    ba.solve(iteration); ba.resubstitute(xo)   # leave the oracle window as the single-threaded path left it
+    e_raw, e_proj = block_err(xg, xo, n), block_err(proj(xg), proj(xo), n)
+    e_step = float(np.abs(sg_own - so).max() / np.abs(so).max())
+    assert e_raw <= max(REL, 3 * sp_raw), (e_raw, sp_raw)
+    assert e_proj <= max(REL, 3 * sp_proj), (e_proj, sp_proj)
+    assert e_step <= max(REL, 3 * sp_step), (e_step, sp_step)
+    if iteration >= 2:
+        N = ba.nullspaces()
+        Q, _ = np.linalg.qr(N / np.linalg.norm(N, axis=0))
+        assert np.abs(Q.T @ xg).max() <= 1e-9 * np.abs(xg).max() + 1e-15, "x must be orthogonal to the gauge nullspace"
+        assert sp_raw < 1e-3   # once orthogonalised the solve is well conditioned in the oracle too
 
 
 def test_marginalisation_prior_enters_the_system(small):
@@ -239,7 +300,7 @@ def test_empty_and_degenerate_windows(pkg, scene):
     po, pg = ba.get_points(), W.get_points()
     assert np.array_equal(pg["HdiF"] == 0, po["HdiF"] == 0)
     assert np.abs(po["step"]).max() > 0
-    assert np.allclose(pg["step"], po["step"], rtol=1e-3, atol=1e-4 * np.abs(po["step"]).max())
+    assert np.allclose(pg["step"], po["step"], rtol=1e-6, atol=1e-7 * np.abs(po["step"]).max())   # same x on both sides
     ctx.close()
 
 
@@ -250,36 +311,58 @@ def test_new_frame_energy_threshold_is_exact(small):
     assert W.new_frame_energy_th() == ba.new_frame_energy_th()
 
 
-@pytest.mark.parametrize("shape", [(4, 300, 21), (7, 1400, 22)])
+OPT_SHAPES = {
+    "small": dict(n=4, P=300, seed=21, w=640, h=192, K=(360.0, 360.0, 319.5, 95.5), spacing=0.5),
+    "config3": dict(n=7, P=2002, seed=22, w=synth.W, h=synth.H, K=synth.K4, spacing=0.5),
+    "config4": dict(n=10, P=20000, seed=23, w=1920, h=1088, K=DENSE_K, spacing=0.42),
+}
+
+
+@pytest.mark.parametrize("shape", ["small", "config3", "config4"])
 def test_optimize_matches_oracle(pkg, scene, shape):
-    """B12: FullSystem::optimize (SSE body, forced accept): same iteration count, final frame states / idepths / energy close to the
-    oracle's. The first two iterations are not gauge-orthogonalised, so absolute states carry the gauge noise of the solve
-    (see test_solve_and_resubstitute); inverse depths and the final RMSE are gauge-free to first order."""
-    n, P, seed = shape
-    win = ba_synth.make_window(scene, n=n, P=P, seed=seed, spacing=0.5, w=640, h=192, K=(360.0, 360.0, 319.5, 95.5), idepth_noise=0.03,
+    """B12: FullSystem::optimize (SSE body, forced accept) at config 3 (1232x368) and config 4 (1920x1088, 10 KF, 20k points): same
+    iteration count; key-frame poses within north_star's 1e-4 (m, and matrix entries) of the oracle's; energy, inverse depths
+    and the active set within max(north_star, 3 x the oracle's own spread under the reference's 6-worker accumulation) — a residual
+    whose energy sits on the outlier threshold flips IN/OUTLIER under float summation noise in the oracle itself and moves its
+    point, which is why inverse depths are asserted as a distribution and compared with the oracle's own distribution."""
+    c = OPT_SHAPES[shape]
+    n = c["n"]
+    win = ba_synth.make_window(scene, n=n, P=c["P"], seed=c["seed"], spacing=c["spacing"], w=c["w"], h=c["h"], K=c["K"], idepth_noise=0.03,
                                state_sigma=3e-3)
-    orc = O.Oracle(640, 192, (360.0, 360.0, 319.5, 95.5), synth.BASELINE)
-    ba, _, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)
-    ctx = pkg.Context(640, 192, (360.0, 360.0, 319.5, 95.5), synth.BASELINE)
+
+    def oracle_run(threads, seed):
+        orc = O.Oracle(c["w"], c["h"], c["K"], synth.BASELINE)
+        ba, _, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)
+        ba.set_reduce(threads, seed)
+        r, it = ba.optimize(6)
+        return r, it, ba.get_state(), ba.get_res(1)["active"].copy(), cw
+
+    ro, io, so, ao, cw = oracle_run(1, 0)
+    ctx = pkg.Context(c["w"], c["h"], c["K"], synth.BASELINE)
     W, _ = ba_synth.fill_device(win, ctx, pkg.Window, cw)
-    ro, io = ba.optimize(6)
     rg, ig = W.optimize(6)
+    sg, ag = W.get_state(), W.get_res(1)["active"]
     assert ig == io
-    so, sg = ba.get_state(), W.get_state()
-    assert np.isclose(rg, ro, rtol=2e-3)
+
+    def metrics(r, s, a):
+        rel = np.abs(s["idepth"] - so["idepth"]) / np.abs(so["idepth"])
+        return dict(rmse=abs(r - ro) / ro, pose=float(np.abs(s["T_w2c"] - so["T_w2c"]).max()), med=float(np.median(rel)),
+                    frac=float((rel < REL).mean()), p995=float(np.quantile(rel, 0.995)), act=float((a != ao).mean()))
+
+    spread = [metrics(r, s, a) for r, _, s, a, _ in (oracle_run(6, seed) for seed in SPREAD_SEEDS[:3])]
+    worst = {k: max(m[k] for m in spread) for k in spread[0]}
+    best_frac = min(m["frac"] for m in spread)
+    g = metrics(rg, sg, ag)
     true_id = np.array([1.0 / win["frames"][p["host"]]["depth"][int(p["v"]), int(p["u"])] for p in win["points"]])
-    # the optimisation must actually have improved the inverse depths, identically on both sides
+    # the optimisation must actually have improved the inverse depths
     assert np.median(np.abs(so["idepth"] - true_id) / true_id) < 0.015
-    # (a residual whose energy sits on the outlier threshold can flip IN/OUTLIER under float summation noise and move its
-    # point; such points are rare and bounded here instead of being hidden by a loose global tolerance)
-    rel = np.abs(sg["idepth"] - so["idepth"]) / np.abs(so["idepth"])
-    assert (rel < 5e-3).mean() > 0.995, float((rel < 5e-3).mean())
-    assert np.median(np.abs(sg["idepth"] - so["idepth"]) / np.abs(so["idepth"])) < 2e-4
-    assert np.abs(sg["T_w2c"] - so["T_w2c"]).max() < 2e-4
+    assert g["pose"] < 1e-4, g                                    # north_star: 1e-4 m
+    assert g["rmse"] <= max(REL, 3 * worst["rmse"]), (g, worst)
+    assert g["med"] < REL, g                                      # the typical point: 1e-4 relative
+    assert g["frac"] >= best_frac - 0.02, (g, best_frac)          # as many points within 1e-4 as the oracle reproduces of itself
+    assert g["p995"] <= max(REL, 3 * worst["p995"]), (g, worst)
+    assert g["act"] <= max(1e-4, 3 * worst["act"]), (g, worst)    # IN/OUTLIER flips: as rare as in the oracle's own re-runs
     assert np.allclose(sg["calib"], so["calib"], rtol=1e-6)
-    ro_, rg_ = ba.get_res(1), W.get_res(1)
-    agree = (ro_["active"] == rg_["active"]).mean()
-    assert agree > 0.995, agree
     ctx.close()
 
 
@@ -338,7 +421,7 @@ def test_lba_edge_error_and_jacobians(window7):
     import lba_edge_inputs as LE
     win, orc, ba, ctx, W = window7
     T_wh, photo, idepth, b0 = LE.make(win, seed=3)
-    cam = LE.cam_vertex((360.0, 360.0, 319.5, 95.5))
+    cam = LE.cam_vertex(synth.K4)
     o = ba.lba_edge_eval(T_wh, photo, idepth, cam, b0)
     g = W.lba_edge_eval(T_wh, photo, idepth, cam, b0)
     assert (g["newState"] == o["newState"]).mean() > 0.9995 and (g["level"] == o["level"]).mean() > 0.9995
@@ -353,12 +436,12 @@ def test_lba_edge_error_and_jacobians(window7):
     assert np.allclose(g["center"][same], o["center"][same], rtol=1e-6, atol=1e-4)
 
 
-@pytest.mark.parametrize("shape", [(5, 500, 3), (7, 1400, 22)])
+@pytest.mark.parametrize("shape", [(5, 500, 3, 640, 192, (360.0, 360.0, 319.5, 95.5)), (7, 2002, 22, synth.W, synth.H, synth.K4)])
 def test_lba_g2o_driver_matches_restated_g2o(pkg, scene, shape):
-    """FullSystem::optimize, g2o body: E2 graph + restated g2o LM with Schur over the per-residual idepth vertices. Iteration-level
-    parity is against the RESTATED driver (oracle/lba_g2o.cpp; g2o is not in the reference tree — unpinned)."""
-    n, P, seed = shape
-    w, h, K = 640, 192, (360.0, 360.0, 319.5, 95.5)
+    """FullSystem::optimize, g2o body: E2 graph + restated g2o LM with Schur over the per-residual idepth vertices (second shape =
+    config 3 as written: 7 key frames, 2002 points, 1232x368). Iteration-level parity is against the RESTATED driver
+    (oracle/lba_g2o.cpp; g2o is not in the reference tree — unpinned)."""
+    n, P, seed, w, h, K = shape
     win = ba_synth.make_window(scene, n=n, P=P, seed=seed, spacing=0.5, w=w, h=h, K=K, idepth_noise=0.03, state_sigma=0)
     orc = O.Oracle(w, h, K, synth.BASELINE)
     ba, _, cw = ba_synth.fill_oracle(win, orc, OB.OracleBA, OB.immature_init)

@@ -14,18 +14,27 @@ import ba_synth
 import synth
 import trace_synth as TS
 
-W_, H_, K_ = 640, 192, (360.0, 360.0, 319.5, 95.5)
-N_KF, N_ACTIVE, PER_HOST, MIN_ACT_DIST = 5, 400, 260, 1.0
+# two shapes: the reduced one and config 3 as written (7 key frames, 2002 active points, 1232x368)
+SHAPES = {"640x192-n5": dict(w=640, h=192, K=(360.0, 360.0, 319.5, 95.5), n_kf=5, n_active=400, per_host=260),
+          "1232x368-n7": dict(w=synth.W, h=synth.H, K=synth.K4, n_kf=7, n_active=2002, per_host=320)}
+MIN_ACT_DIST = 1.0
 
 
 class Backend:
     """the same operator names for the oracle (test infrastructure) and the device library"""
 
-    def __init__(self, pkg=None):
+    def __init__(self, shape, pkg=None, reduce=(1, 0)):
         self.dev = pkg is not None
         self.pkg = pkg
+        self.shape = shape
+        self.reduce = reduce   # oracle only: worker partition of the float accumulators (OracleBA.set_reduce)
+        W_, H_, K_ = shape["w"], shape["h"], shape["K"]
         self.api = pkg.Context(W_, H_, K_, synth.BASELINE) if self.dev else O.Oracle(W_, H_, K_, synth.BASELINE)
         self.dm = None if self.dev else OD.DistMap(self.api)
+
+    def close(self):
+        if self.dev:
+            self.api.close()
 
     def frames(self, win):
         self.fids = []
@@ -69,6 +78,8 @@ class Backend:
                 for t in p["targets"]:
                     Wn.add_residual(q, t)
         Wn.prepare()
+        if not self.dev:
+            Wn.set_reduce(*self.reduce)
         self.W = Wn
         return Wn
 
@@ -93,7 +104,7 @@ class Backend:
                     self.W.set_point_flag(i, int(f))
 
 
-def host_to_newest(win, h, level1=True):
+def host_to_newest(win, h, K_, level1=True):
     """K[1] * R * Ki[0], K[1] * t of host h into the newest key frame (CoarseTracker.cpp:1233-1235), float"""
     newest = win["n"] - 1
     T = synth.T_rel(win["poses"][h], win["poses"][newest])
@@ -104,9 +115,11 @@ def host_to_newest(win, h, level1=True):
     return ((Kt @ R) @ np.linalg.inv(K0).astype(np.float32)).astype(np.float32).reshape(9), (Kt @ t).astype(np.float32)
 
 
-def mapping_step(B, scene):
+def mapping_step(B, scene, win0=None):
     out = {}
-    win = ba_synth.make_window(scene, n=N_KF, P=N_ACTIVE, seed=3, spacing=0.5, w=W_, h=H_, K=K_)
+    W_, H_, K_, PER_HOST = B.shape["w"], B.shape["h"], B.shape["K"], B.shape["per_host"]
+    win = win0 if win0 is not None else make_win(B.shape, scene)
+    win = dict(win); win["points"] = [dict(p) for p in win["points"]]   # the step appends the activated points
     n, newest = win["n"], win["n"] - 1
     B.frames(win)
     # 1. immature candidates of the older key frames, traced into the newest one
@@ -126,7 +139,7 @@ def mapping_step(B, scene):
     out["trace_pts"] = cand.copy()
     # 2. distance map of the active points in the newest frame + the candidate loop
     hosts = list(range(newest))
-    KK = [host_to_newest(win, h) for h in hosts]
+    KK = [host_to_newest(win, h, K_) for h in hosts]
     KRKi1, Kt1 = np.stack([k[0] for k in KK]), np.stack([k[1] for k in KK])
     act = [p for p in win["points"] if p["host"] != newest]
     pt_host = np.array([p["host"] for p in act], np.int32)
@@ -163,19 +176,33 @@ def mapping_step(B, scene):
     return out
 
 
+def make_win(shape, scene):
+    return ba_synth.make_window(scene, n=shape["n_kf"], P=shape["n_active"], seed=3, spacing=0.5, w=shape["w"], h=shape["h"], K=shape["K"])
+
+
 def test_oracle_mapping_step_is_sane(scene):
-    o = mapping_step(Backend(), scene)
+    shape = SHAPES["640x192-n5"]
+    o = mapping_step(Backend(shape), scene)
     assert (o["verdict"] == 1).sum() > 50 and (o["verdict"] == 0).sum() > 50
     assert (o["act_result"] == 1).mean() > 0.5
-    assert o["n_points"] > N_ACTIVE // N_KF * N_KF + 30
+    assert o["n_points"] > shape["n_active"] // shape["n_kf"] * shape["n_kf"] + 30
     assert np.isfinite(o["rmse"]) and o["iterations"] >= 1
     assert np.isfinite(o["HM"]).all() and np.abs(o["HM"]).max() > 0
 
 
 @pytest.mark.gpu
-def test_device_mapping_step_matches_oracle(pkg, scene):
-    o = mapping_step(Backend(), scene)
-    g = mapping_step(Backend(pkg), scene)
+@pytest.mark.parametrize("shape_name", list(SHAPES))
+def test_device_mapping_step_matches_oracle(pkg, scene, shape_name):
+    """Integer results exact; poses within north_star (1e-4 m / 1e-5 rad); the quantities downstream of the windowed solve (RMSE,
+    inverse depths, the marginalisation prior HM / bM formed at the optimised state) within max(1e-4, 3 x the oracle's own spread
+    under the reference's 6-worker float accumulation) — the whole chain is re-run on the oracle with three worker assignments."""
+    shape = SHAPES[shape_name]
+    N_KF = shape["n_kf"]
+    win0 = make_win(shape, scene)
+    o = mapping_step(Backend(shape), scene, win0)
+    Bg = Backend(shape, pkg)
+    g = mapping_step(Bg, scene, win0)
+    Bg.close()
     for h in range(N_KF - 1):
         assert np.array_equal(g[f"trace_status_{h}"], o[f"trace_status_{h}"]), h
     for f in ("idepth_min", "idepth_max", "lastTraceUV", "lastTracePixelInterval", "quality"):
@@ -187,15 +214,25 @@ def test_device_mapping_step_matches_oracle(pkg, scene):
     assert np.array_equal(g["act_result"], o["act_result"]) and np.array_equal(g["act_states"], o["act_states"])
     assert np.allclose(g["act_idepth"], o["act_idepth"], rtol=1e-4, atol=1e-7)
     assert g["n_points"] == o["n_points"] and g["iterations"] == o["iterations"]
-    assert np.isclose(g["rmse"], o["rmse"], rtol=2e-3)
     for k in range(N_KF):
         assert np.abs(g["T_w2c"][k][:, 3] - o["T_w2c"][k][:, 3]).max() < 1e-4, k
         Rg, Ro = g["T_w2c"][k][:, :3], o["T_w2c"][k][:, :3]
         assert np.arccos(np.clip((np.trace(Rg.T @ Ro) - 1) / 2, -1, 1)) < 1e-5, k
-    rel = np.abs(g["idepth"] - o["idepth"]) / np.abs(o["idepth"])
-    assert (rel < 5e-3).mean() > 0.995 and np.median(rel) < 2e-4
-    sc = np.abs(o["HM"]).max()
-    assert np.abs(g["HM"] - o["HM"]).max() < 2e-3 * sc, float(np.abs(g["HM"] - o["HM"]).max() / sc)
-    # bM is the gradient at the optimised state: small numbers made of cancelling terms, so the chained 1e-4 state differences
-    # show up more strongly than in HM (the operator alone, on identical inputs, is held to 1e-4 in tests/test_gpu_ba.py)
-    assert np.abs(g["bM"] - o["bM"]).max() <= 3e-2 * np.abs(o["bM"]).max() + 1e-12
+
+    def metrics(x):
+        rel = np.abs(x["idepth"] - o["idepth"]) / np.abs(o["idepth"])
+        return dict(rmse=abs(x["rmse"] - o["rmse"]) / o["rmse"], med=float(np.median(rel)), frac=float((rel < 1e-4).mean()),
+                    p995=float(np.quantile(rel, 0.995)), HM=float(np.abs(x["HM"] - o["HM"]).max() / np.abs(o["HM"]).max()),
+                    bM=float(np.abs(x["bM"] - o["bM"]).max() / np.abs(o["bM"]).max()))
+
+    spread = [metrics(mapping_step(Backend(shape, reduce=(6, seed)), scene, win0)) for seed in (0, 1, 2)]
+    worst = {k: max(m[k] for m in spread) for k in spread[0]}
+    gm = metrics(g)
+    assert gm["rmse"] <= max(1e-4, 3 * worst["rmse"]), (gm, worst)
+    assert gm["med"] < 1e-4, gm
+    assert gm["frac"] >= min(m["frac"] for m in spread) - 0.02, (gm, spread)
+    assert gm["p995"] <= max(1e-4, 3 * worst["p995"]), (gm, worst)
+    assert gm["HM"] <= max(1e-4, 3 * worst["HM"]), (gm, worst)
+    # bM is the gradient at the optimised state: small numbers made of cancelling terms, so state differences show up more strongly
+    # than in HM — in the oracle's own re-runs as well (the operator alone, on identical inputs, is held to 1e-4 in test_gpu_ba.py)
+    assert gm["bM"] <= max(1e-4, 3 * worst["bM"]), (gm, worst)
