@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """bench.py — photometric residual+Jacobian evals/s of the CoarseTracker hot path (BASELINE.json configs[1]).
 
-A "step" is one new frame for each of SEQS independent sequences that share the GPU, at KITTI shape
+A "step" is one new STEREO frame for each of SEQS independent sequences that share the GPU, at KITTI shape
 (1232x368 working size, 5 pyramid levels, ~2k template points per keyframe dilated to ~10k single-pixel
-residuals on level 0): FrameHessian::makeImages of the new left images (one batched launch pair) +
-CoarseTracker::trackNewestCoarse of every sequence against its own reference keyframe (one thread-block
-cluster per sequence, one launch). A single 2k-point frame occupies 8 of the 148 SMs and is bound by the
+residuals on level 0): FrameHessian::makeImages of the new left AND right images (the reference builds both
+pyramids of every frame, FullSystem.cpp:1083-1085; batched launches) + CoarseTracker::trackNewestCoarse of every
+sequence against its own reference keyframe (one thread-block cluster per sequence, one launch). A single 2k-point frame occupies 8 of the 148 SMs and is bound by the
 latency of its ~25 dependent LM evaluations, so throughput is reached by tracking sequences side by side;
 the latency of one sequence alone is reported under `single_sequence`.
 
@@ -15,6 +15,10 @@ the latency of one sequence alone is reported under `single_sequence`.
                (16 B point record + 4 x 12 B gathered texels), duration from CUDA events
                recorded around that launch on its stream, peak = measured HBM copy bandwidth
   cpu_baseline: the oracle port of the same variant (single thread, as the reference tracks), bounded sample
+
+Extra keys (`legs`, see bench_legs.py): the g2o tracking variant, the windowed BA at configs 3 and 4, the fork's g2o LBA
+driver, the epipolar search (traceOn / traceStereo), the pixel selector, and — under torchrun with N > 1 — the point-sharded
+config-4 LM iteration with its allreduce, each with its own roofline / e2e / cpu_baseline.
 
 `--impl reference` times the CPU oracle port (the reference itself cannot be compiled here: Eigen,
 g2o, Boost, OpenCV are absent — DESIGN.md) on the same workload and prints the same JSON line.
@@ -72,6 +76,7 @@ def build_workload(seed_shift=0.0, seqs=SEQS):
     npos = min(seqs, PATH)
     poses = [synth.camera_pose(step * k, seed_shift) for k in range(npos + POSES)]
     rend = [synth.render(scene, p) for p in poses]
+    rend_r = [None] + [synth.render(scene, synth.right_of(p))[0] for p in poses[1:]]   # right images of the frames that get tracked
     rng = np.random.default_rng(20260118)
     out = []
     for s in range(seqs):
@@ -79,7 +84,8 @@ def build_workload(seed_shift=0.0, seqs=SEQS):
         pts = synth.pick_points(rng, rend[p][1], N_POINTS)
         T_true = [synth.T_rel(poses[p], poses[p + j + 1]) for j in range(POSES)]
         T_init = [synth.perturb_T(T, rng, 0.05, np.deg2rad(0.5)) for T in T_true]
-        out.append(dict(ref_img=rend[p][0], pts=pts, new_imgs=[rend[p + j + 1][0] for j in range(POSES)], T_true=T_true, T_init=T_init, pos=p))
+        out.append(dict(ref_img=rend[p][0], pts=pts, new_imgs=[rend[p + j + 1][0] for j in range(POSES)],
+                        new_imgs_right=[rend_r[p + j + 1] for j in range(POSES)], T_true=T_true, T_init=T_init, pos=p))
     return out
 
 
@@ -122,7 +128,7 @@ class ClockSampler:
 
 def cpu_track_loop(wl, variant, min_seconds, max_frames, threads, warm_frames=3):
     """Oracle port on `threads` host threads, one independent sequence per thread (the reference tracks a sequence on one
-    thread; ctypes releases the GIL): makeImages + trackNewestCoarse per frame. Returns (evals, frames, seconds)."""
+    thread; ctypes releases the GIL): makeImages (left + right) + trackNewestCoarse per stereo frame. Returns (evals, frames, seconds)."""
     import threading
     import oracle_py as O
     import synth
@@ -138,9 +144,11 @@ def cpu_track_loop(wl, variant, min_seconds, max_frames, threads, warm_frames=3)
         orc.make_images(fref, seq["ref_img"])
         orc.tracker_set_ref(fref, seq["pts"])
         fnew = orc.frame_new()
+        fright = orc.frame_new()
         mr = [np.nan] * 5
         for j in range(warm_frames):   # untimed warm-up on the same buffers (page faults, caches)
             orc.make_images(fnew, seq["new_imgs"][j % POSES])
+            orc.make_images(fright, seq["new_imgs_right"][j % POSES])
             orc.track(fnew, seq["T_init"][j % POSES], (0.0, 0.0), orc.levels - 1, mr, variant)
         orc.reset_evals()
         gate.wait()                    # every thread has built its reference before the clock starts
@@ -150,6 +158,7 @@ def cpu_track_loop(wl, variant, min_seconds, max_frames, threads, warm_frames=3)
         while True:
             j = frames % POSES
             orc.make_images(fnew, seq["new_imgs"][j])
+            orc.make_images(fright, seq["new_imgs_right"][j])   # fh_right->makeImages (FullSystem.cpp:1085)
             orc.track(fnew, seq["T_init"][j], (0.0, 0.0), orc.levels - 1, mr, variant)
             frames += 1
             el = time.perf_counter() - t0
@@ -181,6 +190,7 @@ def main():
     ap.add_argument("--probe", action="store_true", help="also time the tracker alone on resident pyramids (no makeImages in between)")
     ap.add_argument("--gather", type=int, default=1, help="points in flight per thread (1: 128-register kernel, 2 with --threads 192: 168-register kernel)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--legs", default="all", help="comma list of extra legs on the JSON line: ba3,ba4,trace,g2o,sharded (or all / none)")
     args = ap.parse_args()
     variant = 0 if args.variant == "sse" else 1
     W_ = max(args.warmup, 3)
@@ -191,12 +201,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     host_cores = os.cpu_count() or 1
     config = dict(workload=f"CoarseTracker pose tracking, 1232x368 (1241x376 cropped), 5-level pyramid, 2000 active points splatted per keyframe (makeCoarseDepthL0 dilates them to ~9.9 k template points at level 0), variant={args.variant}; "
-                           f"step = one new frame for each of {S} independent sequences sharing the GPU: makeImages (8-bit source, batched) + "
+                           f"step = one new STEREO frame for each of {S} independent sequences sharing the GPU: makeImages of the left and the right image (8-bit sources, batched) + "
                            "trackNewestCoarse against each sequence's own reference keyframe ("
                            + ("one CTA per sequence, persistent grid of two CTAs per SM pulling sequences from a work counter" if args.cluster == 1 else
                               f"one {args.cluster if args.cluster > 0 else 2}-CTA cluster per sequence, two CTAs per SM") + ", one launch)",
                   points=N_POINTS, levels=5, variant=args.variant, sequences_per_gpu=S,
-                  cache=f"inputs larger than L2: {S} new pyramids per step x {SETS} rotating slot sets (~{S * SETS * 12} MB of pyramids + sources), {S} templates",
+                  cache=f"inputs larger than L2: {2 * S} new pyramids per step x {SETS} rotating slot sets (~{2 * S * SETS * 12} MB of pyramids + sources), {S} templates",
                   parallelism=(f"{S} independent sequences per GPU; GPUs are replicas (no collective)" if args.gpus > 1 else f"{S} independent sequences on one GPU"))
 
     # ------------------------------------------------------------------------------------------ reference arm
@@ -212,7 +222,7 @@ def main():
                     config=config, impl="reference",
                     tracked_frames_per_s=fr / sec,
                     cpu_baseline=dict(value=val, unit="evals/s", cores=host_cores, kind="port",
-                                      sample=f"{fr} tracked frames over {host_cores} threads, one sequence per thread (oracle port of CoarseTracker; "
+                                      sample=f"{fr} tracked stereo frames (makeImages left + right, trackNewestCoarse) over {host_cores} threads, one sequence per thread (oracle port of CoarseTracker; "
                                              "the reference cannot be compiled here: Eigen/g2o/Boost/OpenCV absent)"),
                     e2e=dict(value=val, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -249,6 +259,8 @@ def main():
         ctx.make_images(fref, seq["ref_img"])
         ctx.tracker_set_ref(fref, seq["pts"])
     slots = [[ctx.frame_create() for _ in range(S)] for _ in range(SETS)]
+    slots_r = [[ctx.frame_create() for _ in range(S)] for _ in range(SETS)]   # the right images' pyramids
+    slots_lr = [slots[k] + slots_r[k] for k in range(SETS)]
     npx = synth.W * synth.H
     # 8-bit sources (the synthetic renderer quantises to integers, so uint8 is exact): device copies for the resident-input
     # number, pinned host copies for the end-to-end number
@@ -256,9 +268,10 @@ def main():
     # so the library can move a step's sources with a single copy
     host8 = []
     for j in range(POSES):
-        slab = torch.empty((S, synth.H, synth.W), dtype=torch.uint8).pin_memory()
+        slab = torch.empty((2 * S, synth.H, synth.W), dtype=torch.uint8).pin_memory()   # [0, S): left images, [S, 2S): right images
         for s_ in range(S):
             slab[s_].copy_(torch.from_numpy(wl[s_]["new_imgs"][j].astype(np.uint8)))
+            slab[S + s_].copy_(torch.from_numpy(wl[s_]["new_imgs_right"][j].astype(np.uint8)))
         host8.append(slab)
     dev8 = [host8[j].to(f"cuda:{dev}") for j in range(POSES)]
     T_init = [np.stack([wl[s_]["T_init"][j].reshape(12) for s_ in range(S)]) for j in range(POSES)]
@@ -267,10 +280,11 @@ def main():
     coarsest = ctx.levels - 1
     ref_slots = list(range(S))
 
-    dev_ptrs = [[dev8[j][s_].data_ptr() for s_ in range(S)] for j in range(POSES)]
+    dev_ptrs = [[dev8[j][s_].data_ptr() for s_ in range(2 * S)] for j in range(POSES)]
+    host_ptrs = [[host8[j][s_].data_ptr() for s_ in range(2 * S)] for j in range(POSES)]
 
     def images_device(i):
-        ctx.make_images_batch_device(slots[i % SETS], dev_ptrs[i % POSES], u8=True)
+        ctx.make_images_batch_device(slots_lr[i % SETS], dev_ptrs[i % POSES], u8=True)
 
     def track_device(i):
         ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, variant)
@@ -279,10 +293,10 @@ def main():
         images_device(i); track_device(i)
 
     def upload(i):
-        ctx.upload_images_async(slots[i % SETS], [host8[i % POSES][s_].data_ptr() for s_ in range(S)], u8=True)
+        ctx.upload_images_async(slots_lr[i % SETS], host_ptrs[i % POSES], u8=True)
 
     def images_host(i):
-        ctx.make_images_uploaded(slots[i % SETS])
+        ctx.make_images_uploaded(slots_lr[i % SETS])
 
     def track_host(i):
         ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, variant)
@@ -383,18 +397,69 @@ def main():
 
     # ---- single-sequence latency (one cluster on the GPU), for information
     lat_n = min(K_, 50)
-    for i in range(3):
-        ctx.make_images_batch_device(slots[0][:1], [dev8[i % POSES][0].data_ptr()], u8=True)
+    one_lr = [slots[0][0], slots_r[0][0]]
+
+    def one_frame(i):
+        ctx.make_images_batch_device(one_lr, [dev8[i % POSES][0].data_ptr(), dev8[i % POSES][S].data_ptr()], u8=True)
         ctx.track_enqueue_multi([0], slots[0][:1], T_init[i % POSES][:1], aff0[:1], coarsest, mr[:1], variant); ctx.track_collect(1)
+
+    for i in range(3):
+        one_frame(i)
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record(stream)
     for i in range(lat_n):
-        ctx.make_images_batch_device(slots[0][:1], [dev8[i % POSES][0].data_ptr()], u8=True)
-        ctx.track_enqueue_multi([0], slots[0][:1], T_init[i % POSES][:1], aff0[:1], coarsest, mr[:1], variant); ctx.track_collect(1)
+        one_frame(i)
     l1.record(stream)
     torch.cuda.synchronize()
     ms_single = l0.elapsed_time(l1) / lat_n
     clocks = sampler.stop() if sampler else None
+
+    # ---- legs: the rest of the path, driver-visible (bench_legs.py) -----------------------------------------
+    want = set(["g2o", "ba3", "ba4", "trace", "sharded"] if args.legs == "all" else [x for x in args.legs.split(",") if x and x != "none"])
+    legs = {}
+    peak_, _ = measured_peak()
+    if "g2o" in want and variant == 0 and world == 1:   # the fork's LIVE tracker (EdgeSE3PosePhotoDSO + restated g2o LM) on the same workload
+        Kg = max(3, min(K_, 20))
+        for i in range(3):
+            ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, 1); ctx.track_collect(S)
+        ctx.profile_enable(True); torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_g = 0
+        g0.record(stream)
+        images_device(0)
+        for i in range(Kg):
+            ctx.track_enqueue_multi(ref_slots, slots[i % SETS], T_init[i % POSES], aff0, coarsest, mr, 1)
+            if i + 1 < Kg:
+                images_device(i + 1)
+            rr = ctx.track_collect(S)
+            ev_g += rr["evals"]
+        g1.record(stream); torch.cuda.synchronize()
+        pg = ctx.profile_read(); ctx.profile_enable(False)
+        ms_g = g0.elapsed_time(g1)
+        conv = float((np.array([np.abs(rr["T"][s_][:, 3] - wl[s_]["T_true"][(Kg - 1) % POSES][:, 3]).max() for s_ in range(S)]) < 2e-2).mean())
+        tk = pg["track_ms"] / max(pg["track_launches"], 1)
+        ach = ev_g / Kg * BYTES_PER_EVAL / (tk * 1e-3) / 1e9
+        cg_ev, cg_fr, cg_sec = cpu_track_loop(wl, 1, min(args.cpu_seconds, 5.0), 100000, host_cores)
+        legs["track_g2o"] = dict(
+            workload=f"the same {S} sequences, variant=g2o (the fork's live code path: EdgeSE3PosePhotoDSO edges + restated g2o LM, 2 iterations per level)",
+            value=ev_g / (ms_g * 1e-3), unit="evals/s", steps=Kg, ms_per_step=ms_g / Kg, tracked_frames_per_s=S * Kg / (ms_g * 1e-3), converged_fraction=conv,
+            roofline=dict(bound="hbm", achieved=ach, peak=peak_, unit="GB/s", frac=ach / peak_, kernel="track_g2o_kernel", avg_launch_ms=tk,
+                          algorithmic_bytes_per_launch=ev_g / Kg * BYTES_PER_EVAL),
+            cpu_baseline=dict(value=cg_ev / cg_sec, unit="evals/s", cores=host_cores, kind="port", tracked_frames_per_s=cg_fr / cg_sec,
+                              sample=f"{cg_fr} tracked stereo frames in {cg_sec:.1f} s over {host_cores} threads (oracle port, g2o variant)"))
+    import bench_legs as BL
+    if world == 1 and (want & {"ba3", "ba4", "trace"}):
+        scene = synth.make_scene()
+        lk = max(10, min(K_, 50))
+        if "ba3" in want:
+            legs["ba_config3"] = BL.leg_ba(pkg, torch, dev, scene, "config3", lk, peak_, want_g2o=True)
+            legs["lba_g2o"] = legs["ba_config3"].pop("lba_g2o", None)
+        if "ba4" in want:
+            legs["ba_config4"] = BL.leg_ba(pkg, torch, dev, scene, "config4", lk, peak_, cpu_seconds=3.0)
+        if "trace" in want:
+            legs.update(BL.leg_trace(pkg, torch, dev, scene, peak_))
+    if world > 1 and "sharded" in want:
+        legs["sharded_ba"] = BL.leg_sharded_ba(pkg, torch, dist, dev, rank, world, synth.make_scene(), max(10, min(K_, 50)), peak_)
 
     # ---- aggregate over ranks (max time, summed work) ---------------------------------------------
     if dist is not None:
@@ -443,9 +508,9 @@ def main():
         config=config,
         tracked_frames_per_s=world * S * K_ / (ms_dev * 1e-3),
         evals_per_step=evals / (world * K_),
-        e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=S * npx, d2h_bytes_per_step=S * (8 * (12 + 2 + 5 + 3) + 4 * 6 + 8),
+        e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=2 * S * npx, d2h_bytes_per_step=S * (8 * (12 + 2 + 5 + 3) + 4 * 6 + 8),
                  ms_per_step=ms_e2e / K_, tracked_frames_per_s=world * S * K_ / (ms_e2e * 1e-3),
-                 h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=S * npx / (ms_e2e / K_ * 1e-3) / 1e9),
+                 h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=2 * S * npx / (ms_e2e / K_ * 1e-3) / 1e9),
         single_sequence=dict(ms_per_frame=ms_single, tracked_frames_per_s=1e3 / ms_single,
                              note="latency of one sequence alone on the GPU in this (throughput) configuration; the latency configuration (8-CTA cluster, gather batch 2) tracks a frame in ~0.2 ms, profiles/r1_bench_sse_first.json"),
         gpu_launches=int(launches),
@@ -454,12 +519,14 @@ def main():
                       kernel="track_kernel" if variant == 0 else "track_g2o_kernel", peak_source=peak_src,
                       algorithmic_bytes_per_launch=evals_per_launch * BYTES_PER_EVAL, avg_launch_ms=track_ms_per_launch,
                       share_of_step=prof["track_ms"] / ms_dev, scattered_gather_ceiling=pattern,
-                      make_images=dict(achieved=img_bytes * S * K_ / max(prof["images_ms"], 1e-9) / 1e6,
+                      make_images=dict(achieved=img_bytes * 2 * S * K_ / max(prof["images_ms"], 1e-9) / 1e6, frac=img_bytes * 2 * S * K_ / max(prof["images_ms"], 1e-9) / 1e6 / peak,
+                                       images_per_step=2 * S,
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
                                        algorithmic_bytes=img_bytes)),
         probe=probe,
+        legs=legs,
         cpu_baseline=(dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",
-                           sample=f"{cfr} tracked frames in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
+                           sample=f"{cfr} tracked stereo frames (makeImages left + right, trackNewestCoarse) in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
                                   "trackNewestCoarse is single-threaded per sequence in the reference)",
                            tracked_frames_per_s=cfr / csec) if world == 1 else None),
     )

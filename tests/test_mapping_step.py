@@ -223,7 +223,7 @@ def test_device_mapping_step_matches_oracle(pkg, scene, shape_name):
         rel = np.abs(x["idepth"] - o["idepth"]) / np.abs(o["idepth"])
         return dict(rmse=abs(x["rmse"] - o["rmse"]) / o["rmse"], med=float(np.median(rel)), frac=float((rel < 1e-4).mean()),
                     p995=float(np.quantile(rel, 0.995)), HM=float(np.abs(x["HM"] - o["HM"]).max() / np.abs(o["HM"]).max()),
-                    bM=float(np.abs(x["bM"] - o["bM"]).max() / np.abs(o["bM"]).max()))
+                    bM=float(np.abs(x["bM"] - o["bM"]).max() / max(np.abs(o["bM"]).max(), 1e-30)))   # (bM is exactly 0 when nothing was linearised before)
 
     spread = [metrics(mapping_step(Backend(shape, reduce=(6, seed)), scene, win0)) for seed in (0, 1, 2)]
     worst = {k: max(m[k] for m in spread) for k in spread[0]}
