@@ -246,6 +246,9 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
 /* FullSystem::setNewFrameEnergyTH (FullSystemOptimize.cpp:98-139): exact 70 % quantile of state_NewEnergyWithOutlier over the
  * active residuals that target the newest frame -> that frame's frameEnergyTH (applied, and returned) */
 int sdso_ba_new_frame_energy_th(sdso_ctx* ctx, float* th);
+/* FrameHessian::frameEnergyTH of every window frame [n] as the last linearizeAll / optimize left them (setNewFrameEnergyTH moves the
+ * newest frame's) */
+int sdso_ba_get_energy_th(sdso_ctx* ctx, float* frameEnergyTH);
 /* FullSystem::optimize, SSE body (FullSystemOptimize.cpp:870-1042) with backupState / solveSystem / doStepFromBackup /
  * linearizeAll / applyRes per iteration (setting_forceAceptStep = true, settings.cpp:53), then the new evaluation point of the
  * newest frame and the final linearizeAll(true). Returns what the reference returns: sqrt(energy / (patternNum * resInA)). */
@@ -341,6 +344,17 @@ int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[
                   sdso_immature_point* pts, int* status /* nullable */);
 /* ImmaturePoint::traceStereo(frame, K, mode_right) (ImmaturePoint.cpp:94-451); baseline = the context's */
 int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, sdso_immature_point* pts, int* status /* nullable */);
+/* The loop of FullSystem::traceNewCoarse over ALL key frames of the window (FullSystem.cpp:745-781) in ONE launch: n points, point i
+ * hosted in key frame host_of_point[i] < n_hosts, whose hostToFrame_KRKi / Kt / affine are KRKi[h][9], Kt[h][3], aff[h][2].
+ * pts == NULL: the device-resident records (sdso_immature_upload) are traced in place and nothing but status[] (nullable) comes back —
+ * the records of a window's immature points then cross the host link once per key frame instead of twice per tracked frame. */
+int sdso_trace_on_hosts(sdso_ctx* ctx, int frame, int n_hosts, const float* KRKi, const float* Kt, const float* aff, int n, const int* host_of_point,
+                        sdso_immature_point* pts /* nullable */, int* status /* nullable */);
+/* traceStereo of the first n device-resident records in place */
+int sdso_trace_stereo_resident(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, int* status /* nullable */);
+/* device-resident immature-point records: upload replaces the pool, download reads records [first, first + n) back */
+int sdso_immature_upload(sdso_ctx* ctx, int n, const sdso_immature_point* pts);
+int sdso_immature_download(sdso_ctx* ctx, int first, int n, sdso_immature_point* pts);
 /* D4: FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:52-238) + ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:886-985)
  * for n candidates, host[i] = index of the candidate's host frame in the window uploaded with sdso_ba_* (its FrameFramePrecalc
  * and calibration are used). variant SDSO_VARIANT_SSE: the original body (Hdd/bd, 3 LM iterations, Hdd >= setting_minIdepthH_act);

@@ -378,6 +378,7 @@ extern "C" {
 // worker partition of the accumulators (oracle_ba.hpp: reduce_threads / reduce_seed); 1, 0 = the single-threaded path
 void orc_ba_set_reduce(void* p, int threads, unsigned seed) { Ctx* c = (Ctx*)p; c->ba.reduce_threads = threads; c->ba.reduce_seed = seed; }
 double orc_ba_optimize(void* p, int iters, int* done) { return ((Ctx*)p)->ba.optimize(iters, done); }
+void orc_ba_get_energy_th(void* p, float* th) { Ctx* c = (Ctx*)p; for (size_t i = 0; i < c->ba.frames.size(); i++) th[i] = c->ba.frames[i].frameEnergyTH; }
 float orc_ba_new_frame_energy_th(void* p) { return ((Ctx*)p)->ba.newFrameEnergyTH(); }
 // frame states [n][10], world-to-camera [n][12], point idepths [P], calibration value_scaled [4]
 void orc_ba_get_state(void* p, double* states, double* T_w2c, float* idepth, double* calib) {

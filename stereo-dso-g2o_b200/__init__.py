@@ -492,9 +492,49 @@ def _trace_stereo(self, fid, K, mode_right, pts):
     return st
 
 
+lib.sdso_trace_on_hosts.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp, _fp, _fp, C.c_int, _ip, C.c_void_p, _ip]
+lib.sdso_trace_stereo_resident.argtypes = [C.c_void_p, C.c_int, _fp, C.c_int, C.c_int, _ip]
+lib.sdso_immature_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.sdso_immature_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+
+
+def _trace_on_hosts(self, fid, KRKi, Kt, aff, host_of_point, pts=None, want_status=True):
+    """traceOn of the points of SEVERAL host key frames in one launch. pts=None: the device-resident pool (immature_upload)."""
+    K_, t_, a_ = _f32(KRKi).reshape(-1, 9), _f32(Kt).reshape(-1, 3), _f32(aff).reshape(-1, 2)
+    ho = np.ascontiguousarray(host_of_point, dtype=np.int32)
+    if pts is not None:
+        assert pts.dtype == IMMATURE_DTYPE and pts.flags["C_CONTIGUOUS"] and pts.size == ho.size
+    st = np.zeros(ho.size, np.int32) if want_status else None
+    self._ck(lib.sdso_trace_on_hosts(self._h, fid, K_.shape[0], _ptr(K_, _fp), _ptr(t_, _fp), _ptr(a_, _fp), ho.size, _ptr(ho, _ip),
+                                     pts.ctypes.data if pts is not None else None, _ptr(st, _ip) if want_status else None))
+    return st
+
+
+def _trace_stereo_resident(self, fid, K, mode_right, n, want_status=True):
+    K_ = _f32(K).reshape(9)
+    st = np.zeros(n, np.int32) if want_status else None
+    self._ck(lib.sdso_trace_stereo_resident(self._h, fid, _ptr(K_, _fp), int(mode_right), n, _ptr(st, _ip) if want_status else None))
+    return st
+
+
+def _immature_upload(self, pts):
+    assert pts.dtype == IMMATURE_DTYPE and pts.flags["C_CONTIGUOUS"]
+    self._ck(lib.sdso_immature_upload(self._h, pts.size, pts.ctypes.data))
+
+
+def _immature_download(self, n, first=0):
+    pts = np.zeros(n, IMMATURE_DTYPE)
+    self._ck(lib.sdso_immature_download(self._h, first, n, pts.ctypes.data))
+    return pts
+
+
 Context.immature_init = _immature_init
 Context.trace_on = _trace_on
 Context.trace_stereo = _trace_stereo
+Context.trace_on_hosts = _trace_on_hosts
+Context.trace_stereo_resident = _trace_stereo_resident
+Context.immature_upload = _immature_upload
+Context.immature_download = _immature_download
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -677,6 +717,16 @@ def _w_get_state(self):
     return dict(states=st, T_w2c=T, idepth=idp, calib=cal)
 
 
+lib.sdso_ba_get_energy_th.argtypes = [C.c_void_p, _fp]
+
+
+def _w_get_energy_th(self):
+    th = np.zeros(self.counts()["frames"], np.float32)
+    self._ck(lib.sdso_ba_get_energy_th(self.h, _ptr(th, _fp)))
+    return th
+
+
+Window.get_energy_th = _w_get_energy_th
 Window.new_frame_energy_th = _w_new_frame_energy_th
 Window.optimize = _w_optimize
 Window.get_state = _w_get_state

@@ -19,13 +19,23 @@ static cudaError_t grow(T*& p, size_t n) {
 }
 #define BA_ALLOC(ptr, n) SDSO_CUDA(ctx, grow(ptr, n))
 
+// captured launch chains (see capture_begin): dropped whenever something a captured kernel node holds BY VALUE changes — counts,
+// array pointers, the shard, the presence of HM. Calibration, frame states and thresholds are read through device pointers.
+static void invalidate_graphs(BAState* b) {
+  if (b->graph_iter) { cudaGraphExecDestroy((cudaGraphExec_t)b->graph_iter); b->graph_iter = nullptr; }
+  if (b->graph_assemble) { cudaGraphExecDestroy((cudaGraphExec_t)b->graph_assemble); b->graph_assemble = nullptr; }
+}
+
 static void free_all(BAState* b) {
+  invalidate_graphs(b);
+  if (b->cap_stream) { cudaStreamDestroy(b->cap_stream); b->cap_stream = nullptr; }
   void* ptrs[] = {b->d_tex0, b->d_frameTH, b->d_precalc, b->d_adHost, b->d_adTarget, b->d_adHostF, b->d_adTargetF, b->d_adHTdeltaF, b->d_cDeltaF,
                   b->d_fprior, b->d_p_host, b->d_p_u, b->d_p_v, b->d_p_idepth, b->d_p_idepth_zero, b->d_p_color, b->d_p_weights, b->d_p_priorF,
                   b->d_p_deltaF, b->d_p_idepth_backup, b->d_p_res_begin, b->d_slot_of, b->d_p_acc, b->d_p_flag, b->d_p_res_list, b->d_s_point, b->d_s_key, b->d_s_state,
                   b->d_s_newstate, b->d_s_flags, b->d_s_sel, b->d_s_energy, b->d_J, b->d_s_rtz, b->d_s_JpJd, b->d_s_center, b->d_s_psum,
                   b->d_slot2rid, b->d_rid2slot, b->d_chunks, b->d_key_chunk_begin, b->d_tpart, b->d_dpart, b->d_pblockpart, b->d_G, b->d_Gf,
-                  b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list, b->d_step_part};
+                  b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list, b->d_step_part,
+                  b->d_frames, b->d_calib, b->d_opt};
   for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -44,6 +54,10 @@ int ba_create(sdso_ctx* ctx) {
   SDSO_CUDA(ctx, cudaMemset(b->d_sys, 0, b->sys_stride * SYS_NUM * sizeof(double)));
   BA_ALLOC(b->d_scalars, 16); BA_ALLOC(b->d_counter, 4); BA_ALLOC(b->d_N, dmax * 7); BA_ALLOC(b->d_xAd, F2 * 8);
   SDSO_CUDA(ctx, cudaMemset(b->d_counter, 0, 4 * sizeof(unsigned)));
+  BA_ALLOC(b->d_frames, F); BA_ALLOC(b->d_calib, 1); BA_ALLOC(b->d_opt, 1);
+  SDSO_CUDA(ctx, cudaMemset(b->d_opt, 0, sizeof(OptDev)));
+  SDSO_CUDA(ctx, cudaStreamCreateWithFlags(&b->cap_stream, cudaStreamNonBlocking));
+  SDSO_CUDA(ctx, cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return SDSO_OK;
 }
 void ba_destroy(sdso_ctx* ctx) {
@@ -55,7 +69,7 @@ void ba_destroy(sdso_ctx* ctx) {
 
 static BAView view(BAState* b) {
   BAView v;
-  v.n = b->n; v.P = b->P; v.R = b->R; v.capP = b->capP; v.capR = b->capR; v.c = b->calib;
+  v.n = b->n; v.P = b->P; v.R = b->R; v.capP = b->capP; v.capR = b->capR; v.cp = b->d_calib; v.done = &b->d_opt->done;
   v.tex0 = b->d_tex0; v.frameTH = b->d_frameTH; v.precalc = b->d_precalc;
   v.adHost = b->d_adHost; v.adTarget = b->d_adTarget; v.adHostF = b->d_adHostF; v.adTargetF = b->d_adTargetF;
   v.adHTdeltaF = b->d_adHTdeltaF; v.cDeltaF = b->d_cDeltaF; v.fprior = b->d_fprior;
@@ -272,6 +286,23 @@ static int prepare_window(sdso_ctx* ctx) {
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_N, Q.data(), Q.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_tex0, tex.data(), tex.size() * sizeof(float4*), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_frameTH, th.data(), th.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  // device mirrors of what the LM loop moves: calibration, frame states, the loop's control block
+  std::vector<FrameDev> fd(kMaxFrames);
+  memset(fd.data(), 0, fd.size() * sizeof(FrameDev));
+  for (int h = 0; h < n; h++) {
+    const HostBAFrame& f = b->frames[h];
+    memcpy(fd[h].T_eval, f.T_eval, sizeof(f.T_eval)); memcpy(fd[h].state, f.state, sizeof(f.state)); memcpy(fd[h].state_zero, f.state_zero, sizeof(f.state_zero));
+    memcpy(fd[h].state_backup, f.state_backup, sizeof(f.state_backup)); memcpy(fd[h].T_w2c, f.T_w2c, sizeof(f.T_w2c)); memcpy(fd[h].T_c2w, f.T_c2w, sizeof(f.T_c2w));
+    fd[h].ab_exposure = f.ab_exposure;
+  }
+  OptDev od;
+  memset(&od, 0, sizeof(od));
+  for (int i = 0; i < 4; i++) { od.calib_value[i] = b->calib_value[i]; od.calib_zero[i] = b->calib_zero[i]; od.calib_backup[i] = b->calib_backup[i]; }
+  od.th_opt = S.thOptIterations; od.min_its = S.minOptIterations;
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_frames, fd.data(), fd.size() * sizeof(FrameDev), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_calib, &b->calib, sizeof(BACalib), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_opt, &od, sizeof(OptDev), cudaMemcpyHostToDevice, st));
+  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_scalars + 8, b->cPrior, 4 * sizeof(double), cudaMemcpyHostToDevice, st));   // cPrior lives at scalars[8..11]
   SDSO_CUDA(ctx, cudaStreamSynchronize(st));  // the host vectors above go out of scope
   // deltaF of the points follows idepth - idepth_zero (EFPoint::takeData / setDeltaF :196-204): device side
   b->prepared = true;
@@ -293,10 +324,7 @@ static int launch_top(sdso_ctx* ctx, int mode, int which, bool usePrior) {
   double* Wm = b->d_U; double* Zm = b->d_U + (size_t)n * n * 64; double* Wc = b->d_V; double* Zc = b->d_V + (size_t)n * n * 40;
   ba_top_finish_kernel<<<n * n, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc); SDSO_CHECK_LAUNCH(ctx);
   if (b->P > 0) { ba_point_sums_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
-  double* dc = nullptr;
-  // cPrior lives at scalars[8..11]
-  SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_scalars + 8, b->cPrior, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  dc = b->d_scalars + 8;
+  double* dc = b->d_scalars + 8;   // cPrior (uploaded by prepare_window)
   ba_stitch_top_kernel<<<n * n + 1, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc, sysH(b, which), sysb(b, which), usePrior ? 1 : 0, dc);
   (void)d;
   SDSO_CHECK_LAUNCH(ctx);
@@ -336,15 +364,70 @@ static void fill_solve_params(sdso_ctx* ctx, SolveParams& S, int iteration) {
   S.HM = sysH(b, SYS_M); S.bM = sysb(b, SYS_M);
   S.fprior = b->d_fprior; S.cDeltaF = b->d_cDeltaF; S.N = b->d_N; S.nrank = b->nrank;
   S.HF = sysH(b, SYS_FINAL); S.bF = sysb(b, SYS_FINAL); S.x = sysb(b, SYS_X);
+  S.done = &b->d_opt->done; S.it_ptr = iteration < 0 ? &b->d_opt->it : nullptr;
 }
 
+// ---- CUDA graphs for the launch chains ----------------------------------------------------------------------------------
+// One LM iteration is a chain of ~17-25 small dependent kernels; launched one by one the chain is bound by launch latency
+// (config 3: 0.2 ms for ~20 us of work). The chain is captured once per uploaded window on an internal stream (the context's
+// stream may be the legacy default stream, which cannot capture) and replayed as one graph launch on the context's stream.
+struct Capture { cudaStream_t user = nullptr; bool active = false; };
+static int capture_begin(sdso_ctx* ctx, Capture& c) {
+  BAState* b = ctx->ba;
+  c.user = ctx->stream;
+  SDSO_CUDA(ctx, cudaStreamBeginCapture(b->cap_stream, cudaStreamCaptureModeThreadLocal));
+  ctx->stream = b->cap_stream;
+  c.active = true;
+  return SDSO_OK;
+}
+static int capture_end(sdso_ctx* ctx, Capture& c, void** exec_out, int rc_body) {
+  BAState* b = ctx->ba;
+  ctx->stream = c.user;
+  c.active = false;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(b->cap_stream, &g);
+  if (rc_body) { if (g) cudaGraphDestroy(g); return rc_body; }
+  if (e != cudaSuccess) return fail(ctx, SDSO_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(ctx, SDSO_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  *exec_out = ex;
+  return SDSO_OK;
+}
+
+static int launch_assemble_chain(sdso_ctx* ctx);
 // accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT (EnergyFunctional.cpp:857-866) over this rank's points, then the
-// (partial) damped reduced system into SYS_FINAL
+// (partial) damped reduced system into SYS_FINAL — replayed as one graph
 static int launch_assemble(sdso_ctx* ctx) {
+  BAState* b = ctx->ba;
+  if (!b->graph_assemble) {
+    Capture c;
+    int rc = capture_begin(ctx, c);
+    if (rc) return rc;
+    const uint64_t l0 = ctx->launches;
+    rc = launch_assemble_chain(ctx);
+    b->graph_assemble_nodes = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    rc = capture_end(ctx, c, &b->graph_assemble, rc);
+    if (rc) return rc;
+  }
+  SDSO_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)b->graph_assemble, ctx->stream));
+  ctx->launches += b->graph_assemble_nodes;   // kernels executed (one graph launch)
+  return SDSO_OK;
+}
+static int launch_assemble_chain(sdso_ctx* ctx) {
   BAState* b = ctx->ba;
   const int d = b->dim();
   int rc = launch_top(ctx, 0, SYS_A, false);
-  if (!rc) rc = launch_top(ctx, 1, SYS_L, b->shard_rank == 0);  // priors enter once
+  if (!rc) {
+    if (b->any_linearized) rc = launch_top(ctx, 1, SYS_L, b->shard_rank == 0);  // priors enter once
+    else {   // nothing linearised: the L system is the priors alone
+      BAView v = view(b);
+      ba_prior_system_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, SYS_L), sysb(b, SYS_L), b->shard_rank == 0 ? 1 : 0, b->d_scalars + 8);
+      SDSO_CHECK_LAUNCH(ctx);
+    }
+  }
   if (!rc) rc = launch_sc(ctx, true, SYS_SC);
   if (rc) return rc;
   SolveParams S{};
@@ -360,9 +443,7 @@ static int launch_factor_solve(sdso_ctx* ctx, int iteration) {
   SolveParams S{};
   fill_solve_params(ctx, S, iteration);
   const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  ba_solve_kernel<<<1, 256, smem, ctx->stream>>>(S);
+  ba_solve_kernel<<<1, 256, smem, ctx->stream>>>(S);   // (dynamic shared-memory limit raised in ba_create)
   SDSO_CHECK_LAUNCH(ctx);
   return SDSO_OK;
 }
@@ -399,6 +480,7 @@ extern "C" {
 
 int sdso_ba_reset(sdso_ctx* ctx) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
   b->n = b->P = b->R = 0;
   b->frames.clear();
   b->prepared = false;
@@ -431,6 +513,7 @@ int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_
 
 int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], double a, double bb, int frameID, int* idx_out) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
   if (!T_w2c || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
   if (b->n >= kMaxFrames) return fail(ctx, SDSO_E_INVALID, "window is full (kMaxFrames)");
   HostBAFrame f;
@@ -476,6 +559,7 @@ int sdso_ba_set_energy_th(sdso_ctx* ctx, int idx, float th) {
 int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                        const float* color8, const float* weights8, const unsigned char* has_prior) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
   if (P < 0 || (P > 0 && (!host || !u || !v || !idepth || !idepth_zero || !color8 || !weights8))) return SDSO_E_INVALID;
   for (int i = 0; i < P; i++) if (host[i] < 0 || host[i] >= b->n) return fail(ctx, SDSO_E_INVALID, "point host index out of range (add the frames first)");
   if (P > b->capP) {
@@ -514,6 +598,8 @@ int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, co
 
 int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* target) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
+  b->any_linearized = false;
   if (R < 0 || (R > 0 && (!point || !target))) return SDSO_E_INVALID;
   const int n = b->n, P = b->P;
   for (int i = 0; i < R; i++) if (point[i] < 0 || point[i] >= P || target[i] < 0 || target[i] >= n) return fail(ctx, SDSO_E_INVALID, "residual index out of range");
@@ -672,6 +758,7 @@ int sdso_ba_apply_res(sdso_ctx* ctx, int copy_jacobians) {
 
 int sdso_ba_fix_linearization(sdso_ctx* ctx, int count, const int* rids) {
   BA_PREPARED(ctx)
+  if (!b->any_linearized) { b->any_linearized = true; invalidate_graphs(b); }   // the captured chains skip the linearised accumulation until now
   BAView v = view(b);
   if (!rids) {
     if (b->R == 0) return SDSO_OK;
@@ -799,6 +886,7 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
 /* ---- point-sharded windows ---- */
 int sdso_ba_set_shard(sdso_ctx* ctx, int rank, int nranks) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
   if (nranks < 1 || rank < 0 || rank >= nranks) return SDSO_E_INVALID;
   b->shard_rank = rank; b->shard_n = nranks;
   return SDSO_OK;
@@ -850,7 +938,7 @@ static void set_calib_value(sdso_ctx* ctx, const double v[4]) {
   for (int i = 0; i < 4; i++) b->calib_delta[i] = b->calib_value[i] - b->calib_zero[i];
 }
 
-static int launch_energy_th(sdso_ctx* ctx, float* th_host) {
+static int launch_energy_th(sdso_ctx* ctx, float* th_host, bool readback = true) {
   BAState* b = ctx->ba;
   BAView v = view(b);
   const sdso_settings& S = ctx->S;
@@ -858,6 +946,7 @@ static int launch_energy_th(sdso_ctx* ctx, float* th_host) {
   ba_energy_th_kernel<<<1, 1024, 0, ctx->stream>>>(v, b->n - 1, S.frameEnergyTHN, S.frameEnergyTHFacMedian, S.frameEnergyTHConstWeight,
                                                     S.overallEnergyTHWeight, b->d_frameTH, d_out);
   SDSO_CHECK_LAUNCH(ctx);
+  if (!readback) return SDSO_OK;   // inside the device-resident LM loop: the host mirror is refreshed once, after the loop
   float th = 0;
   SDSO_CUDA(ctx, cudaMemcpyAsync(&th, d_out, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -869,6 +958,13 @@ static int launch_energy_th(sdso_ctx* ctx, float* th_host) {
 int sdso_ba_new_frame_energy_th(sdso_ctx* ctx, float* th) {
   BA_PREPARED(ctx)
   return launch_energy_th(ctx, th);
+}
+
+int sdso_ba_get_energy_th(sdso_ctx* ctx, float* frameEnergyTH) {
+  BA_CHECK(ctx)
+  if (!frameEnergyTH) return SDSO_E_INVALID;
+  for (int h = 0; h < b->n; h++) frameEnergyTH[h] = b->frames[h].frameEnergyTH;
+  return SDSO_OK;
 }
 
 int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idepth, double* calib) {
@@ -914,52 +1010,77 @@ int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iteration
     SDSO_CUDA(ctx, cudaMalloc(&b->d_step_part, (size_t)(pb + 1) * 2 * sizeof(double)));
     b->step_part_cap = pb;
   }
-  (void)d_part;
-  std::vector<double> x(d);
-  int it = 0;
-  for (; it < mnumOptIts; it++) {
-    // backupState (:309-350)
-    for (int i = 0; i < 4; i++) b->calib_backup[i] = b->calib_value[i];
-    for (auto& f : b->frames) memcpy(f.state_backup, f.state, sizeof(f.state));
-    if (P > 0) { BAView v = view(b); ba_backup_points_kernel<<<pb, 128, 0, st>>>(v); SDSO_CHECK_LAUNCH(ctx); }
-    // solveSystem(iteration, lambda) (:1045-1053): accumulate, stitch, solve, back-substitute — all on the device
-    if ((rc = launch_solve(ctx, it, 1e-1))) return rc;
-    if ((rc = launch_resub(ctx, sysb(b, SYS_X)))) return rc;
-    SDSO_CUDA(ctx, cudaMemcpyAsync(x.data(), sysb(b, SYS_X), d * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SDSO_CUDA(ctx, cudaStreamSynchronize(st));
-    for (int i = 0; i < 4; i++) b->calib_step[i] = -x[i];
-    for (int h = 0; h < n; h++) { for (int i = 0; i < 8; i++) b->frames[h].step[i] = -x[kCPARS + 8 * h + i]; b->frames[h].step[8] = b->frames[h].step[9] = 0; }
-    // doStepFromBackup(1,1,1,1,1) (:207-305)
-    float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
-    {
-      double v4[4];
-      for (int i = 0; i < 4; i++) v4[i] = b->calib_backup[i] + 1.0f * b->calib_step[i];
-      set_calib_value(ctx, v4);
-      for (auto& f : b->frames) {
-        double sn[10];
-        for (int i = 0; i < 10; i++) sn[i] = f.state_backup[i] + 1.0f * f.step[i];
-        frame_set_state(f, sn);
-        sumA += f.step[6] * f.step[6];
-        sumB += f.step[7] * f.step[7];
-        sumT += f.step[0] * f.step[0] + f.step[1] * f.step[1] + f.step[2] * f.step[2];
-        sumR += f.step[3] * f.step[3] + f.step[4] * f.step[4] + f.step[5] * f.step[5];
+  (void)d_part; (void)d;
+  // ---- the LM loop, device-resident: every iteration is ONE graph launch; the convergence decision is latched on the device
+  // (OptDev::done) and turns the iterations enqueued behind it into no-ops, so the host enqueues all mnumOptIts blindly and
+  // synchronises once, after the loop.
+  if (!b->graph_iter) {
+    Capture c;
+    if ((rc = capture_begin(ctx, c))) return rc;
+    const uint64_t l0 = ctx->launches;
+    cudaStream_t cs = ctx->stream;
+    auto body = [&]() -> int {
+      int r = SDSO_OK;
+      if (P > 0) { BAView v = view(b); ba_backup_points_kernel<<<pb, 128, 0, cs>>>(v); SDSO_CHECK_LAUNCH(ctx); }   // backupState (:309-350)
+      // solveSystem(iteration, lambda) (:1045-1053): accumulate, stitch, solve, back-substitute
+      if ((r = launch_assemble_chain(ctx))) return r;
+      if ((r = launch_factor_solve(ctx, -1))) return r;   // iteration index from OptDev::it
+      if ((r = launch_resub(ctx, sysb(b, SYS_X)))) return r;
+      // doStepFromBackup(1,1,1,1,1) (:207-305): points, then frames + calibration + precalc + convergence test
+      if (P > 0) {
+        BAView v = view(b);
+        ba_step_points_kernel<<<pb, 128, 0, cs>>>(v, 1.0f, b->d_step_part); SDSO_CHECK_LAUNCH(ctx);
+        ba_sum_pairs_kernel<<<1, 32, 0, cs>>>(b->d_step_part, pb, b->d_step_part + 2 * (size_t)pb, &b->d_opt->done); SDSO_CHECK_LAUNCH(ctx);
       }
+      FrameUpdateParams U;
+      U.n = n; U.P = P; U.frames = b->d_frames; U.opt = b->d_opt; U.calib = b->d_calib; U.cDeltaF = b->d_cDeltaF; U.fprior = b->d_fprior; U.precalc = b->d_precalc;
+      U.adHostF = b->d_adHostF; U.adTargetF = b->d_adTargetF; U.adHTdeltaF = b->d_adHTdeltaF; U.x = sysb(b, SYS_X); U.step_sums = b->d_step_part + 2 * (size_t)pb;
+      ba_frame_update_kernel<<<1, 256, 0, cs>>>(U); SDSO_CHECK_LAUNCH(ctx);
+      // linearizeAll(false) + setNewFrameEnergyTH + applyRes: setting_forceAceptStep, every step is accepted (:965-978)
+      if (R > 0) { BAView v = view(b); ba_linearize_kernel<<<rb, 128, 0, cs>>>(v, 0); SDSO_CHECK_LAUNCH(ctx); }
+      if ((r = launch_energy_th(ctx, nullptr, false))) return r;
+      if (R > 0) { BAView v = view(b); ba_apply_res_kernel<<<rb, 128, 0, cs>>>(v, 1); SDSO_CHECK_LAUNCH(ctx); }
+      ba_iter_end_kernel<<<1, 1, 0, cs>>>(b->d_opt); SDSO_CHECK_LAUNCH(ctx);
+      return SDSO_OK;
+    };
+    rc = body();
+    b->graph_iter_nodes = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    if ((rc = capture_end(ctx, c, &b->graph_iter, rc))) return rc;
+  }
+  {
+    // reset the loop's control block (it, pending, done, its_done) — the calibration values in front of it stay
+    SDSO_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(b->d_opt) + offsetof(OptDev, it), 0, 4 * sizeof(int), st));
+    for (int k = 0; k < mnumOptIts; k++) {
+      SDSO_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)b->graph_iter, st));
+      ctx->launches += b->graph_iter_nodes;
     }
-    double sums[2] = {0, 0};
-    if (P > 0) {
-      BAView v = view(b);
-      ba_step_points_kernel<<<pb, 128, 0, st>>>(v, 1.0f, b->d_step_part); SDSO_CHECK_LAUNCH(ctx);
-      ba_sum_pairs_kernel<<<1, 32, 0, st>>>(b->d_step_part, pb, b->d_step_part + 2 * (size_t)pb); SDSO_CHECK_LAUNCH(ctx);
-      SDSO_CUDA(ctx, cudaMemcpyAsync(sums, b->d_step_part + 2 * (size_t)pb, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  // host mirrors of what the loop moved (ONE synchronisation for the whole loop)
+  int it = 0;
+  {
+    std::vector<FrameDev> fd(kMaxFrames);
+    OptDev od;
+    BACalib cal;
+    std::vector<float> th(kMaxFrames);
+    SDSO_CUDA(ctx, cudaMemcpyAsync(fd.data(), b->d_frames, fd.size() * sizeof(FrameDev), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaMemcpyAsync(&od, b->d_opt, sizeof(OptDev), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaMemcpyAsync(&cal, b->d_calib, sizeof(BACalib), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaMemcpyAsync(th.data(), b->d_frameTH, th.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+    it = od.its_done;
+    for (int h = 0; h < n; h++) {
+      HostBAFrame& f = b->frames[h];
+      memcpy(f.state_backup, fd[h].state_backup, sizeof(f.state_backup));
+      for (int i = 0; i < 10; i++) f.step[i] = fd[h].state[i] - fd[h].state_backup[i];
+      frame_set_state(f, fd[h].state);   // state, state_scaled, PRE_worldToCam / PRE_camToWorld (host arithmetic, as prepare_window uses them)
+      f.frameEnergyTH = th[h];
     }
-    if ((rc = prepare_window(ctx))) return rc;  // setPrecalcValues (+ setDeltaF); synchronises
-    sumA /= n; sumB /= n; sumR /= n; sumT /= n;
-    const float sumNID = P > 0 ? (float)(sums[1] / P) : 0.f;
-    const float th = ctx->S.thOptIterations;
-    const bool canbreak = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
-    if ((rc = lin(0))) return rc;
-    if ((rc = apply())) return rc;  // setting_forceAceptStep: every step is accepted (:965-978)
-    if (canbreak && it >= ctx->S.minOptIterations) { it++; break; }
+    for (int i = 0; i < 4; i++) { b->calib_value[i] = od.calib_value[i]; b->calib_backup[i] = od.calib_backup[i]; b->calib_step[i] = od.calib_value[i] - od.calib_backup[i];
+                                  b->calib_delta[i] = b->calib_value[i] - b->calib_zero[i]; }
+    b->calib = cal;
+    // the loop is over: clear the latch so that the kernels of the tail below (and of later operator calls) run
+    SDSO_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(b->d_opt) + offsetof(OptDev, it), 0, 4 * sizeof(int), st));
   }
   if (iterations_done) *iterations_done = it;
   // new evaluation point of the newest frame (:996-1005): setEvalPT(PRE_worldToCam, [0.., a, b, 0, 0])
@@ -988,6 +1109,7 @@ int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iteration
 
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
   BA_CHECK(ctx)
+  invalidate_graphs(b);
   if (!HM || !bM) return SDSO_E_INVALID;
   const int d = b->dim();
   SDSO_CUDA(ctx, cudaMemcpyAsync(sysH(b, SYS_M), HM, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1322,6 +1444,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
 // EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736) for the points flagged PS_MARGINALIZE
 int sdso_ba_marginalize_points(sdso_ctx* ctx) {
   BA_PREPARED(ctx)
+  invalidate_graphs(b);
   const int d = b->dim(), P = b->P, R = b->R;
   cudaStream_t st = ctx->stream;
   if (P == 0) return SDSO_OK;
@@ -1344,6 +1467,7 @@ int sdso_ba_marginalize_points(sdso_ctx* ctx) {
 // to be uploaded again before the next operator call (the reference re-indexes with makeIDX at this point).
 int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx) {
   BA_PREPARED(ctx)
+  invalidate_graphs(b);
   if (idx < 0 || idx >= b->n) return SDSO_E_INVALID;
   const int odim = b->dim(), ndim = odim - 8;
   cudaStream_t st = ctx->stream;

@@ -21,7 +21,8 @@ namespace sdso {
 
 struct BAView {  // plain pointers handed to the kernels
   int n, P, R, capP, capR;
-  BACalib c;
+  const BACalib* cp;   // device-resident calibration (moves inside the LM loop)
+  const int* done;     // OptDev::done: kernels of the LM iteration chain exit at once when set (nullptr: never)
   const float4* const* tex0; const float* frameTH; const PrecalcDev* precalc;
   const double* adHost; const double* adTarget; const float* adHostF; const float* adTargetF;
   const float* adHTdeltaF; const float* cDeltaF; const double* fprior;
@@ -36,6 +37,7 @@ struct BAView {  // plain pointers handed to the kernels
   double* G; float* Gf; double* D; double* E; double* Hcc; double* U; double* V;
   double* energy_part; double* scalars; unsigned int* counter;
 };
+#define BA_EXIT_IF_DONE(B) do { if ((B).done && *(B).done) return; } while (0)
 
 __device__ __forceinline__ float* jplane(const BAView& B, int buf, int plane, int s) {
   return B.J + ((size_t)buf * kJ + plane) * B.capR + s;
@@ -97,7 +99,7 @@ __device__ double linearize_slot(const BAView& B, int s, bool fix) {
   const int key = B.s_key[s];
   const int h = key % B.n, t = key / B.n;
   const PrecalcDev& pc = B.precalc[h * B.n + t];
-  const BACalib& c = B.c;
+  const BACalib& c = *B.cp;
   const float pu = B.p_u[pidx], pv = B.p_v[pidx];
   const float idepth_scaled = SCALE_IDEPTH * B.p_idepth[pidx];
   const float idepth_zero_scaled = SCALE_IDEPTH * B.p_idepth_zero[pidx];
@@ -212,6 +214,7 @@ __device__ double linearize_slot(const BAView& B, int s, bool fix) {
 }
 
 __global__ void __launch_bounds__(128) ba_linearize_kernel(BAView B, int fix) {
+  BA_EXIT_IF_DONE(B);
   __shared__ double red[32];
   __shared__ bool last;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(128) ba_linearize_kernel(BAView B, int fix) {
   }
 }
 
-__global__ void ba_apply_res_kernel(BAView B, int copyJ) {  // applyRes_Reductor over activeResiduals
+__global__ void ba_apply_res_kernel(BAView B, int copyJ) {
+  BA_EXIT_IF_DONE(B);  // applyRes_Reductor over activeResiduals
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < B.R && !(B.s_flags[s] & (RF_LINEARIZED | RF_DROPPED))) apply_res_slot(B, s, copyJ != 0);
 }
@@ -252,12 +256,14 @@ __global__ void ba_reset_oob_kernel(BAView B) {
 }
 // backupState (:309-350): idepth_backup = idepth
 __global__ void ba_backup_points_kernel(BAView B) {
+  BA_EXIT_IF_DONE(B);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < B.P) B.p_idepth_backup[p] = B.p_idepth[p];
 }
 // doStepFromBackup (:268-279) / loadSateBackup (:355-362): idepth = idepth_zero = idepth_backup + stepfacD * step (points carry no FEJ
 // point), plus the sums the convergence test needs: out[0] += step^2, out[1] += |idepth_backup| (fixed-order double sums)
 __global__ void __launch_bounds__(128) ba_step_points_kernel(BAView B, float stepfacD, double* part /* [blocks][2] */) {
+  BA_EXIT_IF_DONE(B);
   __shared__ double red[32];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double s2 = 0, sn = 0;
@@ -271,7 +277,8 @@ __global__ void __launch_bounds__(128) ba_step_points_kernel(BAView B, float ste
   const double b = block_sum_d(sn, red);
   if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
 }
-__global__ void ba_sum_pairs_kernel(const double* part, int nblocks, double* out) {
+__global__ void ba_sum_pairs_kernel(const double* part, int nblocks, double* out, const int* done = nullptr) {
+  if (done && *done) return;
   if (threadIdx.x < 2) { double s = 0; for (int i = 0; i < nblocks; i++) s += part[2 * i + threadIdx.x]; out[threadIdx.x] = s; }
 }
 // number of residuals accumulateAF would count (ef->resInA): active, not linearised
@@ -294,6 +301,7 @@ __global__ void ba_drop_inactive_kernel(BAView B) {
 // is the very element std::nth_element would deliver — then the threshold arithmetic in float as written.
 __global__ void __launch_bounds__(1024) ba_energy_th_kernel(BAView B, int newest, float thN, float facMedian, float constWeight, float overallW,
                                                             float* frameTH, float* out) {
+  BA_EXIT_IF_DONE(B);
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_mask, s_k, s_n;
   const int tid = threadIdx.x, n = B.n;
@@ -389,6 +397,7 @@ __device__ __forceinline__ float warp_reduce_transpose32(float (&a)[32], int lan
 
 // ---- B4: residual part of addPoint<mode>; one CTA per chunk of <= 256 slots of one (host,target) pair ----------
 __global__ void __launch_bounds__(kChunk) ba_top_kernel(BAView B, int mode) {
+  BA_EXIT_IF_DONE(B);
   __shared__ float wsum[kChunk / 32][kTopVals];
   const Chunk ch = B.chunks[blockIdx.x];
   const int s = ch.begin + threadIdx.x;
@@ -494,6 +503,7 @@ __global__ void __launch_bounds__(kChunk) ba_top_kernel(BAView B, int mode) {
 // first half of the adjoint stitch for this key: W = adHost*A88, Z = adTarget*A88 (8x8) and Wc = adHost*[A8C | b8],
 // Zc = adTarget*[A8C | b8] (8x5), all in double (AccumulatedTopHessian.cpp:299-322). grid = n*n keys, 256 threads.
 __global__ void __launch_bounds__(256) ba_top_finish_kernel(BAView B, double* W, double* Z, double* Wc, double* Zc) {
+  BA_EXIT_IF_DONE(B);
   __shared__ float v[kTopVals];
   __shared__ double Gs[169];
   const int key = blockIdx.x, tid = threadIdx.x;
@@ -537,6 +547,7 @@ __global__ void __launch_bounds__(256) ba_top_finish_kernel(BAView B, double* W,
 
 // per-point tail: sums of its residuals' terms in residualsAll order
 __global__ void ba_point_sums_kernel(BAView B, int mode) {
+  BA_EXIT_IF_DONE(B);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= B.P) return;
   if (mode == 2 && B.p_flag[p] != PS_MARGINALIZE) return;
@@ -561,6 +572,7 @@ __global__ void ba_point_sums_kernel(BAView B, int mode) {
 
 // ---- B6, per-point part ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ba_sc_point_kernel(BAView B, int shiftPriorToZero) {
+  BA_EXIT_IF_DONE(B);
   __shared__ float red[4][20];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t cP = B.capP;
@@ -601,6 +613,7 @@ __global__ void __launch_bounds__(128) ba_sc_point_kernel(BAView B, int shiftPri
 
 // ---- B6, O(res^2) part: grid = (chunks, n+1); blockIdx.y < n: accD towards target y; == n: accE + accEB -------
 __global__ void __launch_bounds__(kChunk) ba_sc_pair_kernel(BAView B, int shiftPriorToZero) {
+  BA_EXIT_IF_DONE(B);
   __shared__ float wsum[kChunk / 32][64];
   const Chunk ch = B.chunks[blockIdx.x];
   const int t2 = blockIdx.y;
@@ -668,6 +681,7 @@ __global__ void __launch_bounds__(kChunk) ba_sc_pair_kernel(BAView B, int shiftP
 // first half of the adjoint stitch: U = adHost[key]*D, V = adTarget[key]*D (t2 < n) or Uc/Vc = ad*[E | EB] (t2 == n).
 // Block (0,0) also sums accHcc / accbc (AccumulatedSCHessian.cpp:106-195).
 __global__ void __launch_bounds__(96) ba_sc_finish_kernel(BAView B, int pblocks, double* Uc, double* Vc) {
+  BA_EXIT_IF_DONE(B);
   __shared__ double Ds[65];
   const int key = blockIdx.x, t2 = blockIdx.y, e = threadIdx.x;
   const int n = B.n;
@@ -715,6 +729,7 @@ __device__ __forceinline__ double rowdot8(const double* __restrict__ X, int i, c
 // 256 threads = 64 elements x 4 term groups; the groups are summed in fixed order ----------------------------------------
 __global__ void __launch_bounds__(256) ba_stitch_top_kernel(BAView B, const double* W, const double* Z, const double* Wc, const double* Zc,
                                                             double* H, double* bvec, int usePrior, const double* cPrior) {
+  BA_EXIT_IF_DONE(B);
   __shared__ double red[4][64];
   const int n = B.n, d = kCPARS + 8 * n, tid = threadIdx.x;
   if ((int)blockIdx.x < n * n) {
@@ -758,8 +773,33 @@ __global__ void __launch_bounds__(256) ba_stitch_top_kernel(BAView B, const doub
   }
 }
 
+// accumulateLF_MT when NO residual of the window is linearised — the normal case inside FullSystem::optimize: residuals are only
+// linearised (fixLinearizationF) on their way into the marginalisation prior. The linearised top system is then just the priors
+// (AccumulatedTopHessian.cpp:324-336) and every per-point L accumulator is zero; one small kernel instead of four.
+__global__ void ba_prior_system_kernel(BAView B, double* H, double* bvec, int usePrior, const double* cPrior) {
+  BA_EXIT_IF_DONE(B);
+  const int n = B.n, d = kCPARS + 8 * n;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < d * d) {
+    const int r = e / d, c = e % d;
+    double v = 0;
+    if (usePrior && r == c) v = r < 4 ? cPrior[r] : B.fprior[((r - 4) / 8) * 24 + (r - 4) % 8];
+    H[e] = v;
+  } else if (e < d * d + d) {
+    const int r = e - d * d;
+    double v = 0;
+    if (usePrior) v = r < 4 ? cPrior[r] * (double)B.cDeltaF[r] : B.fprior[((r - 4) / 8) * 24 + (r - 4) % 8] * B.fprior[((r - 4) / 8) * 24 + 8 + (r - 4) % 8];
+    bvec[r] = v;
+  }
+  // p_acc planes 6-11: Hdd_L, bd_L, Hcd_L
+  for (int p = e; p < B.P; p += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int k = 6; k < 12; k++) B.p_acc[(size_t)k * B.capP + p] = 0.f;
+}
+
 // ---- B7: second half of the Schur stitch, same decomposition --------------------------------------------------------------
 __global__ void __launch_bounds__(256) ba_stitch_sc_kernel(BAView B, const double* Uc, const double* Vc, double* H, double* bvec) {
+  BA_EXIT_IF_DONE(B);
   __shared__ double red[4][64];
   const int n = B.n, d = kCPARS + 8 * n, tid = threadIdx.x;
   if ((int)blockIdx.x < n * n) {
@@ -811,6 +851,8 @@ struct SolveParams {
   int nrank;
   int plain;         // 1: solve HF x = bF as is (g2o LinearSolver semantics): no (diag+10)^-1/2 scaling, no orthogonalisation
   double* HF; double* bF; double* x;
+  const int* done;   // OptDev::done (nullptr: never)
+  const int* it_ptr; // OptDev::it: iteration index read on the device (nullptr: `iteration` above)
 };
 
 // HFinal = HL + HM + HA, diag *= (1 + lambda), -= H_sc / (1 + lambda); bFinal = bL + (bM + HM delta) + bA - b_sc
@@ -818,6 +860,7 @@ struct SolveParams {
 // produces a PARTIAL (HFinal, bFinal) here (have_M and the priors only on one rank) and the shards are summed by one
 // allreduce before ba_solve_kernel.
 __global__ void ba_assemble_kernel(SolveParams S) {
+  if (S.done && *S.done) return;
   const int d = S.d;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d * d + d) return;
@@ -865,6 +908,7 @@ __device__ void ortho_vec(const double* __restrict__ Q, int d, int rank, double*
 }
 
 __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
+  if (S.done && *S.done) return;
   extern __shared__ double sm[];
   const int d = S.d, tid = threadIdx.x, nt = blockDim.x;
   const int ld = d | 1;           // odd leading dimension: column walks hit distinct banks
@@ -885,6 +929,55 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   for (int r = ty; r < d; r += 16)
     for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
   for (int i = tid; i < d; i += nt) bs[i] = sv[i] * bs[i];
+  __syncthreads();
+  // ---- fast path: LDL^T WITHOUT pivoting, one block barrier per column. The scaled system S H S is symmetric positive definite
+  // (EnergyFunctional.cpp:967-976: damped top Hessian minus the Schur complement, unit-ish diagonal after the (diag+10)^-1/2
+  // scaling), so no pivot search, no row swaps and no column scaling phase are needed: column k stays UNSCALED in place
+  // (L_ik = M_ik / d_k is formed on the fly, here and in the substitutions), every thread reads the pivot itself, and the only
+  // synchronisation per column is the barrier behind the trailing update. A non-positive or non-finite pivot (the matrix was
+  // not positive definite after all) falls through to the pivoted factorisation below, which reloads the system.
+  bool spd = true;
+  for (int k = 0; k < d; k++) {
+    const double mkk = M[k * ld + k];
+    if (!(mkk > 0.0) || !isfinite(mkk)) { spd = false; break; }   // uniform: every thread reads the same value
+    const double rk = 1.0 / mkk;
+    for (int i = k + 1 + ty; i < d; i += 16) {
+      const double lik = M[i * ld + k] * rk;
+      for (int j = k + 1 + tx; j <= i; j += 16) M[i * ld + j] -= lik * M[j * ld + k];
+    }
+    if (tid == 0) dg[k] = rk;
+    __syncthreads();
+  }
+  if (spd) {
+    if (warp == 0) {  // L y = b, z = D^-1 y, L^T x = z with L_ik = M_ik * dg[k]; column oriented, one warp
+      for (int i = lane; i < d; i += 32) y[i] = bs[i];
+      __syncwarp();
+      for (int i = 0; i < d; i++) {
+        const double yi = y[i] * dg[i];
+        for (int j = i + 1 + lane; j < d; j += 32) y[j] -= M[j * ld + i] * yi;
+        __syncwarp();
+      }
+      for (int i = lane; i < d; i += 32) y[i] *= dg[i];
+      __syncwarp();
+      for (int i = d - 1; i >= 0; i--) {
+        const double yi = y[i];
+        for (int j = lane; j < i; j += 32) y[j] -= M[i * ld + j] * dg[j] * yi;
+        __syncwarp();
+      }
+      for (int i = lane; i < d; i += 32) bs[i] = y[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < d; i += nt) bs[i] *= sv[i];
+    __syncthreads();
+    const int iteration_f = S.it_ptr ? *S.it_ptr : S.iteration;
+    if (!S.plain && iteration_f >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
+    for (int i = tid; i < d; i += nt) S.x[i] = bs[i];
+    return;
+  }
+  // ---- fallback: reload, then the pivoted factorisation
+  __syncthreads();
+  for (int r = ty; r < d; r += 16)
+    for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
   __syncthreads();
   // diagonal-pivoted LDLT (the strategy of Eigen::LDLT, which EnergyFunctional.cpp:976 calls). Two block barriers per pivot:
   // after the swap + scale of column k, warp 0 updates the DIAGONAL of the trailing matrix and picks the next pivot from it
@@ -963,7 +1056,8 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   __syncthreads();
   for (int i = tid; i < d; i += nt) bs[i] *= sv[i];
   __syncthreads();
-  if (!S.plain && S.iteration >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
+  const int iteration = S.it_ptr ? *S.it_ptr : S.iteration;
+  if (!S.plain && iteration >= 2 && S.N) ortho_vec(S.N, d, S.nrank, bs, scr);  // SOLVER_ORTHOGONALIZE_X_LATER (:980-984)
   for (int i = tid; i < d; i += nt) S.x[i] = bs[i];
 }
 
@@ -1171,7 +1265,7 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
   const float4 col0 = B.p_color[2 * pidx], col1 = B.p_color[2 * pidx + 1], wt0 = B.p_weights[2 * pidx], wt1 = B.p_weights[2 * pidx + 1];
   const float color[8] = {col0.x, col0.y, col0.z, col0.w, col1.x, col1.y, col1.z, col1.w};
   const float weights[8] = {wt0.x, wt0.y, wt0.z, wt0.w, wt1.x, wt1.y, wt1.z, wt1.w};
-  const int wl = B.c.w0 - 3, hl = B.c.h0 - 3;
+  const int wl = B.cp->w0 - 3, hl = B.cp->h0 - 3;
   const float4* tex = B.tex0[t];
   float energyLeft = 0, wJI2_sum = 0;
   double drs[8], us[8], vs[8], nids[8]; float3 hits[8]; float K0s[8], K1s[8];
@@ -1192,14 +1286,14 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
       E.newState[rid] = RS_OOB; for (int i = 0; i < 8; i++) err[i] = 0; E.level[rid] = 1; return;
     }
     if (kPatternP[idx][0] == 0 && kPatternP[idx][1] == 0) { E.center3[3 * rid] = (float)_Ku; E.center3[3 * rid + 1] = (float)_Kv; E.center3[3 * rid + 2] = (float)new_idepth; }
-    const float3 hit = interp33(tex, (float)_Ku, (float)_Kv, B.c.w0);
+    const float3 hit = interp33(tex, (float)_Ku, (float)_Kv, B.cp->w0);
     drs[idx] = drescale; us[idx] = _u; vs[idx] = _v; nids[idx] = new_idepth; hits[idx] = hit; K0s[idx] = K0; K1s[idx] = K1;
     if (!isfinite(hit.x)) { newState = RS_OOB; err[idx] = 0; finite_all = false; continue; }
     const double e = hit.x - (ab0 * color[idx] + ab1);
     err[idx] = e;
-    float w = sqrtf(B.c.outlierTHSumComponent / (B.c.outlierTHSumComponent + (hit.y * hit.y + hit.z * hit.z)));
+    float w = sqrtf(B.cp->outlierTHSumComponent / (B.cp->outlierTHSumComponent + (hit.y * hit.y + hit.z * hit.z)));
     w = 0.5f * (w + weights[idx]);
-    const float hw = fabsf((float)e) < B.c.huberTH ? 1 : B.c.huberTH / fabsf((float)e);
+    const float hw = fabsf((float)e) < B.cp->huberTH ? 1 : B.cp->huberTH / fabsf((float)e);
     energyLeft += w * w * hw * e * e * (2 - hw);
     wJI2_sum += hw * hw * (hit.y * hit.y + hit.z * hit.z);
   }
@@ -1261,7 +1355,7 @@ __device__ __forceinline__ float act_lin_res(const BAView& B, const sdso_immatur
   if (tr.state_state == RS_OOB) { tr.state_NewState = RS_OOB; return tr.state_energy; }
   const PrecalcDev& pc = B.precalc[host * B.n + target];
   const float4* tex = B.tex0[target];
-  const BACalib& c = B.c;
+  const BACalib& c = *B.cp;
   float Ku[8], Kv[8], uu[8], vv[8], dr[8];
   bool inside[8];
 #pragma unroll
@@ -1542,6 +1636,7 @@ __global__ void lba_activate_kernel(int R, const unsigned char* in_graph, const 
 // ---- B9 -------------------------------------------------------------------------------------------------------
 // xAd[h*n + t] = x_h^T adHostF[h + t*n] + x_t^T adTargetF[h + t*n]   (EnergyFunctional.cpp:283-293)
 __global__ void ba_xad_kernel(BAView B, const double* x, float* xAd) {
+  BA_EXIT_IF_DONE(B);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = B.n;
   if (e >= n * n * 8) return;
@@ -1554,6 +1649,7 @@ __global__ void ba_xad_kernel(BAView B, const double* x, float* xAd) {
 }
 
 __global__ void ba_resub_kernel(BAView B, const double* x, const float* xAd) {
+  BA_EXIT_IF_DONE(B);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= B.P) return;
   const size_t cP = B.capP, cR = B.capR;
@@ -1577,6 +1673,160 @@ __global__ void ba_resub_kernel(BAView B, const double* x, const float* xAd) {
     b -= sacc;
   }
   B.p_acc[14 * cP + p] = -b * B.p_acc[12 * cP + p];
+}
+
+
+// ---- device-resident LM loop of FullSystem::optimize ---------------------------------------------------------------------------
+// doStepFromBackup(1,1,1,1,1) for the frames and the calibration (FullSystemOptimize.cpp:207-305, the point part is
+// ba_step_points_kernel), FrameHessian::setState (HessianBlocks.h:177-199), FullSystem::setPrecalcValues ->
+// FrameFramePrecalc::set at the current state (HessianBlocks.cpp:206-242), EnergyFunctional::setDeltaF (:173-207) and the
+// convergence test (:298-301) — what used to be two host round trips per LM iteration — in ONE small CTA. SE3 arithmetic in
+// double with the formulas of se3_host.cu (the reference computes these on the host in double as well).
+__device__ inline void dev_se3_exp(const double a[6], double T[12]) {
+  const double* w = a + 3;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double A, Bc, C;
+  if (th < 1e-5) { A = 1 - th2 / 6 + th2 * th2 / 120; Bc = 0.5 - th2 / 24 + th2 * th2 / 720; C = 1.0 / 6 - th2 / 120 + th2 * th2 / 5040; }
+  else { A = sin(th) / th; Bc = (1 - cos(th)) / th2; C = (th - sin(th)) / (th2 * th); }
+  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double W2[9];
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) W2[r * 3 + c] = W[r * 3] * W[c] + W[r * 3 + 1] * W[3 + c] + W[r * 3 + 2] * W[6 + c];
+  double R[9], V[9];
+  for (int i = 0; i < 9; i++) { const double I = (i % 4 == 0) ? 1.0 : 0.0; R[i] = I + A * W[i] + Bc * W2[i]; V[i] = I + Bc * W[i] + C * W2[i]; }
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) T[r * 4 + c] = R[r * 3 + c];
+    T[r * 4 + 3] = V[r * 3] * a[0] + V[r * 3 + 1] * a[1] + V[r * 3 + 2] * a[2];
+  }
+}
+__device__ inline void dev_se3_mul(const double A[12], const double B[12], double C[12]) {
+  double out[12];
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) out[r * 4 + c] = A[r * 4] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c];
+    out[r * 4 + 3] = A[r * 4] * B[3] + A[r * 4 + 1] * B[7] + A[r * 4 + 2] * B[11] + A[r * 4 + 3];
+  }
+  for (int i = 0; i < 12; i++) C[i] = out[i];
+}
+__device__ inline void dev_se3_inv(const double A[12], double B[12]) {
+  double out[12];
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) out[r * 4 + c] = A[c * 4 + r];
+    out[r * 4 + 3] = -(A[0 * 4 + r] * A[3] + A[1 * 4 + r] * A[7] + A[2 * 4 + r] * A[11]);
+  }
+  for (int i = 0; i < 12; i++) B[i] = out[i];
+}
+__device__ inline void dev_mat33f_mul(const float A[9], const float B[9], float C[9]) {
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[r * 3 + c] = A[r * 3 + 0] * B[0 * 3 + c] + A[r * 3 + 1] * B[1 * 3 + c] + A[r * 3 + 2] * B[2 * 3 + c];
+}
+__device__ inline void dev_inverse3f(const float m[9], float out[9]) {  // = inverse3f (ctx.cu): cofactors * (1/det)
+  float cofm[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    cofm[i * 3 + j] = m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+  }
+  const float det = (cofm[0] * m[0] + cofm[3] * m[3]) + cofm[6] * m[6];
+  const float invdet = 1.0f / det;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[j * 3 + i] = cofm[i * 3 + j] * invdet;
+}
+
+struct FrameUpdateParams {
+  int n, P;
+  FrameDev* frames; OptDev* opt; BACalib* calib; float* cDeltaF; double* fprior; PrecalcDev* precalc;
+  const float* adHostF; const float* adTargetF; float* adHTdeltaF;
+  const double* x;          // the solved increment (SYS_X); steps are -x
+  const double* step_sums;  // [2]: sum of squared point steps, sum of |idepth_backup| (ba_sum_pairs_kernel)
+};
+
+__global__ void __launch_bounds__(256) ba_frame_update_kernel(FrameUpdateParams U) {
+  if (U.opt->done) return;
+  __shared__ double s_step[kMaxFrames][8];
+  const int tid = threadIdx.x, n = U.n;
+  if (tid < n) {   // backupState + doStepFromBackup + setState of frame tid
+    FrameDev& f = U.frames[tid];
+    double sc[10];
+    for (int i = 0; i < 10; i++) {
+      const double st = i < 8 ? -U.x[kCPARS + 8 * tid + i] : 0.0;
+      if (i < 8) s_step[tid][i] = st;
+      f.state_backup[i] = f.state[i];
+      f.state[i] = f.state_backup[i] + 1.0f * st;
+    }
+    for (int i = 0; i < 3; i++) sc[i] = SCALE_XI_TRANS * f.state[i];
+    for (int i = 3; i < 6; i++) sc[i] = SCALE_XI_ROT * f.state[i];
+    sc[6] = SCALE_A * f.state[6]; sc[7] = SCALE_B * f.state[7]; sc[8] = SCALE_A * f.state[8]; sc[9] = SCALE_B * f.state[9];
+    double E[12];
+    dev_se3_exp(sc, E);
+    dev_se3_mul(E, f.T_eval, f.T_w2c);
+    dev_se3_inv(f.T_w2c, f.T_c2w);
+    for (int i = 0; i < 8; i++) { U.fprior[tid * 24 + 8 + i] = f.state[i]; U.fprior[tid * 24 + 16 + i] = f.state[i] - f.state_zero[i]; }
+  } else if (tid == 32) {   // the calibration: CalibHessian::setValue (HessianBlocks.h:316-331)
+    OptDev& o = *U.opt;
+    BACalib& c = *U.calib;
+    for (int i = 0; i < 4; i++) { o.calib_backup[i] = o.calib_value[i]; o.calib_value[i] = o.calib_backup[i] + 1.0f * (-U.x[i]); }
+    const double vs[4] = {SCALE_F * o.calib_value[0], SCALE_F * o.calib_value[1], SCALE_C * o.calib_value[2], SCALE_C * o.calib_value[3]};
+    c.fxl = (float)vs[0]; c.fyl = (float)vs[1]; c.cxl = (float)vs[2]; c.cyl = (float)vs[3];
+    c.fxli = 1.0f / c.fxl; c.fyli = 1.0f / c.fyl; c.cxli = -c.cxl / c.fxl; c.cyli = -c.cyl / c.fyl;
+    for (int i = 0; i < 4; i++) U.cDeltaF[i] = (float)(o.calib_value[i] - o.calib_zero[i]);
+  }
+  __syncthreads();
+  if (tid == 0) {   // the convergence test (:281-301), float sums in frame order as written
+    float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+    for (int h = 0; h < n; h++) {
+      const double* st = s_step[h];
+      sumA += st[6] * st[6];
+      sumB += st[7] * st[7];
+      sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
+      sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
+    }
+    sumA /= n; sumB /= n; sumR /= n; sumT /= n;
+    const float sumNID = U.P > 0 ? (float)(U.step_sums[1] / U.P) : 0.f;
+    const float th = U.opt->th_opt;
+    const bool canbreak = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
+    U.opt->pending = (canbreak && U.opt->it >= U.opt->min_its) ? 1 : 0;
+  }
+  // FrameFramePrecalc::set at the current state + adHTdeltaF for every (host, target) pair
+  for (int ht = tid; ht < n * n; ht += blockDim.x) {
+    const int h = ht / n, t = ht % n;
+    const FrameDev& host = U.frames[h]; const FrameDev& target = U.frames[t];
+    PrecalcDev& p = U.precalc[(size_t)h * n + t];
+    const BACalib& c = *U.calib;
+    const float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
+    float Kinv[9];
+    dev_inverse3f(K, Kinv);
+    double l[12];
+    dev_se3_mul(target.T_w2c, host.T_c2w, l);
+    for (int r = 0; r < 3; r++) {
+      for (int q = 0; q < 3; q++) p.PRE_RTll[r * 3 + q] = (float)l[r * 4 + q];
+      p.PRE_tTll[r] = (float)l[r * 4 + 3];
+    }
+    p.distanceLL = (float)sqrt(l[3] * l[3] + l[7] * l[7] + l[11] * l[11]);
+    float KR[9];
+    dev_mat33f_mul(K, p.PRE_RTll, KR);
+    dev_mat33f_mul(KR, Kinv, p.PRE_KRKiTll);
+    dev_mat33f_mul(p.PRE_RTll, Kinv, p.PRE_RKiTll);
+    for (int r = 0; r < 3; r++) p.PRE_KtTll[r] = K[r * 3] * p.PRE_tTll[0] + K[r * 3 + 1] * p.PRE_tTll[1] + K[r * 3 + 2] * p.PRE_tTll[2];
+    float eF = host.ab_exposure, eT = target.ab_exposure;
+    if (eF == 0 || eT == 0) { eT = eF = 1; }
+    const double a = exp(SCALE_A * target.state[6] - SCALE_A * host.state[6]) * eT / eF;   // AffLight::fromToVecExposure on state_scaled
+    p.PRE_aff_mode[0] = (float)a; p.PRE_aff_mode[1] = (float)(SCALE_B * target.state[7] - a * (SCALE_B * host.state[7]));
+    // setDeltaF (:181-192): adHTdeltaF[h + t n] = delta_h^T adHostF + delta_t^T adTargetF
+    const size_t idx = (size_t)h + (size_t)t * n;
+    float dh[8], dt[8];
+    for (int i = 0; i < 8; i++) { dh[i] = (float)(host.state[i] - host.state_zero[i]); dt[i] = (float)(target.state[i] - target.state_zero[i]); }
+    for (int j = 0; j < 8; j++) {
+      float a2 = 0, b2 = 0;
+      for (int i = 0; i < 8; i++) a2 += dh[i] * U.adHostF[idx * 64 + i * 8 + j];
+      for (int i = 0; i < 8; i++) b2 += dt[i] * U.adTargetF[idx * 64 + i * 8 + j];
+      U.adHTdeltaF[idx * 8 + j] = a2 + b2;
+    }
+  }
+}
+// end of one LM iteration: count it, and latch the convergence decision so that the iterations the host enqueued behind this one
+// become no-ops
+__global__ void ba_iter_end_kernel(OptDev* o) {
+  if (o->done) return;
+  o->it += 1;
+  o->its_done = o->it;
+  if (o->pending) o->done = 1;
 }
 
 }  // namespace sdso

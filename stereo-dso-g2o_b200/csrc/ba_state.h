@@ -55,6 +55,24 @@ struct HostBAFrame {
 
 struct Chunk { int key, begin, end, pad; };
 
+// Device mirror of the per-frame state the LM loop of FullSystem::optimize moves (FrameHessian state / state_zero / state_backup,
+// worldToCam_evalPT, PRE_worldToCam / PRE_camToWorld; HessianBlocks.h:121-231): with it the loop runs without host round trips.
+struct FrameDev {
+  double T_eval[12];
+  double state[10], state_zero[10], state_backup[10];
+  double T_w2c[12], T_c2w[12];
+  float ab_exposure, pad;
+};
+// Control block of the device-resident LM loop (sdso_ba_optimize): iteration counter, convergence flags, calibration value
+struct OptDev {
+  double calib_value[4], calib_zero[4], calib_backup[4];   // CalibHessian value / value_zero / value_backup (unscaled)
+  int it;          // LM iterations started so far (the solve orthogonalises x from iteration 2 on)
+  int pending;     // the convergence test of this iteration's step passed: the loop ends after its linearizeAll / applyRes
+  int done;        // every kernel of the iteration chain exits at once when set (the host enqueues all mnumOptIts iterations blindly)
+  int its_done;    // what FullSystem::optimize's loop counter would be
+  float th_opt; int min_its; int pad[2];
+};
+
 struct BAState {
   int n = 0, P = 0, R = 0;
   bool prepared = false;
@@ -120,6 +138,14 @@ struct BAState {
   float* d_xAd = nullptr;                 // [n*n][8]
   int* d_list = nullptr;                  // scratch slot list
   double* d_step_part = nullptr; int step_part_cap = 0;  // per-block partial sums of doStepFromBackup
+  FrameDev* d_frames = nullptr;           // [kMaxFrames]
+  BACalib* d_calib = nullptr;             // the kernels read the calibration from here (it moves inside the LM loop)
+  OptDev* d_opt = nullptr;
+  void* graph_iter = nullptr;             // cudaGraphExec_t of one LM iteration of sdso_ba_optimize (captured per prepared window)
+  void* graph_assemble = nullptr;         // cudaGraphExec_t of the accumulate + stitch + assemble chain (sdso_ba_assemble / sdso_ba_solve)
+  int graph_iter_nodes = 0, graph_assemble_nodes = 0;   // kernels per replay (launch accounting)
+  cudaStream_t cap_stream = nullptr;      // capture stream (the context's stream may be the legacy default stream, which cannot capture)
+  bool any_linearized = false;            // some residual has been through fixLinearizationF since the window was uploaded
   int shard_rank = 0, shard_n = 1;        // point-sharded window: priors and HM enter on rank 0 only
   bool have_M = false;                    // HM/bM (marginalisation prior) present in SYS_M
   std::vector<double> h_N, h_adH, h_adT;

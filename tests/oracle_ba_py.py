@@ -38,6 +38,7 @@ lib.orc_ba_energies.restype = C.c_double
 lib.orc_ba_energies.argtypes = [V, _dp]
 lib.orc_ba_nullspaces.argtypes = [V, _dp]
 lib.orc_ba_set_reduce.argtypes = [V, C.c_int, C.c_uint]
+lib.orc_ba_get_energy_th.argtypes = [V, _fp]
 
 _p = O._p
 _f32, _f64 = O._f32, O._f64
@@ -136,6 +137,11 @@ class OracleBA:
         H, b = np.zeros((d, d)), np.zeros(d)
         lib.orc_ba_accumulate_sc(self.h, int(shift), _p(H, _dp), _p(b, _dp))
         return H, b
+
+    def get_energy_th(self):
+        th = np.zeros(self.counts()["frames"], np.float32)
+        lib.orc_ba_get_energy_th(self.h, _p(th, _fp))
+        return th
 
     def set_reduce(self, threads=1, seed=0):
         """Worker partition of the float accumulators (the reference's NUM_THREADS=6 IndexThreadReduce; any seed is an assignment the

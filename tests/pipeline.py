@@ -192,6 +192,7 @@ class StereoPipeline:
         self.T_w2c_hist = []   # worldToCam 3x4 per frame
         self.aff = (0.0, 0.0)
         self.log = []          # per key frame: counts for the report / for comparing two backends
+        self.on_window = None  # diagnostics: called with (window description, marg prior) right before the windowed optimisation
 
     # ---------------------------------------------------------------------------------------------------------------
     def step(self, img_left, img_right):
@@ -252,7 +253,7 @@ class StereoPipeline:
         B, K4 = self.B, self.K4
         K33 = TS.K33(K4)
         kf = dict(fid=fl, fid_right=fr, frameID=self.next_frame_id, T_eval=T_w2c.copy(), T_cur=T_w2c.copy(), a_eval=self.aff[0], b_eval=self.aff[1],
-                  aff_cur=self.aff, state=np.zeros(10), energyTH=8 * 8 * 8, immature=None, my_type=None)
+                  aff_cur=self.aff, state=np.zeros(10), energyTH=8 * 8 * 8, immature=None, my_type=None, frame_index=len(self.traj) - 1)
         kf["state"][6], kf["state"][7] = self.aff[0] / SCALE_A, self.aff[1] / SCALE_B
         self.next_frame_id += 1
         flagged = [self.kfs[0]["frameID"]] if len(self.kfs) >= self.max_kf else []
@@ -320,6 +321,8 @@ class StereoPipeline:
                 m = self.HM.shape[0]
                 HM[:m, :m] = self.HM; bM[:m] = self.bM   # the new frame enters with zero prior (EnergyFunctional::insertFrame, :490-500)
                 Wn.set_marg_prior(HM, bM)
+            if self.on_window:
+                self.on_window(win, (self.HM, self.bM))
             rmse, its = Wn.optimize(self.opt_its)
             st = Wn.get_state()
             res = Wn.get_res(1)
@@ -329,7 +332,7 @@ class StereoPipeline:
                 f["aff_cur"] = (float(st["states"][i][6] * SCALE_A), float(st["states"][i][7] * SCALE_B))
             kf["T_eval"] = st["T_w2c"][newest].copy()     # setEvalPT of the newest frame (FullSystemOptimize.cpp:996-1005)
             kf["a_eval"], kf["b_eval"] = kf["aff_cur"]
-            kf["energyTH"] = float(Wn.new_frame_energy_th())
+            kf["energyTH"] = float(Wn.get_energy_th()[newest])   # what setNewFrameEnergyTH left behind in the final linearizeAll (FullSystemOptimize.cpp:163)
             self.aff = kf["aff_cur"]
             self.T_w2c_hist[-1] = kf["T_cur"].copy()
             self.traj[-1] = np.vstack([inv34(kf["T_cur"]), [0, 0, 0, 1]])

@@ -114,3 +114,55 @@ def test_empty_batch(setup):
     pts, ok = ctx.immature_init(gid["l"], np.zeros((0, 2), np.float32))
     assert pts.size == 0
     assert ctx.trace_on(gid["n"], np.eye(3), np.zeros(3), (1, 0), pts).size == 0
+
+
+def test_multi_host_launch_and_resident_pool_equal_per_host_calls(setup, frames, scene, pkg):
+    """All hosts of a window in ONE launch (per-point transform index), with host records and with the device-resident pool:
+    bit-identical to the per-host calls, which are bit-exact against the oracle above. Long segments (> 32 and > 64 steps)
+    exercise the second search round of a warp."""
+    orc, ctx, oid, gid, uv = setup
+    rng = np.random.default_rng(7)
+    hosts = [synth.camera_pose(0), synth.camera_pose(0.5), synth.camera_pose(2)]
+    imgs = [frames[0][0], synth.render(scene, hosts[1])[0], frames[2][0]]
+    hf = []
+    for im in imgs:
+        f = ctx.frame_create(); ctx.make_images(f, im); hf.append(f)
+    target = synth.camera_pose(1)
+    per_host, xf = [], []
+    for h, pose in enumerate(hosts):
+        pts, ok = ctx.immature_init(hf[h], TS.candidate_pixels(imgs[h], 700, rng))
+        pts = pts[ok]
+        pts["idepth_min"] = rng.uniform(0.005, 0.03, pts.size).astype(np.float32)
+        pts["idepth_max"] = (pts["idepth_min"] * rng.uniform(1.5, 40, pts.size)).astype(np.float32)   # segments of a few to > 64 steps
+        pts["idepth_max"][::17] = np.nan                                                              # unbounded prior
+        per_host.append(pts)
+        KRKi, Kt = TS.krki_kt(pose, target)
+        xf.append((KRKi, Kt, (1.0 + 0.01 * h, -0.5 * h)))
+    ref, ref_st = [], []
+    for pts, (KRKi, Kt, aff) in zip(per_host, xf):
+        q = pts.copy()
+        ref_st.append(ctx.trace_on(gid["n"], KRKi, Kt, aff, q)); ref.append(q)
+    ref, ref_st = np.concatenate(ref), np.concatenate(ref_st)
+    # (maxPixSearch = 0.027 (w + h) caps a segment at 45 steps here: two search rounds per lane)
+    assert ref["numSteps"].max() > 32 and (ref["numSteps"] > 32).sum() > 20 and len(set(np.unique(ref_st))) >= 3
+    allp = np.concatenate(per_host)
+    host_of = np.concatenate([np.full(p.size, h, np.int32) for h, p in enumerate(per_host)])
+    perm = rng.permutation(allp.size)   # points of different hosts interleaved
+    KR, KT, AF = np.stack([x[0] for x in xf]), np.stack([x[1] for x in xf]), np.array([x[2] for x in xf], np.float32)
+    a = np.ascontiguousarray(allp[perm])
+    st = ctx.trace_on_hosts(gid["n"], KR, KT, AF, host_of[perm], a)
+    assert np.array_equal(st, ref_st[perm]) and a.tobytes() == np.ascontiguousarray(ref[perm]).tobytes()
+    # resident pool: upload once, trace in place (twice: the second pass starts from the first one's intervals), read back once
+    ctx.immature_upload(np.ascontiguousarray(allp[perm]))
+    st1 = ctx.trace_on_hosts(gid["n"], KR, KT, AF, host_of[perm], None)
+    assert np.array_equal(st1, ref_st[perm])
+    assert ctx.immature_download(a.size).tobytes() == a.tobytes()
+    ctx.trace_on_hosts(gid["n"], KR, KT, AF, host_of[perm], None, want_status=False)
+    b = a.copy()
+    ctx.trace_on_hosts(gid["n"], KR, KT, AF, host_of[perm], b)
+    assert ctx.immature_download(a.size).tobytes() == b.tobytes()
+    assert ctx.immature_download(10, first=5).tobytes() == b[5:15].tobytes()
+    with pytest.raises(pkg.SdsoError):
+        ctx.trace_on_hosts(gid["n"], KR, KT, AF, np.zeros(a.size + 1, np.int32), None)   # more points than the pool holds
+    for f in hf:
+        ctx.frame_release(f)

@@ -215,3 +215,32 @@ def test_track_g2o_stop_flag_knob(pkg, frames):
     g = ctx.track(f1, T0, (0.0, 0.0), ctx.levels - 1, [np.nan] * 5, 1)
     assert g["ok"] and np.all(g["iterations"] >= 1)
     ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_tracking_with_nonzero_reference_and_initial_brightness(pkg, frames, scene, variant):
+    """lastRef_aff_g2l != 0 and aff_g2l != 0 with an actual brightness change between the frames (the key frames of a running
+    system carry the affine parameters the windowed optimisation gave them): AffLight::fromToVecExposure (NumType.h:159-170) on
+    both sides of the tracker, pose / affine result against the oracle."""
+    ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE)
+    orc = O.Oracle(synth.W, synth.H, synth.K4, synth.BASELINE)
+    img1 = synth.render(scene, synth.camera_pose(1), exposure_ab=(0.05, 4.0))[0]   # the new frame is brighter
+    g0, g1, o0, o1 = ctx.frame_create(), ctx.frame_create(), orc.frame_new(), orc.frame_new()
+    ctx.make_images(g0, frames[0][0]); orc.make_images(o0, frames[0][0])
+    ctx.make_images(g1, img1); orc.make_images(o1, img1)
+    rng = np.random.default_rng(5)
+    pts = synth.pick_points(rng, frames[0][1], 2000)
+    ref_aff = (0.03, -2.5)
+    ctx.tracker_set_ref(g0, pts, ref_aff); orc.tracker_set_ref(o0, pts, ref_aff)
+    Ttrue = synth.T_rel(synth.camera_pose(0), synth.camera_pose(1))
+    T0 = synth.perturb_T(Ttrue, rng, 0.02, np.deg2rad(0.2))
+    for aff0 in ((0.0, 0.0), (0.06, 1.0)):
+        g = ctx.track(g1, T0, aff0, ctx.levels - 1, [np.nan] * 5, variant)
+        o = orc.track(o1, T0, aff0, orc.levels - 1, [np.nan] * 5, variant)
+        assert g["ok"] == o["ok"]
+        assert np.abs(g["T"][:, 3] - o["T"][:, 3]).max() < 1e-4 and rot_angle(g["T"][:, :3], o["T"][:, :3]) < 1e-5, (aff0, g["T"], o["T"])
+        assert np.allclose(g["aff"], o["aff"], rtol=1e-4, atol=1e-4), (aff0, g["aff"], o["aff"])
+        assert np.allclose(g["lastResiduals"], o["lastResiduals"], rtol=1e-4, equal_nan=True)
+        if variant == 0:
+            assert np.abs(g["T"][:, 3] - Ttrue[:, 3]).max() < 2e-2 and abs(g["aff"][0] - 0.08) < 0.03   # a_new - a_ref = 0.05
+    ctx.close()

@@ -20,88 +20,7 @@ SHAPES = {"640x192-n5": dict(w=640, h=192, K=(360.0, 360.0, 319.5, 95.5), n_kf=5
 MIN_ACT_DIST = 1.0
 
 
-class Backend:
-    """the same operator names for the oracle (test infrastructure) and the device library"""
-
-    def __init__(self, shape, pkg=None, reduce=(1, 0)):
-        self.dev = pkg is not None
-        self.pkg = pkg
-        self.shape = shape
-        self.reduce = reduce   # oracle only: worker partition of the float accumulators (OracleBA.set_reduce)
-        W_, H_, K_ = shape["w"], shape["h"], shape["K"]
-        self.api = pkg.Context(W_, H_, K_, synth.BASELINE) if self.dev else O.Oracle(W_, H_, K_, synth.BASELINE)
-        self.dm = None if self.dev else OD.DistMap(self.api)
-
-    def close(self):
-        if self.dev:
-            self.api.close()
-
-    def frames(self, win):
-        self.fids = []
-        for f in win["frames"]:
-            fid = self.api.frame_create() if self.dev else self.api.frame_new()
-            self.api.make_images(fid, f["image"])
-            self.fids.append(fid)
-
-    def immature_init(self, h, uv):
-        return self.api.immature_init(self.fids[h], uv) if self.dev else OT.immature_init(self.api, self.fids[h], uv)
-
-    def trace_on(self, t, KRKi, Kt, pts):
-        return self.api.trace_on(self.fids[t], KRKi, Kt, (1.0, 0.0), pts) if self.dev else OT.trace_on(self.api, self.fids[t], KRKi, Kt, (1.0, 0.0), pts)
-
-    def window(self, win):
-        """(re)build the backend window from the neutral description; colour / weights come from this backend's D1 operator"""
-        pts = win["points"]
-        cw = {}
-        for h in range(win["n"]):
-            idx = [i for i, p in enumerate(pts) if p["host"] == h]
-            if idx:
-                rec, _ = self.immature_init(h, np.array([[pts[i]["u"], pts[i]["v"]] for i in idx], np.float32))
-                for i, r in zip(idx, rec):
-                    cw[i] = (r["color"].copy(), r["weights"].copy())
-        Wn = self.pkg.Window(self.api) if self.dev else OB.OracleBA(self.api)
-        for k, f in enumerate(win["frames"]):
-            i = Wn.add_frame(self.fids[k], f["T_w2c"], f["a"], f["b"], f["frameID"])
-            Wn.set_state(i, f["state"]); Wn.set_energy_th(i, f["energyTH"])
-        if self.dev:
-            Wn.set_points([p["host"] for p in pts], [p["u"] for p in pts], [p["v"] for p in pts], [p["idepth"] for p in pts],
-                          [p["idepth_zero"] for p in pts], np.stack([cw[i][0] for i in range(len(pts))]), np.stack([cw[i][1] for i in range(len(pts))]),
-                          [p["has_prior"] for p in pts])
-            rp, rt = [], []
-            for pi, p in enumerate(pts):
-                for t in p["targets"]:
-                    rp.append(pi); rt.append(t)
-            Wn.set_residuals(rp, rt)
-        else:
-            for pi, p in enumerate(pts):
-                q = Wn.add_point(p["host"], p["u"], p["v"], p["idepth"], p["idepth_zero"], cw[pi][0], cw[pi][1], p["has_prior"])
-                for t in p["targets"]:
-                    Wn.add_residual(q, t)
-        Wn.prepare()
-        if not self.dev:
-            Wn.set_reduce(*self.reduce)
-        self.W = Wn
-        return Wn
-
-    def distmap_make(self, KRKi, Kt, pt_host, pt_uvid):
-        return self.api.distmap_make(KRKi, Kt, pt_host, pt_uvid) if self.dev else self.dm.make(KRKi, Kt, pt_host, pt_uvid)
-
-    def activation_filter(self, KRKi, Kt, flagged, cand_host, pts, my_type, mad):
-        if self.dev:
-            v, m, _ = self.api.activation_filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
-            return v, m
-        return self.dm.filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
-
-    def activate(self, n, host, pts):
-        return self.W.activate_points(host, pts, variant=0) if self.dev else OT.activate_points(self.api, n, host, pts, variant=0)
-
-    def set_point_flags(self, flags):
-        if self.dev:
-            self.W.set_point_flags(flags)
-        else:
-            for i, f in enumerate(flags):
-                if f:
-                    self.W.set_point_flag(i, int(f))
+from pipeline import Backend   # the same operator names for the oracle (test infrastructure) and the device library
 
 
 def host_to_newest(win, h, K_, level1=True):
