@@ -519,6 +519,7 @@ int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], doubl
   HostBAFrame f;
   f.frame_id = frame_id; f.frameID = frameID; f.ab_exposure = ctx->frames[frame_id].ab_exposure;
   memcpy(f.T_eval, T_w2c, sizeof(f.T_eval));
+  so3_normalize(f.T_eval);   // worldToCam_evalPT is an SE3 (unit quaternion) in the reference
   const double init[10] = {0, 0, 0, 0, 0, 0, a, bb, 0, 0};  // setEvalPT_scaled (HessianBlocks.h:223-231)
   frame_set_state_scaled(f, init);
   frame_set_state_zero(f);

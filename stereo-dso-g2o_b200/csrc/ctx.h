@@ -108,6 +108,7 @@ void se3_mul(const double A[12], const double B[12], double C[12]);
 void se3_inv(const double A[12], double B[12]);
 void se3_log(const double T[12], double a[6]);
 void se3_adj(const double T[12], double Ad[36]);  // 6x6 row-major
+void so3_normalize(double T[12]);                 // rotation block back onto SO(3) through a unit quaternion (what Sophus' SE3 type guarantees)
 
 // profiling helpers (ctx.cu)
 void prof_begin(sdso_ctx* ctx, int which);

@@ -92,6 +92,44 @@ void se3_log(const double T[12], double a[6]) {
   }
 }
 
+// The reference's SE3 is a unit quaternion + translation (thirdparty/Sophus/sophus/so3.hpp:95-110, 215-232): a pose that crosses
+// into it as a matrix is converted to a quaternion, and products renormalise it, so a rotation never leaves the manifold. Poses
+// cross the C ABI as double[12]; this puts the 3x3 block back onto SO(3) the same way (matrix -> quaternion (Shepperd, as
+// Eigen::Quaternion(Matrix3)) -> normalise -> matrix). Without it a caller that composes poses with R^T as the inverse (any
+// constant-velocity model does) feeds the round-off non-orthonormality of one frame into the next and it grows exponentially.
+void so3_normalize(double T[12]) {
+  const double m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+  double w, x, y, z;
+  const double tr = m00 + m11 + m22;
+  if (tr > 0) {
+    double t = std::sqrt(tr + 1.0);
+    w = 0.5 * t; t = 0.5 / t;
+    x = (m21 - m12) * t; y = (m02 - m20) * t; z = (m10 - m01) * t;
+  } else {
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > (i == 0 ? m00 : m11)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    auto M = [&](int r, int c) { return T[r * 4 + c]; };
+    double q[3];
+    double t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    w = (M(k, j) - M(j, k)) * t;
+    q[j] = (M(j, i) + M(i, j)) * t;
+    q[k] = (M(k, i) + M(i, k)) * t;
+    x = q[0]; y = q[1]; z = q[2];
+  }
+  const double nrm = std::sqrt(w * w + x * x + y * y + z * z);
+  if (!(nrm > 0) || !std::isfinite(nrm)) return;   // not a rotation at all: leave it to the caller's checks
+  w /= nrm; x /= nrm; y /= nrm; z /= nrm;
+  // Eigen::Quaternion::toRotationMatrix
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  T[0] = 1 - (tyy + tzz); T[1] = txy - twz; T[2] = txz + twy;
+  T[4] = txy + twz; T[5] = 1 - (txx + tzz); T[6] = tyz - twx;
+  T[8] = txz - twy; T[9] = tyz + twx; T[10] = 1 - (txx + tyy);
+}
+
 // 6x6 row-major: [R, hat(t) R; 0, R]
 void se3_adj(const double T[12], double Ad[36]) {
   double R[9], tx[9], tR[9];

@@ -26,13 +26,21 @@ import trace_synth as TS
 SCALE_A, SCALE_B = 10.0, 1000.0
 
 
+def on_so3(R):
+    """nearest rotation (the reference's SE3 is a unit quaternion: products renormalise, so3.hpp:215-232). Without this the R^T-as-
+    inverse below feeds the round-off non-orthonormality of one frame's pose into the constant-velocity guess of the next and it
+    grows by ~2.8x per frame."""
+    U, _, Vt = np.linalg.svd(R)
+    return U @ Vt
+
+
 def inv34(T):
-    R, t = T[:, :3], T[:, 3]
+    R, t = on_so3(T[:, :3]), T[:, 3]
     return np.hstack([R.T, (-R.T @ t)[:, None]])
 
 
 def mul34(A, B):
-    return np.hstack([A[:, :3] @ B[:, :3], (A[:, :3] @ B[:, 3] + A[:, 3])[:, None]])
+    return np.hstack([on_so3(A[:, :3] @ B[:, :3]), (A[:, :3] @ B[:, 3] + A[:, 3])[:, None]])
 
 
 class Backend:
@@ -193,6 +201,8 @@ class StereoPipeline:
         self.aff = (0.0, 0.0)
         self.log = []          # per key frame: counts for the report / for comparing two backends
         self.on_window = None  # diagnostics: called with (window description, marg prior) right before the windowed optimisation
+        self.on_track = None   # diagnostics: called with (frame index, T_guess, aff_guess, result) after every tracked frame
+        self.on_ref = None     # diagnostics: called with (frame index of the key frame, splats, aff) whenever the tracker reference is set
 
     # ---------------------------------------------------------------------------------------------------------------
     def step(self, img_left, img_right):
@@ -211,7 +221,10 @@ class StereoPipeline:
             guess_w2c = mul34(dT, self.T_w2c_hist[-1])
         else:
             guess_w2c = self.T_w2c_hist[-1]
-        r = B.track(fl, mul34(guess_w2c, inv34(T_ref)), self.aff, self.variant)
+        T_guess, aff_guess = mul34(guess_w2c, inv34(T_ref)), self.aff
+        r = B.track(fl, T_guess, aff_guess, self.variant)
+        if self.on_track:
+            self.on_track(k, T_guess, aff_guess, r)
         T_w2c = mul34(r["T"], T_ref)
         self.aff = tuple(float(x) for x in r["aff"])
         self._record(T_w2c)
@@ -230,7 +243,8 @@ class StereoPipeline:
         return kf["T_cur"]
 
     def _trace_immature(self, fid, T_w2c):
-        """traceNewCoarse: every key frame's immature points into the new frame"""
+        """traceNewCoarse: every key frame's immature points into the new frame (the device backend: ONE launch for all hosts)"""
+        jobs = []
         for kf in self.kfs:
             pts = kf["immature"]
             if pts is None or pts.size == 0:
@@ -238,7 +252,21 @@ class StereoPipeline:
             T_h2f = mul34(T_w2c, inv34(self._pose_of(kf)))
             KRKi, Kt = level0_krki_kt(T_h2f, self.K4)
             a = float(np.exp(self.aff[0] - kf["aff_cur"][0])); b = float(self.aff[1] - a * kf["aff_cur"][1])   # AffLight::fromToVecExposure, exposures 1
-            self.B.trace_on_fid(fid, KRKi, Kt, (np.float32(a), np.float32(b)), pts)
+            jobs.append((kf, KRKi, Kt, (np.float32(a), np.float32(b))))
+        if not jobs:
+            return
+        if self.B.dev:
+            allp = np.ascontiguousarray(np.concatenate([j[0]["immature"] for j in jobs]))
+            host_of = np.concatenate([np.full(j[0]["immature"].size, i, np.int32) for i, j in enumerate(jobs)])
+            self.B.api.trace_on_hosts(fid, np.stack([j[1] for j in jobs]), np.stack([j[2] for j in jobs]), np.array([j[3] for j in jobs], np.float32), host_of, allp,
+                                      want_status=False)
+            off = 0
+            for kf, _, _, _ in jobs:
+                m = kf["immature"].size
+                kf["immature"] = np.ascontiguousarray(allp[off:off + m]); off += m
+        else:
+            for kf, KRKi, Kt, aff in jobs:
+                self.B.trace_on_fid(fid, KRKi, Kt, aff, kf["immature"])
 
     # ---------------------------------------------------------------------------------------------------------------
     def _window_description(self):
@@ -362,6 +390,8 @@ class StereoPipeline:
             splat = np.array([[int(c[0] + 0.5), int(c[1] + 0.5), c[2], np.sqrt(np.float32(1e-3 / (np.float64(np.float32(p["HdiF"])) + 1e-12)))]
                               for p, c in zip(self.points, centers) if c is not None], np.float32).reshape(-1, 4)
             B.tracker_set_ref(kf["fid"], splat, self.aff)
+            if self.on_ref:
+                self.on_ref(kf["frame_index"], splat, self.aff)
             entry.update(ref_points=int(splat.shape[0]))
         # ---- makeNewTraces (:1599-1630): selector -> ImmaturePoint constructor; static stereo into the right image for the range
         uv, ty = B.make_maps(kf["fid"], self.immature_density)
@@ -389,6 +419,8 @@ class StereoPipeline:
             kf["immature"], kf["my_type"] = np.ascontiguousarray(pts[keep]), kf["my_type"][keep]
             splat = np.array([[p["u"], p["v"], p["idepth"], 1.0] for p in self.points], np.float32).reshape(-1, 4)
             B.tracker_set_ref(kf["fid"], splat, self.aff)
+            if self.on_ref:
+                self.on_ref(kf["frame_index"], splat, self.aff)
             entry.update(points=len(self.points), ref_points=int(splat.shape[0]))
         # ---- marginalisation of the flagged key frame: its points first (marginalizePointsF), then the frame (marginalizeFrame)
         if flagged:

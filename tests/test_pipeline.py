@@ -84,8 +84,17 @@ def test_device_200_frame_sequence_matches_oracle(pkg, scene, variant):
     # while the oracle reproduces itself to 1e-4 m the device must do so too; afterwards it stays inside the oracle's own envelope
     assert np.all(dt <= env_t), (int(np.argmax(dt - env_t)), float(dt.max()), float(spread_t.max()))
     assert np.all(dr <= env_r), (int(np.argmax(dr - env_r)), float(dr.max()), float(spread_r.max()))
-    # bookkeeping of every key frame: exact where nothing upstream has diverged yet, inside the oracle's own spread afterwards
+    # bookkeeping: exact at the key frames where the oracle's own re-runs still agree with each other (nothing upstream has diverged
+    # yet); afterwards the per-key-frame counts are as chaotic as the trajectories, so the totals over the sequence are compared
+    keys = ("new_immature", "stereo_good", "candidates", "to_optimize", "activated", "points", "ref_points", "marginalized")
+    exact = 0
     for i, (eo, eg) in enumerate(zip(Po.log, Pg.log)):
-        for key in ("new_immature", "stereo_good", "candidates", "to_optimize", "activated", "points", "ref_points"):
-            sp = max(abs(Ps.log[i].get(key, 0) - eo.get(key, 0)) for Ps in runs)
-            assert abs(eo.get(key, 0) - eg.get(key, 0)) <= max(3 * sp, 0.01 * eo.get(key, 0), 3), (i, key, eo, eg, sp)
+        if all(Ps.log[i].get(key) == eo.get(key) for Ps in runs for key in keys):
+            for key in keys:
+                assert eo.get(key) == eg.get(key), (i, key, eo, eg)
+            exact += 1
+    assert exact >= 2
+    for key in ("new_immature", "activated", "marginalized", "points"):
+        so = sum(e.get(key, 0) for e in Po.log); sg = sum(e.get(key, 0) for e in Pg.log)
+        ssp = max(abs(sum(e.get(key, 0) for e in Ps.log) - so) for Ps in runs)
+        assert abs(sg - so) <= max(3 * ssp, 0.03 * so), (key, so, sg, ssp)

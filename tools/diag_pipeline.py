@@ -18,6 +18,52 @@ store = {}
 def hook(win, hm):
     store.update(win=copy.deepcopy(win), hm=hm, kf_idx=[kf["frame_index"] for kf in Po.kfs])
 Po.on_window = hook
+B3 = PL.Backend(shape, pkg)
+tf = {}
+def on_ref(idx, splat, aff):
+    if "fid" in tf: B3.release(tf["fid"])
+    tf["fid"] = B3.new_frame(L[idx]); tf["splat"] = splat.copy(); tf["aff"] = aff; tf["idx"] = idx
+    B3.tracker_set_ref(tf["fid"], splat, aff)
+def on_track(k, T_guess, aff_guess, r):
+    f = B3.new_frame(L[k])
+    g = B3.track(f, T_guess, aff_guess, variant)
+    B3.release(f)
+    dT = np.abs(g["T"] - r["T"]).max()
+    flag = "  <<<<<<" if dT > 1e-5 else ""
+    print(f"   teacher-forced device track of frame {k} vs ref {tf['idx']}: |dT| {dT:.2e} ok {g['ok']}/{r['ok']} its {g['iterations']} / {r.get('iterations')} res0 {g['lastResiduals'][0]:.4f}/{r['lastResiduals'][0]:.4f}{flag}")
+    if dT > 1e-4 and "dumped" not in tf:
+        tf["dumped"] = True
+        np.savez("gpurun_out/r2_track_case.npz", ref_img=L[tf["idx"]], new_img=L[k], splat=tf["splat"], ref_aff=np.array(tf["aff"]), T_guess=T_guess, aff_guess=np.array(aff_guess),
+                 T_oracle=r["T"], T_device=g["T"])
+Po.on_ref = on_ref; Po.on_track = on_track
+gs = {}
+def on_ref_g(idx, splat, aff):
+    o = tf["splat"]
+    ko = {(int(a[0]), int(a[1])): a for a in o}; kg = {(int(a[0]), int(a[1])): a for a in splat}
+    common = [k for k in ko if k in kg]
+    if common:
+        A = np.array([ko[k] for k in common]); G = np.array([kg[k] for k in common])
+        rid = np.abs(G[:, 2] - A[:, 2]) / np.abs(A[:, 2]); rw = np.abs(G[:, 3] - A[:, 3]) / np.abs(A[:, 3])
+        print(f"   ref @ frame {idx}: oracle {len(o)} splats, device {len(splat)}, common pixels {len(common)}; idepth rel diff median {np.median(rid):.2e} p99 {np.quantile(rid, 0.99):.2e} max {rid.max():.2e}; "
+              f"weight rel diff median {np.median(rw):.2e} max {rw.max():.2e}; mean idepth ratio {np.mean(G[:, 2] / A[:, 2]):.6f}; aff o {np.round(tf['aff'], 4)} g {np.round(aff, 4)}")
+Pg.on_ref = on_ref_g
+B4 = PL.Backend(shape)   # oracle tracker with the oracle pipeline's reference
+def on_ref4(idx, splat, aff):
+    if "fid4" in tf: B4.release(tf["fid4"])
+    tf["fid4"] = B4.new_frame(L[idx]); B4.tracker_set_ref(tf["fid4"], splat, aff)
+_old_on_ref = Po.on_ref
+def on_ref_both(idx, splat, aff):
+    _old_on_ref(idx, splat, aff); on_ref4(idx, splat, aff)
+Po.on_ref = on_ref_both
+def on_track_g(k, T_guess, aff_guess, r):
+    # the DEVICE pipeline's initial guess against the ORACLE pipeline's reference: device tracker vs oracle tracker
+    f3, f4 = B3.new_frame(L[k]), B4.new_frame(L[k])
+    g = B3.track(f3, T_guess, aff_guess, variant); o = B4.track(f4, T_guess, aff_guess, variant)
+    B3.release(f3); B4.release(f4)
+    dT = np.abs(g["T"] - o["T"]).max()
+    print(f"   device-guess cross-check frame {k}: device vs oracle tracker |dT| {dT:.2e} its {g['iterations']} / {o.get('iterations')} res0 {g['lastResiduals'][0]:.4f}/{o['lastResiduals'][0]:.4f}; "
+          f"free-running device result vs this: |dT| {np.abs(r['T'] - g['T']).max():.2e}{'  <<<<<<' if dT > 1e-5 else ''}")
+Pg.on_track = on_track_g
 for k in range(N):
     ro, rg = Po.step(L[k], R[k]), Pg.step(L[k], R[k])
     if k % 5 == 0 and k > 0 and "win" in store:
