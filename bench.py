@@ -54,6 +54,22 @@ def load_pkg():
     return mod
 
 
+def native_oracle():
+    """CPU arm: compile the oracle port for THIS host (-O3 -march=native, the reference's own flags, CMakeLists.txt:84) when a
+    compiler is present on the box; otherwise the portable x86-64-v3 build that travelled with the snapshot. Must run before
+    oracle_py is imported. Returns the flags string for the JSON line."""
+    odir = os.path.join(ROOT, "oracle")
+    lib = os.path.join(odir, "_build", "liboracle_native.so")
+    try:
+        subprocess.run(["make", "-C", odir, "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+        if os.path.exists(lib):
+            os.environ["SDSO_ORACLE_LIB"] = lib
+            return "g++ -O3 -march=native -ffp-contract=off (built on this host)"
+    except Exception:
+        pass
+    return "g++ -O3 -march=x86-64-v3 -ffp-contract=off (portable build; no compiler on this host)"
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -187,12 +203,14 @@ def main():
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cache", action="store_true", help="disable the tracker's shared-memory texel / point cache")
+    ap.add_argument("--track-cache", type=int, default=-1, help="tracker shared-memory cache of texel patches / point records: 0 off, 1 on (-1: library default)")
     ap.add_argument("--probe", action="store_true", help="also time the tracker alone on resident pyramids (no makeImages in between)")
     ap.add_argument("--gather", type=int, default=1, help="points in flight per thread (1: 128-register kernel, 2 with --threads 192: 168-register kernel)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--legs", default="all", help="comma list of extra legs on the JSON line: ba3,ba4,trace,g2o,sharded (or all / none)")
     args = ap.parse_args()
     variant = 0 if args.variant == "sse" else 1
+    cpu_flags = native_oracle() if int(os.environ.get("RANK", "0")) == 0 else "n/a"
     W_ = max(args.warmup, 3)
     K_ = args.steps
     S = args.seqs
@@ -221,7 +239,7 @@ def main():
                     ms_per_step=1e3 * sec / max(K_, 1), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=config, impl="reference",
                     tracked_frames_per_s=fr / sec,
-                    cpu_baseline=dict(value=val, unit="evals/s", cores=host_cores, kind="port",
+                    cpu_baseline=dict(value=val, unit="evals/s", cores=host_cores, kind="port", build=cpu_flags,
                                       sample=f"{fr} tracked stereo frames (makeImages left + right, trackNewestCoarse) over {host_cores} threads, one sequence per thread (oracle port of CoarseTracker; "
                                              "the reference cannot be compiled here: Eigen/g2o/Boost/OpenCV absent)"),
                     e2e=dict(value=val, unit="evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -242,11 +260,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
+    # one disjoint slice of the host cores per rank: the step's host side (problem records, launch, collect) must not migrate
+    # between the ranks' cores while 8 processes share the box
+    pinned_cores = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            pinned_cores = len(mine)
+        except Exception:
+            pinned_cores = None
     pkg = load_pkg()
     st = pkg.default_settings()
     st.cluster_size = args.cluster if args.cluster > 0 else 2   # throughput configuration: a 2-CTA cluster per sequence (148 sequences in flight keep their texel working set in L2) ...
     st.block_threads = args.threads
-    st.track_cache = 0 if args.no_cache else 1
+    st.track_cache = 0 if args.no_cache else (args.track_cache if args.track_cache >= 0 else st.track_cache)
     st.gather_batch = args.gather                                # ... compiled for two resident CTAs per SM
     ctx = pkg.Context(synth.W, synth.H, synth.K4, synth.BASELINE, device=dev, settings=st)
     stream = torch.cuda.current_stream()
@@ -393,6 +423,19 @@ def main():
     b1.record(stream)
     torch.cuda.synchronize()
     h2d_gbs = 5 * big.numel() / (b0.elapsed_time(b1) * 1e-3) / 1e9
+    # ... and with EVERY rank copying at the same time: what the host (memory + PCIe root) delivers to N GPUs at once — the
+    # ceiling of the end-to-end number at N > 1
+    h2d_gbs_all = h2d_gbs
+    if dist is not None:
+        barrier()
+        b0.record(stream)
+        for _ in range(5):
+            dst.copy_(big, non_blocking=True)
+        b1.record(stream)
+        torch.cuda.synchronize()
+        tq = torch.tensor([5 * big.numel() / (b0.elapsed_time(b1) * 1e-3) / 1e9], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(tq, op=dist.ReduceOp.SUM)
+        h2d_gbs_all = float(tq[0])
     del dst
 
     # ---- single-sequence latency (one cluster on the GPU), for information
@@ -510,7 +553,10 @@ def main():
         evals_per_step=evals / (world * K_),
         e2e=dict(value=e2e_val, unit="evals/s", h2d_bytes_per_step=2 * S * npx, d2h_bytes_per_step=S * (8 * (12 + 2 + 5 + 3) + 4 * 6 + 8),
                  ms_per_step=ms_e2e / K_, tracked_frames_per_s=world * S * K_ / (ms_e2e * 1e-3),
-                 h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=2 * S * npx / (ms_e2e / K_ * 1e-3) / 1e9),
+                 h2d_gbs_plain_copy=h2d_gbs, h2d_gbs_in_step=2 * S * npx / (ms_e2e / K_ * 1e-3) / 1e9,
+                 h2d_gbs_all_ranks_plain_copy=h2d_gbs_all, h2d_gbs_all_ranks_in_step=world * 2 * S * npx / (ms_e2e / K_ * 1e-3) / 1e9,
+                 limiter="host link: the step moves 2 x S 8-bit images per GPU; compare h2d_gbs_all_ranks_in_step with h2d_gbs_all_ranks_plain_copy",
+                 host_threads_pinned=pinned_cores),
         single_sequence=dict(ms_per_frame=ms_single, tracked_frames_per_s=1e3 / ms_single,
                              note="latency of one sequence alone on the GPU in this (throughput) configuration; the latency configuration (8-CTA cluster, gather batch 2) tracks a frame in ~0.2 ms, profiles/r1_bench_sse_first.json"),
         gpu_launches=int(launches),
@@ -525,7 +571,7 @@ def main():
                                        algorithmic_bytes=img_bytes)),
         probe=probe,
         legs=legs,
-        cpu_baseline=(dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port",
+        cpu_baseline=(dict(value=cev / csec, unit="evals/s", cores=host_cores, kind="port", build=cpu_flags,
                            sample=f"{cfr} tracked stereo frames (makeImages left + right, trackNewestCoarse) in {csec:.1f} s over {host_cores} threads, one sequence per thread (oracle port; "
                                   "trackNewestCoarse is single-threaded per sequence in the reference)",
                            tracked_frames_per_s=cfr / csec) if world == 1 else None),

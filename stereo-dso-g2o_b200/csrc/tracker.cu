@@ -252,14 +252,6 @@ struct TexCache {
 __host__ __device__ constexpr size_t cache_bytes(int block_threads) {
   return (size_t)kCacheRounds * block_threads * (12 * sizeof(float) + sizeof(int) + sizeof(float4)) + 16;
 }
-// Coarse pyramid levels whose {I, dx, dy} fit the same region are made RESIDENT instead: the whole level is read once per
-// (sequence, level) with coalesced loads and every LM iteration of the level gathers from shared memory — no tags, no misses.
-// At the KITTI working size that is level 3 (154 x 46 x 12 B = 85 KB) and level 4 (21 KB): a third of a sequence's evaluations,
-// and the ones with the fewest points per thread, i.e. the least latency hiding when they gather from L2 / HBM.
-constexpr size_t kResidentBytes = 88 * 1024;
-__host__ __device__ constexpr size_t cache_region_bytes(int block_threads) {
-  return cache_bytes(block_threads) > kResidentBytes ? cache_bytes(block_threads) : kResidentBytes;
-}
 
 struct PhaseTimer {  // phase breakdown of the persistent kernel, enabled by TrackParams::timing
   long long last = 0;
@@ -432,10 +424,10 @@ __device__ __forceinline__ void warp_solve8(double (&row)[9], int lane, double (
 template <int U, int CS /* slots of the texel cache = component stride: a constant, so the 12 offsets are immediates */>
 __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex,
                                 const EvalConst& ec, float (&acc)[kAccPad], unsigned& evals, int gtid, int gthreads,
-                                float* dump, const float4* __restrict__ pc, const int n, const TexCache tc, const float* __restrict__ res_img) {
+                                float* dump, const float4* __restrict__ pc, const int n, const TexCache tc) {
 #pragma unroll
   for (int k = 0; k < kAccPad; k++) acc[k] = 0.f;
-  const bool use_cache = tc.tex != nullptr && res_img == nullptr;   // a resident level needs neither the patch nor the point cache
+  const bool use_cache = tc.tex != nullptr;
   const bool pc_cached = use_cache && *tc.pc_lvl == lvl;
   const float fxl = L.fx, fyl = L.fy, cxl = L.cx, cyl = L.cy;
   const int wl = L.w, hl = L.h;
@@ -478,26 +470,17 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
       acc[A_SN] += 2.f;
     }
   }
-  // point records are fetched one batch AHEAD of the arithmetic: the record load (L2) and the texel gathers it feeds are two
-  // dependent long-latency steps per point; prefetching takes the first one off the chain for four registers
-  float4 pn[U];
-  auto fetch = [&](int base2, int m2) {
-#pragma unroll
-    for (int q = 0; q < U; q++) {
-      const int i = base2 + q * gthreads;
-      const int m = m2 + q;                                      // this thread's m-th point
-      const int slot = (use_cache && m < kCacheRounds) ? m * (CS / kCacheRounds) + (int)threadIdx.x : -1;
-      if (i >= n) pn[q] = make_float4(0.f, 0.f, 1.f, 0.f);
-      else if (slot >= 0 && pc_cached) pn[q] = tc.pc[slot];
-      else { pn[q] = __ldg(pc + i); if (slot >= 0) tc.pc[slot] = pn[q]; }
-    }
-  };
-  fetch(gtid, 0);
   for (int base = gtid, m0 = 0; base < n; base += gthreads * U, m0 += U) {
     float4 p[U];
 #pragma unroll
-    for (int q = 0; q < U; q++) p[q] = pn[q];
-    fetch(base + gthreads * U, m0 + U);
+    for (int q = 0; q < U; q++) {
+      const int i = base + q * gthreads;
+      const int m = m0 + q;                                      // this thread's m-th point
+      const int slot = (use_cache && m < kCacheRounds) ? m * (CS / kCacheRounds) + (int)threadIdx.x : -1;
+      if (i >= n) p[q] = make_float4(0.f, 0.f, 1.f, 0.f);
+      else if (slot >= 0 && pc_cached) p[q] = tc.pc[slot];
+      else { p[q] = __ldg(pc + i); if (slot >= 0) tc.pc[slot] = p[q]; }
+    }
     float uu[U], vv[U], Kuu[U], Kvv[U], nid[U];
     bool inb[U];
     float4 t00[U], t10[U], t01[U], t11[U];
@@ -521,12 +504,7 @@ __device__ void eval_points_sse(const TrackParams& P, const TrackLevel& L, int l
         const int m = m0 + q;
         const int slot = (use_cache && m < kCacheRounds) ? m * (CS / kCacheRounds) + (int)threadIdx.x : -1;
         const int tag = (lvl << 28) | (iy << 14) | ix;
-        if (res_img) {   // the level lives in shared memory as {I, dx, dy} triples
-          const float* b0 = res_img + 3 * (ix + iy * wl);
-          const float* b1 = b0 + 3 * wl;
-          t00[q] = make_float4(b0[0], b0[1], b0[2], 0.f); t10[q] = make_float4(b0[3], b0[4], b0[5], 0.f);
-          t01[q] = make_float4(b1[0], b1[1], b1[2], 0.f); t11[q] = make_float4(b1[3], b1[4], b1[5], 0.f);
-        } else if (slot >= 0 && tc.tag[slot] == tag) {   // same texels as in the last evaluation of this point
+        if (slot >= 0 && tc.tag[slot] == tag) {   // same texels as in the last evaluation of this point
           const float* c = tc.tex + slot;
           constexpr int cs = CS;
           t00[q] = make_float4(c[0 * cs], c[1 * cs], c[2 * cs], 0.f);
@@ -877,10 +855,8 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   __shared__ int s_prob;
   __shared__ int s_pc_lvl;
   TexCache tc{nullptr, nullptr, nullptr, &s_pc_lvl, kCacheRounds * kBT};
-  float* region = nullptr;   // the cache region, reused as a whole by a resident level
   if (P.use_cache) {
     unsigned char* cb = smem_raw + ((sizeof(TrackSmem) + 15) & ~(size_t)15);
-    region = reinterpret_cast<float*>(cb);
     tc.pc = reinterpret_cast<float4*>(cb);
     tc.tex = reinterpret_cast<float*>(cb + (size_t)tc.slots * sizeof(float4));
     tc.tag = reinterpret_cast<int*>(tc.tex + 12 * tc.slots);
@@ -904,7 +880,6 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   }
   TrackProblem& prob = P.problems[prob_id];
   unsigned evals = 0;
-  int res_lvl = -1;   // level whose texels are resident in the region (uniform over the CTA)
   if (tc.tex) for (int k = tid; k < tc.slots; k += blockDim.x) tc.tag[k] = -1;   // a new frame: nothing cached
   if (tid == 0) {
     s_pc_lvl = -1;
@@ -938,25 +913,6 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
   while (true) {
     const TrackLevel& L = P.L[lvl];
     const float cutoff = single ? P.eval_cutoff : P.coarseCutoffTH * levelCutoffRepeat;
-    // ---- resident level: (re)load on entering a level that fits, hand the region back to the cache on leaving one. Every
-    // thread is past its last read of the region here (block barriers of the previous evaluation's reduction / epilogue), and
-    // the prologue's barrier below publishes the new contents.
-    if (region) {
-      const bool fits = (size_t)L.w * L.h * 3 * sizeof(float) <= kResidentBytes;
-      if (fits && res_lvl != lvl) {
-        const float4* __restrict__ src = prob.tex[lvl];
-        const int ntex = L.w * L.h;
-        for (int k = tid; k < ntex; k += blockDim.x) {
-          const float4 v = __ldg(src + k);
-          region[3 * k] = v.x; region[3 * k + 1] = v.y; region[3 * k + 2] = v.z;   // stride-3 words: conflict-free
-        }
-        res_lvl = lvl;
-      } else if (!fits && res_lvl >= 0) {
-        for (int k = tid; k < tc.slots; k += blockDim.x) tc.tag[k] = -1;
-        if (tid == 0) s_pc_lvl = -1;
-        res_lvl = -1;
-      }
-    }
     // ---- prologue: constants of this evaluation (warp 0) ----
     if (tid < 64) {
       eval_prologue(P, L, prob, lm, sm->ec, cutoff, stage == ST_ITER, tid, tm.cyc);
@@ -966,13 +922,12 @@ __global__ void __launch_bounds__(kBT, kMB) track_kernel(TrackParams P) {
     __syncthreads();
     tm.tick(0);
     // ---- the evaluation + the exchange: the only instance of this code in the kernel ----
-    eval_points_sse<kU, kCacheRounds * kBT>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl], tc,
-                                            res_lvl == lvl ? region : nullptr);
+    eval_points_sse<kU, kCacheRounds * kBT>(P, L, lvl, prob.tex[lvl], sm->ec, acc, evals, gtid, gthreads, single ? P.dump : nullptr, prob.pc[lvl], prob.pc_n[lvl], tc);
     tm.tick(1);
     const int pb = reduce_exchange<false>(acc, sm, ex, C, rank, 0.0, &tm);
     // behind the block barriers of the reduction: every thread has read the flag for this evaluation and stored its point
     // records of this level; the next evaluation reads the flag behind the prologue's barrier
-    if (tid == 0 && res_lvl != lvl) s_pc_lvl = lvl;
+    if (tid == 0) s_pc_lvl = lvl;
     const float sumE = gather_sumf(sm, pb, C, A_E), sumNE = gather_sumf(sm, pb, C, A_NE);
 
     // ---- epilogue ----
@@ -1190,10 +1145,10 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   size_t smem = sizeof(TrackSmem);
   const bool use_cache = !g2o && ctx->S.track_cache != 0;
   // (the cache is sized for the thread count the kernel instance was compiled for: 256, or 192 for the 168-register build)
-  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_region_bytes((ctx->S.gather_batch == 2 && BT <= 192 && C == 1) ? 192 : 256);
+  if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes((ctx->S.gather_batch == 2 && BT <= 192 && C == 1) ? 192 : 256);
   static bool attr_set = false;
   if (!attr_set) {
-    const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_region_bytes(256));
+    const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(256));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));

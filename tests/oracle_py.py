@@ -10,7 +10,8 @@ import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(_ROOT, "oracle")
-LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+# SDSO_ORACLE_LIB: bench.py points this at the -march=native build it makes on the box it times the CPU arm on
+LIB_PATH = os.environ.get("SDSO_ORACLE_LIB") or os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 
 def build(force=False):
@@ -23,6 +24,8 @@ def build(force=False):
 
 def _load():
     if not os.path.exists(LIB_PATH):
+        if os.environ.get("SDSO_ORACLE_LIB"):
+            raise ImportError(f"SDSO_ORACLE_LIB={LIB_PATH} does not exist")
         build()
     return C.CDLL(LIB_PATH)
 
