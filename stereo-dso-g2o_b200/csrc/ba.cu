@@ -29,13 +29,16 @@ static void invalidate_graphs(BAState* b) {
 static void free_all(BAState* b) {
   invalidate_graphs(b);
   if (b->cap_stream) { cudaStreamDestroy(b->cap_stream); b->cap_stream = nullptr; }
+  if (b->cap_stream2) { cudaStreamDestroy(b->cap_stream2); b->cap_stream2 = nullptr; }
+  if (b->ev_fork) { cudaEventDestroy(b->ev_fork); b->ev_fork = nullptr; }
+  if (b->ev_join) { cudaEventDestroy(b->ev_join); b->ev_join = nullptr; }
   void* ptrs[] = {b->d_tex0, b->d_frameTH, b->d_precalc, b->d_adHost, b->d_adTarget, b->d_adHostF, b->d_adTargetF, b->d_adHTdeltaF, b->d_cDeltaF,
                   b->d_fprior, b->d_p_host, b->d_p_u, b->d_p_v, b->d_p_idepth, b->d_p_idepth_zero, b->d_p_color, b->d_p_weights, b->d_p_priorF,
                   b->d_p_deltaF, b->d_p_idepth_backup, b->d_p_res_begin, b->d_slot_of, b->d_p_acc, b->d_p_flag, b->d_p_res_list, b->d_s_point, b->d_s_key, b->d_s_state,
                   b->d_s_newstate, b->d_s_flags, b->d_s_sel, b->d_s_energy, b->d_J, b->d_s_rtz, b->d_s_JpJd, b->d_s_center, b->d_s_psum,
                   b->d_slot2rid, b->d_rid2slot, b->d_chunks, b->d_key_chunk_begin, b->d_tpart, b->d_dpart, b->d_pblockpart, b->d_G, b->d_Gf,
                   b->d_D, b->d_E, b->d_Hcc, b->d_U, b->d_V, b->d_sys, b->d_energy_part, b->d_scalars, b->d_counter, b->d_N, b->d_xAd, b->d_list, b->d_step_part,
-                  b->d_frames, b->d_calib, b->d_opt};
+                  b->d_frames, b->d_calib, b->d_opt, b->lba_scratch, b->d_W};
   for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -57,6 +60,10 @@ int ba_create(sdso_ctx* ctx) {
   BA_ALLOC(b->d_frames, F); BA_ALLOC(b->d_calib, 1); BA_ALLOC(b->d_opt, 1);
   SDSO_CUDA(ctx, cudaMemset(b->d_opt, 0, sizeof(OptDev)));
   SDSO_CUDA(ctx, cudaStreamCreateWithFlags(&b->cap_stream, cudaStreamNonBlocking));
+  SDSO_CUDA(ctx, cudaStreamCreateWithFlags(&b->cap_stream2, cudaStreamNonBlocking));
+  SDSO_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  SDSO_CUDA(ctx, cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  BA_ALLOC(b->d_W, (size_t)F2 * (64 + 64 + 40 + 40));
   SDSO_CUDA(ctx, cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return SDSO_OK;
 }
@@ -315,20 +322,35 @@ __global__ void ba_point_delta_kernel(int P, const float* idepth, const float* i
 }
 
 // ---- launches ---------------------------------------------------------------------------------------------
-static int launch_top(sdso_ctx* ctx, int mode, int which, bool usePrior) {
+// AccumulatedTopHessianSSE in three pieces, so that a captured chain can run the frame-block half beside the per-point / Schur half
+static int launch_top_accumulate(sdso_ctx* ctx, int mode) {   // addPoint<mode> over the residual chunks: 13x13 partials + per-residual point terms
   BAState* b = ctx->ba;
   BAView v = view(b);
-  const int d = b->dim(), n = b->n;
   if (b->nchunks > 0) { ba_top_kernel<<<b->nchunks, kChunk, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
-  // W/Z/Wc/Zc scratch lives in the U/V arenas (the Schur stitch, which owns them, runs after both top stitches)
-  double* Wm = b->d_U; double* Zm = b->d_U + (size_t)n * n * 64; double* Wc = b->d_V; double* Zc = b->d_V + (size_t)n * n * 40;
+  return SDSO_OK;
+}
+static int launch_top_frames(sdso_ctx* ctx, int which, bool usePrior) {   // fixed-order sums of the partials + stitchDouble
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  const int n = b->n;
+  double* Wm = b->d_W; double* Zm = Wm + (size_t)kMaxFrames * kMaxFrames * 64; double* Wc = Zm + (size_t)kMaxFrames * kMaxFrames * 64; double* Zc = Wc + (size_t)kMaxFrames * kMaxFrames * 40;
   ba_top_finish_kernel<<<n * n, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc); SDSO_CHECK_LAUNCH(ctx);
-  if (b->P > 0) { ba_point_sums_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
   double* dc = b->d_scalars + 8;   // cPrior (uploaded by prepare_window)
   ba_stitch_top_kernel<<<n * n + 1, 256, 0, ctx->stream>>>(v, Wm, Zm, Wc, Zc, sysH(b, which), sysb(b, which), usePrior ? 1 : 0, dc);
-  (void)d;
   SDSO_CHECK_LAUNCH(ctx);
   return SDSO_OK;
+}
+static int launch_top_points(sdso_ctx* ctx, int mode) {   // bd_acc / Hdd_acc / Hcd_acc per point (AccumulatedTopHessian.cpp:160-192)
+  BAState* b = ctx->ba;
+  BAView v = view(b);
+  if (b->P > 0) { ba_point_sums_kernel<<<(b->P + 127) / 128, 128, 0, ctx->stream>>>(v, mode); SDSO_CHECK_LAUNCH(ctx); }
+  return SDSO_OK;
+}
+static int launch_top(sdso_ctx* ctx, int mode, int which, bool usePrior) {
+  int rc = launch_top_accumulate(ctx, mode);
+  if (!rc) rc = launch_top_points(ctx, mode);
+  if (!rc) rc = launch_top_frames(ctx, which, usePrior);
+  return rc;
 }
 
 static int launch_sc(sdso_ctx* ctx, bool shift, int which) {
@@ -419,17 +441,36 @@ static int launch_assemble(sdso_ctx* ctx) {
 static int launch_assemble_chain(sdso_ctx* ctx) {
   BAState* b = ctx->ba;
   const int d = b->dim();
-  int rc = launch_top(ctx, 0, SYS_A, false);
-  if (!rc) {
-    if (b->any_linearized) rc = launch_top(ctx, 1, SYS_L, b->shard_rank == 0);  // priors enter once
-    else {   // nothing linearised: the L system is the priors alone
-      BAView v = view(b);
-      ba_prior_system_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, SYS_L), sysb(b, SYS_L), b->shard_rank == 0 ? 1 : 0, b->d_scalars + 8);
-      SDSO_CHECK_LAUNCH(ctx);
-    }
+  int rc = SDSO_OK;
+  auto priors_only = [&]() -> int {   // nothing linearised: the L system is the priors alone
+    BAView v = view(b);
+    ba_prior_system_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(v, sysH(b, SYS_L), sysb(b, SYS_L), b->shard_rank == 0 ? 1 : 0, b->d_scalars + 8);
+    SDSO_CHECK_LAUNCH(ctx);
+    return SDSO_OK;
+  };
+  if (ctx->stream == b->cap_stream && !b->any_linearized) {
+    // Inside a capture: after the accumulation kernel the chain forks — {fixed-order block sums, top stitch, priors} on a second
+    // stream beside {per-point sums, Schur point / pair / finish kernels, Schur stitch} — and joins in front of the assembly. The
+    // two halves share no output (the top stitch has its own W/Z scratch), so the graph runs them concurrently.
+    cudaStream_t s1 = b->cap_stream, s2 = b->cap_stream2;
+    if ((rc = launch_top_accumulate(ctx, 0))) return rc;
+    SDSO_CUDA(ctx, cudaEventRecord(b->ev_fork, s1));
+    SDSO_CUDA(ctx, cudaStreamWaitEvent(s2, b->ev_fork, 0));
+    ctx->stream = s2;
+    rc = launch_top_frames(ctx, SYS_A, false);
+    if (!rc) rc = priors_only();
+    ctx->stream = s1;
+    if (rc) return rc;
+    SDSO_CUDA(ctx, cudaEventRecord(b->ev_join, s2));
+    if ((rc = launch_top_points(ctx, 0))) return rc;
+    if ((rc = launch_sc(ctx, true, SYS_SC))) return rc;
+    SDSO_CUDA(ctx, cudaStreamWaitEvent(s1, b->ev_join, 0));
+  } else {
+    rc = launch_top(ctx, 0, SYS_A, false);
+    if (!rc) rc = b->any_linearized ? launch_top(ctx, 1, SYS_L, b->shard_rank == 0) /* priors enter once */ : priors_only();
+    if (!rc) rc = launch_sc(ctx, true, SYS_SC);
+    if (rc) return rc;
   }
-  if (!rc) rc = launch_sc(ctx, true, SYS_SC);
-  if (rc) return rc;
   SolveParams S{};
   fill_solve_params(ctx, S, 0);
   ba_assemble_kernel<<<(d * d + d + 127) / 128, 128, 0, ctx->stream>>>(S);
@@ -1248,8 +1289,13 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
                     + (size_t)n * (12 + 12 + 2 + 1 + 2)                            // T_wh, T_tw, photo, b0, target aff
                     + (size_t)(b->nchunks + 1) * 96 * 2 + (size_t)n * 96 * 2 + rb + 64;
   const size_t bytes = nd * sizeof(double) + (size_t)R * (4 * sizeof(float) + 2 * sizeof(int) + 2) + (size_t)n * (sizeof(float) + sizeof(int)) + 256;
-  unsigned char* raw = nullptr;
-  SDSO_CUDA(ctx, cudaMalloc(&raw, bytes));
+  if (bytes > b->lba_scratch_bytes) {   // kept across calls: cudaMalloc / cudaFree per call are device-wide synchronisations
+    if (b->lba_scratch) cudaFree(b->lba_scratch);
+    b->lba_scratch = nullptr; b->lba_scratch_bytes = 0;
+    SDSO_CUDA(ctx, cudaMalloc(&b->lba_scratch, bytes));
+    b->lba_scratch_bytes = bytes;
+  }
+  unsigned char* raw = reinterpret_cast<unsigned char*>(b->lba_scratch);
   SDSO_CUDA(ctx, cudaMemsetAsync(raw, 0, bytes, st));
   double* pd = reinterpret_cast<double*>(raw);
   auto takeD = [&](size_t k) { double* q = pd; pd += k; return q; };
@@ -1265,7 +1311,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   int* pi = reinterpret_cast<int*>(pf);
   int* d_ns = pi; pi += R; int* d_level = pi; pi += R; int* d_used = pi; pi += n;
   unsigned char* d_active = reinterpret_cast<unsigned char*>(pi); unsigned char* d_ingraph = d_active + R;
-  auto cleanup = [&](int rc) { cudaStreamSynchronize(st); cudaFree(raw); return rc; };
+  auto cleanup = [&](int rc) { cudaStreamSynchronize(st); return rc; };
 
   // ---- graph build on the host side: active residuals (not linearised, not dropped), used hosts, b0 (:438-542)
   std::vector<unsigned char> flags(R);
@@ -1335,7 +1381,6 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   fill_solve_params(ctx, S, 0);
   S.plain = 1; S.N = nullptr; S.have_M = 0;
   const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
-  cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   std::vector<double> x(d), bp(d);
   double lambda = 0, ni = 2, lastChi = 0;
   int it = 0, trials = 0;

@@ -145,6 +145,10 @@ struct BAState {
   void* graph_assemble = nullptr;         // cudaGraphExec_t of the accumulate + stitch + assemble chain (sdso_ba_assemble / sdso_ba_solve)
   int graph_iter_nodes = 0, graph_assemble_nodes = 0;   // kernels per replay (launch accounting)
   cudaStream_t cap_stream = nullptr;      // capture stream (the context's stream may be the legacy default stream, which cannot capture)
+  cudaStream_t cap_stream2 = nullptr;     // second capture stream: the forked half of the accumulate / stitch chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  double* d_W = nullptr;                  // [F^2][64 + 64 + 40 + 40]: adHost*A, adTarget*A and their calibration columns (top stitch scratch)
+  void* lba_scratch = nullptr; size_t lba_scratch_bytes = 0;   // sdso_lba_g2o's graph arrays
   bool any_linearized = false;            // some residual has been through fixLinearizationF since the window was uploaded
   int shard_rank = 0, shard_n = 1;        // point-sharded window: priors and HM enter on rank 0 only
   bool have_M = false;                    // HM/bM (marginalisation prior) present in SYS_M
