@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--probe", action="store_true", help="also time the tracker alone on resident pyramids (no makeImages in between)")
     ap.add_argument("--gather", type=int, default=1, help="points in flight per thread (1: 128-register kernel, 2 with --threads 192: 168-register kernel)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--legs", default="all", help="comma list of extra legs on the JSON line: ba3,ba4,trace,g2o,sharded (or all / none)")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs on the JSON line: g2o,ba3,ba4,trace,sequence,sharded (or all / none)")
     args = ap.parse_args()
     variant = 0 if args.variant == "sse" else 1
     cpu_flags = native_oracle() if int(os.environ.get("RANK", "0")) == 0 else "n/a"
@@ -458,7 +458,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- legs: the rest of the path, driver-visible (bench_legs.py) -----------------------------------------
-    want = set(["g2o", "ba3", "ba4", "trace", "sharded"] if args.legs == "all" else [x for x in args.legs.split(",") if x and x != "none"])
+    want = set(["g2o", "ba3", "ba4", "trace", "sequence", "sharded"] if args.legs == "all" else [x for x in args.legs.split(",") if x and x != "none"])
     legs = {}
     peak_, _ = measured_peak()
     if "g2o" in want and variant == 0 and world == 1:   # the fork's LIVE tracker (EdgeSE3PosePhotoDSO + restated g2o LM) on the same workload
@@ -491,7 +491,7 @@ def main():
             cpu_baseline=dict(value=cg_ev / cg_sec, unit="evals/s", cores=host_cores, kind="port", tracked_frames_per_s=cg_fr / cg_sec,
                               sample=f"{cg_fr} tracked stereo frames in {cg_sec:.1f} s over {host_cores} threads (oracle port, g2o variant)"))
     import bench_legs as BL
-    if world == 1 and (want & {"ba3", "ba4", "trace"}):
+    if world == 1 and (want & {"ba3", "ba4", "trace", "sequence"}):
         scene = synth.make_scene()
         lk = max(10, min(K_, 50))
         if "ba3" in want:
@@ -501,6 +501,8 @@ def main():
             legs["ba_config4"] = BL.leg_ba(pkg, torch, dev, scene, "config4", lk, peak_, cpu_seconds=3.0)
         if "trace" in want:
             legs.update(BL.leg_trace(pkg, torch, dev, scene, peak_))
+        if "sequence" in want:
+            legs["sequence"] = BL.leg_sequence(pkg, torch, dev, scene)
     if world > 1 and "sharded" in want:
         legs["sharded_ba"] = BL.leg_sharded_ba(pkg, torch, dist, dev, rank, world, synth.make_scene(), max(10, min(K_, 50)), peak_)
 

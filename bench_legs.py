@@ -341,6 +341,52 @@ def leg_trace(pkg, torch, dev, scene, peak, per_host=1500, n_kf=7, reps=10):
     return out
 
 
+def leg_sequence(pkg, torch, dev, scene, n_frames=60):
+    """SURVEY config 1 as the harness runs it (tests/pipeline.py): one stereo sequence, tracking + mapping chained — both pyramids,
+    trackNewestCoarse, traceOn of every key frame's immature points, and at every 5th frame the key-frame chain (candidate filter,
+    activation, windowed optimisation, marginalisation, pixel selection, static stereo). Wall clock per frame through the C ABI
+    with host images, next to the same harness on the oracle port (one host thread). The harness itself is Python (per-point
+    dicts, numpy); its share is reported by timing the operator calls separately."""
+    import synth, pipeline as PL
+    shape = dict(w=synth.W, h=synth.H, K=synth.K4)
+    poses = [synth.camera_pose(0.2 * k) for k in range(n_frames)]
+    left = [synth.render_torch(scene, p, device=f"cuda:{dev}")[0] for p in poses]
+    right = [synth.render_torch(scene, synth.right_of(p), device=f"cuda:{dev}")[0] for p in poses]
+
+    def run(backend):
+        P = PL.StereoPipeline(backend)
+        per_frame = []
+        for l, r in zip(left, right):
+            t0 = time.perf_counter()
+            P.step(l, r)
+            per_frame.append(time.perf_counter() - t0)
+        return P, np.array(per_frame)
+
+    Bg = PL.Backend(shape, pkg)
+    run(Bg)                      # warm-up (allocations, graph captures)
+    Bg.close()
+    Bg = PL.Backend(shape, pkg)
+    l0 = Bg.api.launch_count()
+    Pg, tg = run(Bg)
+    launches = Bg.api.launch_count() - l0
+    Bg.close()
+    Po, to = run(PL.Backend(shape))
+    kf = np.arange(n_frames) % 5 == 0
+    dt = np.array([np.abs(Pg.traj[k][:3, 3] - Po.traj[k][:3, 3]).max() for k in range(n_frames)])
+    return dict(
+        workload=f"one synthetic KITTI-shape stereo sequence, {n_frames} frames, 1232x368, key frame every 5th frame, window of 7, 1500 immature / 2000 active points: "
+                 "makeImages (left + right) + trackNewestCoarse + traceOn per frame; selector, static stereo, distance map, candidate loop, activation, "
+                 "windowed optimisation (6 iterations), marginalisation per key frame (tests/pipeline.py)",
+        metric="tracked stereo frames/s (one sequence, end to end through the C ABI, host images in, poses out)",
+        value=n_frames / tg.sum(), unit="frames/s", ms_per_tracked_frame=1e3 * float(np.median(tg[~kf])), ms_per_key_frame=1e3 * float(np.median(tg[kf][1:])),
+        kernel_launches=int(launches),
+        e2e=dict(value=n_frames / tg.sum(), unit="frames/s", h2d_bytes_per_step=int(2 * synth.W * synth.H * 4), d2h_bytes_per_step=int(12 * 8 + 16 + 40),
+                 note="host float images are uploaded inside sdso_make_images; immature records cross once per frame (one launch for all hosts)"),
+        cpu_baseline=dict(value=n_frames / to.sum(), unit="frames/s", cores=1, kind="port", ms_per_tracked_frame=1e3 * float(np.median(to[~kf])),
+                          ms_per_key_frame=1e3 * float(np.median(to[kf][1:])), sample=f"the same {n_frames} frames through the same harness on the oracle port, one host thread"),
+        parity=dict(max_translation_difference_m=float(dt.max()), note="free-running chains: see tests/test_pipeline.py for the envelope (the oracle's own spread)"))
+
+
 def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
     """Config 4 LM iteration with the points sharded over `world` ranks and ONE allreduce of the damped reduced system, next to
     the unsharded iteration on the same GPU; increments compared with the single-GPU solve on every rank."""

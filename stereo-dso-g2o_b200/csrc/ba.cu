@@ -520,6 +520,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_ba_reset(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   b->n = b->P = b->R = 0;
@@ -534,6 +535,7 @@ int sdso_ba_reset(sdso_ctx* ctx) {
 }
 
 int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_value_zero[4]) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (!K) return SDSO_E_INVALID;
   BACalib& c = b->calib;
@@ -553,6 +555,7 @@ int sdso_ba_set_calib(sdso_ctx* ctx, const float K[4], const double value_minus_
 }
 
 int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], double a, double bb, int frameID, int* idx_out) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   if (!T_w2c || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
@@ -583,6 +586,7 @@ int sdso_ba_add_frame(sdso_ctx* ctx, int frame_id, const double T_w2c[12], doubl
 }
 
 int sdso_ba_set_state(sdso_ctx* ctx, int idx, const double state[10]) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (idx < 0 || idx >= b->n || !state) return SDSO_E_INVALID;
   frame_set_state(b->frames[idx], state);
@@ -591,6 +595,7 @@ int sdso_ba_set_state(sdso_ctx* ctx, int idx, const double state[10]) {
 }
 
 int sdso_ba_set_energy_th(sdso_ctx* ctx, int idx, float th) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (idx < 0 || idx >= b->n) return SDSO_E_INVALID;
   b->frames[idx].frameEnergyTH = th;
@@ -600,6 +605,7 @@ int sdso_ba_set_energy_th(sdso_ctx* ctx, int idx, float th) {
 
 int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero,
                        const float* color8, const float* weights8, const unsigned char* has_prior) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   if (P < 0 || (P > 0 && (!host || !u || !v || !idepth || !idepth_zero || !color8 || !weights8))) return SDSO_E_INVALID;
@@ -639,6 +645,7 @@ int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, co
 }
 
 int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* target) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   b->any_linearized = false;
@@ -720,6 +727,7 @@ int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* tar
 }
 
 int sdso_ba_set_point_flags(sdso_ctx* ctx, const unsigned char* flags) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (!flags) return SDSO_E_INVALID;
   SDSO_CUDA(ctx, cudaMemcpyAsync(b->d_p_flag, flags, b->P, cudaMemcpyHostToDevice, ctx->stream));
@@ -728,12 +736,14 @@ int sdso_ba_set_point_flags(sdso_ctx* ctx, const unsigned char* flags) {
 }
 
 int sdso_ba_prepare(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (b->n < 1) return fail(ctx, SDSO_E_STATE, "no frames in the window");
   return prepare_window(ctx);
 }
 
 int sdso_ba_counts(sdso_ctx* ctx, int* n, int* P, int* R, int* dim) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (n) *n = b->n;
   if (P) *P = b->P;
@@ -743,6 +753,7 @@ int sdso_ba_counts(sdso_ctx* ctx, int* n, int* P, int* R, int* dim) {
 }
 
 int sdso_ba_get_precalc(sdso_ctx* ctx, int h, int t, float out[49]) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (h < 0 || t < 0 || h >= b->n || t >= b->n || !out) return SDSO_E_INVALID;
   const PrecalcDev& q = b->h_pre[(size_t)h * b->n + t];
@@ -759,6 +770,7 @@ int sdso_ba_get_precalc(sdso_ctx* ctx, int h, int t, float out[49]) {
 }
 
 int sdso_ba_get_adjoints(sdso_ctx* ctx, double* adHost, double* adTarget, float* adHTdeltaF) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (adHost) memcpy(adHost, b->h_adH.data(), b->h_adH.size() * sizeof(double));
   if (adTarget) memcpy(adTarget, b->h_adT.data(), b->h_adT.size() * sizeof(double));
@@ -767,6 +779,7 @@ int sdso_ba_get_adjoints(sdso_ctx* ctx, double* adHost, double* adTarget, float*
 }
 
 int sdso_ba_nullspaces(sdso_ctx* ctx, double* N) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (!N) return SDSO_E_INVALID;
   memcpy(N, b->h_N.data(), b->h_N.size() * sizeof(double));
@@ -774,6 +787,7 @@ int sdso_ba_nullspaces(sdso_ctx* ctx, double* N) {
 }
 
 int sdso_ba_linearize_all(sdso_ctx* ctx, int fix, double* energy) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   double e = 0;
   if (b->R > 0) {
@@ -790,6 +804,7 @@ int sdso_ba_linearize_all(sdso_ctx* ctx, int fix, double* energy) {
 }
 
 int sdso_ba_apply_res(sdso_ctx* ctx, int copy_jacobians) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (b->R == 0) return SDSO_OK;
   BAView v = view(b);
@@ -799,6 +814,7 @@ int sdso_ba_apply_res(sdso_ctx* ctx, int copy_jacobians) {
 }
 
 int sdso_ba_fix_linearization(sdso_ctx* ctx, int count, const int* rids) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (!b->any_linearized) { b->any_linearized = true; invalidate_graphs(b); }   // the captured chains skip the linearised accumulation until now
   BAView v = view(b);
@@ -824,6 +840,7 @@ int sdso_ba_fix_linearization(sdso_ctx* ctx, int count, const int* rids) {
 // Readback in the CALLER's residual order. which: 0 = candidate J (PointFrameResidual::J), 1 = EFResidual::J.
 int sdso_ba_get_res(sdso_ctx* ctx, int which, int* newState, int* state, double* newEnergy, double* newEnergyWO, int* active, int* linearized,
                     float* J74, float* JpJdF8, float* center3, float* resToZero8) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   const int R = b->R;
   const size_t cR = b->capR;
@@ -860,6 +877,7 @@ int sdso_ba_get_res(sdso_ctx* ctx, int which, int* newState, int* state, double*
 
 // per point: Hdd_accAF, bd_accAF, Hcd_accAF[4], Hdd_accLF, bd_accLF, Hcd_accLF[4], HdiF, bdSumF, step, priorF (16 floats)
 int sdso_ba_get_points(sdso_ctx* ctx, float* out16) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (!out16) return SDSO_E_INVALID;
   const int P = b->P;
@@ -877,6 +895,7 @@ int sdso_ba_get_points(sdso_ctx* ctx, float* out16) {
 }
 
 int sdso_ba_accumulate_top(sdso_ctx* ctx, int mode, int use_prior, double* H, double* bv, float* blocks) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (mode < 0 || mode > 2) return SDSO_E_INVALID;
   int rc = launch_top(ctx, mode, SYS_TMP, use_prior != 0);
@@ -886,6 +905,7 @@ int sdso_ba_accumulate_top(sdso_ctx* ctx, int mode, int use_prior, double* H, do
 }
 
 int sdso_ba_accumulate_sc(sdso_ctx* ctx, int shift_prior_to_zero, double* H, double* bv) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   int rc = launch_sc(ctx, shift_prior_to_zero != 0, SYS_TMP);
   if (rc) return rc;
@@ -893,6 +913,7 @@ int sdso_ba_accumulate_sc(sdso_ctx* ctx, int shift_prior_to_zero, double* H, dou
 }
 
 int sdso_ba_solve(sdso_ctx* ctx, int iteration, double lambda, double* x, double* Hfinal, double* bfinal) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   int rc = launch_solve(ctx, iteration, lambda);
   if (rc) return rc;
@@ -904,6 +925,7 @@ int sdso_ba_solve(sdso_ctx* ctx, int iteration, double lambda, double* x, double
 }
 
 int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, double* calib_step) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   const int d = b->dim(), n = b->n;
   std::vector<double> xv(d);
@@ -927,6 +949,7 @@ int sdso_ba_resubstitute(sdso_ctx* ctx, const double* x, double* frame_steps, do
 
 /* ---- point-sharded windows ---- */
 int sdso_ba_set_shard(sdso_ctx* ctx, int rank, int nranks) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   if (nranks < 1 || rank < 0 || rank >= nranks) return SDSO_E_INVALID;
@@ -935,6 +958,7 @@ int sdso_ba_set_shard(sdso_ctx* ctx, int rank, int nranks) {
 }
 
 int sdso_ba_assemble(sdso_ctx* ctx, void** device_system, int* count) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   int rc = launch_assemble(ctx);
   if (rc) return rc;
@@ -946,6 +970,7 @@ int sdso_ba_assemble(sdso_ctx* ctx, void** device_system, int* count) {
 
 // one NCCL allreduce of the partial system [(4+8n)^2 + (4+8n)] plus the linearisation energy (scalars[0]) appended to it
 int sdso_ba_allreduce(sdso_ctx* ctx, double* energy_out) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   const int d = b->dim();
   double* buf = sysH(b, SYS_FINAL);
@@ -960,6 +985,7 @@ int sdso_ba_allreduce(sdso_ctx* ctx, double* energy_out) {
 }
 
 int sdso_ba_solve_assembled(sdso_ctx* ctx, int iteration, double* x, double* Hfinal, double* bfinal) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   int rc = launch_factor_solve(ctx, iteration);
   if (!rc) rc = launch_resub(ctx, sysb(b, SYS_X));
@@ -998,11 +1024,13 @@ static int launch_energy_th(sdso_ctx* ctx, float* th_host, bool readback = true)
 }
 
 int sdso_ba_new_frame_energy_th(sdso_ctx* ctx, float* th) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   return launch_energy_th(ctx, th);
 }
 
 int sdso_ba_get_energy_th(sdso_ctx* ctx, float* frameEnergyTH) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   if (!frameEnergyTH) return SDSO_E_INVALID;
   for (int h = 0; h < b->n; h++) frameEnergyTH[h] = b->frames[h].frameEnergyTH;
@@ -1010,6 +1038,7 @@ int sdso_ba_get_energy_th(sdso_ctx* ctx, float* frameEnergyTH) {
 }
 
 int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idepth, double* calib) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   for (int h = 0; h < b->n; h++) {
     if (states) memcpy(states + 10 * h, b->frames[h].state, 10 * sizeof(double));
@@ -1024,6 +1053,7 @@ int sdso_ba_get_state(sdso_ctx* ctx, double* states, double* T_w2c, float* idept
 }
 
 int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iterations_done) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   const int n = b->n, d = b->dim(), R = b->R, P = b->P;
   if (rmse) *rmse = 0;
@@ -1150,6 +1180,7 @@ int sdso_ba_optimize(sdso_ctx* ctx, int mnumOptIts, double* rmse, int* iteration
 }
 
 int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   invalidate_graphs(b);
   if (!HM || !bM) return SDSO_E_INVALID;
@@ -1165,6 +1196,7 @@ int sdso_ba_set_marg_prior(sdso_ctx* ctx, const double* HM, const double* bM) {
 // the original 3-iteration LM on the inverse depth, SDSO_VARIANT_G2O = the live frozen-projection semantics)
 int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immature_point* pts, int variant, int min_obs, int* result,
                          float* idepth, int* states, float* energy) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (n < 0 || (n > 0 && (!host || !pts || !result || !idepth || !states || !energy))) return SDSO_E_INVALID;
   if (variant != SDSO_VARIANT_SSE && variant != SDSO_VARIANT_G2O) return SDSO_E_INVALID;
@@ -1204,6 +1236,7 @@ int sdso_activate_points(sdso_ctx* ctx, int n, const int* host, const sdso_immat
 int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, const double* idepth, const double cam[4], const double* b0,
                        double* error8, double* J_xi, double* J_photo, double* J_idepth, double* J_C, int* newState, double* newEnergy,
                        double* newEnergyWithOutlier, float* center3, float* idepth_hessian, int* level) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (!T_wh || !photo || !idepth || !cam || !b0 || !error8 || !J_xi || !J_photo || !J_idepth || !J_C || !newState || !newEnergy ||
       !newEnergyWithOutlier || !center3 || !idepth_hessian || !level) return SDSO_E_INVALID;
@@ -1275,6 +1308,7 @@ int sdso_lba_edge_eval(sdso_ctx* ctx, const double* T_wh, const double* photo, c
 // host loop moves the (4+8n)-vector increment and the n host poses per trial.
 int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, double* photo, double* idepth, int* used_host, double* chi2_out,
                  int* newState, float* center3, float* idepth_hessian, int* iterations_out, int* trials_out) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   if (!cam || !T_wh || !photo || !idepth || !used_host) return SDSO_E_INVALID;
   const int n = b->n, R = b->R, d = b->dim();
@@ -1489,6 +1523,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
 
 // EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:663-736) for the points flagged PS_MARGINALIZE
 int sdso_ba_marginalize_points(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   invalidate_graphs(b);
   const int d = b->dim(), P = b->P, R = b->R;
@@ -1512,6 +1547,7 @@ int sdso_ba_marginalize_points(sdso_ctx* ctx) {
 // asserts). HM / bM shrink to dimension d-8 on the device; the host window loses the frame, so points / residuals / states have
 // to be uploaded again before the next operator call (the reference re-indexes with makeIDX at this point).
 int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   invalidate_graphs(b);
   if (idx < 0 || idx >= b->n) return SDSO_E_INVALID;
@@ -1519,7 +1555,8 @@ int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx) {
   cudaStream_t st = ctx->stream;
   if (!b->have_M) { SDSO_CUDA(ctx, cudaMemsetAsync(sysH(b, SYS_M), 0, ((size_t)odim * odim + odim) * sizeof(double), st)); b->have_M = true; }
   const size_t smem = ((size_t)odim * odim + 2 * (size_t)odim + 64 + (size_t)ndim * 8) * sizeof(double);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};   // function attributes are per device
+  bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) { cudaFuncSetAttribute(ba_marg_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   double* out = sysH(b, SYS_TMP);
   ba_marg_frame_kernel<<<1, 256, smem, st>>>(odim, idx, sysH(b, SYS_M), sysb(b, SYS_M), b->d_fprior, out, out + (size_t)ndim * ndim);
@@ -1535,6 +1572,7 @@ int sdso_ba_marginalize_frame(sdso_ctx* ctx, int idx) {
 
 // EnergyFunctional::calcMEnergyF (:344-351) and calcLEnergyF_MT (:354-442)
 int sdso_ba_energies(sdso_ctx* ctx, double* menergy, double* lenergy) {
+  sdso::enter(ctx);
   BA_PREPARED(ctx)
   const int d = b->dim(), P = b->P;
   cudaStream_t st = ctx->stream;
@@ -1569,6 +1607,7 @@ int sdso_ba_energies(sdso_ctx* ctx, double* menergy, double* lenergy) {
 }
 
 int sdso_ba_get_marg_prior(sdso_ctx* ctx, double* HM, double* bM) {
+  sdso::enter(ctx);
   BA_CHECK(ctx)
   return download_sys(ctx, SYS_M, HM, bM);
 }

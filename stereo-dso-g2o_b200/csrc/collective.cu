@@ -76,6 +76,7 @@ int sdso_nccl_unique_id(unsigned char id[128]) {
 }
 
 int sdso_nccl_init(sdso_ctx* ctx, int rank, int nranks, const unsigned char id[128]) {
+  sdso::enter(ctx);
   if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return SDSO_E_INVALID;
   std::string err;
   NcclApi* api = nccl_api(&err);
@@ -92,6 +93,7 @@ int sdso_nccl_init(sdso_ctx* ctx, int rank, int nranks, const unsigned char id[1
 }
 
 int sdso_nccl_destroy(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   collective_destroy(ctx);
   return SDSO_OK;
@@ -99,6 +101,7 @@ int sdso_nccl_destroy(sdso_ctx* ctx) {
 
 // In-place sum over ranks of a device buffer of doubles on the context's stream (asynchronous).
 int sdso_allreduce_f64(sdso_ctx* ctx, void* device_buffer, int count) {
+  sdso::enter(ctx);
   if (!ctx || !device_buffer || count < 0) return SDSO_E_INVALID;
   if (!ctx->nccl_comm) return fail(ctx, SDSO_E_STATE, "sdso_nccl_init has not been called");
   NcclApi* api = nccl_api(nullptr);

@@ -69,6 +69,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_profile_enable(sdso_ctx* ctx, int on) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   ctx->profile = on != 0;
   ctx->ev_track_used = ctx->ev_images_used = 0;
@@ -76,6 +77,7 @@ int sdso_profile_enable(sdso_ctx* ctx, int on) {
 }
 
 int sdso_profile_read(sdso_ctx* ctx, double* track_ms, int* track_launches, double* images_ms, int* images_launches) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double t = 0, m = 0;
@@ -196,11 +198,13 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
 const char* sdso_last_error(const sdso_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int sdso_set_stream(sdso_ctx* ctx, void* s) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   ctx->stream = (cudaStream_t)s;
   return SDSO_OK;
 }
 int sdso_synchronize(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   SDSO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SDSO_OK;
@@ -221,11 +225,13 @@ int sdso_level_K(const sdso_ctx* ctx, int lvl, float K[9], float Ki[9]) {
 uint64_t sdso_launch_count(const sdso_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int sdso_set_gamma(sdso_ctx* ctx, const float B[256]) {
+  sdso::enter(ctx);
   if (!ctx || !B) return SDSO_E_INVALID;
   return set_gamma_table(ctx, B);
 }
 
 int sdso_frame_create(sdso_ctx* ctx, int* frame_id) {
+  sdso::enter(ctx);
   if (!ctx || !frame_id) return SDSO_E_INVALID;
   int id = -1;
   for (size_t i = 0; i < ctx->frames.size(); i++) if (!ctx->frames[i].in_use) { id = (int)i; break; }
@@ -247,6 +253,7 @@ int sdso_frame_create(sdso_ctx* ctx, int* frame_id) {
 }
 
 int sdso_frame_release(sdso_ctx* ctx, int frame_id) {
+  sdso::enter(ctx);
   if (!ctx || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
   ctx->frames[frame_id].in_use = false;  // device memory is kept for reuse
   ctx->frames[frame_id].valid = false;
@@ -254,6 +261,7 @@ int sdso_frame_release(sdso_ctx* ctx, int frame_id) {
 }
 
 int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float ab_exposure, int use_hcalib) {
+  sdso::enter(ctx);
   if (!ctx || !host_image || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
   Frame& f = ctx->frames[frame_id];
   const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
@@ -266,6 +274,7 @@ int sdso_make_images(sdso_ctx* ctx, int frame_id, const float* host_image, float
 }
 
 int sdso_make_images_device(sdso_ctx* ctx, int frame_id, const float* device_image, float ab_exposure, int use_hcalib) {
+  sdso::enter(ctx);
   if (!ctx || !device_image || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].in_use) return SDSO_E_INVALID;
   Frame& f = ctx->frames[frame_id];
   const size_t n = (size_t)ctx->G.w[0] * ctx->G.h[0];
@@ -287,6 +296,7 @@ static int check_batch(sdso_ctx* ctx, int nb, const int* frame_ids) {
 // Asynchronous H2D upload of nb source images (float32 or uint8, w*h each, ideally pinned) on the context's copy stream.
 // Returns immediately; sdso_make_images_uploaded makes the compute stream wait for exactly these copies.
 int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* host_images, int src_u8) {
+  sdso::enter(ctx);
   int rc = check_batch(ctx, nb, frame_ids);
   if (rc) return rc;
   if (nb > 0 && !host_images) return SDSO_E_INVALID;
@@ -350,6 +360,7 @@ int sdso_upload_images_async(sdso_ctx* ctx, int nb, const int* frame_ids, const 
 
 // makeImages of nb frames whose sources were uploaded with sdso_upload_images_async: ONE pyramid + ONE gradient launch.
 int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const float* ab_exposure, int use_hcalib) {
+  sdso::enter(ctx);
   int rc = check_batch(ctx, nb, frame_ids);
   if (rc) return rc;
   if (nb == 0) return SDSO_OK;
@@ -388,6 +399,7 @@ int sdso_make_images_uploaded(sdso_ctx* ctx, int nb, const int* frame_ids, const
 // makeImages of nb frames from images already on the device (float32 or uint8): ONE pyramid + ONE gradient launch.
 int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, const void* const* device_images, int src_u8,
                                   const float* ab_exposure, int use_hcalib) {
+  sdso::enter(ctx);
   int rc = check_batch(ctx, nb, frame_ids);
   if (rc) return rc;
   if (nb == 0) return SDSO_OK;
@@ -403,6 +415,7 @@ int sdso_make_images_batch_device(sdso_ctx* ctx, int nb, const int* frame_ids, c
 }
 
 int sdso_frame_download(sdso_ctx* ctx, int frame_id, int lvl, float* dI3, float* absgrad) {
+  sdso::enter(ctx);
   if (!ctx || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
   if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
   const size_t n = (size_t)ctx->G.w[lvl] * ctx->G.h[lvl];
@@ -428,6 +441,7 @@ __global__ void interp_kernel(const float4* tex, int width, const float2* xy, in
 }  // namespace sdso
 
 extern "C" int sdso_interp33(sdso_ctx* ctx, int frame_id, int lvl, const float* xy, int n, float* out3, int bilin_variant) {
+  sdso::enter(ctx);
   if (!ctx || !xy || !out3 || n < 0 || frame_id < 0 || frame_id >= (int)ctx->frames.size() || !ctx->frames[frame_id].valid) return SDSO_E_INVALID;
   if (lvl < 0 || lvl >= ctx->G.levels) return SDSO_E_INVALID;
   if (n == 0) return SDSO_OK;

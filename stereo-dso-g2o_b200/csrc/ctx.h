@@ -83,6 +83,13 @@ inline int fail(sdso_ctx* c, int code, const std::string& msg) {
   return code;
 }
 
+// A context belongs to ONE device (sdso_ctx_create). Entry points that allocate or launch make that device current first, so two
+// contexts on different GPUs can live in one process (the bench uses one process per GPU, where this is a no-op).
+inline void enter(const sdso_ctx* c) {
+  int cur = -1;
+  if (c && cudaGetDevice(&cur) == cudaSuccess && cur != c->device) cudaSetDevice(c->device);
+}
+
 #define SDSO_CUDA(ctx, expr)                                                                       \
   do {                                                                                             \
     cudaError_t e__ = (expr);                                                                      \

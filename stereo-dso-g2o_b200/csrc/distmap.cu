@@ -350,6 +350,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_distmap_make(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float* Kt, int n_pts, const int* pt_host, const float* pt_uvid, float* map_out) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->distmap || n_hosts < 0 || n_pts < 0) return SDSO_E_INVALID;
   DistMapState* s = ctx->distmap;
   if (!s->d_map) return fail(ctx, SDSO_E_INVALID, "distmap: needs pyramid level 1");
@@ -382,6 +383,7 @@ int sdso_distmap_make(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float
 }
 
 int sdso_distmap_add(sdso_ctx* ctx, int n, const int* uv, float* map_out) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->distmap || n < 0 || (n > 0 && !uv)) return SDSO_E_INVALID;
   DistMapState* s = ctx->distmap;
   if (!s->d_map) return fail(ctx, SDSO_E_INVALID, "distmap: needs pyramid level 1");
@@ -401,6 +403,7 @@ int sdso_distmap_add(sdso_ctx* ctx, int n, const int* uv, float* map_out) {
 
 int sdso_activation_filter(sdso_ctx* ctx, int n_hosts, const float* KRKi, const float* Kt, const unsigned char* host_flagged, int n, const int* cand_host,
                            const sdso_immature_point* pts, const float* my_type, float currentMinActDist, int* verdict, int* rounds, float* map_out) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->distmap || n < 0 || n_hosts < 0) return SDSO_E_INVALID;
   DistMapState* s = ctx->distmap;
   if (!s->d_map) return fail(ctx, SDSO_E_INVALID, "distmap: needs pyramid level 1");

@@ -86,6 +86,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_vertex_oplus(sdso_ctx* ctx, int kind, int n, double* estimate, const double* update, const double* aux) {
+  sdso::enter(ctx);
   if (!ctx || n < 0 || (n > 0 && (!estimate || !update))) return SDSO_E_INVALID;
   int es = 0, us = 0;
   switch (kind) {
@@ -119,6 +120,7 @@ int sdso_vertex_oplus(sdso_ctx* ctx, int kind, int n, double* estimate, const do
 
 int sdso_edge_trace_uv_eval(sdso_ctx* ctx, int frame, int n, const double* uv, const float* rotatePattern, const double* measurement,
                             const float affLL[2], const double* dxdy, double* error, double* J, int* flag) {
+  sdso::enter(ctx);
   if (!ctx || n < 0 || !affLL || (n > 0 && (!uv || !rotatePattern || !measurement || !dxdy || !error || !J))) return SDSO_E_INVALID;
   if (frame < 0 || frame >= (int)ctx->frames.size() || !ctx->frames[frame].in_use || !ctx->frames[frame].valid)
     return fail(ctx, SDSO_E_INVALID, "bad frame id (not created or makeImages not run)");

@@ -362,7 +362,8 @@ int make_images_batch_launch(sdso_ctx* ctx, int nb, Frame* const* frames, const 
     size_t smem = 0;
     for (int l = 0, R = kTile + 2 * H0; l < P.levels; l++, R >>= 1) smem += (size_t)R * R * sizeof(float);
     dim3 grid((P.w[0] + kTile - 1) / kTile, (P.h[0] + kTile - 1) / kTile, nb);
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};   // function attributes are per device
+  bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {   // the 6-level region needs 87 KB of dynamic shared memory
       SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       SDSO_CUDA(ctx, cudaFuncSetAttribute(pyr_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -516,6 +516,7 @@ extern "C" {
 void sdso_selector_pattern_host(unsigned seed, unsigned char* out, size_t n) { if (out) glibc_rand_bytes(seed, out, n); }
 
 int sdso_selector_reset(sdso_ctx* ctx) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->selector) return SDSO_E_INVALID;
   ctx->selector->currentPotential = 3;
   ctx->selector->histFrame = -1;
@@ -524,12 +525,14 @@ int sdso_selector_reset(sdso_ctx* ctx) {
 }
 
 int sdso_selector_random_pattern(sdso_ctx* ctx, unsigned char* out) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->selector || !out) return SDSO_E_INVALID;
   memcpy(out, ctx->selector->h_rp.data(), ctx->selector->h_rp.size());
   return SDSO_OK;
 }
 
 int sdso_selector_potential(sdso_ctx* ctx, int set, int* potential) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->selector) return SDSO_E_INVALID;
   if (set > 0) ctx->selector->currentPotential = set;
   if (potential) *potential = ctx->selector->currentPotential;
@@ -537,6 +540,7 @@ int sdso_selector_potential(sdso_ctx* ctx, int set, int* potential) {
 }
 
 int sdso_selector_make_hists(sdso_ctx* ctx, int frame, float* ths, float* ths_smoothed) {
+  sdso::enter(ctx);
   int rc = check_frame(ctx, frame);
   if (rc) return rc;
   rc = launch_hists(ctx, frame);
@@ -550,6 +554,7 @@ int sdso_selector_make_hists(sdso_ctx* ctx, int frame, float* ths, float* ths_sm
 }
 
 int sdso_selector_select(sdso_ctx* ctx, int frame, int pot, float thFactor, float* map_out, int n[3]) {
+  sdso::enter(ctx);
   int rc = check_frame(ctx, frame);
   if (rc) return rc;
   rc = launch_select(ctx, frame, pot, thFactor);
@@ -563,6 +568,7 @@ int sdso_selector_select(sdso_ctx* ctx, int frame, int pot, float thFactor, floa
 }
 
 int sdso_make_maps(sdso_ctx* ctx, int frame, float density, int recursionsLeft, float thFactor, float* map_out, int* num_selected) {
+  sdso::enter(ctx);
   int rc = check_frame(ctx, frame);
   if (rc) return rc;
   SelectorState* s = ctx->selector;
@@ -604,6 +610,7 @@ int sdso_make_maps(sdso_ctx* ctx, int frame, float density, int recursionsLeft, 
 }
 
 int sdso_selector_points(sdso_ctx* ctx, int max_n, float* uv, float* type, int* n) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->selector || !n) return SDSO_E_INVALID;
   SelectorState* s = ctx->selector;
   if (!s->list_valid) {

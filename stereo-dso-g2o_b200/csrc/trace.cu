@@ -456,6 +456,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_immature_init(sdso_ctx* ctx, int host_frame, int n, const float* uv, sdso_immature_point* out, int* ok) {
+  sdso::enter(ctx);
   if (!ctx || host_frame < 0 || host_frame >= (int)ctx->frames.size() || !ctx->frames[host_frame].valid) return SDSO_E_INVALID;
   if (n < 0 || (n > 0 && (!uv || !out))) return SDSO_E_INVALID;
   if (n == 0) return SDSO_OK;
@@ -484,6 +485,7 @@ int sdso_immature_init(sdso_ctx* ctx, int host_frame, int n, const float* uv, sd
 }
 
 int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[3], const float aff[2], int n, sdso_immature_point* pts, int* status) {
+  sdso::enter(ctx);
   if (!ctx || !KRKi || !Kt || !aff || (n > 0 && !pts)) return SDSO_E_INVALID;
   TraceXf X{};
   for (int i = 0; i < 9; i++) X.KRKi[i] = KRKi[i];
@@ -493,6 +495,7 @@ int sdso_trace_on(sdso_ctx* ctx, int frame, const float KRKi[9], const float Kt[
 }
 
 int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, sdso_immature_point* pts, int* status) {
+  sdso::enter(ctx);
   if (!ctx || !K || (n > 0 && !pts)) return SDSO_E_INVALID;
   TraceXf X{};
   stereo_xf(ctx, K, mode_right, X);
@@ -501,6 +504,7 @@ int sdso_trace_stereo(sdso_ctx* ctx, int frame, const float K[9], int mode_right
 
 int sdso_trace_on_hosts(sdso_ctx* ctx, int frame, int n_hosts, const float* KRKi, const float* Kt, const float* aff, int n, const int* host_of_point,
                         sdso_immature_point* pts, int* status) {
+  sdso::enter(ctx);
   if (!ctx || !KRKi || !Kt || !aff || n_hosts < 1 || n_hosts > kMaxTraceHosts || (n > 0 && !host_of_point)) return SDSO_E_INVALID;
   for (int i = 0; i < n; i++) if (host_of_point[i] < 0 || host_of_point[i] >= n_hosts) return fail(ctx, SDSO_E_INVALID, "trace: host index out of range");
   TraceXf X[kMaxTraceHosts];
@@ -514,6 +518,7 @@ int sdso_trace_on_hosts(sdso_ctx* ctx, int frame, int n_hosts, const float* KRKi
 }
 
 int sdso_trace_stereo_resident(sdso_ctx* ctx, int frame, const float K[9], int mode_right, int n, int* status) {
+  sdso::enter(ctx);
   if (!ctx || !K) return SDSO_E_INVALID;
   TraceXf X{};
   stereo_xf(ctx, K, mode_right, X);
@@ -521,6 +526,7 @@ int sdso_trace_stereo_resident(sdso_ctx* ctx, int frame, const float K[9], int m
 }
 
 int sdso_immature_upload(sdso_ctx* ctx, int n, const sdso_immature_point* pts) {
+  sdso::enter(ctx);
   if (!ctx || n < 0 || (n > 0 && !pts)) return SDSO_E_INVALID;
   TraceState* t = ctx->trace;
   if (n > t->pool_cap) {
@@ -537,6 +543,7 @@ int sdso_immature_upload(sdso_ctx* ctx, int n, const sdso_immature_point* pts) {
 }
 
 int sdso_immature_download(sdso_ctx* ctx, int first, int n, sdso_immature_point* pts) {
+  sdso::enter(ctx);
   if (!ctx || first < 0 || n < 0 || (n > 0 && !pts)) return SDSO_E_INVALID;
   TraceState* t = ctx->trace;
   if (first + n > t->pool_n) return fail(ctx, SDSO_E_INVALID, "immature_download: range exceeds the resident pool");

@@ -1146,7 +1146,8 @@ static int launch_track(sdso_ctx* ctx, const TrackParams& P, int nb, bool g2o) {
   const bool use_cache = !g2o && ctx->S.track_cache != 0;
   // (the cache is sized for the thread count the kernel instance was compiled for: 256, or 192 for the 168-register build)
   if (use_cache) smem = ((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes((ctx->S.gather_batch == 2 && BT <= 192 && C == 1) ? 192 : 256);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};   // function attributes are per device
+  bool& attr_set = attr_set_dev[ctx->device & 63];
   if (!attr_set) {
     const int big = (int)(((sizeof(TrackSmem) + 15) & ~(size_t)15) + cache_bytes(256));
     SDSO_CUDA(ctx, cudaFuncSetAttribute(track_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1227,6 +1228,7 @@ using namespace sdso;
 extern "C" {
 
 int sdso_tracker_make_k(sdso_ctx* ctx, const float K[4]) {
+  sdso::enter(ctx);
   if (!ctx || !K) return SDSO_E_INVALID;
   ctx->tracker->K.set(ctx->G.w[0], ctx->G.h[0], K[0], K[1], K[2], K[3], false);
   ctx->tracker->K.levels = ctx->G.levels;
@@ -1235,6 +1237,7 @@ int sdso_tracker_make_k(sdso_ctx* ctx, const float K[4]) {
 
 int sdso_tracker_set_pc(sdso_ctx* ctx, int ref_frame, int lvl, int n, const float* u, const float* v, const float* idepth,
                         const float* color, const double ref_aff[2]) {
+  sdso::enter(ctx);
   if (!ctx || lvl < 0 || lvl >= ctx->G.levels || n < 0) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (ref_frame < 0 || ref_frame >= (int)ctx->frames.size() || !ctx->frames[ref_frame].in_use) return fail(ctx, SDSO_E_INVALID, "bad ref_frame");
@@ -1252,6 +1255,7 @@ int sdso_tracker_set_pc(sdso_ctx* ctx, int ref_frame, int lvl, int n, const floa
 }
 
 int sdso_tracker_get_pc(sdso_ctx* ctx, int lvl, int* n, float* u, float* v, float* idepth, float* color) {
+  sdso::enter(ctx);
   if (!ctx || lvl < 0 || lvl >= ctx->G.levels || !n) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   *n = t->pc_n[lvl];
@@ -1274,6 +1278,7 @@ static int check_frame(sdso_ctx* ctx, int f) {
 
 int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNew[12], const double aff[2], float cutoffTH,
                      double rs[6], double H[64], double b[8], int* warped_n, float* warped) {
+  sdso::enter(ctx);
   if (!ctx || !refToNew || !aff) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (!t->have_ref) return fail(ctx, SDSO_E_STATE, "calcRes before setCoarseTrackingRef");
@@ -1333,6 +1338,7 @@ int sdso_calc_res_gs(sdso_ctx* ctx, int new_frame, int lvl, const double refToNe
 
 int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[12], const double T_pose[12], const double photo[2],
                    int* n_out, double* err, double* J8) {
+  sdso::enter(ctx);
   if (!ctx || !T_select || !T_pose || !photo || !n_out) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (!t->have_ref) return fail(ctx, SDSO_E_STATE, "edge evaluation before setCoarseTrackingRef");
@@ -1382,10 +1388,12 @@ int sdso_edge_eval(sdso_ctx* ctx, int new_frame, int lvl, const double T_select[
 
 int sdso_track_enqueue(sdso_ctx* ctx, int nb, const int* new_frames, const double* T_in, const double* aff_in, int coarsest_lvl,
                        const double* minResForAbort, int variant) {
+  sdso::enter(ctx);
   return sdso_track_enqueue_multi(ctx, nb, nullptr, new_frames, T_in, aff_in, coarsest_lvl, minResForAbort, variant);
 }
 
 int sdso_tracker_select_ref(sdso_ctx* ctx, int slot) {
+  sdso::enter(ctx);
   if (!ctx || slot < 0 || slot >= 1024) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (slot == t->cur_slot) return SDSO_OK;
@@ -1408,6 +1416,7 @@ int sdso_tracker_select_ref(sdso_ctx* ctx, int slot) {
 
 int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const int* new_frames, const double* T_in, const double* aff_in,
                              int coarsest_lvl, const double* minResForAbort, int variant) {
+  sdso::enter(ctx);
   if (!ctx || nb <= 0 || !new_frames || !T_in || !aff_in || !minResForAbort) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (!ref_slots && !t->have_ref) return fail(ctx, SDSO_E_STATE, "trackNewestCoarse before setCoarseTrackingRef");
@@ -1447,6 +1456,7 @@ int sdso_track_enqueue_multi(sdso_ctx* ctx, int nb, const int* ref_slots, const 
 
 int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, double* lastResiduals, double* flowIndicators,
                        int* iterations, int* ok, uint64_t* evals) {
+  sdso::enter(ctx);
   if (!ctx) return SDSO_E_INVALID;
   TrackerState* t = ctx->tracker;
   if (nb != t->last_nb) return fail(ctx, SDSO_E_STATE, "collect does not match the last enqueue");
@@ -1472,6 +1482,7 @@ int sdso_track_collect(sdso_ctx* ctx, int nb, double* T_out, double* aff_out, do
 int sdso_track_batch(sdso_ctx* ctx, int nb, const int* new_frames, double* T_io, double* aff_io, int coarsest_lvl,
                      const double* minResForAbort, int variant, double* lastResiduals, double* flowIndicators, int* iterations,
                      int* ok) {
+  sdso::enter(ctx);
   int rc = sdso_track_enqueue(ctx, nb, new_frames, T_io, aff_io, coarsest_lvl, minResForAbort, variant);
   if (rc) return rc;
   return sdso_track_collect(ctx, nb, T_io, aff_io, lastResiduals, flowIndicators, iterations, ok, nullptr);
@@ -1479,6 +1490,7 @@ int sdso_track_batch(sdso_ctx* ctx, int nb, const int* new_frames, double* T_io,
 
 int sdso_track(sdso_ctx* ctx, int new_frame, double T_io[12], double aff_io[2], int coarsest_lvl, const double minResForAbort[5],
                int variant, double lastResiduals[5], double flowIndicators[3], int iterations[5], int* ok) {
+  sdso::enter(ctx);
   return sdso_track_batch(ctx, 1, &new_frame, T_io, aff_io, coarsest_lvl, minResForAbort, variant, lastResiduals, flowIndicators,
                           iterations, ok);
 }
@@ -1488,6 +1500,7 @@ int sdso_track(sdso_ctx* ctx, int new_frame, double T_io[12], double aff_io[2], 
 // phase cycles (clock64 on rank 0 / thread 0) of the last collected track launch, when profiling is enabled:
 // [0] serial LM step, [1] point loop, [2] block reduction, [3] cluster barrier + final sum, [4] accept/reject bookkeeping
 extern "C" int sdso_track_phase_cycles(sdso_ctx* ctx, long long cyc[16]) {
+  sdso::enter(ctx);
   if (!ctx || !cyc) return SDSO_E_INVALID;
   for (int i = 0; i < 16; i++) cyc[i] = ctx->tracker->last_cyc[i];
   return SDSO_OK;

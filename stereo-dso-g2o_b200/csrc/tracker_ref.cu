@@ -127,6 +127,7 @@ __global__ void compact_kernel(const float* idepthl, const float* wsl, const flo
 using namespace sdso;
 
 extern "C" int sdso_tracker_set_ref(sdso_ctx* ctx, int ref_frame, const float* uvidw, int n, const double ref_aff[2]) {
+  sdso::enter(ctx);
   if (!ctx || n < 0 || (n > 0 && !uvidw) || !ref_aff) return SDSO_E_INVALID;
   if (ref_frame < 0 || ref_frame >= (int)ctx->frames.size() || !ctx->frames[ref_frame].valid) return fail(ctx, SDSO_E_INVALID, "bad ref_frame");
   TrackerState* t = ctx->tracker;

@@ -66,6 +66,7 @@ extern "C" {
 
 int sdso_undistort_setup(sdso_ctx* ctx, int wOrg, int hOrg, const float* remapX, const float* remapY, const float* G, const float* vignetteMapInv,
                          int photometricCalibration, int useExposure) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->undistort || wOrg < 2 || hOrg < 2 || !remapX || !remapY) return SDSO_E_INVALID;
   if (photometricCalibration < 0 || photometricCalibration > 2) return SDSO_E_INVALID;
   if (photometricCalibration == 2 && G && !vignetteMapInv) return fail(ctx, SDSO_E_INVALID, "undistort: photometricCalibration 2 needs the inverse vignette");
@@ -96,6 +97,7 @@ int sdso_undistort_setup(sdso_ctx* ctx, int wOrg, int hOrg, const float* remapX,
 }
 
 int sdso_undistort(sdso_ctx* ctx, const unsigned char* raw, float exposure, float factor, float* out_image, int frame, int use_hcalib, float* exposure_out) {
+  sdso::enter(ctx);
   if (!ctx || !ctx->undistort || !raw) return SDSO_E_INVALID;
   UndistortState* s = ctx->undistort;
   if (!s->ready) return fail(ctx, SDSO_E_STATE, "undistort before undistort_setup");
