@@ -458,6 +458,12 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ---- legs: the rest of the path, driver-visible (bench_legs.py) -----------------------------------------
+    def traffic_of(vname):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"track_{vname}_batch{S}_dram_bytes_per_launch")
+        except Exception:
+            return None
+
     want = set(["g2o", "ba3", "ba4", "trace", "sequence", "sharded"] if args.legs == "all" else [x for x in args.legs.split(",") if x and x != "none"])
     legs = {}
     peak_, _ = measured_peak()
@@ -486,7 +492,7 @@ def main():
         legs["track_g2o"] = dict(
             workload=f"the same {S} sequences, variant=g2o (the fork's live code path: EdgeSE3PosePhotoDSO edges + restated g2o LM, 2 iterations per level)",
             value=ev_g / (ms_g * 1e-3), unit="evals/s", steps=Kg, ms_per_step=ms_g / Kg, tracked_frames_per_s=S * Kg / (ms_g * 1e-3), converged_fraction=conv,
-            roofline=dict(bound="hbm", achieved=ach, peak=peak_, unit="GB/s", frac=ach / peak_, kernel="track_g2o_kernel", avg_launch_ms=tk,
+            roofline=dict(bound="hbm", achieved=ach, peak=peak_, unit="GB/s", frac=ach / peak_, kernel="track_g2o_kernel", avg_launch_ms=tk, traffic=traffic_of("g2o"),
                           algorithmic_bytes_per_launch=ev_g / Kg * BYTES_PER_EVAL),
             cpu_baseline=dict(value=cg_ev / cg_sec, unit="evals/s", cores=host_cores, kind="port", tracked_frames_per_s=cg_fr / cg_sec,
                               sample=f"{cg_fr} tracked stereo frames in {cg_sec:.1f} s over {host_cores} threads (oracle port, g2o variant)"))
@@ -564,6 +570,7 @@ def main():
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                      traffic_source="ncu --set full capture of this kernel in this command, profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch); not measurable inside an unprofiled run",
                       kernel="track_kernel" if variant == 0 else "track_g2o_kernel", peak_source=peak_src,
                       algorithmic_bytes_per_launch=evals_per_launch * BYTES_PER_EVAL, avg_launch_ms=track_ms_per_launch,
                       share_of_step=prof["track_ms"] / ms_dev, scattered_gather_ceiling=pattern,

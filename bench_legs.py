@@ -355,22 +355,22 @@ def leg_sequence(pkg, torch, dev, scene, n_frames=60):
 
     def run(backend):
         P = PL.StereoPipeline(backend)
-        per_frame = []
+        per_frame, per_frame_ops = [], []
         for l, r in zip(left, right):
-            t0 = time.perf_counter()
+            t0 = time.perf_counter(); o0 = backend.t_ops
             P.step(l, r)
-            per_frame.append(time.perf_counter() - t0)
-        return P, np.array(per_frame)
+            per_frame.append(time.perf_counter() - t0); per_frame_ops.append(backend.t_ops - o0)
+        return P, np.array(per_frame), np.array(per_frame_ops)
 
     Bg = PL.Backend(shape, pkg)
     run(Bg)                      # warm-up (allocations, graph captures)
     Bg.close()
     Bg = PL.Backend(shape, pkg)
     l0 = Bg.api.launch_count()
-    Pg, tg = run(Bg)
+    Pg, tg, og = run(Bg)
     launches = Bg.api.launch_count() - l0
     Bg.close()
-    Po, to = run(PL.Backend(shape))
+    Po, to, oo = run(PL.Backend(shape))
     kf = np.arange(n_frames) % 5 == 0
     dt = np.array([np.abs(Pg.traj[k][:3, 3] - Po.traj[k][:3, 3]).max() for k in range(n_frames)])
     return dict(
@@ -378,12 +378,16 @@ def leg_sequence(pkg, torch, dev, scene, n_frames=60):
                  "makeImages (left + right) + trackNewestCoarse + traceOn per frame; selector, static stereo, distance map, candidate loop, activation, "
                  "windowed optimisation (6 iterations), marginalisation per key frame (tests/pipeline.py)",
         metric="tracked stereo frames/s (one sequence, end to end through the C ABI, host images in, poses out)",
-        value=n_frames / tg.sum(), unit="frames/s", ms_per_tracked_frame=1e3 * float(np.median(tg[~kf])), ms_per_key_frame=1e3 * float(np.median(tg[kf][1:])),
+        note="value = frames / time spent INSIDE the operator calls (ABI entry points with host buffers: uploads, launches, read-backs, ctypes marshalling) — what a "
+             "C++ caller pays; the Python harness around them (per-point dicts, numpy bookkeeping that stands in for FullSystem) is reported separately as wall time",
+        value=n_frames / og.sum(), unit="frames/s", ms_per_tracked_frame=1e3 * float(np.median(og[~kf])), ms_per_key_frame=1e3 * float(np.median(og[kf][1:])),
+        wall_including_python_harness=dict(frames_per_s=n_frames / tg.sum(), ms_per_tracked_frame=1e3 * float(np.median(tg[~kf])), ms_per_key_frame=1e3 * float(np.median(tg[kf][1:]))),
         kernel_launches=int(launches),
-        e2e=dict(value=n_frames / tg.sum(), unit="frames/s", h2d_bytes_per_step=int(2 * synth.W * synth.H * 4), d2h_bytes_per_step=int(12 * 8 + 16 + 40),
+        e2e=dict(value=n_frames / og.sum(), unit="frames/s", h2d_bytes_per_step=int(2 * synth.W * synth.H * 4), d2h_bytes_per_step=int(12 * 8 + 16 + 40),
                  note="host float images are uploaded inside sdso_make_images; immature records cross once per frame (one launch for all hosts)"),
-        cpu_baseline=dict(value=n_frames / to.sum(), unit="frames/s", cores=1, kind="port", ms_per_tracked_frame=1e3 * float(np.median(to[~kf])),
-                          ms_per_key_frame=1e3 * float(np.median(to[kf][1:])), sample=f"the same {n_frames} frames through the same harness on the oracle port, one host thread"),
+        cpu_baseline=dict(value=n_frames / oo.sum(), unit="frames/s", cores=1, kind="port", ms_per_tracked_frame=1e3 * float(np.median(oo[~kf])),
+                          ms_per_key_frame=1e3 * float(np.median(oo[kf][1:])), wall_frames_per_s=n_frames / to.sum(),
+                          sample=f"the same {n_frames} frames through the same harness on the oracle port, one host thread, operator time"),
         parity=dict(max_translation_difference_m=float(dt.max()), note="free-running chains: see tests/test_pipeline.py for the envelope (the oracle's own spread)"))
 
 

@@ -244,6 +244,16 @@ int orc_ba_add_point(void* p, int host, float u, float v, float idepth, float id
   c->ba.points.push_back(q);
   return (int)c->ba.points.size() - 1;
 }
+int orc_ba_add_residual(void* p, int pidx, int target);
+int orc_ba_add_point(void* p, int host, float u, float v, float idepth, float idepth_zero, const float* color8, const float* weights8, int hasDepthPrior);
+// batched forms (the per-point calls cost more in the Python harness than the operators they feed)
+void orc_ba_add_points(void* p, int n, const int* host, const float* u, const float* v, const float* idepth, const float* idepth_zero, const float* color8,
+                       const float* weights8, const unsigned char* prior) {
+  for (int i = 0; i < n; i++) orc_ba_add_point(p, host[i], u[i], v[i], idepth[i], idepth_zero[i], color8 + 8 * i, weights8 + 8 * i, prior[i]);
+}
+void orc_ba_add_residuals(void* p, int n, const int* point, const int* target) {
+  for (int i = 0; i < n; i++) orc_ba_add_residual(p, point[i], target[i]);
+}
 int orc_ba_add_residual(void* p, int pidx, int target) {
   Ctx* c = (Ctx*)p;
   BARes r; r.point = pidx; r.host = c->ba.points[pidx].host; r.target = target;

@@ -907,6 +907,71 @@ __device__ void ortho_vec(const double* __restrict__ Q, int d, int rank, double*
   __syncthreads();
 }
 
+// LDL^T without pivoting of the scaled system with the matrix in REGISTERS: element (i, j), i >= j, of the (d+1) x d augmented
+// matrix [S H S ; (S b)^T] lives in thread (i % 16, j % 16) at local index (i / 16, j / 16) — T x T doubles per thread, T = 4 for
+// d <= 63, T = 6 for d <= 95. Step k: the owners of column k publish it (all rows, the right-hand-side row included) in one of two
+// shared buffers, ONE block barrier, every thread forms its <= T(T+1)/2 rank-1 updates from registers. The right-hand side rides
+// along as row d, so the forward substitution L w = b costs nothing. Returns false (uniformly) on a non-positive pivot. On
+// success: M (shared, leading dimension ld) holds the factor in the layout the substitutions below expect (column k unscaled,
+// dg[k] = 1 / d_k) and y[] holds w.
+template <int T>
+__device__ bool ldlt_registers(int d, int ld, const double* __restrict__ HF, const double* __restrict__ sv, const double* __restrict__ bs,
+                               double* M, double* dg, double* y, double* colbuf /* 2 x (16 T) */) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  constexpr int CB = 16 * T;
+  double m[T][T];
+#pragma unroll
+  for (int a = 0; a < T; a++)
+#pragma unroll
+    for (int b = 0; b < T; b++) {
+      const int i = a * 16 + ty, j = b * 16 + tx;
+      double v = 0.0;
+      if (j < d && i >= j) {
+        if (i < d) v = sv[i] * HF[(size_t)i * d + j] * sv[j];
+        else if (i == d) v = bs[j];   // (already scaled)
+      }
+      m[a][b] = v;
+    }
+  bool ok = true;
+  for (int k = 0; k < d; k++) {
+    double* cb = colbuf + (k & 1) * CB;
+    const int kb = k >> 4, kx = k & 15;
+    if (tx == kx) {   // owners of column k: rows a * 16 + ty
+#pragma unroll
+      for (int a = 0; a < T; a++)
+#pragma unroll
+        for (int b = 0; b < T; b++) if (b == kb) cb[a * 16 + ty] = m[a][b];
+    }
+    __syncthreads();
+    const double mkk = cb[k];
+    if (!(mkk > 0.0) || !isfinite(mkk)) { ok = false; break; }   // uniform
+    const double rk = 1.0 / mkk;
+    double r[T], c[T];
+#pragma unroll
+    for (int a = 0; a < T; a++) { r[a] = cb[a * 16 + ty] * rk; c[a] = cb[a * 16 + tx]; }
+#pragma unroll
+    for (int a = 0; a < T; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) {
+        const int i = a * 16 + ty, j = b * 16 + tx;
+        if (j > k && i >= j && i <= d) m[a][b] -= r[a] * c[b];
+      }
+    if (tid == 0) dg[k] = rk;
+  }
+  if (!ok) return false;
+  __syncthreads();
+  // hand the factor to the substitutions: lower triangle into shared memory, w = row d
+#pragma unroll
+  for (int a = 0; a < T; a++)
+#pragma unroll
+    for (int b = 0; b < T; b++) {
+      const int i = a * 16 + ty, j = b * 16 + tx;
+      if (j < d && i >= j) { if (i < d) M[i * ld + j] = m[a][b]; else if (i == d) y[j] = m[a][b]; }
+    }
+  __syncthreads();
+  return true;
+}
+
 __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   if (S.done && *S.done) return;
   extern __shared__ double sm[];
@@ -926,8 +991,9 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 tiling of the trailing update
   for (int i = tid; i < d; i += nt) { bs[i] = S.bF[i]; sv[i] = S.plain ? 1.0 : 1.0 / sqrt(S.HF[(size_t)i * d + i] + 10); perm[i] = i; }
   __syncthreads();
-  for (int r = ty; r < d; r += 16)
-    for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
+  if (d + 1 > 96)   // (the register-tiled factorisation below loads its elements straight from global memory)
+    for (int r = ty; r < d; r += 16)
+      for (int c = tx; c < d; c += 16) M[r * ld + c] = sv[r] * S.HF[(size_t)r * d + c] * sv[c];
   for (int i = tid; i < d; i += nt) bs[i] = sv[i] * bs[i];
   __syncthreads();
   // ---- fast path: LDL^T WITHOUT pivoting, one block barrier per column. The scaled system S H S is symmetric positive definite
@@ -937,25 +1003,32 @@ __global__ void __launch_bounds__(256) ba_solve_kernel(SolveParams S) {
   // synchronisation per column is the barrier behind the trailing update. A non-positive or non-finite pivot (the matrix was
   // not positive definite after all) falls through to the pivoted factorisation below, which reloads the system.
   bool spd = true;
-  for (int k = 0; k < d; k++) {
-    const double mkk = M[k * ld + k];
-    if (!(mkk > 0.0) || !isfinite(mkk)) { spd = false; break; }   // uniform: every thread reads the same value
-    const double rk = 1.0 / mkk;
-    for (int i = k + 1 + ty; i < d; i += 16) {
-      const double lik = M[i * ld + k] * rk;
-      for (int j = k + 1 + tx; j <= i; j += 16) M[i * ld + j] -= lik * M[j * ld + k];
+  bool have_w = false;   // the forward substitution was folded into the factorisation (y holds w)
+  if (d + 1 <= 64) { spd = ldlt_registers<4>(d, ld, S.HF, sv, bs, M, dg, y, scr); have_w = spd; }
+  else if (d + 1 <= 96) { spd = ldlt_registers<6>(d, ld, S.HF, sv, bs, M, dg, y, scr); have_w = spd; }
+  else {   // larger windows: the same factorisation on the shared-memory copy
+    for (int k = 0; k < d; k++) {
+      const double mkk = M[k * ld + k];
+      if (!(mkk > 0.0) || !isfinite(mkk)) { spd = false; break; }   // uniform: every thread reads the same value
+      const double rk = 1.0 / mkk;
+      for (int i = k + 1 + ty; i < d; i += 16) {
+        const double lik = M[i * ld + k] * rk;
+        for (int j = k + 1 + tx; j <= i; j += 16) M[i * ld + j] -= lik * M[j * ld + k];
+      }
+      if (tid == 0) dg[k] = rk;
+      __syncthreads();
     }
-    if (tid == 0) dg[k] = rk;
-    __syncthreads();
   }
   if (spd) {
     if (warp == 0) {  // L y = b, z = D^-1 y, L^T x = z with L_ik = M_ik * dg[k]; column oriented, one warp
-      for (int i = lane; i < d; i += 32) y[i] = bs[i];
-      __syncwarp();
-      for (int i = 0; i < d; i++) {
-        const double yi = y[i] * dg[i];
-        for (int j = i + 1 + lane; j < d; j += 32) y[j] -= M[j * ld + i] * yi;
+      if (!have_w) {
+        for (int i = lane; i < d; i += 32) y[i] = bs[i];
         __syncwarp();
+        for (int i = 0; i < d; i++) {
+          const double yi = y[i] * dg[i];
+          for (int j = i + 1 + lane; j < d; j += 32) y[j] -= M[j * ld + i] * yi;
+          __syncwarp();
+        }
       }
       for (int i = lane; i < d; i += 32) y[i] *= dg[i];
       __syncwarp();

@@ -14,6 +14,8 @@ lib.orc_ba_set_state.argtypes = [V, C.c_int, _dp]
 lib.orc_ba_set_energy_th.argtypes = [V, C.c_int, C.c_float]
 lib.orc_ba_add_point.argtypes = [V, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _fp, C.c_int]
 lib.orc_ba_add_residual.argtypes = [V, C.c_int, C.c_int]
+lib.orc_ba_add_points.argtypes = [V, C.c_int, _ip, _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(C.c_ubyte)]
+lib.orc_ba_add_residuals.argtypes = [V, C.c_int, _ip, _ip]
 lib.orc_ba_set_point_flag.argtypes = [V, C.c_int, C.c_int]
 lib.orc_ba_prepare.argtypes = [V]
 lib.orc_ba_counts.argtypes = [V, _ip, _ip, _ip]
@@ -77,6 +79,19 @@ class OracleBA:
     def add_point(self, host, u, v, idepth, idepth_zero, color, weights, has_prior=False):
         c, w = _f32(color), _f32(weights)
         return lib.orc_ba_add_point(self.h, host, u, v, idepth, idepth_zero, _p(c, _fp), _p(w, _fp), int(has_prior))
+
+    def set_points(self, host, u, v, idepth, idepth_zero, color8, weights8, has_prior):
+        """batched add_point (same argument layout as the device Window.set_points)"""
+        host = np.ascontiguousarray(host, np.int32)
+        u, v, idepth, idepth_zero = _f32(u), _f32(v), _f32(idepth), _f32(idepth_zero)
+        c, w = _f32(color8).reshape(-1, 8), _f32(weights8).reshape(-1, 8)
+        hp = np.ascontiguousarray(has_prior, np.uint8)
+        lib.orc_ba_add_points(self.h, host.size, _p(host, _ip), _p(u, _fp), _p(v, _fp), _p(idepth, _fp), _p(idepth_zero, _fp), _p(c, _fp), _p(w, _fp),
+                              hp.ctypes.data_as(C.POINTER(C.c_ubyte)))
+
+    def set_residuals(self, point, target):
+        p, t = np.ascontiguousarray(point, np.int32), np.ascontiguousarray(target, np.int32)
+        lib.orc_ba_add_residuals(self.h, p.size, _p(p, _ip), _p(t, _ip))
 
     def add_residual(self, pidx, target):
         return lib.orc_ba_add_residual(self.h, pidx, target)

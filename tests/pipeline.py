@@ -14,6 +14,7 @@ graph is a list of dicts): it strings the operators together in the order the re
 
 — once per backend. Every stage consumes what the SAME backend produced before; the oracle and the device are never
 re-synchronised, so per-frame trajectory agreement is a statement about the whole chain."""
+import time
 import numpy as np
 import oracle_py as O
 import oracle_ba_py as OB
@@ -56,10 +57,17 @@ class Backend:
         self.dm = None if self.dev else OD.DistMap(self.api)
         self.sel = None if self.dev else OS.Selector(self.api)
         self.free = []
+        self.t_ops = 0.0   # seconds spent inside operator calls (ABI / oracle entry points incl. argument marshalling): what a C++ caller pays
 
     def close(self):
         if self.dev:
             self.api.close()
+
+    def _op(self, fn, *a, **kw):
+        t0 = time.perf_counter()
+        r = fn(*a, **kw)
+        self.t_ops += time.perf_counter() - t0
+        return r
 
     # -- frames
     def new_frame(self, img):
@@ -67,7 +75,7 @@ class Backend:
             fid = self.api.frame_create()
         else:
             fid = self.free.pop() if self.free else self.api.frame_new()
-        self.api.make_images(fid, img)
+        self._op(self.api.make_images, fid, img)
         return fid
 
     def release(self, fid):
@@ -81,35 +89,35 @@ class Backend:
 
     # -- tracking
     def tracker_set_ref(self, fid, uvidw, aff):
-        self.api.tracker_set_ref(fid, uvidw, aff)
+        self._op(self.api.tracker_set_ref, fid, uvidw, aff)
 
     def track(self, fid, T, aff, variant):
-        return self.api.track(fid, T, aff, self.api.levels - 1, [np.nan] * 5, variant)
+        return self._op(self.api.track, fid, T, aff, self.api.levels - 1, [np.nan] * 5, variant)
 
     # -- immature points
     def immature_init(self, h, uv):
         return self.immature_init_fid(self.fids[h], uv)
 
     def immature_init_fid(self, fid, uv):
-        return self.api.immature_init(fid, uv) if self.dev else OT.immature_init(self.api, fid, uv)
+        return self._op(self.api.immature_init, fid, uv) if self.dev else self._op(OT.immature_init, self.api, fid, uv)
 
     def trace_on(self, t, KRKi, Kt, pts):
         return self.trace_on_fid(self.fids[t], KRKi, Kt, (1.0, 0.0), pts)
 
     def trace_on_fid(self, fid, KRKi, Kt, aff, pts):
-        return self.api.trace_on(fid, KRKi, Kt, aff, pts) if self.dev else OT.trace_on(self.api, fid, KRKi, Kt, aff, pts)
+        return self._op(self.api.trace_on, fid, KRKi, Kt, aff, pts) if self.dev else self._op(OT.trace_on, self.api, fid, KRKi, Kt, aff, pts)
 
     def trace_stereo(self, fid, K33, mode_right, pts):
-        return self.api.trace_stereo(fid, K33, mode_right, pts) if self.dev else OT.trace_stereo(self.api, fid, K33, mode_right, pts)
+        return self._op(self.api.trace_stereo, fid, K33, mode_right, pts) if self.dev else self._op(OT.trace_stereo, self.api, fid, K33, mode_right, pts)
 
     def make_maps(self, fid, density):
         """PixelSelector::makeMaps + the selectionMap walk of makeNewTraces: (uv [n,2], type [n]) in raster order"""
         if self.dev:
-            self.api.make_maps(fid, density, want_map=False)
-            uv, ty = self.api.selector_points()
+            self._op(self.api.make_maps, fid, density, want_map=False)
+            uv, ty = self._op(self.api.selector_points)
             return uv, ty
         self.sel.forget_hist()   # (frame slots are recycled: never trust the selector's per-frame cache)
-        m, _ = self.sel.make_maps(fid, density)
+        m, _ = self._op(self.sel.make_maps, fid, density)
         ys, xs = np.nonzero(m)
         return np.stack([xs, ys], 1).astype(np.float32), m[ys, xs].astype(np.float32)
 
@@ -118,56 +126,55 @@ class Backend:
         """(re)build the backend window from the neutral description; colour / weights come from this backend's D1 operator"""
         fids = self.fids if fids is None else fids
         pts = win["points"]
-        cw = {}
+        P = len(pts)
+        host = np.array([p["host"] for p in pts], np.int32)
+        uv = np.array([[p["u"], p["v"]] for p in pts], np.float32).reshape(-1, 2)
+        col, wts = np.zeros((P, 8), np.float32), np.zeros((P, 8), np.float32)
         for h in range(win["n"]):
-            idx = [i for i, p in enumerate(pts) if p["host"] == h]
-            if idx:
-                rec, _ = self.immature_init_fid(fids[h], np.array([[pts[i]["u"], pts[i]["v"]] for i in idx], np.float32))
-                for i, r in zip(idx, rec):
-                    cw[i] = (r["color"].copy(), r["weights"].copy())
+            idx = np.nonzero(host == h)[0]
+            if idx.size:
+                rec, _ = self.immature_init_fid(fids[h], uv[idx])
+                col[idx] = rec["color"]; wts[idx] = rec["weights"]
+        idp = np.array([p["idepth"] for p in pts], np.float32); idz = np.array([p["idepth_zero"] for p in pts], np.float32)
+        prior = np.array([p["has_prior"] for p in pts], np.uint8)
+        counts = [len(p["targets"]) for p in pts]
+        rp = np.repeat(np.arange(P, dtype=np.int32), counts)
+        rt = np.array([t for p in pts for t in p["targets"]], np.int32)
+        t0 = time.perf_counter()
         Wn = self.pkg.Window(self.api) if self.dev else OB.OracleBA(self.api)
         for k, f in enumerate(win["frames"]):
             i = Wn.add_frame(fids[k], f["T_w2c"], f["a"], f["b"], f["frameID"])
             Wn.set_state(i, f["state"]); Wn.set_energy_th(i, f["energyTH"])
-        if self.dev:
-            Wn.set_points([p["host"] for p in pts], [p["u"] for p in pts], [p["v"] for p in pts], [p["idepth"] for p in pts],
-                          [p["idepth_zero"] for p in pts], np.stack([cw[i][0] for i in range(len(pts))]) if pts else np.zeros((0, 8), np.float32),
-                          np.stack([cw[i][1] for i in range(len(pts))]) if pts else np.zeros((0, 8), np.float32), [p["has_prior"] for p in pts])
-            rp, rt = [], []
-            for pi, p in enumerate(pts):
-                for t in p["targets"]:
-                    rp.append(pi); rt.append(t)
-            Wn.set_residuals(rp, rt)
-        else:
-            for pi, p in enumerate(pts):
-                q = Wn.add_point(p["host"], p["u"], p["v"], p["idepth"], p["idepth_zero"], cw[pi][0], cw[pi][1], p["has_prior"])
-                for t in p["targets"]:
-                    Wn.add_residual(q, t)
+        Wn.set_points(host, uv[:, 0].copy(), uv[:, 1].copy(), idp, idz, col, wts, prior)
+        Wn.set_residuals(rp, rt)
         Wn.prepare()
+        self.t_ops += time.perf_counter() - t0
         if not self.dev:
             Wn.set_reduce(*self.reduce)
         self.W = Wn
         return Wn
 
     def distmap_make(self, KRKi, Kt, pt_host, pt_uvid):
-        return self.api.distmap_make(KRKi, Kt, pt_host, pt_uvid) if self.dev else self.dm.make(KRKi, Kt, pt_host, pt_uvid)
+        return self._op(self.api.distmap_make, KRKi, Kt, pt_host, pt_uvid) if self.dev else self._op(self.dm.make, KRKi, Kt, pt_host, pt_uvid)
 
     def activation_filter(self, KRKi, Kt, flagged, cand_host, pts, my_type, mad):
         if self.dev:
-            v, m, _ = self.api.activation_filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
+            v, m, _ = self._op(self.api.activation_filter, KRKi, Kt, flagged, cand_host, pts, my_type, mad)
             return v, m
-        return self.dm.filter(KRKi, Kt, flagged, cand_host, pts, my_type, mad)
+        return self._op(self.dm.filter, KRKi, Kt, flagged, cand_host, pts, my_type, mad)
 
     def activate(self, n, host, pts):
-        return self.W.activate_points(host, pts, variant=0) if self.dev else OT.activate_points(self.api, n, host, pts, variant=0)
+        return self._op(self.W.activate_points, host, pts, variant=0) if self.dev else self._op(OT.activate_points, self.api, n, host, pts, variant=0)
 
     def set_point_flags(self, flags):
+        t0 = time.perf_counter()
         if self.dev:
             self.W.set_point_flags(flags)
         else:
             for i, f in enumerate(flags):
                 if f:
                     self.W.set_point_flag(i, int(f))
+        self.t_ops += time.perf_counter() - t0
 
 
 def level1_krki_kt(T_host_to_new, K4):
@@ -258,8 +265,8 @@ class StereoPipeline:
         if self.B.dev:
             allp = np.ascontiguousarray(np.concatenate([j[0]["immature"] for j in jobs]))
             host_of = np.concatenate([np.full(j[0]["immature"].size, i, np.int32) for i, j in enumerate(jobs)])
-            self.B.api.trace_on_hosts(fid, np.stack([j[1] for j in jobs]), np.stack([j[2] for j in jobs]), np.array([j[3] for j in jobs], np.float32), host_of, allp,
-                                      want_status=False)
+            self.B._op(self.B.api.trace_on_hosts, fid, np.stack([j[1] for j in jobs]), np.stack([j[2] for j in jobs]), np.array([j[3] for j in jobs], np.float32), host_of, allp,
+                       want_status=False)
             off = 0
             for kf, _, _, _ in jobs:
                 m = kf["immature"].size
@@ -351,9 +358,9 @@ class StereoPipeline:
                 Wn.set_marg_prior(HM, bM)
             if self.on_window:
                 self.on_window(win, (self.HM, self.bM))
-            rmse, its = Wn.optimize(self.opt_its)
-            st = Wn.get_state()
-            res = Wn.get_res(1)
+            rmse, its = B._op(Wn.optimize, self.opt_its)
+            st = B._op(Wn.get_state)
+            res = B._op(Wn.get_res, 1)
             for i, f in enumerate(self.kfs):
                 f["state"] = st["states"][i].copy()
                 f["T_cur"] = st["T_w2c"][i].copy()
@@ -368,7 +375,7 @@ class StereoPipeline:
             ridx = 0
             alive = []
             centers = []   # per surviving point: centerProjectedTo of its residual into the newest key frame (if IN)
-            pts_dev = Wn.get_points()
+            pts_dev = B._op(Wn.get_points)
             for pi, p in enumerate(self.points):
                 tg = [t for t in p["targets"] if any(t == f["frameID"] for f in self.kfs)]
                 keep_t, center = [], None
@@ -435,11 +442,11 @@ class StereoPipeline:
                 m = self.HM.shape[0]
                 HM[:m, :m] = self.HM; bM[:m] = self.bM
                 Wn.set_marg_prior(HM, bM)
-            Wn.linearize_all(True)
+            B._op(Wn.linearize_all, True)
             B.set_point_flags(flags)
-            Wn.marginalize_points()
-            Wn.marginalize_frame(0)
-            self.HM, self.bM = Wn.get_marg_prior()
+            B._op(Wn.marginalize_points)
+            B._op(Wn.marginalize_frame, 0)
+            self.HM, self.bM = B._op(Wn.get_marg_prior)
             old = self.kfs.pop(0)
             B.release(old["fid"]); B.release(old["fid_right"])
             self.points = [p for p in self.points if p["host"] != fid0]
