@@ -111,7 +111,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -546,7 +546,8 @@ def main():
             import subprocess
             pattern = json.loads(subprocess.run([gm, "--json"], capture_output=True, text=True, timeout=60,
                                                 env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev))).stdout.strip().splitlines()[-1])
-            pattern["frac_of_pattern_ceiling"] = achieved / pattern["gather_gbs"]
+            pattern["kernel_over_microbench"] = achieved / pattern["gather_gbs"]   # a data point, not a roofline: the kernel re-reads on chip and ends up above it
+            pattern["note"] = "tools/gather_microbench.cu: the same 2x2-texel gather pattern with no arithmetic; the roofline anchor is MEASURED_PEAKS.json (frac above)"
         except Exception:
             pattern = None
     img_bytes = npx * 1 + 16 * 603911  # per image: u8 read + texels written
@@ -573,7 +574,7 @@ def main():
                       traffic_source="ncu --set full capture of this kernel in this command, profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch); not measurable inside an unprofiled run",
                       kernel="track_kernel" if variant == 0 else "track_g2o_kernel", peak_source=peak_src,
                       algorithmic_bytes_per_launch=evals_per_launch * BYTES_PER_EVAL, avg_launch_ms=track_ms_per_launch,
-                      share_of_step=prof["track_ms"] / ms_dev, scattered_gather_ceiling=pattern,
+                      share_of_step=prof["track_ms"] / ms_dev, gather_microbench=pattern,
                       make_images=dict(achieved=img_bytes * 2 * S * K_ / max(prof["images_ms"], 1e-9) / 1e6, frac=img_bytes * 2 * S * K_ / max(prof["images_ms"], 1e-9) / 1e6 / peak,
                                        images_per_step=2 * S,
                                        unit="GB/s", avg_ms=prof["images_ms"] / max(prof["images_launches"], 1),
