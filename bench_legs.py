@@ -356,10 +356,13 @@ def leg_sequence(pkg, torch, dev, scene, n_frames=60):
     def run(backend):
         P = PL.StereoPipeline(backend)
         per_frame, per_frame_ops = [], []
-        for l, r in zip(left, right):
-            t0 = time.perf_counter(); o0 = backend.t_ops
+        for k, (l, r) in enumerate(zip(left, right)):
+            t0 = time.perf_counter(); o0 = backend.t_ops; b0 = dict(backend.t_by_op)
             P.step(l, r)
             per_frame.append(time.perf_counter() - t0); per_frame_ops.append(backend.t_ops - o0)
+            if os.environ.get("SDSO_BENCH_VERBOSE") and k % 5 == 0:
+                d = {n: round(1e3 * (v - b0.get(n, 0.0)), 2) for n, v in backend.t_by_op.items() if v - b0.get(n, 0.0) > 2e-4}
+                print(f"[sequence] frame {k}: {d}", file=sys.stderr)
         return P, np.array(per_frame), np.array(per_frame_ops)
 
     Bg = PL.Backend(shape, pkg)
@@ -369,6 +372,7 @@ def leg_sequence(pkg, torch, dev, scene, n_frames=60):
     l0 = Bg.api.launch_count()
     Pg, tg, og = run(Bg)
     launches = Bg.api.launch_count() - l0
+    by_op = {k: round(1e3 * v, 3) for k, v in sorted(Bg.t_by_op.items(), key=lambda kv: -kv[1])}
     Bg.close()
     Po, to, oo = run(PL.Backend(shape))
     kf = np.arange(n_frames) % 5 == 0
@@ -382,7 +386,7 @@ def leg_sequence(pkg, torch, dev, scene, n_frames=60):
              "value = frames / time spent INSIDE the operator calls (ABI entry points with host buffers: uploads, launches, read-backs, ctypes marshalling) — what a "
              "C++ caller pays; the Python harness around them (per-point dicts, numpy bookkeeping that stands in for FullSystem) is reported separately as wall time",
         value=(n_frames - 1) / og[1:].sum(), unit="frames/s", ms_per_tracked_frame=1e3 * float(np.median(og[~kf])), ms_per_key_frame=1e3 * float(np.median(og[kf][1:])),
-        first_frame_ms=1e3 * float(og[0]),
+        first_frame_ms=1e3 * float(og[0]), operator_ms_per_frame=[round(1e3 * float(x), 3) for x in og], operator_ms_total_by_name=by_op,
         wall_including_python_harness=dict(frames_per_s=(n_frames - 1) / tg[1:].sum(), ms_per_tracked_frame=1e3 * float(np.median(tg[~kf])), ms_per_key_frame=1e3 * float(np.median(tg[kf][1:]))),
         kernel_launches=int(launches),
         e2e=dict(value=(n_frames - 1) / og[1:].sum(), unit="frames/s", h2d_bytes_per_step=int(2 * synth.W * synth.H * 4), d2h_bytes_per_step=int(12 * 8 + 16 + 40),

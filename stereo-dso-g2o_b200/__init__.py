@@ -396,11 +396,18 @@ class Window:
             r = np.ascontiguousarray(rids, np.int32)
             self._ck(lib.sdso_ba_fix_linearization(self.h, r.size, _ptr(r, _ip)))
 
-    def get_res(self, which=0):
+    def get_res(self, which=0, brief=False):
+        """per-residual read-back in the caller's order. brief=True: states, energies, flags and centerProjectedTo only (what
+        FullSystem's bookkeeping after optimize() reads) — the Jacobian blocks (600 B per residual) stay on the device."""
         R = self.counts()["res"]
         ns, st, ac, li = (np.zeros(R, np.int32) for _ in range(4))
         ne, nw = np.zeros(R), np.zeros(R)
-        J, jp, ce, rz = np.zeros((R, 74), np.float32), np.zeros((R, 8), np.float32), np.zeros((R, 3), np.float32), np.zeros((R, 8), np.float32)
+        ce = np.zeros((R, 3), np.float32)
+        if brief:
+            self._ck(lib.sdso_ba_get_res(self.h, which, _ptr(ns, _ip), _ptr(st, _ip), _ptr(ne, _dp), _ptr(nw, _dp), _ptr(ac, _ip), _ptr(li, _ip),
+                                         None, None, _ptr(ce, _fp), None))
+            return dict(newState=ns, state=st, newEnergy=ne, newEnergyWithOutlier=nw, active=ac, linearized=li, center=ce)
+        J, jp, rz = np.zeros((R, 74), np.float32), np.zeros((R, 8), np.float32), np.zeros((R, 8), np.float32)
         self._ck(lib.sdso_ba_get_res(self.h, which, _ptr(ns, _ip), _ptr(st, _ip), _ptr(ne, _dp), _ptr(nw, _dp), _ptr(ac, _ip), _ptr(li, _ip),
                                      _ptr(J, _fp), _ptr(jp, _fp), _ptr(ce, _fp), _ptr(rz, _fp)))
         return dict(newState=ns, state=st, newEnergy=ne, newEnergyWithOutlier=nw, active=ac, linearized=li, J=J, JpJdF=jp, center=ce, res_toZero=rz)

@@ -611,7 +611,7 @@ int sdso_ba_set_points(sdso_ctx* ctx, int P, const int* host, const float* u, co
   if (P < 0 || (P > 0 && (!host || !u || !v || !idepth || !idepth_zero || !color8 || !weights8))) return SDSO_E_INVALID;
   for (int i = 0; i < P; i++) if (host[i] < 0 || host[i] >= b->n) return fail(ctx, SDSO_E_INVALID, "point host index out of range (add the frames first)");
   if (P > b->capP) {
-    const int cap = std::max(P, 1024);
+    const int cap = std::max(P + P / 2, 8192);   // geometric growth: a growing window must not reallocate at every key frame
     BA_ALLOC(b->d_p_host, cap); BA_ALLOC(b->d_p_u, cap); BA_ALLOC(b->d_p_v, cap); BA_ALLOC(b->d_p_idepth, cap); BA_ALLOC(b->d_p_idepth_zero, cap);
     BA_ALLOC(b->d_p_color, 2 * (size_t)cap); BA_ALLOC(b->d_p_weights, 2 * (size_t)cap); BA_ALLOC(b->d_p_priorF, cap); BA_ALLOC(b->d_p_deltaF, cap); BA_ALLOC(b->d_p_idepth_backup, cap);
     BA_ALLOC(b->d_p_res_begin, cap + 1); BA_ALLOC(b->d_slot_of, (size_t)cap * kMaxFrames); BA_ALLOC(b->d_p_acc, 16 * (size_t)cap);
@@ -685,7 +685,7 @@ int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* tar
     so = b->h_rid2slot[i];
   }
   if (R > b->capR) {
-    const int cap = std::max(R, 4096);
+    const int cap = std::max(R + R / 2, 32768);
     BA_ALLOC(b->d_p_res_list, cap); BA_ALLOC(b->d_s_point, cap); BA_ALLOC(b->d_s_key, cap);
     BA_ALLOC(b->d_s_state, cap); BA_ALLOC(b->d_s_newstate, cap); BA_ALLOC(b->d_s_flags, cap); BA_ALLOC(b->d_s_sel, cap);
     BA_ALLOC(b->d_s_energy, 3 * (size_t)cap); BA_ALLOC(b->d_J, 2 * (size_t)kJ * cap); BA_ALLOC(b->d_s_rtz, 8 * (size_t)cap);
@@ -695,7 +695,7 @@ int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* tar
     b->capR = cap;
   }
   if (b->nchunks > b->capChunks) {
-    const int cap = b->nchunks + 64;
+    const int cap = std::max(b->nchunks + b->nchunks / 2, 512);
     BA_ALLOC(b->d_chunks, cap); BA_ALLOC(b->d_tpart, (size_t)cap * kTopVals); BA_ALLOC(b->d_dpart, (size_t)cap * (kMaxFrames + 1) * 65);
     b->capChunks = cap;
   }

@@ -153,6 +153,20 @@ int sdso_ctx_create(sdso_ctx** out, int device, int w, int h, const float K[4], 
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return SDSO_E_CUDA; }
   c->num_sms = prop.multiProcessorCount;
   if (cudaMallocHost(&c->staging, (size_t)w * h * sizeof(float)) != cudaSuccess) { delete c; return SDSO_E_NOMEM; }
+  {
+    cudaMemPoolProps pp = {};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &pp) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      c->pool = nullptr;   // fall back to the device's default pool
+      cudaGetLastError();
+    }
+  }
   float B[256];
   for (int i = 0; i < 256; i++) B[i] = (float)i;
   int rc = set_gamma_table(c, B);
@@ -185,6 +199,7 @@ void sdso_ctx_destroy(sdso_ctx* ctx) {
   }
   for (void* a : ctx->arenas) cudaFree(a);
   if (ctx->staging) cudaFreeHost(ctx->staging);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   for (int i = 0; i < sdso_ctx::kEventRing; i++) {
     if (ctx->upload_events[i]) cudaEventDestroy(ctx->upload_events[i]);
     if (ctx->consume_events[i]) cudaEventDestroy(ctx->consume_events[i]);

@@ -52,6 +52,10 @@ struct sdso_ctx {
   std::vector<sdso::Frame> frames;
   size_t tex_total = 0;  // float4 texels per frame over all levels
   float* staging = nullptr;  // pinned host staging for image upload
+  // stream-ordered scratch of the per-call operators (set_ref, vertex / edge batches): a private pool that KEEPS its memory across
+  // synchronisations (release threshold = max); the device's default pool hands everything back at every sync, which turns each
+  // cudaMallocAsync of a key frame into a driver allocation (measured: sporadic 10-700 ms stalls in tracker_set_ref)
+  cudaMemPool_t pool = nullptr;
   std::vector<void*> arenas;           // batch allocations of 8-bit staging
   cudaStream_t copy_stream = nullptr;  // H2D uploads that overlap the kernels of the previous step (sdso_upload_images_async)
   // one event per upload batch / per makeImages batch, shared by every frame of the batch. Rings: a slot that is re-recorded while an
@@ -85,6 +89,12 @@ inline int fail(sdso_ctx* c, int code, const std::string& msg) {
 
 // A context belongs to ONE device (sdso_ctx_create). Entry points that allocate or launch make that device current first, so two
 // contexts on different GPUs can live in one process (the bench uses one process per GPU, where this is a no-op).
+inline cudaError_t alloc_async(sdso_ctx* c, void** p, size_t bytes, cudaStream_t st) {
+  return c->pool ? cudaMallocFromPoolAsync(p, bytes, c->pool, st) : cudaMallocAsync(p, bytes, st);
+}
+template <typename T>
+inline cudaError_t alloc_async(sdso_ctx* c, T** p, size_t bytes, cudaStream_t st) { return alloc_async(c, reinterpret_cast<void**>(p), bytes, st); }
+
 inline void enter(const sdso_ctx* c) {
   int cur = -1;
   if (c && cudaGetDevice(&cur) == cudaSuccess && cur != c->device) cudaSetDevice(c->device);

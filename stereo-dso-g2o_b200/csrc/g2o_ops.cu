@@ -100,12 +100,12 @@ int sdso_vertex_oplus(sdso_ctx* ctx, int kind, int n, double* estimate, const do
   if (n == 0) return SDSO_OK;
   double *d_e = nullptr, *d_u = nullptr, *d_a = nullptr;
   cudaStream_t st = ctx->stream;
-  SDSO_CUDA(ctx, cudaMallocAsync(&d_e, (size_t)n * es * sizeof(double), st));
-  SDSO_CUDA(ctx, cudaMallocAsync(&d_u, (size_t)n * us * sizeof(double), st));
+  SDSO_CUDA(ctx, sdso::alloc_async(ctx, &d_e, (size_t)n * es * sizeof(double), st));
+  SDSO_CUDA(ctx, sdso::alloc_async(ctx, &d_u, (size_t)n * us * sizeof(double), st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_e, estimate, (size_t)n * es * sizeof(double), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_u, update, (size_t)n * us * sizeof(double), cudaMemcpyHostToDevice, st));
   if (kind == SDSO_VERTEX_UV) {
-    SDSO_CUDA(ctx, cudaMallocAsync(&d_a, (size_t)n * 2 * sizeof(double), st));
+    SDSO_CUDA(ctx, sdso::alloc_async(ctx, &d_a, (size_t)n * 2 * sizeof(double), st));
     SDSO_CUDA(ctx, cudaMemcpyAsync(d_a, aux, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   vertex_oplus_kernel<<<(n + 127) / 128, 128, 0, st>>>(kind, n, d_e, d_u, d_a);
@@ -129,7 +129,7 @@ int sdso_edge_trace_uv_eval(sdso_ctx* ctx, int frame, int n, const double* uv, c
   // one staging block: uv (2n d) | meas (n d) | dxdy (2n d) | err (n d) | J (n d) | rot (2n f) | flag (n i)
   const size_t nd = (size_t)7 * n * sizeof(double), nf = (size_t)2 * n * sizeof(float), ni = (size_t)n * sizeof(int);
   char* d = nullptr;
-  SDSO_CUDA(ctx, cudaMallocAsync(&d, nd + nf + ni, st));
+  SDSO_CUDA(ctx, sdso::alloc_async(ctx, &d, nd + nf + ni, st));
   double* d_uv = reinterpret_cast<double*>(d); double* d_me = d_uv + 2 * (size_t)n; double* d_dx = d_me + n; double* d_er = d_dx + 2 * (size_t)n; double* d_J = d_er + n;
   float* d_rot = reinterpret_cast<float*>(d + nd); int* d_fl = reinterpret_cast<int*>(d + nd + nf);
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_uv, uv, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));

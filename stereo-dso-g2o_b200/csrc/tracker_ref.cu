@@ -139,7 +139,7 @@ extern "C" int sdso_tracker_set_ref(sdso_ctx* ctx, int ref_frame, const float* u
   SDSO_CUDA(ctx, cudaMemsetAsync(t->wsum[0], 0, (size_t)w0 * h0 * sizeof(float), st));
   float4* dpts = nullptr;
   if (n > 0) {
-    SDSO_CUDA(ctx, cudaMallocAsync(&dpts, (size_t)n * sizeof(float4), st));
+    SDSO_CUDA(ctx, sdso::alloc_async(ctx, &dpts, (size_t)n * sizeof(float4), st));
     SDSO_CUDA(ctx, cudaMemcpyAsync(dpts, uvidw, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
     int* owner = t->scan_tmp;                              // free until the row counts below
     int* count = reinterpret_cast<int*>(t->wsum_bak[0]);   // free until the dilation backup below

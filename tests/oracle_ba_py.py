@@ -127,7 +127,7 @@ class OracleBA:
     def fix_linearization(self, ridx):
         lib.orc_ba_fix_linearization(self.h, ridx)
 
-    def get_res(self, which=0):
+    def get_res(self, which=0, brief=False):
         R = self.counts()["res"]
         ns, st, ne, nw, ac = np.zeros(R, np.int32), np.zeros(R, np.int32), np.zeros(R), np.zeros(R), np.zeros(R, np.int32)
         J, jp, ce, rz = np.zeros((R, 74), np.float32), np.zeros((R, 8), np.float32), np.zeros((R, 3), np.float32), np.zeros((R, 8), np.float32)

@@ -58,6 +58,7 @@ class Backend:
         self.sel = None if self.dev else OS.Selector(self.api)
         self.free = []
         self.t_ops = 0.0   # seconds spent inside operator calls (ABI / oracle entry points incl. argument marshalling): what a C++ caller pays
+        self.t_by_op = {}  # the same, per operator name
 
     def close(self):
         if self.dev:
@@ -66,8 +67,12 @@ class Backend:
     def _op(self, fn, *a, **kw):
         t0 = time.perf_counter()
         r = fn(*a, **kw)
-        self.t_ops += time.perf_counter() - t0
+        self._account(getattr(fn, "__name__", "op"), time.perf_counter() - t0)
         return r
+
+    def _account(self, name, dt):
+        self.t_ops += dt
+        self.t_by_op[name] = self.t_by_op.get(name, 0.0) + dt
 
     # -- frames
     def new_frame(self, img):
@@ -145,10 +150,13 @@ class Backend:
         for k, f in enumerate(win["frames"]):
             i = Wn.add_frame(fids[k], f["T_w2c"], f["a"], f["b"], f["frameID"])
             Wn.set_state(i, f["state"]); Wn.set_energy_th(i, f["energyTH"])
+        t1 = time.perf_counter(); self._account("window_frames", t1 - t0)
         Wn.set_points(host, uv[:, 0].copy(), uv[:, 1].copy(), idp, idz, col, wts, prior)
+        t2 = time.perf_counter(); self._account("window_set_points", t2 - t1)
         Wn.set_residuals(rp, rt)
+        t3 = time.perf_counter(); self._account("window_set_residuals", t3 - t2)
         Wn.prepare()
-        self.t_ops += time.perf_counter() - t0
+        self._account("window_prepare", time.perf_counter() - t3)
         if not self.dev:
             Wn.set_reduce(*self.reduce)
         self.W = Wn
@@ -174,7 +182,7 @@ class Backend:
             for i, f in enumerate(flags):
                 if f:
                     self.W.set_point_flag(i, int(f))
-        self.t_ops += time.perf_counter() - t0
+        self._account("set_point_flags", time.perf_counter() - t0)
 
 
 def level1_krki_kt(T_host_to_new, K4):
@@ -360,7 +368,7 @@ class StereoPipeline:
                 self.on_window(win, (self.HM, self.bM))
             rmse, its = B._op(Wn.optimize, self.opt_its)
             st = B._op(Wn.get_state)
-            res = B._op(Wn.get_res, 1)
+            res = B._op(Wn.get_res, 1, brief=True)
             for i, f in enumerate(self.kfs):
                 f["state"] = st["states"][i].copy()
                 f["T_cur"] = st["T_w2c"][i].copy()
