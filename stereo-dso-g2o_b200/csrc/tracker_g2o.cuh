@@ -31,7 +31,10 @@ __device__ __forceinline__ void d_huber(double e2, double delta, double& rho0, d
 
 // MODE 0: calcRes edge construction (+ first computeError)   MODE 1: computeActiveErrors
 // MODE 2: computeActiveErrors + buildSystem (linearizeOplus + constructQuadraticForm)
-template <int MODE>
+// BUILD: also linearizeOplus + constructQuadraticForm of the edges that stay. <0, true> is the first pass of a level: the first LM
+// iteration's computeActiveErrors + buildSystem run at the estimate the edges were built at, so their errors, Jacobians and sums are
+// the ones of this pass (same gc, same points in the same order per thread) and are not recomputed.
+template <int MODE, bool BUILD = (MODE == 2)>
 __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int lvl, const float4* __restrict__ tex, const G2OConst& gc,
                                 unsigned char* __restrict__ flag, double* __restrict__ eerr, float (&acc)[kAccPad], double& chi,
                                 unsigned& evals, int gtid, int gthreads, double* dump, const float4* __restrict__ pc, const int npc) {
@@ -125,7 +128,7 @@ __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int l
     double rho0, rho1;
     d_huber(err * err, delta, rho0, rho1);
     chi += rho0;
-    if (MODE == 2 || dump) {
+    if (BUILD || dump) {
       // linearizeOplus (dso_g2o_edge.cpp:425-500, VERSION2)
       double J[8];
       if (oob) {
@@ -144,7 +147,7 @@ __device__ void eval_points_g2o(const TrackParams& P, const TrackLevel& L, int l
         J[6] = (double)gc.ab[0] * (gc.b0 - (double)p.w);
         J[7] = -1.0;
       }
-      if (MODE == 2) {
+      if (BUILD) {
         // constructQuadraticForm: b += J^T (-rho' e), H += J^T rho' J  (accumulated in float; summed in double)
         const float wr = (float)rho1, wre = (float)(-err * rho1);
         float Jf[8];
@@ -186,27 +189,6 @@ __device__ void make_g2o_const(const TrackParams& P, const TrackLevel& L, const 
   gc.cutoff10 = cutoffTH * 10;
 }
 
-// Cholesky (LLT) as g2o::LinearSolverEigen; fails (returns false) on a non-positive pivot
-__device__ bool d_llt_solve8(const double* A, const double* b, double* x) {
-  double Lm[64];
-  for (int j = 0; j < 8; j++) {
-    double s = A[j * 8 + j];
-    for (int k = 0; k < j; k++) s -= Lm[j * 8 + k] * Lm[j * 8 + k];
-    if (!(s > 0) || !isfinite(s)) return false;
-    const double d = sqrt(s);
-    Lm[j * 8 + j] = d;
-    for (int i = j + 1; i < 8; i++) {
-      double v = A[i * 8 + j];
-      for (int k = 0; k < j; k++) v -= Lm[i * 8 + k] * Lm[j * 8 + k];
-      Lm[i * 8 + j] = v / d;
-    }
-  }
-  double y[8];
-  for (int i = 0; i < 8; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= Lm[i * 8 + k] * y[k]; y[i] = v / Lm[i * 8 + i]; }
-  for (int i = 7; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < 8; k++) v -= Lm[k * 8 + i] * x[k]; x[i] = v / Lm[i * 8 + i]; }
-  return true;
-}
-
 struct G2OState {  // shared memory, thread-0 owned, read by all after barriers
   double R[9], t[3], photo[2];        // vertex estimates
   double Rb[9], tb[3], photob[2];     // push()/pop() backup
@@ -214,7 +196,7 @@ struct G2OState {  // shared memory, thread-0 owned, read by all after barriers
   double H[64], b[8], x[8];
   double lambda, ni, currentChi, tempChi, lastChi, rho;
   double levelChi;                    // activeRobustChi2 of the current level's edges
-  int ok2, qmax, forceStop, okIter, again;
+  int ok2, qmax, forceStop, okIter, again, accepted, have_sys;
   unsigned long long totalEdges;
 };
 
@@ -275,17 +257,26 @@ __global__ void __launch_bounds__(256, 2) track_g2o_kernel(TrackParams P) {
     const float4* tex = prob.tex[lvl];
     unsigned char* flag = P.edge_flag[lvl] + (size_t)prob_id * P.edge_stride[lvl];
     double* eerr = P.edge_err[lvl] + (size_t)prob_id * P.edge_stride[lvl];
-    // ---- calcRes: build this level's edges (:894)
+    // ---- calcRes: build this level's edges (:894). The pass also linearises the edges it keeps: the first iteration's
+    // computeActiveErrors + buildSystem below run at this same estimate (see eval_points_g2o)
     if (tid == 0) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
     __syncthreads();
-    eval_points_g2o<0>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+    eval_points_g2o<0, true>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
     reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
     const int nEdges = (int)tot[G_NE];
     {
       const float sT = (float)tot[G_ST], sRT = (float)tot[G_SRT], sN = (float)tot[G_SN];
       flow[0] = sT / (sN + 0.1); flow[1] = 0; flow[2] = sRT / (sN + 0.1);
     }
-    if (tid == 0) { gs.totalEdges += (unsigned long long)nEdges; gs.levelChi = chiTot; gs.okIter = 1; }
+    auto take_system = [&]() {   // thread 0: H, b and chi2 of the pass just reduced
+      int idx = 0;
+      for (int r = 0; r < 8; r++) {
+        for (int c = r; c < 8; c++) { gs.H[r * 8 + c] = gs.H[c * 8 + r] = tot[G_H + idx]; idx++; }
+        gs.b[r] = tot[G_B + r];
+      }
+      gs.currentChi = chiTot; gs.tempChi = chiTot;
+    };
+    if (tid == 0) { gs.totalEdges += (unsigned long long)nEdges; gs.levelChi = chiTot; gs.okIter = 1; gs.have_sys = 0; take_system(); }
     __syncthreads();
 
     // ---- optimizer->initializeOptimization(lvl); optimize(maxIterations) (:923-926)
@@ -293,43 +284,51 @@ __global__ void __launch_bounds__(256, 2) track_g2o_kernel(TrackParams P) {
       for (int it = 0; it < maxIterations; it++) {
         if (gs.forceStop || !gs.okIter) break;  // uniform: written before the last barrier
         iters[lvl]++;
-        // LM.solve(it): computeActiveErrors + buildSystem at the current estimate
-        __syncthreads();
-        if (tid == 0) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
-        __syncthreads();
-        eval_points_g2o<2>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
-        reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
+        // LM.solve(it): computeActiveErrors + buildSystem at the current estimate (gc is current: it was last written for exactly
+        // this estimate — by the level's first pass, or behind the last trial of the previous iteration). When the previous
+        // iteration ended on an accepted trial, that trial's pass already linearised the edges at this estimate (have_sys).
+        if (it > 0 && !gs.have_sys) {
+          eval_points_g2o<2>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+          reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
+          if (tid == 0) take_system();
+        }
+        const bool speculate = it + 1 < maxIterations;   // a later iteration of this level could reuse the trial's linearisation
         if (tid == 0) {
-          int idx = 0;
-          for (int r = 0; r < 8; r++) {
-            for (int c = r; c < 8; c++) { gs.H[r * 8 + c] = gs.H[c * 8 + r] = tot[G_H + idx]; idx++; }
-            gs.b[r] = tot[G_B + r];
-          }
-          gs.currentChi = chiTot; gs.tempChi = chiTot;
           if (it == 0) { gs.lambda = 0.01; gs.ni = 2; }  // setUserLambdaInit(0.01) (:840)
           gs.rho = 0; gs.qmax = 0;
         }
         __syncthreads();
         do {  // trials
-          if (tid == 0) {
-            for (int i = 0; i < 9; i++) gs.Rb[i] = gs.R[i];
-            for (int i = 0; i < 3; i++) gs.tb[i] = gs.t[i];
-            gs.photob[0] = gs.photo[0]; gs.photob[1] = gs.photo[1];  // push()
-            double Hl[64];
-            for (int i = 0; i < 64; i++) Hl[i] = gs.H[i];
-            for (int i = 0; i < 8; i++) Hl[i * 8 + i] += gs.lambda;  // additive damping
-            for (int i = 0; i < 8; i++) gs.x[i] = 0;
-            gs.ok2 = d_llt_solve8(Hl, gs.b, gs.x) ? 1 : 0;
-            double Rn[9], tn[3], xs[8];
-            for (int i = 0; i < 8; i++) xs[i] = gs.x[i];
-            d_se3_exp_mul(xs, gs.R, gs.t, Rn, tn);  // oplus (dso_g2o_vertex.cpp:15-18)
-            for (int i = 0; i < 9; i++) gs.R[i] = Rn[i];
-            for (int i = 0; i < 3; i++) gs.t[i] = tn[i];
-            gs.photo[0] += gs.x[6]; gs.photo[1] += gs.x[7];  // (:30-40)
-            make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
+          if (tid < 32) {
+            // (H + lambda I) x = b by warp 0 (LinearSolverEigen's LLT succeeds exactly when every pivot is finite and positive)
+            double row[9], xs[8];
+            const int l = tid & 7;
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = gs.H[l * 8 + j] + (j == l ? gs.lambda : 0.0);
+            row[8] = gs.b[l];
+            bool pd;
+            warp_solve8(row, tid, xs, pd);
+            __syncwarp();
+            if (tid == 0) {
+              for (int i = 0; i < 9; i++) gs.Rb[i] = gs.R[i];
+              for (int i = 0; i < 3; i++) gs.tb[i] = gs.t[i];
+              gs.photob[0] = gs.photo[0]; gs.photob[1] = gs.photo[1];  // push()
+              if (!pd) { for (int i = 0; i < 8; i++) xs[i] = 0; }     // the solver failed: x stays zero
+              for (int i = 0; i < 8; i++) gs.x[i] = xs[i];
+              gs.ok2 = pd ? 1 : 0;
+              double Rn[9], tn[3];
+              d_se3_exp_mul(xs, gs.R, gs.t, Rn, tn);  // oplus (dso_g2o_vertex.cpp:15-18)
+              for (int i = 0; i < 9; i++) gs.R[i] = Rn[i];
+              for (int i = 0; i < 3; i++) gs.t[i] = tn[i];
+              gs.photo[0] += gs.x[6]; gs.photo[1] += gs.x[7];  // (:30-40)
+              make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
+            }
           }
           __syncthreads();
-          eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+          // computeActiveErrors at the trial estimate. With another iteration to come the pass also linearises (speculatively):
+          // if the trial is accepted, the next iteration's buildSystem would evaluate the same edges at the same estimate
+          if (speculate) eval_points_g2o<1, true>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+          else eval_points_g2o<1, false>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
           reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
           if (tid == 0) {
             double tempChi = chiTot;
@@ -343,30 +342,42 @@ __global__ void __launch_bounds__(256, 2) track_g2o_kernel(TrackParams P) {
               double alpha = 1. - pow((2 * rho - 1), 3);
               alpha = fmin(alpha, 2. / 3.);
               const double scaleFactor = fmax(1. / 3., alpha);
-              gs.lambda *= scaleFactor; gs.ni = 2; gs.currentChi = tempChi;
+              gs.lambda *= scaleFactor; gs.ni = 2;
+              gs.accepted = 1;
+              if (speculate) take_system();   // (scale above used the old b; x is not read again)
+              gs.currentChi = tempChi;
             } else {
               gs.lambda *= gs.ni; gs.ni *= 2;
               for (int i = 0; i < 9; i++) gs.R[i] = gs.Rb[i];
               for (int i = 0; i < 3; i++) gs.t[i] = gs.tb[i];
               gs.photo[0] = gs.photob[0]; gs.photo[1] = gs.photob[1];  // pop()
+              gs.accepted = 0;
             }
+            gs.have_sys = (gs.accepted && speculate) ? 1 : 0;   // read by every thread behind the iteration's last barrier
             gs.rho = rho;
             gs.qmax++;
             gs.again = (rho < 0 && gs.qmax < 10) ? 1 : 0;
             if (!gs.again && (gs.qmax == 10 || rho == 0)) gs.okIter = 0;  // SolverResult::Terminate
-            if (!gs.again) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
+            // after a rejected last trial gc has to follow the estimate back (an accepted one left it where it is)
+            if (!gs.again && !gs.accepted) make_g2o_const(P, L, prob, gs.Rsel, gs.tsel, gs.R, gs.t, gs.photo, P.coarseCutoffTH, gc);
           }
           __syncthreads();
         } while (gs.again);
-        // postIteration(it): SparseOptimizerTerminateAction -> computeActiveErrors, gain test (1e-3, :845-848)
-        eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
-        reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
+        // postIteration(it): SparseOptimizerTerminateAction -> computeActiveErrors, gain test (1e-3, :845-848). Behind an ACCEPTED
+        // trial that pass re-evaluates the edges at the estimate the trial pass just evaluated them at (same gc, same order): its
+        // errors and its chi2 are the trial's, bit for bit, so it is not run. Behind a rejected one the estimate went back and the
+        // pass runs (the stale-error rule of computeError, :413-415, makes it differ from the build pass on non-finite pixels).
+        if (!gs.accepted) {
+          eval_points_g2o<1>(P, L, lvl, tex, gc, flag, eerr, acc, chi, evals, gtid, gthreads, nullptr, prob.pc[lvl], prob.pc_n[lvl]);
+          reduce_all(acc, sm, parity, cluster, tot, chi, &chiTot);
+        }
         if (tid == 0) {
-          gs.levelChi = chiTot;
-          if (it == 0) gs.lastChi = chiTot;
+          const double chiPost = gs.accepted ? gs.currentChi : chiTot;
+          gs.levelChi = chiPost;
+          if (it == 0) gs.lastChi = chiPost;
           else {
-            const double gain = (gs.lastChi - chiTot) / chiTot;
-            gs.lastChi = chiTot;
+            const double gain = (gs.lastChi - chiPost) / chiPost;
+            gs.lastChi = chiPost;
             if (gain >= 0 && gain < 1e-3) gs.forceStop = 1;
           }
         }
