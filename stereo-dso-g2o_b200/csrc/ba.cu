@@ -1320,7 +1320,8 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   const int rb = (R + 127) / 128;
   // ---- one scratch allocation for the graph
   const size_t nd = (size_t)R * (1 + 1 + 8 + 48 + 16 + 8 + 32 + 1 + 1 + 12 + 2)   // idepth, bak, err, J blocks, hll, bl, hpl, energies
-                    + (size_t)n * (12 + 12 + 2 + 1 + 2)                            // T_wh, T_tw, photo, b0, target aff
+                    + (size_t)n * (12 + 12 + 2 + 1 + 2) + 4                        // T_wh, T_tw, photo, b0, target aff, cam
+                    + (size_t)n * 14 + 4                                           // push() copy of T_wh, photo, cam
                     + (size_t)(b->nchunks + 1) * 96 * 2 + (size_t)n * 96 * 2 + rb + 64;
   const size_t bytes = nd * sizeof(double) + (size_t)R * (4 * sizeof(float) + 2 * sizeof(int) + 2) + (size_t)n * (sizeof(float) + sizeof(int)) + 256;
   if (bytes > b->lba_scratch_bytes) {   // kept across calls: cudaMalloc / cudaFree per call are device-wide synchronisations
@@ -1336,7 +1337,7 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   double* d_idepth = takeD(R); double* d_idbak = takeD(R); double* d_err = takeD((size_t)R * 8);
   double* d_Jxi = takeD((size_t)R * 48); double* d_Jph = takeD((size_t)R * 16); double* d_Jid = takeD((size_t)R * 8); double* d_JC = takeD((size_t)R * 32);
   double* d_hll = takeD(R); double* d_bl = takeD(R); double* d_hpl = takeD((size_t)R * 12); double* d_ne = takeD(R); double* d_newo = takeD(R);
-  double* d_est = takeD((size_t)n * 29);
+  double* d_est = takeD((size_t)n * 29 + 4); double* d_estbak = takeD((size_t)n * 14 + 4);
   double* d_partA = takeD((size_t)(b->nchunks + 1) * 96); double* d_partS = takeD((size_t)(b->nchunks + 1) * 96);
   double* d_hostA = takeD((size_t)n * 96); double* d_hostS = takeD((size_t)n * 96);
   double* d_bpart = takeD(rb); double* d_sc = takeD(64);
@@ -1368,137 +1369,127 @@ int sdso_lba_g2o(sdso_ctx* ctx, int mnumOptIts, double cam[4], double* T_wh, dou
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_idepth, id_slot.data(), R * sizeof(double), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_ns, ns_init.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_used, used_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  // the vertex estimates live on the device from here on (uploaded once; the trials update them there)
   std::vector<float> h_exp(n);
-  std::vector<double> est((size_t)n * 29);
-  auto upload_est = [&]() -> int {
+  std::vector<double> est((size_t)n * 29 + 4);
+  {
     double* e = est.data();
     memcpy(e, T_wh, sizeof(double) * n * 12);
     for (int i = 0; i < n; i++) memcpy(e + n * 12 + 12 * i, b->frames[i].T_w2c, sizeof(double) * 12);
     memcpy(e + n * 24, photo, sizeof(double) * n * 2);
     memcpy(e + n * 26, b0.data(), sizeof(double) * n);
     for (int i = 0; i < n; i++) { e[n * 27 + 2 * i] = b->frames[i].state_scaled[6]; e[n * 27 + 2 * i + 1] = b->frames[i].state_scaled[7]; }
+    for (int k = 0; k < 4; k++) e[n * 29 + k] = cam[k];
     SDSO_CUDA(ctx, cudaMemcpyAsync(d_est, e, est.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    return SDSO_OK;
-  };
+  }
   for (int i = 0; i < n; i++) h_exp[i] = b->frames[i].ab_exposure;
   SDSO_CUDA(ctx, cudaMemcpyAsync(d_exp, h_exp.data(), n * sizeof(float), cudaMemcpyHostToDevice, st));
 
   BAView v = view(b);
   LBAEdgeParams E{};
   E.T_wh = d_est; E.T_tw = d_est + n * 12; E.photo = d_est + n * 24; E.b0 = d_est + n * 26; E.target_aff = d_est + n * 27; E.exposure = d_exp;
+  E.cam_dev = d_est + n * 29;
   E.idepth = d_idepth; E.slot2rid = nullptr; E.driver = 1;
   E.error8 = d_err; E.Jxi = d_Jxi; E.Jphoto = d_Jph; E.Jid = d_Jid; E.JC = d_JC;
   E.newState = d_ns; E.newEnergy = d_ne; E.newEnergyWO = d_newo; E.center3 = d_center; E.idepth_hessian = d_ih; E.level = d_level;
   LBAGraph G;
   G.R = R; G.active = d_active; G.idepth = d_idepth; G.idepth_bak = d_idbak; G.err = d_err; G.Jxi = d_Jxi; G.Jph = d_Jph; G.Jid = d_Jid; G.JC = d_JC;
   G.hll = d_hll; G.bl = d_bl; G.hpl = d_hpl; G.delta = ctx->S.huberTH;
-  auto eval = [&](const unsigned char* active, int linearize) -> int {
-    for (int i = 0; i < 4; i++) E.cam[i] = cam[i];
-    E.active = active; E.linearize = linearize;
+  auto eval = [&](const unsigned char* active, int linearize, const double* run_if) -> int {
+    E.active = active; E.linearize = linearize; E.run_if = run_if;
     ba_lba_edge_kernel<<<rb, 128, 0, st>>>(v, E); SDSO_CHECK_LAUNCH(ctx);
     return SDSO_OK;
   };
-  auto chi2 = [&](double* out) -> int {
+  auto chi2_to = [&](int slot) -> int {   // activeRobustChi2 into the scalar block, no host round trip
     lba_chi2_kernel<<<rb, 128, 0, st>>>(G, d_bpart); SDSO_CHECK_LAUNCH(ctx);
-    lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc); SDSO_CHECK_LAUNCH(ctx);
-    SDSO_CUDA(ctx, cudaMemcpyAsync(out, d_sc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc + slot); SDSO_CHECK_LAUNCH(ctx);
+    return SDSO_OK;
+  };
+  double hsc[LS_NUM];
+  auto read_scalars = [&]() -> int {      // the ONE host round trip of a damping trial
+    SDSO_CUDA(ctx, cudaMemcpyAsync(hsc, d_sc, sizeof(hsc), cudaMemcpyDeviceToHost, st));
     SDSO_CUDA(ctx, cudaStreamSynchronize(st));
     return SDSO_OK;
   };
-  int rc = upload_est();
-  if (rc) return cleanup(rc);
+  int rc;
   // first computeError of every edge while the graph is built (:538), then initializeOptimization(): level-0 edges are active
-  if ((rc = eval(d_ingraph, 0))) return cleanup(rc);
+  if ((rc = eval(d_ingraph, 0, nullptr))) return cleanup(rc);
   lba_activate_kernel<<<rb, 128, 0, st>>>(R, d_ingraph, d_level, d_active); ctx->launches++;
 
   SolveParams S{};
   fill_solve_params(ctx, S, 0);
   S.plain = 1; S.N = nullptr; S.have_M = 0;
   const size_t smem = ((size_t)d * (d | 1) + 6 * (size_t)d + 7 * (size_t)d + 256) * sizeof(double);
-  std::vector<double> x(d), bp(d);
-  double lambda = 0, ni = 2, lastChi = 0;
+  double lambda = 0, ni = 2, lastChi = 0, currentChi = 0;
   int it = 0, trials = 0;
-  bool stop = false;
+  bool stop = false, have_current = false;
   for (; it < mnumOptIts && !stop; it++) {
-    double currentChi = 0;
-    if ((rc = eval(d_active, 0))) return cleanup(rc);           // computeActiveErrors
-    if ((rc = chi2(&currentChi))) return cleanup(rc);
-    if ((rc = eval(d_active, 1))) return cleanup(rc);           // buildSystem: linearizeOplus ...
+    // computeActiveErrors + activeRobustChi2. From the second iteration on the edges were last evaluated at exactly this estimate
+    // (behind the accepted trial, or by the terminate action's pass after a rejected one) and currentChi is that pass's chi2.
+    if (!have_current) {
+      if ((rc = eval(d_active, 0, nullptr))) return cleanup(rc);
+      if ((rc = chi2_to(LS_CUR))) return cleanup(rc);
+    }
+    if ((rc = eval(d_active, 1, nullptr))) return cleanup(rc);           // buildSystem: linearizeOplus ...
     if (b->nchunks > 0) { lba_build_kernel<<<b->nchunks, kChunk, 0, st>>>(v, G, 0, 0.0, d_partA); SDSO_CHECK_LAUNCH(ctx); }
     lba_host_sum_kernel<<<n, 96, 0, st>>>(v, d_partA, d_hostA); SDSO_CHECK_LAUNCH(ctx);
     if (it == 0) { lambda = 0.1; ni = 2; }                       // setUserLambdaInit(0.1) (:425)
-    double rho = 0;
+    double rho = 0, tempChi = 0;
     int qmax = 0;
-    bool have_bp = false;
+    bool accepted = false;
     do {
-      // push()
+      // push() of the inverse depths (the vertices are pushed by lba_trial_update_kernel)
       lba_copy_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, d_idepth, d_idbak); SDSO_CHECK_LAUNCH(ctx);
-      std::vector<double> T_b(T_wh, T_wh + 12 * n), ph_b(photo, photo + 2 * n);
-      double cam_b[4] = {cam[0], cam[1], cam[2], cam[3]};
-      if (b->nchunks > 0) { lba_build_kernel<<<b->nchunks, kChunk, 0, st>>>(v, G, 1, lambda, d_partS); SDSO_CHECK_LAUNCH(ctx); }
+      if (b->nchunks > 0) { lba_schur_kernel<<<b->nchunks, kChunk, 0, st>>>(v, G, lambda, d_partS); SDSO_CHECK_LAUNCH(ctx); }
       lba_host_sum_kernel<<<n, 96, 0, st>>>(v, d_partS, d_hostS); SDSO_CHECK_LAUNCH(ctx);
       lba_assemble_kernel<<<(d * d + d + 127) / 128, 128, 0, st>>>(n, d_hostA, d_hostS, d_used, lambda, S.HF, S.bF); SDSO_CHECK_LAUNCH(ctx);
       ba_solve_kernel<<<1, 256, smem, st>>>(S); SDSO_CHECK_LAUNCH(ctx);
-      SDSO_CUDA(ctx, cudaMemcpyAsync(x.data(), S.x, d * sizeof(double), cudaMemcpyDeviceToHost, st));
-      if (!have_bp) {  // the un-reduced b of the non-marginalised block, for computeScale: bp = A's b part per host / cam
-        std::vector<double> hA((size_t)n * 96);
-        SDSO_CUDA(ctx, cudaMemcpyAsync(hA.data(), d_hostA, hA.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        SDSO_CUDA(ctx, cudaStreamSynchronize(st));
-        std::fill(bp.begin(), bp.end(), 0.0);
-        for (int h = 0; h < n; h++) if (used_host[h]) {
-          for (int l = 0; l < 8; l++) bp[kCPARS + 8 * h + l] = hA[(size_t)h * 96 + 78 + l];
-          for (int c = 0; c < 4; c++) bp[c] += hA[(size_t)h * 96 + 78 + 8 + c];
-        }
-        have_bp = true;
-      } else {
-        SDSO_CUDA(ctx, cudaStreamSynchronize(st));
-      }
-      bool ok = true;
-      for (int k = 0; k < d; k++) ok = ok && std::isfinite(x[k]);
-      double tempChi = std::numeric_limits<double>::max(), scale = 0;
-      if (ok) {
-        for (int k = 0; k < 4; k++) cam[k] += x[k];
-        for (int h = 0; h < n; h++) if (used_host[h]) {
-          double Ex[12], Tn[12];
-          se3_exp(&x[kCPARS + 8 * h], Ex);
-          se3_mul(Ex, T_wh + 12 * h, Tn);
-          memcpy(T_wh + 12 * h, Tn, sizeof(Tn));
-          photo[2 * h] += x[kCPARS + 8 * h + 6]; photo[2 * h + 1] += x[kCPARS + 8 * h + 7];
-        }
-        for (int k = 0; k < d; k++) scale += x[k] * (lambda * x[k] + bp[k]);
-        lba_update_kernel<<<rb, 128, 0, st>>>(v, G, S.x, lambda, d_bpart); SDSO_CHECK_LAUNCH(ctx);
-        lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc + 1); SDSO_CHECK_LAUNCH(ctx);
-        double sl = 0;
-        SDSO_CUDA(ctx, cudaMemcpyAsync(&sl, d_sc + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
-        if ((rc = upload_est())) return cleanup(rc);
-        if ((rc = eval(d_active, 0))) return cleanup(rc);
-        if ((rc = chi2(&tempChi))) return cleanup(rc);
-        scale += sl;
-      }
+      lba_trial_update_kernel<<<1, 32 * ((n + 31) / 32), 0, st>>>(n, d_used, S.x, lambda, d_hostA, d_est, d_estbak, d_sc); SDSO_CHECK_LAUNCH(ctx);
+      lba_update_kernel<<<rb, 128, 0, st>>>(v, G, S.x, lambda, d_bpart, d_sc + LS_OK); SDSO_CHECK_LAUNCH(ctx);
+      lba_sum_kernel<<<1, 32, 0, st>>>(d_bpart, rb, 1, 1, d_sc + LS_SL); SDSO_CHECK_LAUNCH(ctx);
+      if ((rc = eval(d_active, 0, d_sc + LS_OK))) return cleanup(rc);
+      if ((rc = chi2_to(LS_TEMP))) return cleanup(rc);
+      if ((rc = read_scalars())) return cleanup(rc);
+      if (!have_current) { currentChi = hsc[LS_CUR]; have_current = true; }
+      const bool ok = hsc[LS_OK] != 0.0;
+      tempChi = ok ? hsc[LS_TEMP] : std::numeric_limits<double>::max();
+      const double scale = ok ? hsc[LS_SCALE] + hsc[LS_SL] : 0.0;
       rho = (currentChi - tempChi) / (scale + 1e-3);
       if (rho > 0 && std::isfinite(tempChi)) {
         double alpha = 1. - std::pow((2 * rho - 1), 3);
         alpha = std::min(alpha, 2. / 3.);
         lambda *= std::max(1. / 3., alpha);
         ni = 2; currentChi = tempChi;
+        accepted = true;
       } else {
         lambda *= ni; ni *= 2;
-        lba_copy_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, d_idbak, d_idepth); SDSO_CHECK_LAUNCH(ctx);   // pop()
-        memcpy(T_wh, T_b.data(), sizeof(double) * 12 * n); memcpy(photo, ph_b.data(), sizeof(double) * 2 * n);
-        for (int k = 0; k < 4; k++) cam[k] = cam_b[k];
-        if ((rc = upload_est())) return cleanup(rc);
+        lba_pop_kernel<<<(std::max(R, 12 * n) + 255) / 256, 256, 0, st>>>(n, R, d_estbak, d_est, d_idbak, d_idepth); SDSO_CHECK_LAUNCH(ctx);   // pop()
+        accepted = false;
         if (!std::isfinite(lambda)) break;
       }
       qmax++; trials++;
     } while (rho < 0 && qmax < 10);
     const bool terminate_lm = (qmax == 10 || rho == 0 || !std::isfinite(lambda));
-    double chi = 0;
-    if ((rc = eval(d_active, 0))) return cleanup(rc);           // SparseOptimizerTerminateAction: computeActiveErrors + chi2
-    if ((rc = chi2(&chi))) return cleanup(rc);
+    // SparseOptimizerTerminateAction: computeActiveErrors + chi2. Behind an accepted trial the edges already hold the errors of this
+    // estimate and the chi2 is tempChi; behind a rejected one the estimate went back, so the pass runs.
+    double chi = currentChi;
+    if (!accepted) {
+      if ((rc = eval(d_active, 0, nullptr))) return cleanup(rc);
+      if ((rc = chi2_to(LS_POST))) return cleanup(rc);
+      if ((rc = read_scalars())) return cleanup(rc);
+      chi = hsc[LS_POST];
+      currentChi = chi;     // what the next iteration's computeActiveErrors would find
+    }
     if (it == 0) lastChi = chi;
     else { const double gain = (lastChi - chi) / chi; lastChi = chi; if (gain >= 0 && gain < 1e-3) stop = true; }
     if (terminate_lm) { it++; break; }
   }
+  // the vertices back to the caller
+  SDSO_CUDA(ctx, cudaMemcpyAsync(est.data(), d_est, est.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SDSO_CUDA(ctx, cudaStreamSynchronize(st));
+  memcpy(T_wh, est.data(), sizeof(double) * n * 12);
+  memcpy(photo, est.data() + n * 24, sizeof(double) * n * 2);
+  for (int k = 0; k < 4; k++) cam[k] = est[(size_t)n * 29 + k];
   // ---- results in the caller's residual order
   std::vector<double> id_out(R);
   std::vector<int> ns_out(R);

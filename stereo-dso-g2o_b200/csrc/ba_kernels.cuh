@@ -1293,6 +1293,8 @@ struct LBAEdgeParams {
   const double* target_aff;  // [n][2] aff_g2l of the frames
   const float* exposure;     // [n]
   double cam[4];
+  const double* cam_dev;     // driver: the camera vertex lives on the device (null: cam[] above)
+  const double* run_if;      // driver: skip the launch's work when *run_if == 0 (the damping trial's x was not finite)
   const int* slot2rid;   // operator mode: outputs in the caller's residual order; null (driver mode): slot order
   int driver;            // 1: g2o driver semantics — skip inactive edges, keep stale Jacobians / energies where the edge returns early,
                          //    sticky level, idepth / outputs indexed by slot
@@ -1307,6 +1309,7 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
   if (s >= B.R) return;
   const int rid = E.slot2rid ? E.slot2rid[s] : s;
   if (E.driver && E.active && !E.active[s]) return;
+  if (E.run_if && *E.run_if == 0.0) return;
   const int key = B.s_key[s], h = key % B.n, t = key / B.n, pidx = B.s_point[s];
   double* err = E.error8 + 8 * (size_t)rid;
   double* Jxi = E.Jxi + 48 * (size_t)rid; double* Jph = E.Jphoto + 16 * (size_t)rid; double* Jid = E.Jid + 8 * (size_t)rid; double* JC = E.JC + 32 * (size_t)rid;
@@ -1319,7 +1322,8 @@ __global__ void __launch_bounds__(128) ba_lba_edge_kernel(BAView B, LBAEdgeParam
     E.center3[3 * rid] = E.center3[3 * rid + 1] = E.center3[3 * rid + 2] = 0;
   }
   int newState = E.driver ? E.newState[rid] : B.s_newstate[s];
-  const double fx = E.cam[0], fy = E.cam[1], cx = E.cam[2], cy = E.cam[3];
+  const double* camv = E.cam_dev ? E.cam_dev : E.cam;
+  const double fx = camv[0], fy = camv[1], cx = camv[2], cy = camv[3];
   // Tth = Ttw * Twh in double, then cast to float (:23-29)
   const double* A = E.T_tw + 12 * t; const double* Bm = E.T_wh + 12 * h;
   float R[9], tt[3];
@@ -1681,11 +1685,11 @@ __global__ void lba_assemble_kernel(int n, const double* A /* [n][96] */, const 
 }
 
 // idepth_r += (bl - hpl^T dx) / (hll + lambda); partial sums of dl (lambda dl + bl) for computeScale
-__global__ void __launch_bounds__(128) lba_update_kernel(BAView B, LBAGraph G, const double* x, double lambda, double* part) {
+__global__ void __launch_bounds__(128) lba_update_kernel(BAView B, LBAGraph G, const double* x, double lambda, double* part, const double* run_if) {
   __shared__ double red[32];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0;
-  if (s < G.R && G.active[s]) {
+  if (s < G.R && G.active[s] && (!run_if || *run_if != 0.0)) {
     const int hb = kCPARS + 8 * (B.s_key[s] % B.n);
     double t = G.bl[s];
     for (int a = 0; a < 12; a++) t -= G.hpl[(size_t)s * 12 + a] * x[a < 8 ? hb + a : a - 8];
@@ -1900,6 +1904,94 @@ __global__ void ba_iter_end_kernel(OptDev* o) {
   o->it += 1;
   o->its_done = o->it;
   if (o->pending) o->done = 1;
+}
+
+// ---- g2o LBA driver, per-trial kernels (sdso_lba_g2o) ------------------------------------------------------------------------------
+// slots of the driver's scalar block (doubles)
+enum { LS_CUR = 0, LS_SL = 1, LS_TEMP = 2, LS_SCALE = 3, LS_OK = 4, LS_POST = 5, LS_NUM = 8 };
+
+// Schur complement terms of one chunk for the current lambda: sum_e hpl_e hpl_e^T / (hll_e + lambda) (78 values, upper triangle by
+// rows) and sum_e hpl_e bl_e / (hll_e + lambda) (12). The chunk's edges are staged once in shared memory; thread t < 90 then sums
+// ITS output element over the edges in slot order (fixed order, no barriers inside the sum). Replaces the 13-phase
+// lba_build_kernel(what = 1) on the per-trial path (one launch per damping trial).
+__global__ void __launch_bounds__(kChunk) lba_schur_kernel(BAView B, LBAGraph G, double lambda, double* part /* [nchunks][96] */) {
+  __shared__ double hs[kChunk][13];   // hpl (12) and bl; odd stride: a warp's staging stores hit distinct banks
+  __shared__ double wv[kChunk];       // 1 / (hll + lambda), 0 for inactive edges
+  const Chunk ch = B.chunks[blockIdx.x];
+  const int cnt = ch.end - ch.begin;
+  const int tid = threadIdx.x;
+  if (tid < cnt) {
+    const int s = ch.begin + tid;
+    const bool use = G.active[s] != 0;
+    wv[tid] = use ? 1.0 / (G.hll[s] + lambda) : 0.0;
+#pragma unroll
+    for (int a = 0; a < 12; a++) hs[tid][a] = use ? G.hpl[(size_t)s * 12 + a] : 0.0;
+    hs[tid][12] = use ? G.bl[s] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 90) {
+    int a = 0, c = 12;
+    if (tid < 78) { int rem = tid; while (rem >= 12 - a) { rem -= 12 - a; a++; } c = a + rem; }
+    else a = tid - 78;
+    double t = 0;
+    for (int e = 0; e < cnt; e++) t += hs[e][a] * wv[e] * hs[e][c];
+    part[(size_t)blockIdx.x * 96 + tid] = t;
+  }
+}
+
+// One damping trial's vertex update on the device (the host used to read x back for this): push() of the pose / photometric /
+// camera vertices, x finite?, oplus of every used host (dso_g2o_vertex.cpp:15-18, 30-40, 100-106) and the vertex part of
+// computeScale, sum_k x_k (lambda x_k + b_k) with b the un-reduced gradient of the non-marginalised block.
+// est = [T_wh n*12 | T_tw n*12 | photo n*2 | b0 n | target aff n*2 | cam 4]; bak = [T_wh n*12 | photo n*2 | cam 4]
+__global__ void lba_trial_update_kernel(int n, const int* used, const double* x, double lambda, const double* hostA /* [n][96] */, double* est,
+                                        double* bak, double* sc) {
+  __shared__ int ok_s;
+  const int h = threadIdx.x, d = kCPARS + 8 * n;
+  double* T_wh = est; double* photo = est + (size_t)n * 24; double* cam = est + (size_t)n * 29;
+  if (h == 0) {
+    bool ok = true;
+    for (int k = 0; k < d; k++) ok = ok && isfinite(x[k]);
+    ok_s = ok ? 1 : 0;
+    sc[LS_OK] = ok ? 1.0 : 0.0;
+    for (int k = 0; k < 4; k++) bak[(size_t)n * 14 + k] = cam[k];
+    double scale = 0;
+    if (ok) {
+      // b of the cam block: sum over the used hosts; of a pose block: that host's own 8 entries
+      for (int k = 0; k < 4; k++) {
+        double bp = 0;
+        for (int g = 0; g < n; g++) if (used[g]) bp += hostA[(size_t)g * 96 + 78 + 8 + k];
+        scale += x[k] * (lambda * x[k] + bp);
+      }
+      for (int g = 0; g < n; g++)
+        for (int l = 0; l < 8; l++) {
+          const double xk = x[kCPARS + 8 * g + l];
+          const double bp = used[g] ? hostA[(size_t)g * 96 + 78 + l] : 0.0;
+          scale += xk * (lambda * xk + bp);
+        }
+      for (int k = 0; k < 4; k++) cam[k] += x[k];
+    }
+    sc[LS_SCALE] = scale;
+  }
+  __syncthreads();
+  if (h < n) {
+    for (int k = 0; k < 12; k++) bak[(size_t)h * 12 + k] = T_wh[(size_t)h * 12 + k];
+    bak[(size_t)n * 12 + 2 * h] = photo[2 * h]; bak[(size_t)n * 12 + 2 * h + 1] = photo[2 * h + 1];
+    if (ok_s && used[h]) {
+      double Ex[12], Tn[12];
+      dev_se3_exp(x + kCPARS + 8 * h, Ex);
+      dev_se3_mul(Ex, T_wh + (size_t)h * 12, Tn);
+      for (int k = 0; k < 12; k++) T_wh[(size_t)h * 12 + k] = Tn[k];
+      photo[2 * h] += x[kCPARS + 8 * h + 6]; photo[2 * h + 1] += x[kCPARS + 8 * h + 7];
+    }
+  }
+}
+// pop(): vertices and inverse depths back to the pushed values
+__global__ void lba_pop_kernel(int n, int R, const double* bak, double* est, const double* idbak, double* idepth) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) idepth[i] = idbak[i];
+  if (i < n * 12) est[i] = bak[i];
+  if (i < n * 2) est[(size_t)n * 24 + i] = bak[(size_t)n * 12 + i];
+  if (i < 4) est[(size_t)n * 29 + i] = bak[(size_t)n * 14 + i];
 }
 
 }  // namespace sdso
