@@ -136,6 +136,7 @@ int orc_edge_eval(void* p, int new_fid, int lvl, const double Tsel[12], const do
 }
 unsigned long long orc_evals(void* p) { return ((Ctx*)p)->tracker.evals; }
 void orc_reset_evals(void* p) { ((Ctx*)p)->tracker.evals = 0; }
+void orc_g2o_trial_counts(void* p, int out[2]) { out[0] = ((Ctx*)p)->tracker.g2o_trials; out[1] = ((Ctx*)p)->tracker.g2o_rejected; }
 
 // ---- SE3 -------------------------------------------------------------------------------------
 void orc_se3_exp(const double a[6], double T[12]) { SE3::exp(a).toMat34(T); }

@@ -89,6 +89,7 @@ struct CoarseTracker {
   void edgeComputeError(Edge& e, const SE3& pose, const double photo[2]) const;
   bool edgeLinearizeOplus(const Edge& e, const SE3& pose, const double photo[2], double Jpose[6], double Jphoto[2]) const;
   uint64_t evals = 0;  // number of project+gather+residual evaluations performed (for the metric)
+  int g2o_trials = 0, g2o_rejected = 0;  // damping trials of the last trackNewestCoarseG2O and how many of them were popped (test coverage)
 };
 
 }  // namespace orc

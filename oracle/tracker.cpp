@@ -538,6 +538,7 @@ bool CoarseTracker::trackNewestCoarseG2O(const Frame* fh, SE3& lastToNew_out, do
   double lastChi = 0;
   const double delta = S.huberTH;
   if (lm_iterations_out) for (int i = 0; i < 5; i++) lm_iterations_out[i] = 0;
+  g2o_trials = g2o_rejected = 0;
 
   for (int lvl = coarsestLvl; lvl >= 0; lvl--) {
     double resOld[6];
@@ -593,8 +594,9 @@ bool CoarseTracker::trackNewestCoarseG2O(const Frame* fh, SE3& lastToNew_out, do
           } else {
             lambda *= ni; ni *= 2;
             vtx_pose = pose_bak; vtx_photo[0] = photo_bak[0]; vtx_photo[1] = photo_bak[1];  // pop()
+            g2o_rejected++;
           }
-          qmax++;
+          qmax++; g2o_trials++;
         } while (rho < 0 && qmax < 10 && !forceStop);
         if (qmax == 10 || rho == 0) ok = false;  // SolverResult::Terminate
         // ---- postIteration(it): SparseOptimizerTerminateAction, gain threshold 1e-3 (:845-848)

@@ -71,6 +71,7 @@ lib.orc_edge_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, 
 lib.orc_evals.restype = C.c_ulonglong
 lib.orc_evals.argtypes = [C.c_void_p]
 lib.orc_reset_evals.argtypes = [C.c_void_p]
+lib.orc_g2o_trial_counts.argtypes = [C.c_void_p, _ip]
 for name in ("orc_se3_exp", "orc_se3_log", "orc_se3_adj", "orc_se3_inv"):
     getattr(lib, name).argtypes = [_dp, _dp]
 lib.orc_se3_mul.argtypes = [_dp, _dp, _dp]
@@ -236,6 +237,12 @@ class Oracle:
         err, J = np.zeros(w * h), np.zeros((w * h, 8))
         n = lib.orc_edge_eval(self._h, new_fid, lvl, _p(Ts, _dp), _p(Tp, _dp), _p(ph, _dp), _p(err, _dp), _p(J, _dp), None)
         return err[:n].copy(), J[:n].copy()
+
+    def g2o_trial_counts(self):
+        """(damping trials, rejected trials) of the last g2o track call"""
+        o = np.zeros(2, np.int32)
+        lib.orc_g2o_trial_counts(self._h, _p(o, _ip))
+        return int(o[0]), int(o[1])
 
     def evals(self):
         return int(lib.orc_evals(self._h))

@@ -201,6 +201,29 @@ def test_track_g2o_matches_restated_g2o(pair, init):
     assert np.allclose(g["flow"], o["flow"], rtol=REL)
 
 
+@pytest.mark.parametrize("new_k,seed,dt,ddeg,converges", [(2, 0, 0.02, 0.1, True), (1, 0, 0.3, 1.5, True), (2, 2, 0.6, 3.0, False)])
+def test_track_g2o_rejected_trials(pair, new_k, seed, dt, ddeg, converges):
+    """Damping trials that are REJECTED (pop, lambda *= ni): the kernel's fused passes only stand in for g2o's separate passes behind
+    accepted trials, so the rejected path — estimate restored, the terminate action's pass and the next buildSystem run on their own
+    — needs its own cases. The oracle counts its trials; each case must contain rejections (10 of 13, 9 of 13, 4 of 14 trials)."""
+    ctx, orc, ids, pts = pair
+    Ttrue = synth.T_rel(synth.camera_pose(0), synth.camera_pose(new_k))
+    T0 = synth.perturb_T(Ttrue, np.random.default_rng(seed), dt, np.deg2rad(ddeg))
+    o = orc.track(ids[new_k][1], T0, (0.0, 0.0), orc.levels - 1, [np.nan] * 5, 1)
+    trials, rejected = orc.g2o_trial_counts()
+    assert rejected >= 3 and trials > rejected, (trials, rejected)
+    g = ctx.track(ids[new_k][0], T0, (0.0, 0.0), ctx.levels - 1, [np.nan] * 5, 1)
+    assert g["ok"] == o["ok"] == converges
+    assert np.array_equal(g["iterations"], o["iterations"])
+    if converges:
+        assert np.abs(g["T"][:, 3] - o["T"][:, 3]).max() < 1e-4
+        assert rot_angle(g["T"][:, :3], o["T"][:, :3]) < 1e-5
+        assert np.allclose(g["aff"], o["aff"], rtol=1e-3, atol=1e-3)
+        assert np.allclose(g["lastResiduals"], o["lastResiduals"], rtol=1e-3, equal_nan=True)
+    else:   # outside the basin the LM path is chaotic in the last bits of the sums: verdict, iteration pattern, coarse agreement
+        assert np.abs(g["T"][:, 3] - o["T"][:, 3]).max() < 5e-2
+
+
 def test_track_g2o_stop_flag_knob(pkg, frames):
     """SURVEY.md Appendix C open point (1): with the terminate flag NOT persisting, finer levels keep iterating."""
     s = pkg.default_settings()
