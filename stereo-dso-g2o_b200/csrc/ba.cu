@@ -653,16 +653,20 @@ int sdso_ba_set_residuals(sdso_ctx* ctx, int R, const int* point, const int* tar
   const int n = b->n, P = b->P;
   for (int i = 0; i < R; i++) if (point[i] < 0 || point[i] >= P || target[i] < 0 || target[i] >= n) return fail(ctx, SDSO_E_INVALID, "residual index out of range");
   // stable sort by key = host + target*n  (slot order)
-  std::vector<int> key(R), order(R);
-  for (int i = 0; i < R; i++) { key[i] = b->h_p_host[point[i]] + target[i] * n; order[i] = i; }
-  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return key[a] < key[c]; });
+  // (a counting sort: there are at most kMaxFrames^2 keys; stable, so the residuals of a key keep the caller's order)
+  std::vector<int> key(R), order(R), seg(n * n + 1, 0);
+  for (int i = 0; i < R; i++) { key[i] = b->h_p_host[point[i]] + target[i] * n; seg[key[i] + 1]++; }
+  for (int k = 0; k < n * n; k++) seg[k + 1] += seg[k];
+  {
+    std::vector<int> pos(seg.begin(), seg.end() - 1);
+    for (int i = 0; i < R; i++) order[pos[key[i]]++] = i;
+  }
   b->h_slot2rid = order;
   b->h_rid2slot.assign(R, 0);
   for (int s = 0; s < R; s++) b->h_rid2slot[order[s]] = s;
   b->h_r_point.assign(point, point + R); b->h_r_target.assign(target, target + R);
-  std::vector<int> s_point(R), s_key(R), seg(n * n + 1, 0);
-  for (int s = 0; s < R; s++) { s_point[s] = point[order[s]]; s_key[s] = key[order[s]]; seg[s_key[s] + 1]++; }
-  for (int k = 0; k < n * n; k++) seg[k + 1] += seg[k];
+  std::vector<int> s_point(R), s_key(R);
+  for (int s = 0; s < R; s++) { s_point[s] = point[order[s]]; s_key[s] = key[order[s]]; }
   b->h_seg_begin = seg;
   // chunks of <= kChunk slots, never crossing a key boundary
   b->h_chunks.clear();

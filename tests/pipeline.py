@@ -135,11 +135,15 @@ class Backend:
         host = np.array([p["host"] for p in pts], np.int32)
         uv = np.array([[p["u"], p["v"]] for p in pts], np.float32).reshape(-1, 2)
         col, wts = np.zeros((P, 8), np.float32), np.zeros((P, 8), np.float32)
-        for h in range(win["n"]):
-            idx = np.nonzero(host == h)[0]
-            if idx.size:
-                rec, _ = self.immature_init_fid(fids[h], uv[idx])
-                col[idx] = rec["color"]; wts[idx] = rec["weights"]
+        if P and all("color" in p for p in pts):
+            # PointHessian keeps the colour / weights of the ImmaturePoint it was made from (HessianBlocks.cpp:36-53)
+            col[:] = np.stack([p["color"] for p in pts]); wts[:] = np.stack([p["weights"] for p in pts])
+        else:
+            for h in range(win["n"]):
+                idx = np.nonzero(host == h)[0]
+                if idx.size:
+                    rec, _ = self.immature_init_fid(fids[h], uv[idx])
+                    col[idx] = rec["color"]; wts[idx] = rec["weights"]
         idp = np.array([p["idepth"] for p in pts], np.float32); idz = np.array([p["idepth_zero"] for p in pts], np.float32)
         prior = np.array([p["has_prior"] for p in pts], np.uint8)
         counts = [len(p["targets"]) for p in pts]
@@ -289,7 +293,7 @@ class StereoPipeline:
         pos = {fid: i for i, fid in enumerate(ids)}
         frames = [dict(T_w2c=kf["T_eval"], a=kf["a_eval"], b=kf["b_eval"], frameID=kf["frameID"], state=kf["state"], energyTH=kf["energyTH"]) for kf in self.kfs]
         pts = [dict(host=pos[p["host"]], u=p["u"], v=p["v"], idepth=p["idepth"], idepth_zero=p["idepth_zero"], has_prior=p["has_prior"],
-                    targets=[pos[t] for t in p["targets"] if t in pos]) for p in self.points]
+                    targets=[pos[t] for t in p["targets"] if t in pos], color=p["color"], weights=p["weights"]) for p in self.points]
         return dict(n=len(self.kfs), frames=frames, points=pts), [kf["fid"] for kf in self.kfs]
 
     def _make_keyframe(self, fl, fr, T_w2c, first):
@@ -344,7 +348,8 @@ class StereoPipeline:
                     c = cand[sel[k_]]
                     targets = [self.kfs[t]["frameID"] for t in range(n) if a["states"][k_, t] == 0]
                     self.points.append(dict(host=hosts[int(cand_host[sel[k_]])]["frameID"], u=float(c["u"]), v=float(c["v"]), idepth=np.float32(a["idepth"][k_]),
-                                            idepth_zero=np.float32(a["idepth"][k_]), has_prior=False, targets=targets))
+                                            idepth_zero=np.float32(a["idepth"][k_]), has_prior=False, targets=targets,
+                                            color=np.array(c["color"], np.float32), weights=np.array(c["weights"], np.float32)))
                     n_act += 1
                 keep = verdict == 0   # 1: consumed by optimizeImmaturePoint (activated or discarded), 2: deleted
                 off = 0
@@ -429,7 +434,8 @@ class StereoPipeline:
             gi = gi[:: max(1, gi.size // int(self.point_density))]
             for i in gi:
                 self.points.append(dict(host=kf["frameID"], u=float(pts["u"][i]), v=float(pts["v"][i]), idepth=np.float32(pts["idepth_stereo"][i]),
-                                        idepth_zero=np.float32(pts["idepth_stereo"][i]), has_prior=True, targets=[], HdiF=1e-3))
+                                        idepth_zero=np.float32(pts["idepth_stereo"][i]), has_prior=True, targets=[], HdiF=1e-3,
+                                        color=np.array(pts["color"][i], np.float32), weights=np.array(pts["weights"][i], np.float32)))
             keep = np.ones(pts.size, bool); keep[gi] = False
             kf["immature"], kf["my_type"] = np.ascontiguousarray(pts[keep]), kf["my_type"][keep]
             splat = np.array([[p["u"], p["v"], p["idepth"], 1.0] for p in self.points], np.float32).reshape(-1, 4)
