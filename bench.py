@@ -41,9 +41,8 @@ BYTES_PER_EVAL = 64  # tracking eval = 16 B point record + 4 tex
 N_POINTS = 2000
 SEQS = 592           # independent sequences per GPU per step (4 x 148: whole waves of 2-CTA clusters at two CTAs per SM)
 PATH = 37            # distinct positions along the rendered path; sequence s starts at position s % PATH
-# new stereo frames per sequence (cycled). Every pose set is a pinned host slab of 2 x SEQS images (537 MB): 6 on one GPU, 3 per rank
-# under torchrun so that eight ranks pin 13 GB of host memory, as in round 1, not 26 GB
-POSES = int(os.environ.get("SDSO_BENCH_POSES", "6" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "3"))
+# new stereo frames per sequence (cycled); the same at every N — the mix of motions sets the LM iteration counts (3 pose sets read 7 % slower per launch than 6)
+POSES = int(os.environ.get("SDSO_BENCH_POSES", "6"))
 SETS = 2             # frame-slot sets (double buffering: upload of step i+1 overlaps the kernels of step i)
 
 
