@@ -408,6 +408,12 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
         uid = [pkg.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.nccl_init(rank, world, uid[0])
+        # the hand-written exchange over NVLink peer memory (csrc/collective.cu): every rank exports its block, all map all
+        dsys = 4 + 8 * c["n"]
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_alloc(world, dsys * dsys + dsys + 1))
+        ctx.peer_connect(rank, world, handles)
+        dist.barrier()
     fids = []
     for f in win["frames"]:
         fid = ctx.frame_create(); ctx.make_images(fid, f["image"]); fids.append(fid)
@@ -442,9 +448,8 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
     steps_s = Ws.get_points()["step"].copy()
     ms_sharded = timed(Ws, True)
     ms_no_ar = timed(Ws, True, allreduce=False) if world > 1 else ms_sharded
-    # allreduce alone
-    ar_us = None
-    if world > 1:
+
+    def exchange_alone():
         for _ in range(5):
             Ws.allreduce()
         dist.barrier(); torch.cuda.synchronize()
@@ -453,7 +458,19 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
         for _ in range(50):
             Ws.allreduce()
         e1.record(stream); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device=f"cuda:{dev}", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ar_us = float(t[0])
+        t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device=f"cuda:{dev}", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    ar_us = ar_nccl_us = ms_sharded_nccl = None
+    timed_out = 0
+    if world > 1:
+        ar_us = exchange_alone()
+        timed_out = ctx.peer_status()
+        dist.barrier()
+        ctx.peer_select(0)                       # the same iteration with NCCL's allreduce in place of the peer-memory kernel
+        ms_sharded_nccl = timed(Ws, True)
+        ar_nccl_us = exchange_alone()
+        ctx.peer_select(1)
     Wf, _, _ = device_window(pkg, ctx, win, fids)
     Ef = Wf.linearize_all(True)
     xf, Hf, bf = Wf.solve(2)
@@ -468,10 +485,13 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
     ctx.close()
     evals = 8 * R
     return dict(
-        workload=f"config 4 LM iteration ({c['n']} KF, {P} points, {R} residuals, {c['w']}x{c['h']}), points sharded over {world} GPU(s), one allreduce of the "
+        workload=f"config 4 LM iteration ({c['n']} KF, {P} points, {R} residuals, {c['w']}x{c['h']}), points sharded over {world} GPU(s), one exchange of the "
                  f"(4+8n)^2+(4+8n)+1 = {(4 + 8 * c['n']) ** 2 + 4 + 8 * c['n'] + 1} doubles per iteration",
         n_gpus=world, ms_per_lm_iteration_sharded=ms_sharded, ms_per_lm_iteration_1gpu=ms_full, speedup_vs_1gpu=ms_full / ms_sharded,
         ms_per_lm_iteration_sharded_without_allreduce=ms_no_ar, allreduce_us=ar_us,
+        exchange="one kernel per rank over NVLink peer memory (CUDA IPC): push into every peer's block, signal, wait on local flags, rank-ordered sum (csrc/collective.cu)",
+        exchange_timed_out=timed_out, with_nccl_allreduce=dict(ms_per_lm_iteration_sharded=ms_sharded_nccl, allreduce_us=ar_nccl_us,
+                                                                speedup_vs_1gpu=(ms_full / ms_sharded_nccl) if ms_sharded_nccl else None),
         value=evals / (ms_sharded * 1e-3), unit="evals/s",
         roofline=dict(bound="hbm", achieved=evals * BA_BYTES_PER_EVAL / (ms_sharded * 1e-3) / 1e9, peak=peak * world, unit="GB/s",
                       frac=evals * BA_BYTES_PER_EVAL / (ms_sharded * 1e-3) / 1e9 / (peak * world)),

@@ -321,6 +321,15 @@ int sdso_nccl_unique_id(unsigned char id[128]);                 /* ncclGetUnique
 int sdso_nccl_init(sdso_ctx* ctx, int rank, int nranks, const unsigned char id[128]);
 int sdso_nccl_destroy(sdso_ctx* ctx);
 int sdso_allreduce_f64(sdso_ctx* ctx, void* device_buffer, int count);  /* in-place sum on the context's stream */
+/* The same exchange as ONE hand-written kernel over NVLink peer memory instead of NCCL (57 KB per iteration: NCCL's launch and
+ * protocol latency is the whole cost — 99 us on 8 GPUs): every rank allocates an exchange block (sdso_peer_alloc returns its
+ * 64-byte CUDA IPC handle), the host's rendezvous gathers the handles, sdso_peer_connect maps the peers' blocks; from then on
+ * sdso_ba_allreduce / sdso_allreduce_f64 push the local part into every peer's block (flag-carrying words) and reduce in one launch (csrc/collective.cu). One process per
+ * GPU on one node; all ranks must issue the same sequence of exchanges. */
+int sdso_peer_alloc(sdso_ctx* ctx, int nranks, int max_doubles, unsigned char handle_out[64]);
+int sdso_peer_connect(sdso_ctx* ctx, int rank, int nranks, const unsigned char* handles /* nranks x 64 bytes in rank order */);
+int sdso_peer_select(sdso_ctx* ctx, int which /* 0 = NCCL, 1 = peer-memory kernel (default once connected) */);
+int sdso_peer_status(sdso_ctx* ctx, int* timed_out /* 1: a wait on a peer gave up; synchronises */);
 
 /* ---- D1-D3, E3: immature points — constructor, temporal and static-stereo epipolar search ------------------------
  * One record per ImmaturePoint (FullSystem/ImmaturePoint.h:59-114): the fields the constructor, traceOn and

@@ -616,6 +616,41 @@ def _nccl_init(self, rank, nranks, uid):
 
 Context.nccl_init = _nccl_init
 
+lib.sdso_peer_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.sdso_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.sdso_peer_select.argtypes = [C.c_void_p, C.c_int]
+lib.sdso_peer_status.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+
+
+def _peer_alloc(self, nranks, max_doubles):
+    """allocate this rank's exchange block; returns its 64-byte CUDA IPC handle (to be all-gathered by the caller's rendezvous)"""
+    buf = (C.c_ubyte * 64)()
+    self._ck(lib.sdso_peer_alloc(self._h, int(nranks), int(max_doubles), buf))
+    return bytes(buf)
+
+
+def _peer_connect(self, rank, nranks, handles):
+    blob = b"".join(handles)
+    assert len(blob) == 64 * nranks
+    buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+    self._ck(lib.sdso_peer_connect(self._h, rank, nranks, buf))
+
+
+def _peer_select(self, which):
+    self._ck(lib.sdso_peer_select(self._h, int(which)))
+
+
+def _peer_status(self):
+    v = C.c_int()
+    self._ck(lib.sdso_peer_status(self._h, C.byref(v)))
+    return v.value
+
+
+Context.peer_alloc = _peer_alloc
+Context.peer_connect = _peer_connect
+Context.peer_select = _peer_select
+Context.peer_status = _peer_status
+
 
 def _w_set_shard(self, rank, nranks):
     self._ck(lib.sdso_ba_set_shard(self.h, rank, nranks))

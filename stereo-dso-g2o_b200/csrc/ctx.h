@@ -43,6 +43,8 @@ struct UndistortState; // undistort.cu
 
 }  // namespace sdso
 
+namespace sdso { struct PeerExchange; }
+
 struct sdso_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -76,6 +78,7 @@ struct sdso_ctx {
   size_t ev_track_used = 0, ev_images_used = 0;
   int num_sms = 0;
   void* nccl_comm = nullptr;  // ncclComm_t of the sharded-BA allreduce (collective.cu), null unless sdso_nccl_init ran
+  sdso::PeerExchange* peer = nullptr;   // one-shot allreduce over NVLink peer memory (collective.cu), null unless sdso_peer_connect ran
   int nccl_rank = 0, nccl_nranks = 1;
   std::string err;
 };
