@@ -501,20 +501,31 @@ def main():
             cpu_baseline=dict(value=cg_ev / cg_sec, unit="evals/s", cores=host_cores, kind="port", tracked_frames_per_s=cg_fr / cg_sec,
                               sample=f"{cg_fr} tracked stereo frames in {cg_sec:.1f} s over {host_cores} threads (oracle port, g2o variant)"))
     import bench_legs as BL
+
+    def guarded(name, fn):
+        """a leg that fails must not take the headline line with it: the error is recorded in its place"""
+        try:
+            return fn()
+        except Exception as ex:   # noqa: BLE001
+            import traceback
+            print(f"[bench] leg {name} failed:\n{traceback.format_exc()}", file=sys.stderr)
+            return dict(error=f"{type(ex).__name__}: {ex}")
+
     if world == 1 and (want & {"ba3", "ba4", "trace", "sequence"}):
         scene = synth.make_scene()
         lk = max(10, min(K_, 50))
         if "ba3" in want:
-            legs["ba_config3"] = BL.leg_ba(pkg, torch, dev, scene, "config3", lk, peak_, want_g2o=True)
+            legs["ba_config3"] = guarded("ba3", lambda: BL.leg_ba(pkg, torch, dev, scene, "config3", lk, peak_, want_g2o=True))
             legs["lba_g2o"] = legs["ba_config3"].pop("lba_g2o", None)
         if "ba4" in want:
-            legs["ba_config4"] = BL.leg_ba(pkg, torch, dev, scene, "config4", lk, peak_, cpu_seconds=3.0)
+            legs["ba_config4"] = guarded("ba4", lambda: BL.leg_ba(pkg, torch, dev, scene, "config4", lk, peak_, cpu_seconds=3.0))
         if "trace" in want:
-            legs.update(BL.leg_trace(pkg, torch, dev, scene, peak_))
+            tr = guarded("trace", lambda: BL.leg_trace(pkg, torch, dev, scene, peak_))
+            legs.update({"trace_on": tr} if "error" in tr else tr)
         if "sequence" in want:
-            legs["sequence"] = BL.leg_sequence(pkg, torch, dev, scene)
+            legs["sequence"] = guarded("sequence", lambda: BL.leg_sequence(pkg, torch, dev, scene))
     if world > 1 and "sharded" in want:
-        legs["sharded_ba"] = BL.leg_sharded_ba(pkg, torch, dist, dev, rank, world, synth.make_scene(), max(10, min(K_, 50)), peak_)
+        legs["sharded_ba"] = guarded("sharded", lambda: BL.leg_sharded_ba(pkg, torch, dist, dev, rank, world, synth.make_scene(), max(10, min(K_, 50)), peak_))
 
     # ---- aggregate over ranks (max time, summed work) ---------------------------------------------
     if dist is not None:

@@ -409,16 +409,36 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
         dist.broadcast_object_list(uid, src=0)
         ctx.nccl_init(rank, world, uid[0])
         # the hand-written exchange over NVLink peer memory (csrc/collective.cu): every rank exports its block, all map all
+        # (if any rank cannot export / map a block — no peer access, IPC not permitted — every rank stays on NCCL)
         dsys = 4 + 8 * c["n"]
+        peer_ok, peer_why = 1, ""
+        try:
+            handle = ctx.peer_alloc(world, dsys * dsys + dsys + 1)
+        except Exception as ex:   # noqa: BLE001
+            handle, peer_ok, peer_why = b"\0" * 64, 0, str(ex)
         handles = [None] * world
-        dist.all_gather_object(handles, ctx.peer_alloc(world, dsys * dsys + dsys + 1))
-        ctx.peer_connect(rank, world, handles)
+        dist.all_gather_object(handles, (handle, peer_ok))
+        if all(h[1] for h in handles):
+            try:
+                ctx.peer_connect(rank, world, [h[0] for h in handles])
+            except Exception as ex:   # noqa: BLE001
+                peer_ok, peer_why = 0, str(ex)
+        else:
+            peer_ok = 0
+        flag = torch.tensor([peer_ok], device=f"cuda:{dev}", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        have_peer = bool(int(flag[0]))
+        if not have_peer and peer_ok:
+            ctx.peer_select(0)
         dist.barrier()
     fids = []
     for f in win["frames"]:
         fid = ctx.frame_create(); ctx.make_images(fid, f["image"]); fids.append(fid)
     P = len(win["points"])
     b, e = pkg.shard_range(P, rank, world)
+
+    if world <= 1:
+        have_peer, peer_why = False, ""
 
     def timed(W, sharded, allreduce=True):
         def it():
@@ -465,12 +485,15 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
     timed_out = 0
     if world > 1:
         ar_us = exchange_alone()
-        timed_out = ctx.peer_status()
-        dist.barrier()
-        ctx.peer_select(0)                       # the same iteration with NCCL's allreduce in place of the peer-memory kernel
-        ms_sharded_nccl = timed(Ws, True)
-        ar_nccl_us = exchange_alone()
-        ctx.peer_select(1)
+        if have_peer:
+            timed_out = ctx.peer_status()
+            dist.barrier()
+            ctx.peer_select(0)                   # the same iteration with NCCL's allreduce in place of the peer-memory kernel
+            ms_sharded_nccl = timed(Ws, True)
+            ar_nccl_us = exchange_alone()
+            ctx.peer_select(1)
+        else:
+            ms_sharded_nccl, ar_nccl_us = ms_sharded, ar_us
     Wf, _, _ = device_window(pkg, ctx, win, fids)
     Ef = Wf.linearize_all(True)
     xf, Hf, bf = Wf.solve(2)
