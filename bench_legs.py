@@ -512,7 +512,8 @@ def leg_sharded_ba(pkg, torch, dist, dev, rank, world, scene, iters, peak):
                  f"(4+8n)^2+(4+8n)+1 = {(4 + 8 * c['n']) ** 2 + 4 + 8 * c['n'] + 1} doubles per iteration",
         n_gpus=world, ms_per_lm_iteration_sharded=ms_sharded, ms_per_lm_iteration_1gpu=ms_full, speedup_vs_1gpu=ms_full / ms_sharded,
         ms_per_lm_iteration_sharded_without_allreduce=ms_no_ar, allreduce_us=ar_us,
-        exchange="one kernel per rank over NVLink peer memory (CUDA IPC): push into every peer's block, signal, wait on local flags, rank-ordered sum (csrc/collective.cu)",
+        exchange=("one kernel per rank over NVLink peer memory (CUDA IPC): flag-carrying words pushed into every peer's block, polled locally, rank-ordered sum; "
+                  "no fence / atomic / barrier (csrc/collective.cu)") if have_peer else f"NCCL allreduce (peer-memory set-up not available: {peer_why})",
         exchange_timed_out=timed_out, with_nccl_allreduce=dict(ms_per_lm_iteration_sharded=ms_sharded_nccl, allreduce_us=ar_nccl_us,
                                                                 speedup_vs_1gpu=(ms_full / ms_sharded_nccl) if ms_sharded_nccl else None),
         value=evals / (ms_sharded * 1e-3), unit="evals/s",
