@@ -470,7 +470,7 @@ void BAWindow::accumulateTop(int mode, std::vector<double>& H, std::vector<doubl
       const RawResidualJacobian& rJ = r.efJ;
       int htIDX = r.host + r.target * nf;
       const float* dp = &adHTdeltaF[(size_t)htIDX * 8];
-      float resApprox[8];
+      float resApprox[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // (every mode fills it; the initialiser only quiets -Wmaybe-uninitialized)
       if (mode == 0) for (int i = 0; i < 8; i++) resApprox[i] = rJ.resF[i];
       if (mode == 1) {
         float Jp_delta_x = (rJ.Jpdxi[0][0] * dp[0] + rJ.Jpdxi[0][1] * dp[1] + rJ.Jpdxi[0][2] * dp[2] + rJ.Jpdxi[0][3] * dp[3] + rJ.Jpdxi[0][4] * dp[4] + rJ.Jpdxi[0][5] * dp[5]) +
