@@ -139,3 +139,21 @@ def test_g2o_variant_improves_from_near_truth(setup):
     r = orc.track(f1, Tn, (0, 0), orc.levels - 1, [np.nan] * 5, 1)
     assert r["ok"]
     assert np.abs(r["T"][:, 3] - Ttrue[:, 3]).max() < np.abs(Tn[:, 3] - Ttrue[:, 3]).max()
+
+
+def test_g2o_lm_trial_accounting(setup, frames):
+    """The restated g2o LM reports its damping trials (test infrastructure: the GPU cases of
+    tests/test_gpu_tracker.py::test_track_g2o_rejected_trials rely on these scenarios containing rejected trials).
+    Per level the LM runs at most 2 iterations of at most 10 trials; a converged run near the truth accepts all of them."""
+    orc, f0, f1, pts, Ttrue = setup
+    T0 = synth.perturb_T(Ttrue, np.random.default_rng(5), 0.02, np.deg2rad(0.1))
+    r = orc.track(f1, T0, (0.0, 0.0), orc.levels - 1, [np.nan] * 5, 1)
+    trials, rejected = orc.g2o_trial_counts()
+    assert r["ok"] and rejected == 0 and trials == int(r["iterations"].sum())
+    # a larger offset: trials are rejected (lambda grows) and the run still converges
+    T1 = synth.perturb_T(Ttrue, np.random.default_rng(0), 0.3, np.deg2rad(1.5))
+    r = orc.track(f1, T1, (0.0, 0.0), orc.levels - 1, [np.nan] * 5, 1)
+    trials, rejected = orc.g2o_trial_counts()
+    assert r["ok"] and rejected >= 3 and trials - rejected >= 1
+    assert trials <= 10 * int(r["iterations"].sum())
+    assert np.abs(r["T"][:, 3] - Ttrue[:, 3]).max() < 1e-2
